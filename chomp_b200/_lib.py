@@ -1,0 +1,133 @@
+"""ctypes binding of libchomp_b200.so (the C ABI in include/chomp_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is
+usable, every compute entry point raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libchomp_b200.so")
+
+# enums of include/chomp_b200.h
+N_COSMO, N_HALO, N_HOD = 10, 6, 5
+COSMO_KEYS = ("omega_m0", "omega_b0", "omega_l0", "omega_r0", "cmb_temp", "h",
+              "sigma_8", "n_scalar", "w0", "wa")
+HALO_KEYS = ("stq", "st_little_a", "c0", "beta", "alpha", "delta_v")
+HOD_ZHENG_KEYS = ("log_M_min", "sigma", "log_M_0", "log_M_1p", "alpha")
+HOD_MANDELBAUM_KEYS = ("log_M_0", "w")
+HOD_ZHENG, HOD_MANDELBAUM = 0, 1
+P_LINEAR, P_MM, P_GM, P_GG = 0, 1, 2, 3
+POWER_SPEC = {"linear_power": P_LINEAR, "power_mm": P_MM, "power_gm": P_GM,
+              "power_mg": P_GM, "power_gg": P_GG}
+DNDZ_GAUSSIAN, DNDZ_MAGLIM = 0, 1
+WINDOW_GALAXY, WINDOW_CONVERGENCE = 0, 1
+ST_NONFINITE, ST_MASS_WALK, ST_NODE_OVERFLOW, ST_DOMAIN = 1, 2, 4, 8
+(EVAL_LINEAR_POWER, EVAL_SIGMA_R, EVAL_NU_OF_MASS, EVAL_MASS_OF_NU, EVAL_F_NU,
+ EVAL_BIAS_NU, EVAL_KERNEL, EVAL_WINDOW_A, EVAL_WINDOW_B, EVAL_Y_NFW,
+ EVAL_FIRST_MOMENT, EVAL_SECOND_MOMENT) = range(12)
+(T_ZBAR, T_DBAR, T_KERNEL_NODES, T_CHI_NODES, T_WINDOW_NODES, T_WINDOW_CHI,
+ T_EPOCH, T_LNM_NODES, T_NU_NODES, T_HALO_NODES, T_NBAR, T_NU_QUAD_COUNT) = range(12)
+KERNEL_NAMES = ("limber_tables_kernel", "mass_tables_kernel", "nu_nodes_kernel",
+                "halo_sums_kernel", "halo_splines_kernel", "wtheta_kernel")
+EPOCH_FIELDS = ("z", "growth", "sigma_norm", "delta_c", "delta_v", "rho_bar",
+                "ln_mass_min", "ln_mass_max", "nu_min", "nu_max", "f_norm",
+                "bias_norm", "ln_m_star", "pk_amp", "chi", "walk_steps")
+
+
+class Config(ctypes.Structure):
+    """Mirror of ``chomp_b200_config``."""
+    _fields_ = [
+        ("n_cosmo", ctypes.c_int32), ("n_mass", ctypes.c_int32),
+        ("n_halo", ctypes.c_int32), ("n_window", ctypes.c_int32),
+        ("n_kernel", ctypes.c_int32),
+        ("nq_nu", ctypes.c_int32), ("nq_hankel", ctypes.c_int32),
+        ("nq_limber", ctypes.c_int32), ("nq_lens", ctypes.c_int32),
+        ("hod_kind", ctypes.c_int32), ("bessel_order", ctypes.c_int32),
+        ("exclusion", ctypes.c_int32), ("extrapolate", ctypes.c_int32),
+        ("window_kind", ctypes.c_int32*2), ("dndz_kind", ctypes.c_int32*2),
+        ("reserved_i", ctypes.c_int32*3),
+        ("halo_precision", ctypes.c_double), ("cosmo_precision", ctypes.c_double),
+        ("window_precision", ctypes.c_double),
+        ("k_min", ctypes.c_double), ("k_max", ctypes.c_double),
+        ("mass_min", ctypes.c_double), ("mass_max", ctypes.c_double),
+        ("zk_min", ctypes.c_double), ("zk_max", ctypes.c_double),
+        ("dndz_zmin", ctypes.c_double*2), ("dndz_zmax", ctypes.c_double*2),
+        ("dndz_p", (ctypes.c_double*3)*2),
+        ("ktheta_min", ctypes.c_double), ("ktheta_max", ctypes.c_double),
+        ("bessel_limit", ctypes.c_double),
+        ("corr_k_min", ctypes.c_double), ("corr_k_max", ctypes.c_double),
+        ("reserved_d", ctypes.c_double*4),
+    ]
+
+
+class ChompError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGNATURES = {
+    "chomp_b200_version": (ctypes.c_int, []),
+    "chomp_b200_last_error": (ctypes.c_char_p, []),
+    "chomp_b200_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "chomp_b200_destroy": (None, [ctypes.c_void_p]),
+    "chomp_b200_configure": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Config)]),
+    "chomp_b200_reserve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "chomp_b200_limber_tables": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_void_p]),
+    "chomp_b200_mass_tables": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p]),
+    "chomp_b200_halo_tables": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "chomp_b200_power": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "chomp_b200_wtheta": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]),
+    "chomp_b200_wtheta_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p]),
+    "chomp_b200_wtheta_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_void_p]),
+    "chomp_b200_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
+    "chomp_b200_copy_table": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
+                                             ctypes.c_void_p]),
+    "chomp_b200_dfma_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.POINTER(ctypes.c_double)]),
+    "chomp_b200_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "chomp_b200_get_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "chomp_b200_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+
+def load():
+    """Load the shared library (once) and declare the argument types."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ChompError(
+                "%s is missing: build it with `make -C chomp_b200/csrc` or "
+                "`python -c 'import __graft_entry__ as g; g.build()'`; there is "
+                "no CPU fallback" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise ChompError("chomp_b200: %s" % load().chomp_b200_last_error().decode())

@@ -1,0 +1,617 @@
+// chomp_b200: host side of the C ABI (include/chomp_b200.h) -- handle, device scratch,
+// launches.  All arithmetic of the hot path lives in the kernels included below; there is
+// no CPU implementation of any stage in this library.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/chomp_b200.h"
+#include "common.cuh"
+#include "halo_tables.cuh"
+#include "hankel.cuh"
+#include "limber_tables.cuh"
+#include "mass_tables.cuh"
+#include "special.cuh"
+#include "spline.cuh"
+
+using namespace chomp;
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            g_err = buf_;                                                                          \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(msg)        \
+    do {                 \
+        g_err = (msg);   \
+        return 2;        \
+    } while (0)
+
+namespace {
+
+struct Handle {
+    int device = 0;
+    bool configured = false;
+    Cfg cfg;
+    int same_window = 0;
+    int cap_points = 0;
+    int node_cap = 0;
+    long long launches = 0;
+    // device scratch (all FP64 unless noted)
+    double *zbar = nullptr, *dbar = nullptr, *knodes = nullptr, *kcoef = nullptr, *chi_nodes = nullptr,
+           *win_nodes = nullptr, *win_chi = nullptr, *win_coef = nullptr, *kchi = nullptr;
+    double *epoch = nullptr, *lnm_nodes = nullptr, *nu_nodes = nullptr, *c_lnm_nu = nullptr, *c_nu_lnm = nullptr;
+    double *nodes = nullptr, *nbar = nullptr, *raw = nullptr, *htab = nullptr, *hcoef = nullptr;
+    int32_t* n_nodes = nullptr;
+    // parameter copies of the last batch (the evaluators need them)
+    double *cosmo = nullptr, *halo = nullptr, *hod = nullptr;
+    // staging for the *_host entry point
+    double *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *d_theta = nullptr;
+    int32_t *d_status = nullptr, *h_status = nullptr;
+    size_t stage_in = 0, stage_out = 0;
+    int stage_theta = 0;
+    cudaStream_t own_stream = nullptr;
+    // optional per-kernel timing (bench.py's roofline): events recorded around every launch
+    bool timing = false;
+    cudaEvent_t ev[CHOMP_N_KERNELS + 1] = {};
+    std::vector<void*> allocs;
+};
+
+void gauss_legendre(int n, double* x, double* w) {
+    for (int i = 0; i < n; ++i) {
+        double z = cos(M_PI * (i + 0.75) / (n + 0.5));
+        double pp = 1.0;
+        for (int it = 0; it < 100; ++it) {
+            double p1 = 1.0, p2 = 0.0;
+            for (int j = 0; j < n; ++j) {
+                const double p3 = p2;
+                p2 = p1;
+                p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0);
+            }
+            pp = n * (z * p1 - p2) / (z * z - 1.0);
+            const double dz = p1 / pp;
+            z -= dz;
+            if (fabs(dz) < 1e-16) break;
+        }
+        x[n - 1 - i] = z;
+        w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+    }
+}
+
+// event slot `i` is recorded before kernel i; slot i+1 after it
+inline void mark(Handle* h, int i, cudaStream_t s) {
+    if (h->timing) cudaEventRecord(h->ev[i], s);
+}
+
+template <typename T>
+int dev_alloc(Handle* h, T** p, size_t count) {
+    CK(cudaMalloc((void**)p, count * sizeof(T)));
+    CK(cudaMemset(*p, 0, count * sizeof(T)));
+    h->allocs.push_back((void*)*p);
+    return 0;
+}
+
+void free_scratch(Handle* h) {
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    h->cap_points = 0;
+}
+
+int check_cfg(const Cfg& c) {
+    if (c.n_cosmo < 4 || c.n_mass < 4 || c.n_halo < 8 || c.n_window < 4 || c.n_kernel < 4) FAIL("table sizes must be >= 4 (n_halo >= 8)");
+    if (c.n_cosmo > 512 || c.n_mass > 512 || c.n_halo > 1024 || c.n_window > 1024 || c.n_kernel > 512) FAIL("table size too large");
+    const int32_t orders[4] = {c.nq_nu, c.nq_hankel, c.nq_limber, c.nq_lens};
+    for (int i = 0; i < 4; ++i)
+        if (orders[i] < 1 || orders[i] > CHOMP_MAX_GL) FAIL("quadrature order out of range 1..16");
+    if (c.hod_kind != CHOMP_HOD_ZHENG && c.hod_kind != CHOMP_HOD_MANDELBAUM) FAIL("unknown hod_kind");
+    if (c.bessel_order != 0 && c.bessel_order != 2) FAIL("bessel_order must be 0 or 2");
+    if (!(c.k_min > 0 && c.k_max > c.k_min)) FAIL("bad k limits");
+    if (!(c.ktheta_min > 0 && c.ktheta_max > c.ktheta_min)) FAIL("bad ktheta limits");
+    if (c.corr_k_min > 0 && c.corr_k_min != c.k_min) FAIL("Correlation(k_min != halo k_min) is not supported yet");
+    if (c.corr_k_max > 0 && c.corr_k_max != c.k_max) FAIL("Correlation(k_max != halo k_max) is not supported yet");
+    for (int i = 0; i < 2; ++i) {
+        if (c.window_kind[i] != CHOMP_WINDOW_GALAXY && c.window_kind[i] != CHOMP_WINDOW_CONVERGENCE) FAIL("unknown window_kind");
+        if (c.dndz_kind[i] != CHOMP_DNDZ_GAUSSIAN && c.dndz_kind[i] != CHOMP_DNDZ_MAGLIM) FAIL("unknown dndz_kind");
+        if (!(c.dndz_zmax[i] > c.dndz_zmin[i])) FAIL("dndz z range empty");
+    }
+    return 0;
+}
+
+size_t mass_smem(const Cfg& c) { return (14 * (size_t)c.n_mass + 64) * sizeof(double); }
+size_t nodes_smem(const Cfg& c) { return (10 * (size_t)c.n_mass + 2 * MAX_EXTRA_BREAKS + 64 + 8) * sizeof(double); }
+size_t splines_smem(const Cfg& c) { return 36 * (size_t)c.n_halo * sizeof(double); }
+size_t wtheta_smem(const Cfg& c) { return (12 * (size_t)c.n_halo + 4 * (size_t)c.n_kernel + 8) * sizeof(double); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int chomp_b200_version(void) { return CHOMP_B200_VERSION; }
+const char* chomp_b200_last_error(void) { return g_err.c_str(); }
+
+int chomp_b200_create(void** handle, int device) {
+    if (!handle) FAIL("null handle pointer");
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) FAIL("no such CUDA device");
+    CK(cudaSetDevice(device));
+    static double glx[CHOMP_MAX_GL + 1][CHOMP_MAX_GL], glw[CHOMP_MAX_GL + 1][CHOMP_MAX_GL];
+    memset(glx, 0, sizeof glx);
+    memset(glw, 0, sizeof glw);
+    for (int n = 1; n <= CHOMP_MAX_GL; ++n) gauss_legendre(n, glx[n], glw[n]);
+    CK(cudaMemcpyToSymbol(c_glx, glx, sizeof glx));
+    CK(cudaMemcpyToSymbol(c_glw, glw, sizeof glw));
+    Handle* h = new Handle();
+    h->device = device;
+    CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    *handle = h;
+    return 0;
+}
+
+void chomp_b200_destroy(void* handle) {
+    Handle* h = (Handle*)handle;
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_scratch(h);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->d_theta) cudaFree(h->d_theta);
+    if (h->d_status) cudaFree(h->d_status);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->ev[0]) for (int i = 0; i <= CHOMP_N_KERNELS; ++i) cudaEventDestroy(h->ev[i]);
+    delete h;
+}
+
+int chomp_b200_configure(void* handle, const chomp_b200_config* cfg) {
+    Handle* h = (Handle*)handle;
+    if (!h || !cfg) FAIL("null argument");
+    if (int rc = check_cfg(*cfg)) return rc;
+    CK(cudaSetDevice(h->device));
+    const bool resize = !h->configured || h->cfg.n_cosmo != cfg->n_cosmo || h->cfg.n_mass != cfg->n_mass ||
+                        h->cfg.n_halo != cfg->n_halo || h->cfg.n_window != cfg->n_window ||
+                        h->cfg.n_kernel != cfg->n_kernel || h->cfg.nq_nu != cfg->nq_nu;
+    h->cfg = *cfg;
+    h->same_window = (cfg->window_kind[0] == cfg->window_kind[1] && cfg->dndz_kind[0] == cfg->dndz_kind[1] &&
+                      cfg->dndz_zmin[0] == cfg->dndz_zmin[1] && cfg->dndz_zmax[0] == cfg->dndz_zmax[1] &&
+                      cfg->dndz_p[0][0] == cfg->dndz_p[1][0] && cfg->dndz_p[0][1] == cfg->dndz_p[1][1] &&
+                      cfg->dndz_p[0][2] == cfg->dndz_p[1][2]);
+    h->configured = true;
+    // opt in to > 48 KB dynamic shared memory where a stage needs it
+    CK(cudaFuncSetAttribute(limber_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(limber_smem_doubles(h->cfg) * sizeof(double))));
+    CK(cudaFuncSetAttribute(halo_splines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)splines_smem(h->cfg)));
+    CK(cudaFuncSetAttribute(wtheta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wtheta_smem(h->cfg)));
+    if (resize && h->cap_points > 0) {
+        const int n = h->cap_points;
+        CK(cudaDeviceSynchronize());
+        free_scratch(h);
+        return chomp_b200_reserve(handle, n);
+    }
+    return 0;
+}
+
+int chomp_b200_reserve(void* handle, int max_points) {
+    Handle* h = (Handle*)handle;
+    if (!h || !h->configured) FAIL("configure the handle first");
+    if (max_points <= 0) FAIL("max_points must be positive");
+    if (max_points <= h->cap_points) return 0;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    free_scratch(h);
+    const Cfg& c = h->cfg;
+    const size_t B = (size_t)max_points;
+    h->node_cap = (((c.n_mass - 1 + MAX_EXTRA_BREAKS) * c.nq_nu + 31) / 32) * 32;
+    int rc = 0;
+    rc |= dev_alloc(h, &h->zbar, B);
+    rc |= dev_alloc(h, &h->dbar, B);
+    rc |= dev_alloc(h, &h->knodes, B * c.n_kernel);
+    rc |= dev_alloc(h, &h->kcoef, B * 4 * c.n_kernel);
+    rc |= dev_alloc(h, &h->chi_nodes, B * 3 * c.n_cosmo);
+    rc |= dev_alloc(h, &h->win_nodes, B * 2 * c.n_window);
+    rc |= dev_alloc(h, &h->win_chi, B * 4);
+    rc |= dev_alloc(h, &h->win_coef, B * 8 * c.n_window);
+    rc |= dev_alloc(h, &h->kchi, B * 2);
+    rc |= dev_alloc(h, &h->epoch, B * CHOMP_EPOCH_LEN);
+    rc |= dev_alloc(h, &h->lnm_nodes, B * c.n_mass);
+    rc |= dev_alloc(h, &h->nu_nodes, B * c.n_mass);
+    rc |= dev_alloc(h, &h->c_lnm_nu, B * 4 * c.n_mass);
+    rc |= dev_alloc(h, &h->c_nu_lnm, B * 4 * c.n_mass);
+    rc |= dev_alloc(h, &h->nodes, B * NODE_FIELDS * h->node_cap);
+    rc |= dev_alloc(h, &h->n_nodes, B);
+    rc |= dev_alloc(h, &h->nbar, B);
+    rc |= dev_alloc(h, &h->raw, B * 5 * c.n_halo);
+    rc |= dev_alloc(h, &h->htab, B * 5 * c.n_halo);
+    rc |= dev_alloc(h, &h->hcoef, B * 20 * c.n_halo);
+    rc |= dev_alloc(h, &h->cosmo, B * CHOMP_N_COSMO);
+    rc |= dev_alloc(h, &h->halo, B * CHOMP_N_HALO);
+    rc |= dev_alloc(h, &h->hod, B * CHOMP_N_HOD);
+    if (rc) { free_scratch(h); return rc; }
+    h->cap_points = max_points;
+    return 0;
+}
+
+static int ensure(Handle* h, int B) {
+    if (!h) FAIL("null handle");
+    if (!h->configured) FAIL("handle not configured");
+    if (B <= 0) FAIL("B must be positive");
+    CK(cudaSetDevice(h->device));
+    if (B > h->cap_points) return chomp_b200_reserve(h, B);
+    return 0;
+}
+
+int chomp_b200_limber_tables(void* handle, int B, const double* cosmo_dev, int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cosmo_dev != h->cosmo)
+        CK(cudaMemcpyAsync(h->cosmo, cosmo_dev, sizeof(double) * B * CHOMP_N_COSMO, cudaMemcpyDeviceToDevice, s));
+    LimberOut out{h->zbar, h->dbar, h->knodes, h->kcoef, h->chi_nodes, h->win_nodes, h->win_chi, h->win_coef, h->kchi};
+    const size_t smem = limber_smem_doubles(h->cfg) * sizeof(double);
+    mark(h, CHOMP_K_LIMBER, s);
+    limber_tables_kernel<<<B, LIMBER_THREADS, smem, s>>>(h->cfg, B, h->same_window, h->cosmo, out, status_dev);
+    mark(h, CHOMP_K_LIMBER + 1, s);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int chomp_b200_mass_tables(void* handle, int B, const double* cosmo_dev, const double* halo_dev,
+                           const double* z_dev, int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cosmo_dev != h->cosmo)
+        CK(cudaMemcpyAsync(h->cosmo, cosmo_dev, sizeof(double) * B * CHOMP_N_COSMO, cudaMemcpyDeviceToDevice, s));
+    if (halo_dev != h->halo)
+        CK(cudaMemcpyAsync(h->halo, halo_dev, sizeof(double) * B * CHOMP_N_HALO, cudaMemcpyDeviceToDevice, s));
+    MassOut out{h->epoch, h->lnm_nodes, h->nu_nodes, h->c_lnm_nu, h->c_nu_lnm};
+    mark(h, CHOMP_K_MASS, s);
+    mass_tables_kernel<<<B, 256, mass_smem(h->cfg), s>>>(h->cfg, B, h->cosmo, h->halo, z_dev, h->zbar, out, status_dev);
+    mark(h, CHOMP_K_MASS + 1, s);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const double* hod_dev,
+                           int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Cfg& c = h->cfg;
+    if (halo_dev != h->halo)
+        CK(cudaMemcpyAsync(h->halo, halo_dev, sizeof(double) * B * CHOMP_N_HALO, cudaMemcpyDeviceToDevice, s));
+    if (hod_dev != h->hod)
+        CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
+    NodesOut no{h->nodes, h->n_nodes, h->nbar, h->node_cap};
+    mark(h, CHOMP_K_NODES, s);
+    nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
+                                                  h->c_lnm_nu, h->c_nu_lnm, no, status_dev);
+    CK(cudaGetLastError());
+    const int warps = 8;
+    dim3 grid((c.n_halo + warps - 1) / warps, B);
+    mark(h, CHOMP_K_SUMS, s);
+    halo_sums_kernel<<<grid, warps * 32, 0, s>>>(c, B, h->nodes, h->n_nodes, h->node_cap, h->raw);
+    CK(cudaGetLastError());
+    mark(h, CHOMP_K_SPLINES, s);
+    halo_splines_kernel<<<B, 64, splines_smem(c), s>>>(c, B, h->raw, h->nbar, h->epoch, h->htab, h->hcoef, status_dev);
+    mark(h, CHOMP_K_SPLINES + 1, s);
+    CK(cudaGetLastError());
+    h->launches += 3;
+    return 0;
+}
+
+int chomp_b200_power(void* handle, int B, int which, int n_k, const double* k_dev, double* P_out_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    if (which < CHOMP_P_LINEAR || which > CHOMP_P_GG) FAIL("unknown power spectrum");
+    if (n_k <= 0) FAIL("n_k must be positive");
+    dim3 grid((n_k + 255) / 256, B);
+    power_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->cfg, B, which, n_k, k_dev, h->cosmo, h->epoch, h->htab,
+                                                        h->hcoef, P_out_dev);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int chomp_b200_wtheta(void* handle, int B, int which, int n_theta, const double* theta_dev, double* w_out_dev,
+                      int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    if (which < CHOMP_P_LINEAR || which > CHOMP_P_GG) FAIL("unknown power spectrum");
+    if (n_theta <= 0) FAIL("n_theta must be positive");
+    mark(h, CHOMP_K_WTHETA, (cudaStream_t)stream);
+    wtheta_kernel<<<B, 256, wtheta_smem(h->cfg), (cudaStream_t)stream>>>(
+        h->cfg, B, which, n_theta, theta_dev, h->cosmo, h->epoch, h->dbar, h->htab, h->hcoef, h->knodes, h->kcoef,
+        w_out_dev, status_dev);
+    mark(h, CHOMP_K_WTHETA + 1, (cudaStream_t)stream);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int chomp_b200_wtheta_batch(void* handle, int B, const double* cosmo_dev, const double* halo_dev,
+                            const double* hod_dev, int which, int n_theta, const double* theta_dev,
+                            double* w_out_dev, int32_t* status_dev, void* stream) {
+    if (status_dev) CK(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * (size_t)(B > 0 ? B : 0), (cudaStream_t)stream));
+    if (int rc = chomp_b200_limber_tables(handle, B, cosmo_dev, status_dev, stream)) return rc;
+    Handle* h = (Handle*)handle;
+    if (int rc = chomp_b200_mass_tables(handle, B, h->cosmo, halo_dev, nullptr, status_dev, stream)) return rc;
+    if (int rc = chomp_b200_halo_tables(handle, B, h->halo, hod_dev, status_dev, stream)) return rc;
+    return chomp_b200_wtheta(handle, B, which, n_theta, theta_dev, w_out_dev, status_dev, stream);
+}
+
+int chomp_b200_wtheta_batch_host(void* handle, int B, const double* cosmo_host, const double* halo_host,
+                                 const double* hod_host, int which, int n_theta, const double* theta_host,
+                                 double* w_out_host, int32_t* status_host) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    if (n_theta <= 0) FAIL("n_theta must be positive");
+    const size_t per = CHOMP_N_COSMO + CHOMP_N_HALO + CHOMP_N_HOD;
+    const size_t need_in = (size_t)B * per, need_out = (size_t)B * n_theta;
+    if (need_in > h->stage_in) {
+        if (h->h_in) cudaFreeHost(h->h_in);
+        if (h->d_in) cudaFree(h->d_in);
+        if (h->d_status) cudaFree(h->d_status);
+        if (h->h_status) cudaFreeHost(h->h_status);
+        CK(cudaMallocHost((void**)&h->h_in, need_in * sizeof(double)));
+        CK(cudaMalloc((void**)&h->d_in, need_in * sizeof(double)));
+        CK(cudaMalloc((void**)&h->d_status, (size_t)B * sizeof(int32_t)));
+        CK(cudaMallocHost((void**)&h->h_status, (size_t)B * sizeof(int32_t)));
+        h->stage_in = need_in;
+    }
+    if (need_out > h->stage_out) {
+        if (h->h_out) cudaFreeHost(h->h_out);
+        if (h->d_out) cudaFree(h->d_out);
+        CK(cudaMallocHost((void**)&h->h_out, need_out * sizeof(double)));
+        CK(cudaMalloc((void**)&h->d_out, need_out * sizeof(double)));
+        h->stage_out = need_out;
+    }
+    if (n_theta > h->stage_theta) {
+        if (h->d_theta) cudaFree(h->d_theta);
+        CK(cudaMalloc((void**)&h->d_theta, (size_t)n_theta * sizeof(double)));
+        h->stage_theta = n_theta;
+    }
+    cudaStream_t s = h->own_stream;
+    double* hc = h->h_in;
+    double* hh = hc + (size_t)B * CHOMP_N_COSMO;
+    double* ho = hh + (size_t)B * CHOMP_N_HALO;
+    memcpy(hc, cosmo_host, sizeof(double) * B * CHOMP_N_COSMO);
+    memcpy(hh, halo_host, sizeof(double) * B * CHOMP_N_HALO);
+    memcpy(ho, hod_host, sizeof(double) * B * CHOMP_N_HOD);
+    CK(cudaMemcpyAsync(h->d_in, h->h_in, need_in * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_theta, theta_host, (size_t)n_theta * sizeof(double), cudaMemcpyHostToDevice, s));
+    double* dc = h->d_in;
+    double* dh = dc + (size_t)B * CHOMP_N_COSMO;
+    double* dd = dh + (size_t)B * CHOMP_N_HALO;
+    if (int rc = chomp_b200_wtheta_batch(handle, B, dc, dh, dd, which, n_theta, h->d_theta, h->d_out, h->d_status, s)) return rc;
+    CK(cudaMemcpyAsync(h->h_out, h->d_out, need_out * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_status, h->d_status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(w_out_host, h->h_out, need_out * sizeof(double));
+    if (status_host) memcpy(status_host, h->h_status, (size_t)B * sizeof(int32_t));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// element-wise evaluators for the drop-in classes
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct EvalCtx {
+    const double *cosmo, *halo, *hod, *epoch, *lnm, *nu, *c_lnm_nu, *c_nu_lnm, *knodes, *kcoef, *win_chi, *win_coef;
+};
+
+__global__ void __launch_bounds__(128)
+eval_kernel(const Cfg cfg, int what, int n, const double* __restrict__ x, double aux, EvalCtx cx, double* __restrict__ out) {
+    __shared__ SiciTables tabs;
+    sici_tables_load(&tabs);
+    __syncthreads();
+    const Cosmo c = load_cosmo(cx.cosmo, cfg.cosmo_precision);
+    const double* e = cx.epoch;
+    if (what == CHOMP_EVAL_SIGMA_R) {
+        // one warp per abscissa
+        const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+        const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const int nw = (gridDim.x * blockDim.x) >> 5;
+        for (int i = w; i < n; i += nw) {
+            const double s2 = warp_sigma2(pk, x[i], cfg.k_min, cfg.k_max);
+            if ((threadIdx.x & 31) == 0) out[i] = sqrt(s2);
+        }
+        return;
+    }
+    const int nm = cfg.n_mass;
+    NuTab t{nm, cx.lnm, cx.nu, cx.c_lnm_nu, cx.c_nu_lnm};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double v = x[i];
+        double r = 0.0;
+        switch (what) {
+            case CHOMP_EVAL_LINEAR_POWER: r = linear_power(make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]), v); break;
+            case CHOMP_EVAL_NU_OF_MASS: r = nu_of_lnm(t, log(v)); break;
+            case CHOMP_EVAL_MASS_OF_NU: r = exp(mass_of_nu_ln(t, v)); break;
+            case CHOMP_EVAL_F_NU: case CHOMP_EVAL_BIAS_NU: {
+                double nf, bi;
+                st_raw(v, cx.halo[CHOMP_H_ST_LITTLE_A], cx.halo[CHOMP_H_STQ], e[EP_DELTA_C], nf, bi);
+                r = (what == CHOMP_EVAL_F_NU) ? nf * e[EP_F_NORM] / v : bi * e[EP_B_NORM];
+            } break;
+            case CHOMP_EVAL_KERNEL: {
+                KernelTab K{cfg.n_kernel, log(cfg.ktheta_min), log(cfg.ktheta_max),
+                            (log(cfg.ktheta_max) - log(cfg.ktheta_min)) / (cfg.n_kernel - 1), cx.knodes, cx.kcoef};
+                r = kernel_eval(K, v);
+            } break;
+            case CHOMP_EVAL_WINDOW_A: case CHOMP_EVAL_WINDOW_B: {
+                const int wi = (what == CHOMP_EVAL_WINDOW_B) ? 1 : 0;
+                Window W{cfg.n_window, cx.win_chi[2 * wi], cx.win_chi[2 * wi + 1], nullptr,
+                         const_cast<double*>(cx.win_coef) + (size_t)wi * 4 * cfg.n_window};
+                r = window_eval(W, v);
+            } break;
+            case CHOMP_EVAL_Y_NFW: {
+                const double lm = log(v);
+                const double con = cx.halo[CHOMP_H_C0] / (1.0 + e[EP_Z]) * exp(cx.halo[CHOMP_H_BETA] * (lm - e[EP_LNM_STAR]));
+                const double r_v = cbrt(3.0 * v / (4.0 * M_PI * e[EP_DELTA_V] * e[EP_RHO_BAR]));
+                const double cp = 1.0 + con, lncp = log(cp);
+                r = nfw_rho_k(&tabs, exp(aux) * r_v / con, cp, lncp) / (lncp - con / cp);
+            } break;
+            case CHOMP_EVAL_FIRST_MOMENT: case CHOMP_EVAL_SECOND_MOMENT: {
+                const HodP h = load_hod(cfg.hod_kind, cx.hod, cfg.halo_precision);
+                double n1, n2;
+                hod_moments(h, v, n1, n2);
+                r = (what == CHOMP_EVAL_FIRST_MOMENT) ? n1 : n2;
+            } break;
+            default: r = nan("");
+        }
+        out[i] = r;
+    }
+}
+
+__global__ void dfma_peak_kernel(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+           a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 0.999999999, c = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;
+}
+}  // namespace
+
+int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_dev, double aux, double* out_dev,
+                    void* stream) {
+    Handle* h = (Handle*)handle;
+    if (!h || !h->configured || h->cap_points <= 0) FAIL("no batch has been computed on this handle");
+    if (point < 0 || point >= h->cap_points) FAIL("point index out of range");
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const Cfg& c = h->cfg;
+    const size_t p = (size_t)point;
+    EvalCtx cx{h->cosmo + p * CHOMP_N_COSMO, h->halo + p * CHOMP_N_HALO, h->hod + p * CHOMP_N_HOD,
+               h->epoch + p * CHOMP_EPOCH_LEN, h->lnm_nodes + p * c.n_mass, h->nu_nodes + p * c.n_mass,
+               h->c_lnm_nu + p * 4 * c.n_mass, h->c_nu_lnm + p * 4 * c.n_mass, h->knodes + p * c.n_kernel,
+               h->kcoef + p * 4 * c.n_kernel, h->win_chi + p * 4, h->win_coef + p * 8 * c.n_window};
+    int blocks = (what == CHOMP_EVAL_SIGMA_R) ? (n + 3) / 4 : (n + 127) / 128;
+    if (blocks > 1184) blocks = 1184;
+    eval_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(c, what, n, x_dev, aux, cx, out_dev);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int chomp_b200_copy_table(void* handle, int B, int table, double* out_dev, int* len_out, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (!h || !h->configured || B <= 0 || B > h->cap_points) FAIL("bad handle or batch size");
+    CK(cudaSetDevice(h->device));
+    const Cfg& c = h->cfg;
+    const double* src = nullptr;
+    int len = 0;
+    switch (table) {
+        case CHOMP_T_ZBAR: src = h->zbar; len = 1; break;
+        case CHOMP_T_DBAR: src = h->dbar; len = 1; break;
+        case CHOMP_T_KERNEL_NODES: src = h->knodes; len = c.n_kernel; break;
+        case CHOMP_T_CHI_NODES: src = h->chi_nodes; len = 3 * c.n_cosmo; break;
+        case CHOMP_T_WINDOW_NODES: src = h->win_nodes; len = 2 * c.n_window; break;
+        case CHOMP_T_WINDOW_CHI: src = h->win_chi; len = 4; break;
+        case CHOMP_T_EPOCH: src = h->epoch; len = CHOMP_EPOCH_LEN; break;
+        case CHOMP_T_LNM_NODES: src = h->lnm_nodes; len = c.n_mass; break;
+        case CHOMP_T_NU_NODES: src = h->nu_nodes; len = c.n_mass; break;
+        case CHOMP_T_HALO_NODES: src = h->htab; len = 5 * c.n_halo; break;
+        case CHOMP_T_NBAR: src = h->nbar; len = 1; break;
+        case CHOMP_T_NU_QUAD_COUNT: len = 1; break;
+        default: FAIL("unknown table id");
+    }
+    if (len_out) *len_out = len;
+    if (!out_dev) return 0;
+    if (table == CHOMP_T_NU_QUAD_COUNT) {
+        std::vector<int32_t> tmp(B);
+        CK(cudaMemcpyAsync(tmp.data(), h->n_nodes, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CK(cudaStreamSynchronize((cudaStream_t)stream));
+        std::vector<double> d(B);
+        for (int i = 0; i < B; ++i) d[i] = (double)tmp[i];
+        CK(cudaMemcpyAsync(out_dev, d.data(), sizeof(double) * B, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        CK(cudaStreamSynchronize((cudaStream_t)stream));
+        return 0;
+    }
+    CK(cudaMemcpyAsync(out_dev, src, sizeof(double) * (size_t)B * len, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int chomp_b200_dfma_peak(void* handle, int iters, double* tflops_out) {
+    Handle* h = (Handle*)handle;
+    if (!h || !tflops_out) FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    double* sink = nullptr;
+    CK(cudaMalloc((void**)&sink, sizeof(double)));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    dfma_peak_kernel<<<blocks, threads>>>(iters / 4 + 1, sink);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        dfma_peak_kernel<<<blocks, threads>>>(iters, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    h->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops_out = best;
+    return 0;
+}
+
+int chomp_b200_set_timing(void* handle, int on) {
+    Handle* h = (Handle*)handle;
+    if (!h) FAIL("null handle");
+    CK(cudaSetDevice(h->device));
+    if (on && !h->ev[0])
+        for (int i = 0; i <= CHOMP_N_KERNELS; ++i) CK(cudaEventCreate(&h->ev[i]));
+    h->timing = on != 0;
+    return 0;
+}
+
+int chomp_b200_get_timing(void* handle, double* ms_out) {
+    Handle* h = (Handle*)handle;
+    if (!h || !ms_out || !h->ev[0]) FAIL("timing was never enabled on this handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev[CHOMP_N_KERNELS]));
+    for (int i = 0; i < CHOMP_N_KERNELS; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+        ms_out[i] = ms;
+    }
+    return 0;
+}
+
+long long chomp_b200_launch_count(void* handle) {
+    Handle* h = (Handle*)handle;
+    return h ? h->launches : 0;
+}
+
+}  // extern "C"

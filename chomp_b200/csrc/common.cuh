@@ -1,0 +1,155 @@
+// Shared device helpers: Gauss-Legendre tables, reductions, cosmology closed forms.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/chomp_b200.h"
+
+namespace chomp {
+
+#define CHOMP_MAX_GL 16
+// nodes / weights on [-1, 1] for orders 1..16 (filled once per device by chomp_b200_create)
+__constant__ double c_glx[CHOMP_MAX_GL + 1][CHOMP_MAX_GL];
+__constant__ double c_glw[CHOMP_MAX_GL + 1][CHOMP_MAX_GL];
+
+typedef chomp_b200_config Cfg;
+
+#define CHOMP_EPOCH_LEN 16
+enum { EP_Z = 0, EP_GROWTH, EP_SIGMA_NORM, EP_DELTA_C, EP_DELTA_V, EP_RHO_BAR, EP_LNM_MIN, EP_LNM_MAX, EP_NU_MIN,
+       EP_NU_MAX, EP_F_NORM, EP_B_NORM, EP_LNM_STAR, EP_PK_AMP, EP_CHI, EP_WALK };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block-wide sum; `red` is shared scratch of >= 32 doubles; all threads get the result
+__device__ inline double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += red[i];
+    return t;
+}
+
+// ---------------------------------------------------------------------------
+// cosmology closed forms (reference cosmology.py)
+// ---------------------------------------------------------------------------
+struct Cosmo {
+    double om, ob, ol, orad, tcmb, h, s8, ns, H0;
+    int flat, open;
+    int bad;
+};
+
+__device__ inline Cosmo load_cosmo(const double* __restrict__ p, double cosmo_precision) {
+    Cosmo c;
+    c.om = p[CHOMP_C_OMEGA_M0]; c.ob = p[CHOMP_C_OMEGA_B0]; c.ol = p[CHOMP_C_OMEGA_L0];
+    c.orad = p[CHOMP_C_OMEGA_R0]; c.tcmb = p[CHOMP_C_CMB_TEMP]; c.h = p[CHOMP_C_H];
+    c.s8 = p[CHOMP_C_SIGMA_8]; c.ns = p[CHOMP_C_N_SCALAR];
+    c.H0 = 100.0 / (2.998 * 100000.0);                           // cosmology.py:59
+    const double tot = c.om + c.ol + c.orad;                       // cosmology.py:65-79
+    c.flat = (tot <= 1.0 + cosmo_precision) && (tot >= 1.0 - cosmo_precision);
+    c.open = (tot <= 1.0 - cosmo_precision);
+    c.bad = (p[CHOMP_C_W0] != -1.0 || p[CHOMP_C_WA] != 0.0);       // dynamical dark energy: out of scope
+    return c;
+}
+
+// (H(z)/H0)^2, no curvature term (cosmology.py:175-178)
+__device__ __forceinline__ double E0(const Cosmo& c, double z) {
+    const double a = 1.0 / (1.0 + z);
+    return c.ol + c.om / (a * a * a) + c.orad / (a * a * a * a);
+}
+// 1/H(z) in Mpc/h (cosmology.py:153-162)
+__device__ __forceinline__ double inv_hubble(const Cosmo& c, double z) { return 1.0 / (c.H0 * sqrt(E0(c, z))); }
+
+// Carroll et al. closed form, which is what growth_factor_eval returns (cosmology.py:215-231, 326)
+__device__ __forceinline__ double growth_approx(const Cosmo& c, double a) {
+    const double om = c.om / (a * a * a);
+    const double den = c.ol + om;
+    const double Om = om / den, Ol = c.ol / den;
+    return (5.0 * Om / (2.0 / a)) / (Om * (4.0 / 7.0) - Ol + (1.0 + 0.5 * Om) * (1.0 + Ol / 70.0));
+}
+
+__device__ __forceinline__ double omega_m_z(const Cosmo& c, double z) {
+    return c.om * (1.0 + z) * (1.0 + z) * (1.0 + z) / E0(c, z);
+}
+// cosmology.py:393-407
+__device__ inline double delta_c_z(const Cosmo& c, double z) {
+    double d = 0.15 * pow(12.0 * M_PI, 2.0 / 3.0);
+    if (c.open) d *= pow(omega_m_z(c, z), 0.0185);
+    if (c.flat && c.om < 1.0001) d *= pow(omega_m_z(c, z), 0.0055);
+    return d;
+}
+// cosmology.py:409-423 (divided by the growth factor)
+__device__ inline double delta_v_z(const Cosmo& c, double z, double growth) {
+    double d = 178.0;
+    if (c.open) d /= pow(omega_m_z(c, z), 0.7);
+    if (c.flat && c.om < 1.0001) d /= pow(omega_m_z(c, z), 0.55);
+    return d / growth;
+}
+// cosmology.py:425-447
+__device__ __forceinline__ double rho_bar_z(const Cosmo& c, double z) {
+    return 1.879 / 1.989 * (3.086 * 3.086 * 3.086) * 1e10 * E0(c, z) * omega_m_z(c, z);
+}
+
+// Eisenstein-Hu zero-baryon transfer function with the reference's Python-2
+// arithmetic (cosmology.py:449-472: (Omb2)**(3/4) has exponent 0) and the
+// dimensionless spectrum Delta^2(k) (cosmology.py:574-587).
+struct PkParams {
+    double amp;      // delta_H^2 / h * growth^2 * sigma_norm^2
+    double expo;     // 3 + n_scalar
+    double ln_H0;
+    double s, alpha, omh, theta;
+};
+
+__device__ inline PkParams make_pk(const Cosmo& c, double growth, double sigma_norm) {
+    PkParams p;
+    const double delta_H = 1.94e-5 * pow(c.om, -0.785 - 0.05 * log(c.om)) *
+                           exp(-0.95 * (c.ns - 1.0) - 0.169 * (c.ns - 1.0) * (c.ns - 1.0));  // cosmology.py:83-85
+    p.amp = delta_H * delta_H / c.h * growth * growth * sigma_norm * sigma_norm;
+    p.expo = 3.0 + c.ns;
+    p.ln_H0 = log(c.H0);
+    const double omh2 = c.om * c.h * c.h;
+    const double fb = c.ob / c.om;
+    p.s = 44.5 * log(9.83 / omh2) / sqrt(1.0 + 10.0 * 1.0);
+    p.alpha = 1.0 - 0.328 * log(431.0 * omh2) * fb + 0.38 * log(22.3 * omh2) * fb * fb;
+    p.omh = c.om * c.h;
+    p.theta = c.tcmb / 2.7;
+    return p;
+}
+
+__device__ __forceinline__ double transfer_eh(const PkParams& p, double k) {
+    const double t = 1.0 + 0.43 * k * p.s;
+    const double t2 = t * t;
+    const double gamma = p.omh * (p.alpha + (1.0 - p.alpha) / (t2 * t2));
+    const double q = k * p.theta / gamma;
+    const double L0 = log(2.0 * M_E + 1.8 * q);
+    const double C0 = 14.2 + 731.0 / (1.0 + 62.5 * q);
+    return L0 / (L0 + C0 * q * q);
+}
+
+// Delta^2(k) = k^3 P(k) / (2 pi^2)
+__device__ __forceinline__ double delta2(const PkParams& p, double k, double lnk) {
+    const double T = transfer_eh(p, k);
+    return p.amp * exp(p.expo * (lnk - p.ln_H0)) * T * T;
+}
+// P(k) (cosmology.py:589-600)
+__device__ __forceinline__ double linear_power(const PkParams& p, double k) {
+    if (!(k > 1e-16)) return 1e-16;
+    return 2.0 * M_PI * M_PI * delta2(p, k, log(k)) / (k * k * k);
+}
+
+// Sheth-Tormen multiplicity and bias without their normalisations
+// (mass_function.py:243-256, 290-303)
+__device__ __forceinline__ void st_raw(double nu, double sta, double stq, double delta_c, double& nu_f, double& bias) {
+    const double nup = nu * sta;
+    const double pq = pow(nup, -stq);
+    nu_f = (1.0 + pq) * sqrt(nup) * exp(-0.5 * nup);  // nu * f(nu) / f_norm
+    bias = 1.0 + (nup - 1.0) / delta_c + 2.0 * stq / (delta_c * (1.0 + 1.0 / pq));
+}
+
+}  // namespace chomp

@@ -1,0 +1,346 @@
+// Stage 3: the nu-space halo-model mass integrals.
+//
+//   nu_nodes_kernel    per point: kink-aware Gauss-Legendre node list in ln(nu) with every
+//                      k-independent factor folded into per-node weights, plus n_bar
+//   halo_sums_kernel   one warp per (point, k): NFW Fourier profile at every node and the
+//                      five sums h_m, pp_mm, h_g, pp_gm, pp_gg               (the hot kernel)
+//   halo_splines_kernel per point: normalisations and the five not-a-knot splines in ln k
+//
+// Replaces (reference): Halo._calculate_n_bar halo.py:674-707; _initialize_h_m :904-927,
+// _h_g :929-969, _pp_mm :971-994, _pp_gg :996-1041, _pp_gm :1043-1086; y_nfw :561-585;
+// _concentration / _virial_radius :869-902; HaloExclusion._mass_window :1223-1233;
+// HODZheng hod.py:141-230; HODMandelbaum hod.py:232-299.
+//
+// The reference integrates each of these with Romberg over ln(nu) and ignores the kinks of
+// the integrands; here the range is cut at every point where an integrand is not smooth
+// (knots of the ln M(nu) spline, HOD lower limits, the satellite turn-on M_0, the
+// <N> = 1 and <N(N-1)> = 1 exponent switches) and each panel gets an nq_nu-point rule.
+#pragma once
+#include "common.cuh"
+#include "special.cuh"
+#include "spline.cuh"
+
+namespace chomp {
+
+#define NODE_FIELDS 11
+enum { NF_C = 0, NF_RS, NF_INV_MK, NF_LNCP, NF_W_HM, NF_W_PMM, NF_W_HG, NF_W_GM1, NF_W_GM2, NF_W_GG1, NF_W_GG2 };
+#define MAX_EXTRA_BREAKS 8
+
+struct HodP {
+    int kind;
+    double log_M_min, sigma, log_M_0, log_M_1p, alpha, w;
+    double M0, M1p, Mmin;          // 10**log_M_0, 10**log_M_1p, 10**log_M_min
+    double first_zero, second_zero; // hod.py:176-185; -1 for Mandelbaum
+};
+
+__device__ inline HodP load_hod(int kind, const double* __restrict__ p, double halo_precision) {
+    HodP h;
+    h.kind = kind;
+    if (kind == CHOMP_HOD_ZHENG) {
+        h.log_M_min = p[0]; h.sigma = p[1]; h.log_M_0 = p[2]; h.log_M_1p = p[3]; h.alpha = p[4]; h.w = 0.0;
+        h.first_zero = pow(10.0, h.log_M_min + h.sigma * erfinv(2.0 * halo_precision - 1.0));
+        h.second_zero = pow(10.0, h.log_M_0);   // the reference's clamp is a typo'd no-op (hod.py:183-184)
+    } else {
+        h.log_M_0 = p[0]; h.w = p[1]; h.log_M_min = log10(3.0) + p[0];
+        h.sigma = 0.0; h.log_M_1p = 0.0; h.alpha = 0.0;
+        h.first_zero = -1.0; h.second_zero = -1.0;
+    }
+    h.M0 = pow(10.0, h.log_M_0);
+    h.M1p = pow(10.0, h.log_M_1p);
+    h.Mmin = pow(10.0, h.log_M_min);
+    return h;
+}
+
+// <N>, <N(N-1)>  (hod.py:188-230 Zheng, 262-299 Mandelbaum)
+__device__ __forceinline__ void hod_moments(const HodP& h, double M, double& n1, double& n2) {
+    const double lg = log10(M);
+    double nc, ns;
+    if (h.kind == CHOMP_HOD_ZHENG) {
+        if (h.sigma <= 0.0) nc = (lg > h.log_M_min) ? 1.0 : 0.0;
+        else nc = 0.5 * (1.0 + erf((lg - h.log_M_min) / h.sigma));
+        const double d = M - h.M0;
+        ns = (d > 0.0) ? nc * pow(d / h.M1p, h.alpha) : 0.0;
+    } else {
+        nc = (lg >= h.log_M_0) ? 1.0 : 0.0;
+        const double r = M / h.Mmin;
+        ns = (lg < h.log_M_min) ? r * r * h.w : r * h.w;
+    }
+    n1 = nc + ns;
+    n2 = (2.0 + ns) * ns;
+}
+
+struct NuTab {   // shared-memory view of stage 2's tables for one point
+    int n;
+    const double *lnm, *nu, *c_lnm_nu, *c_nu_lnm;
+};
+
+__device__ __forceinline__ double mass_of_nu_ln(const NuTab& t, double nu) {
+    return spline_eval_search(t.c_lnm_nu, nu, t.nu, t.n);    // MassFunction.ln_mass, mass_function.py:326
+}
+__device__ __forceinline__ double nu_of_lnm(const NuTab& t, double lnm) {
+    const double h = (t.lnm[t.n - 1] - t.lnm[0]) / (t.n - 1);
+    return spline_eval_uniform(t.c_nu_lnm, lnm, t.lnm[0], h, t.n);  // MassFunction.nu, :315
+}
+
+// ln(nu) at which exp(ln_mass(nu)) equals the target mass; NaN if outside (nu_min, nu_max).
+__device__ inline double lnnu_of_lnm_inverse(const NuTab& t, double lnm_t, double nu_min, double nu_max) {
+    if (!(mass_of_nu_ln(t, nu_min) < lnm_t) || !(mass_of_nu_ln(t, nu_max) > lnm_t)) return nan("");
+    int i = 0;
+    while (i < t.n - 2 && t.lnm[i + 1] <= lnm_t) ++i;       // node values bracket the root
+    double lo = t.nu[i], hi = t.nu[i + 1];
+    for (int it = 0; it < 64; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (spline_poly(t.c_lnm_nu, i, mid - t.nu[i]) < lnm_t) lo = mid; else hi = mid;
+    }
+    return log(0.5 * (lo + hi));
+}
+
+// ln(nu) in (a, b) where moment(mass(nu)) crosses 1 (which = 1: <N>, 2: <N(N-1)>); NaN if none.
+// Both moments are non-decreasing in mass.
+__device__ inline double lnnu_moment_crossing(const NuTab& t, const HodP& h, int which, double a, double b) {
+    double n1, n2;
+    hod_moments(h, exp(mass_of_nu_ln(t, exp(a))), n1, n2);
+    if (!((which == 1 ? n1 : n2) < 1.0)) return nan("");
+    hod_moments(h, exp(mass_of_nu_ln(t, exp(b))), n1, n2);
+    if ((which == 1 ? n1 : n2) < 1.0) return nan("");
+    double lo = a, hi = b;
+    for (int it = 0; it < 64; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        hod_moments(h, exp(mass_of_nu_ln(t, exp(mid))), n1, n2);
+        if ((which == 1 ? n1 : n2) < 1.0) lo = mid; else hi = mid;
+    }
+    return hi;   // first abscissa on the ">= 1" side
+}
+
+struct NodesOut {
+    double* nodes;     // [B, NODE_FIELDS, cap]
+    int32_t* n_nodes;  // [B]
+    double* nbar;      // [B] n_bar / rho_bar
+    int cap;
+};
+
+__global__ void __launch_bounds__(128)
+nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const double* __restrict__ hod,
+                const double* __restrict__ epoch, const double* __restrict__ g_lnm, const double* __restrict__ g_nu,
+                const double* __restrict__ g_c1, const double* __restrict__ g_c2, NodesOut out,
+                int32_t* __restrict__ status) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    const int n = cfg.n_mass, tid = threadIdx.x;
+    double* lnm = sm;
+    double* nu = lnm + n;
+    double* c1 = nu + n;
+    double* c2 = c1 + 4 * n;
+    double* edge = c2 + 4 * n;                 // n + MAX_EXTRA_BREAKS
+    double* extra = edge + n + MAX_EXTRA_BREAKS;  // MAX_EXTRA_BREAKS
+    double* red = extra + MAX_EXTRA_BREAKS;    // 64
+    __shared__ int n_edge;
+    __shared__ double x_singular;
+    for (int i = tid; i < n; i += blockDim.x) { lnm[i] = g_lnm[(size_t)b * n + i]; nu[i] = g_nu[(size_t)b * n + i]; }
+    for (int i = tid; i < 4 * (n - 1); i += blockDim.x) {
+        c1[i] = g_c1[(size_t)b * 4 * n + i];
+        c2[i] = g_c2[(size_t)b * 4 * n + i];
+    }
+    __syncthreads();
+    NuTab t{n, lnm, nu, c1, c2};
+    const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
+    const double nu_min = e[EP_NU_MIN], nu_max = e[EP_NU_MAX];
+    const double l_min = log(nu_min), l_max = log(nu_max);
+    const HodP h = load_hod(cfg.hod_kind, hod + (size_t)b * CHOMP_N_HOD, cfg.halo_precision);
+    // lower limits of the galaxy integrals (halo.py:675-679, 935-939, 1002-1006, 1049-1053)
+    double x_lo1 = l_min, x_lo2 = l_min;
+    if (h.first_zero > -1.0 && h.first_zero > exp(e[EP_LNM_MIN])) x_lo1 = log(nu_of_lnm(t, log(h.first_zero)));
+    if (h.second_zero > -1.0 && h.second_zero > exp(e[EP_LNM_MIN])) x_lo2 = log(nu_of_lnm(t, log(h.second_zero)));
+    // ---- break points, one per thread -----------------------------------------------------
+    if (tid < MAX_EXTRA_BREAKS) {
+        double x = nan("");
+        switch (tid) {
+            case 0: x = x_lo1; break;
+            case 1: x = x_lo2; break;
+            case 2: x = lnnu_of_lnm_inverse(t, log(h.M0), nu_min, nu_max); break;          // satellite turn-on / central step
+            case 3:   // Mandelbaum satellite slope change at 3 M_0; Zheng central step when sigma <= 0
+                if (h.kind == CHOMP_HOD_MANDELBAUM || h.sigma <= 0.0)
+                    x = lnnu_of_lnm_inverse(t, log(h.Mmin), nu_min, nu_max);
+                break;
+            case 4: x = lnnu_moment_crossing(t, h, 1, fmax(x_lo1, l_min), l_max); break;   // halo.py:1084-1086
+            case 5: x = lnnu_moment_crossing(t, h, 2, fmax(x_lo2, l_min), l_max); break;   // halo.py:1038-1041
+            default: break;
+        }
+        extra[tid] = x;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int cnt = 0;
+        edge[cnt++] = l_min;
+        for (int i = 1; i < n - 1; ++i) {
+            const double x = log(nu[i]);
+            if (x > l_min && x < l_max) edge[cnt++] = x;
+        }
+        edge[cnt++] = l_max;
+        double x_sing = nan("");
+        if (h.kind == CHOMP_HOD_ZHENG) x_sing = extra[2];
+        for (int j = 0; j < MAX_EXTRA_BREAKS; ++j) {
+            const double x = extra[j];
+            if (!(x > l_min && x < l_max)) continue;
+            int pos = 0;
+            while (pos < cnt && edge[pos] < x) ++pos;
+            const double tol = 1e-12;
+            if ((pos < cnt && fabs(edge[pos] - x) < tol) || (pos > 0 && fabs(edge[pos - 1] - x) < tol)) continue;
+            for (int k = cnt; k > pos; --k) edge[k] = edge[k - 1];
+            edge[pos] = x;
+            ++cnt;
+        }
+        n_edge = cnt;
+        x_singular = x_sing;
+    }
+    __syncthreads();
+    // ---- nodes ------------------------------------------------------------------------------
+    const int nq = cfg.nq_nu;
+    const int n_pan = n_edge - 1;
+    const int total = n_pan * nq;
+    const double* hp = halo + (size_t)b * CHOMP_N_HALO;
+    const double stq = hp[CHOMP_H_STQ], sta = hp[CHOMP_H_ST_LITTLE_A], beta = hp[CHOMP_H_BETA];
+    const double c0 = hp[CHOMP_H_C0] / (1.0 + e[EP_Z]);                   // halo.py:65
+    const double f_norm = e[EP_F_NORM], b_norm = e[EP_B_NORM], delta_c = e[EP_DELTA_C];
+    const double rho_bar = e[EP_RHO_BAR], delta_v = e[EP_DELTA_V], lnm_star = e[EP_LNM_STAR];
+    double* rec = out.nodes + (size_t)b * NODE_FIELDS * out.cap;
+    double nbar = 0.0;
+    if (total > out.cap) {
+        if (tid == 0 && status) atomicOr(status + b, CHOMP_ST_NODE_OVERFLOW);
+    }
+    for (int idx = tid; idx < total && idx < out.cap; idx += blockDim.x) {
+        const int p = idx / nq, q = idx - p * nq;
+        const double a = edge[p], bb = edge[p + 1];
+        double x, wq;
+        if (a >= x_singular - 1e-12 && a <= x_singular + 0.02) {
+            // x = a + (b - a) t^4 removes the (M - M0)^alpha end-point behaviour (hod.py:226-230);
+            // also applied when the panel starts just above M0 (lower limit from the forward spline)
+            const double tt = 0.5 * (c_glx[nq][q] + 1.0);
+            const double t2 = tt * tt;
+            x = a + (bb - a) * t2 * t2;
+            wq = (bb - a) * 4.0 * t2 * tt * 0.5 * c_glw[nq][q];
+        } else {
+            const double half = 0.5 * (bb - a);
+            x = 0.5 * (a + bb) + half * c_glx[nq][q];
+            wq = half * c_glw[nq][q];
+        }
+        const double xmid = 0.5 * (a + bb);
+        const double v = exp(x);
+        const double lm = mass_of_nu_ln(t, v);
+        const double M = exp(lm);
+        double nf, bias;
+        st_raw(v, sta, stq, delta_c, nf, bias);
+        const double wt = wq * nf * f_norm;          // d ln(nu) * nu f(nu)
+        bias *= b_norm;
+        const double con = c0 * exp(beta * (lm - lnm_star));                           // halo.py:869-873
+        const double r_v = cbrt(3.0 * M / (4.0 * M_PI * delta_v * rho_bar));           // halo.py:890-893
+        const double cp = 1.0 + con;
+        const double lncp = log(cp);
+        double n1, n2;
+        hod_moments(h, M, n1, n2);
+        const double in1 = (xmid > x_lo1) ? 1.0 : 0.0, in2 = (xmid > x_lo2) ? 1.0 : 0.0;
+        rec[NF_C * out.cap + idx] = con;
+        rec[NF_RS * out.cap + idx] = r_v / con;
+        rec[NF_INV_MK * out.cap + idx] = 1.0 / (lncp - con / cp);
+        rec[NF_LNCP * out.cap + idx] = lncp;
+        rec[NF_W_HM * out.cap + idx] = wt * bias;                                       // halo.py:923-927
+        rec[NF_W_PMM * out.cap + idx] = wt * M / rho_bar;                               // halo.py:990-994, :919
+        rec[NF_W_HG * out.cap + idx] = in1 * wt * bias * n1 / M;                        // halo.py:964-969
+        const double wgm = in1 * wt * n1;                                               // halo.py:1078-1086
+        rec[NF_W_GM1 * out.cap + idx] = (n1 < 1.0) ? wgm : 0.0;
+        rec[NF_W_GM2 * out.cap + idx] = (n1 < 1.0) ? 0.0 : wgm;
+        const double wgg = in2 * wt * n2 / M;                                           // halo.py:1032-1041
+        rec[NF_W_GG1 * out.cap + idx] = (n2 < 1.0) ? wgg : 0.0;
+        rec[NF_W_GG2 * out.cap + idx] = (n2 < 1.0) ? 0.0 : wgg;
+        nbar += in1 * wt * n1 / M;                                                      // halo.py:704-707
+    }
+    nbar = block_sum(nbar, red);
+    if (tid == 0) {
+        out.n_nodes[b] = total < out.cap ? total : out.cap;
+        out.nbar[b] = nbar;
+        if (!isfinite(nbar) && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
+    }
+}
+
+// HaloExclusion._mass_window (halo.py:1223-1233), kR = 2 k r_v
+__device__ __forceinline__ double exclusion_window(const SiciTables* t, double kR) {
+    double si, ci, s, c;
+    sici(t, kR, si, ci);
+    sincos(kR, &s, &c);
+    return (kR * c + kR * kR * kR * ci + (2.0 - kR * kR) * s) / (3.0 * kR);
+}
+
+// One warp per (point, ln k node); lanes stride the nu nodes.
+__global__ void __launch_bounds__(256)
+halo_sums_kernel(const Cfg cfg, int B, const double* __restrict__ nodes, const int32_t* __restrict__ n_nodes,
+                 int cap, double* __restrict__ raw /* [B, 5, n_halo] */) {
+    __shared__ SiciTables tabs;
+    sici_tables_load(&tabs);
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ik = blockIdx.x * (blockDim.x >> 5) + w;
+    const int nk = cfg.n_halo;
+    if (b >= B || ik >= nk) return;
+    const double l0 = log(cfg.k_min), l1 = log(cfg.k_max);
+    const double lnk = (ik == nk - 1) ? l1 : l0 + (l1 - l0) / (nk - 1) * ik;      // halo.py:49-51
+    const double k = exp(lnk);
+    const double* __restrict__ rec = nodes + (size_t)b * NODE_FIELDS * cap;
+    const int nn = n_nodes[b];
+    double a_hm = 0.0, a_pmm = 0.0, a_hg = 0.0, a_gm = 0.0, a_gg = 0.0;
+    for (int i = lane; i < nn; i += 32) {
+        const double con = rec[NF_C * cap + i];
+        const double rs = rec[NF_RS * cap + i];
+        const double rho = nfw_rho_k(&tabs, k * rs, 1.0 + con, rec[NF_LNCP * cap + i]);
+        const double y = rho * rec[NF_INV_MK * cap + i];                            // halo.py:584-585
+        const double y2 = y * y;
+        double y2h = y;
+        if (cfg.exclusion) y2h = y * exclusion_window(&tabs, 2.0 * k * rs * con);
+        a_hm = fma(rec[NF_W_HM * cap + i], y2h, a_hm);
+        a_pmm = fma(rec[NF_W_PMM * cap + i], y2, a_pmm);
+        a_hg = fma(rec[NF_W_HG * cap + i], y2h, a_hg);
+        a_gm = fma(rec[NF_W_GM1 * cap + i], y, fma(rec[NF_W_GM2 * cap + i], y2, a_gm));
+        a_gg = fma(rec[NF_W_GG1 * cap + i], y, fma(rec[NF_W_GG2 * cap + i], y2, a_gg));
+    }
+    a_hm = warp_sum(a_hm); a_pmm = warp_sum(a_pmm); a_hg = warp_sum(a_hg);
+    a_gm = warp_sum(a_gm); a_gg = warp_sum(a_gg);
+    if (lane == 0) {
+        double* r = raw + (size_t)b * 5 * nk;
+        r[0 * nk + ik] = a_hm; r[1 * nk + ik] = a_pmm; r[2 * nk + ik] = a_hg;
+        r[3 * nk + ik] = a_gm; r[4 * nk + ik] = a_gg;
+    }
+}
+
+// Normalise (halo.py:919, 958, 988, 1028, 1074) and spline the five tables in ln k.
+__global__ void __launch_bounds__(64)
+halo_splines_kernel(const Cfg cfg, int B, const double* __restrict__ raw, const double* __restrict__ nbar,
+                    const double* __restrict__ epoch, double* __restrict__ tab /* [B,5,n_halo] */,
+                    double* __restrict__ coef /* [B,5,4 n_halo] */, int32_t* __restrict__ status) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    const int nk = cfg.n_halo, tid = threadIdx.x;
+    double* x = sm;              // nk
+    double* y = x + nk;          // 5 nk
+    double* cf = y + 5 * nk;     // 5 * 4 nk
+    double* work = cf + 20 * nk; // 5 * 2 nk
+    const double l0 = log(cfg.k_min), l1 = log(cfg.k_max);
+    const double nb = nbar[b], rho_bar = epoch[(size_t)b * CHOMP_EPOCH_LEN + EP_RHO_BAR];
+    const double scale[5] = {1.0, 1.0, 1.0 / nb, 1.0 / (nb * rho_bar), 1.0 / (nb * nb * rho_bar)};
+    for (int i = tid; i < nk; i += blockDim.x) x[i] = (i == nk - 1) ? l1 : l0 + (l1 - l0) / (nk - 1) * i;
+    bool bad = false;
+    for (int i = tid; i < 5 * nk; i += blockDim.x) {
+        const double v = raw[(size_t)b * 5 * nk + i] * scale[i / nk];
+        y[i] = v;
+        tab[(size_t)b * 5 * nk + i] = v;
+        if (!isfinite(v)) bad = true;
+    }
+    if (bad && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
+    __syncthreads();
+    if (tid < 5) spline_build(nk, x, y + tid * nk, cf + tid * 4 * nk, work + tid * 2 * nk);
+    __syncthreads();
+    for (int i = tid; i < 20 * nk; i += blockDim.x) coef[(size_t)b * 20 * nk + i] = cf[i];
+}
+
+}  // namespace chomp

@@ -1,0 +1,186 @@
+// Stage 4: halo-model power spectra from the splined tables and the Hankel-type k integral
+//     w(theta) = int dln k  k^2/(2 pi) P(k)/D(z_bar)^2  K(ln k theta)
+// Replaces (reference): Halo.linear_power / power_mm / power_gm / power_gg halo.py:266-439,
+// _h_m ... _pp_gg wrappers :649-672; Correlation.correlation / _correlation_integrand
+// correlation.py:242-275.
+//
+// The integrand is a product of splines: smooth between the ln k knots of the halo tables
+// and the (theta-shifted) ln k theta knots of the kernel table.  Each halo-table interval is
+// cut at the kernel knot that falls inside it (there is at most one as long as the halo grid
+// is finer than the kernel grid; otherwise at its midpoint) and each piece gets an
+// nq_hankel-point Gauss-Legendre rule.  One warp per (point, theta).
+#pragma once
+#include "common.cuh"
+#include "spline.cuh"
+
+namespace chomp {
+
+struct HaloTabs {          // per-point views
+    int nk;
+    double l0, l1, h;       // ln k_min, ln k_max, knot spacing
+    double k_min, k_max;
+    const double* tab;      // [5, nk] node values
+    const double* coef;     // [5, 4 nk]
+    int extrapolate;
+};
+
+__device__ __forceinline__ void which_tables(int which, int& a, int& b, int& pp) {
+    // h_m = 0, pp_mm = 1, h_g = 2, pp_gm = 3, pp_gg = 4
+    if (which == CHOMP_P_MM) { a = 0; b = 0; pp = 1; }
+    else if (which == CHOMP_P_GM) { a = 2; b = 0; pp = 3; }
+    else { a = 2; b = 2; pp = 4; }
+}
+
+// value of table t at ln k inside [l0, l1], interval index i given
+__device__ __forceinline__ double tab_at(const HaloTabs& T, int t, int i, double dx) {
+    return spline_poly(T.coef + (size_t)t * 4 * T.nk, i, dx);
+}
+
+// Halo.power_xx(k) for any k (halo.py:277-439)
+__device__ inline double halo_power(const HaloTabs& T, const PkParams& pk, int which, double k) {
+    const double pl = linear_power(pk, k);
+    if (which == CHOMP_P_LINEAR) return pl;
+    int a, b, pp;
+    which_tables(which, a, b, pp);
+    const int nk = T.nk;
+    if (k < T.k_min) {
+        // P_lin(k) * [h_a h_b + pp / P_lin] at k_min
+        const double va = T.tab[a * nk], vb = T.tab[b * nk], vp = T.tab[pp * nk];
+        return pl * (va * vb + vp / linear_power(pk, T.k_min));
+    }
+    const bool inside = T.extrapolate ? (k < T.k_max) : (k <= T.k_max);
+    if (inside) {
+        const double x = log(k);
+        const int i = uniform_index(x, T.l0, 1.0 / T.h, nk);
+        const double dx = x - (T.l0 + T.h * i);
+        return pl * tab_at(T, a, i, dx) * tab_at(T, b, i, dx) + tab_at(T, pp, i, dx);
+    }
+    if (!T.extrapolate) return 0.0;
+    const double pmax = linear_power(pk, T.k_max);
+    const double at_max = pmax * T.tab[a * nk + nk - 1] * T.tab[b * nk + nk - 1] + T.tab[pp * nk + nk - 1];
+    if (which == CHOMP_P_MM) return pl * at_max / pmax;                       // halo.py:308-312
+    // power law with the mean log-slope over nodes [-7:-1] (halo.py:343-351, 407-415)
+    double lv[6];
+    for (int j = 0; j < 6; ++j) {
+        const int i = nk - 7 + j;
+        const double kk = exp(T.l0 + T.h * i);
+        lv[j] = log(linear_power(pk, kk) * T.tab[a * nk + i] * T.tab[b * nk + i] + T.tab[pp * nk + i]);
+    }
+    double slope = 0.0;
+    for (int j = 0; j < 5; ++j) slope += (lv[j + 1] - lv[j]) / T.h;
+    slope /= 5.0;
+    return pow(k / T.k_max, slope) * at_max;
+}
+
+struct KernelTab {
+    int n;
+    double x0, x1, h;       // ln ktheta_min, ln ktheta_max, spacing
+    const double* nodes;    // [n]
+    const double* coef;     // [4 n]
+};
+// Kernel.kernel (kernel.py:714-729)
+__device__ __forceinline__ double kernel_eval(const KernelTab& K, double u) {
+    if (u < K.x0) return K.nodes[0];
+    if (!(u <= K.x1)) return 0.0;
+    const int i = uniform_index(u, K.x0, 1.0 / K.h, K.n);
+    return spline_poly(K.coef, i, u - (K.x0 + K.h * i));
+}
+
+__global__ void __launch_bounds__(256)
+power_kernel(const Cfg cfg, int B, int which, int n_k, const double* __restrict__ k_in,
+             const double* __restrict__ cosmo, const double* __restrict__ epoch,
+             const double* __restrict__ htab, const double* __restrict__ hcoef, double* __restrict__ P_out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || i >= n_k) return;
+    const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
+    const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
+    const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    HaloTabs T;
+    T.nk = cfg.n_halo; T.l0 = log(cfg.k_min); T.l1 = log(cfg.k_max); T.h = (T.l1 - T.l0) / (T.nk - 1);
+    T.k_min = cfg.k_min; T.k_max = cfg.k_max; T.extrapolate = cfg.extrapolate;
+    T.tab = htab + (size_t)b * 5 * T.nk; T.coef = hcoef + (size_t)b * 20 * T.nk;
+    P_out[(size_t)b * n_k + i] = halo_power(T, pk, which, k_in[i]);
+}
+
+// grid (B), 256 threads: warps loop over theta.
+__global__ void __launch_bounds__(256)
+wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __restrict__ theta,
+              const double* __restrict__ cosmo, const double* __restrict__ epoch, const double* __restrict__ dbar,
+              const double* __restrict__ htab, const double* __restrict__ hcoef,
+              const double* __restrict__ knodes, const double* __restrict__ kcoef,
+              double* __restrict__ w_out, int32_t* __restrict__ status) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+    const int nk = cfg.n_halo, nkt = cfg.n_kernel, nq = cfg.nq_hankel;
+    // stage the tables this point needs in shared memory
+    int ta = 0, tb = 0, tpp = 1;
+    if (which != CHOMP_P_LINEAR) which_tables(which, ta, tb, tpp);
+    double* s_a = sm;                 // 4 nk
+    double* s_b = s_a + 4 * nk;       // 4 nk
+    double* s_pp = s_b + 4 * nk;      // 4 nk
+    double* s_kc = s_pp + 4 * nk;     // 4 nkt
+    double* s_ends = s_kc + 4 * nkt;  // 8: node values needed by the branches outside the table
+    const double* hc = hcoef + (size_t)b * 20 * nk;
+    for (int i = tid; i < 4 * (nk - 1); i += blockDim.x) {
+        s_a[i] = hc[(size_t)ta * 4 * nk + i];
+        s_b[i] = hc[(size_t)tb * 4 * nk + i];
+        s_pp[i] = hc[(size_t)tpp * 4 * nk + i];
+    }
+    for (int i = tid; i < 4 * (nkt - 1); i += blockDim.x) s_kc[i] = kcoef[(size_t)b * 4 * nkt + i];
+    if (tid == 0) s_ends[0] = knodes[(size_t)b * nkt];
+    __syncthreads();
+    const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
+    const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
+    const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    const double D = dbar[b];
+    const double inv_norm = 1.0 / (2.0 * M_PI * D * D);
+    const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hP = (l1 - l0) / (nk - 1);
+    const double x0 = log(cfg.ktheta_min), x1 = log(cfg.ktheta_max), hK = (x1 - x0) / (nkt - 1);
+    const double k_first = s_ends[0];
+    const int per_int = 2 * nq;
+    const int total = (nk - 1) * per_int;
+    for (int it = wid; it < n_theta; it += nwarp) {
+        const double lt = log(theta[it]);
+        double acc = 0.0;
+        for (int idx = lane; idx < total; idx += 32) {
+            const int i = idx / per_int, r = idx - i * per_int;
+            const int s = r / nq, q = r - s * nq;
+            const double a = l0 + hP * i;
+            const double bb = (i == nk - 2) ? l1 : l0 + hP * (i + 1);
+            // kernel knot inside (a, b)?
+            const double m = ceil((a + lt - x0) / hK);
+            double split = x0 + m * hK - lt;
+            const double tol = 1e-9 * hP;
+            if (!(m >= 0.0 && m <= (double)(nkt - 1) && split > a + tol && split < bb - tol)) split = 0.5 * (a + bb);
+            const double pa = s ? split : a, pb = s ? bb : split;
+            const double half = 0.5 * (pb - pa), mid = 0.5 * (pa + pb);
+            const double x = mid + half * c_glx[nq][q];
+            const double k = exp(x);
+            const double dx = x - a;
+            double P = 2.0 * M_PI * M_PI * delta2(pk, k, x) / (k * k * k);
+            if (which != CHOMP_P_LINEAR)
+                P = P * spline_poly(s_a, i, dx) * spline_poly(s_b, i, dx) + spline_poly(s_pp, i, dx);
+            // kernel table: the piece lies inside one kernel interval, pick it from the midpoint
+            const double um = mid + lt, u = x + lt;
+            double Kv;
+            if (um < x0) Kv = k_first;
+            else if (um > x1) Kv = 0.0;
+            else {
+                int j = (int)floor((um - x0) / hK);
+                j = j < 0 ? 0 : (j > nkt - 2 ? nkt - 2 : j);
+                Kv = spline_poly(s_kc, j, u - (x0 + hK * j));
+            }
+            acc += half * c_glw[nq][q] * k * k * P * Kv;
+        }
+        acc = warp_sum(acc) * inv_norm;
+        if (lane == 0) {
+            w_out[(size_t)b * n_theta + it] = acc;
+            if (!isfinite(acc) && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
+        }
+    }
+}
+
+}  // namespace chomp

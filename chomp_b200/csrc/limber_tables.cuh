@@ -1,0 +1,389 @@
+// Stage 1: comoving-distance / growth tables, redshift windows, z_bar and the Limber
+// kernel table K(ln k theta).  One CTA (128 threads) per parameter point.
+//
+// Replaces (reference): MultiEpoch._initialize_splines cosmology.py:787-817 and accessors
+// :873-953; dNdz.normalize kernel.py:43-54; dNdzGaussian :89-112; dNdzMagLim :148-179;
+// WindowFunction.set_cosmology_object / _initialize_spline / window_function :289-340;
+// WindowFunctionGalaxy.raw_window_function :382-387; WindowFunctionConvergence
+// .raw_window_function / _lensing_integrand :443-484; Kernel.__init__ / _find_z_bar /
+// raw_kernel / _kernel_integrand / _initialize_spline :584-712; GalaxyGalaxyLensingKernel
+// :784-839.
+//
+// Where the reference runs an adaptive Romberg per table node, the device integrates
+// panel-wise between the knots of the splines that make up each integrand (those are the
+// only places the integrands are not smooth) with fixed Gauss-Legendre orders.
+#pragma once
+#include "common.cuh"
+#include "special.cuh"
+#include "spline.cuh"
+
+namespace chomp {
+
+#define LIMBER_THREADS 128
+#define DNDZ_PANELS 16
+
+struct EpochGrid {     // one MultiEpoch tabulation (cosmology.py:747-817)
+    int n;
+    double z_min, z_max;
+    double *z, *chi, *growth;           // nodes
+    double *c_chi_z, *c_z_chi, *c_g_z;  // spline coefficients
+};
+
+// MultiEpoch.comoving_distance (cosmology.py:873-893)
+__device__ __forceinline__ double grid_chi(const EpochGrid& g, double z) {
+    if (!(z <= g.z_max && z >= g.z_min)) return 0.0;
+    return spline_eval_uniform(g.c_chi_z, z, g.z_min, (g.z_max - g.z_min) / (g.n - 1), g.n);
+}
+// MultiEpoch.redshift (cosmology.py:922-932)
+__device__ __forceinline__ double grid_z(const EpochGrid& g, double chi) {
+    return spline_eval_search(g.c_z_chi, chi, g.chi, g.n);
+}
+// MultiEpoch.growth_factor (cosmology.py:934-953)
+__device__ __forceinline__ double grid_growth(const EpochGrid& g, double z) {
+    if (!(z <= g.z_max && z >= g.z_min)) return 1.0;
+    return spline_eval_uniform(g.c_g_z, z, g.z_min, (g.z_max - g.z_min) / (g.n - 1), g.n);
+}
+
+struct Dndz {
+    int kind;
+    double z_min, z_max, p0, p1, p2, norm;
+};
+__device__ __forceinline__ double dndz_raw(const Dndz& d, double z) {
+    if (d.kind == CHOMP_DNDZ_GAUSSIAN)                          // kernel.py:110-112
+        return exp(-1.0 * (z - d.p0) * (z - d.p0) / (2.0 * d.p1 * d.p1));
+    return pow(z, d.p0) * exp(-1.0 * pow(z / d.p1, d.p2));      // kernel.py:177-179
+}
+__device__ __forceinline__ double dndz_eval(const Dndz& d, double z) {   // kernel.py:67-86
+    return (z <= d.z_max && z >= d.z_min) ? d.norm * dndz_raw(d, z) : 0.0;
+}
+
+struct Window {
+    int n;
+    double chi_min, chi_max;
+    double *wf, *coef;
+};
+// WindowFunction.window_function (kernel.py:326-340)
+__device__ __forceinline__ double window_eval(const Window& w, double chi) {
+    if (!(chi >= w.chi_min && chi <= w.chi_max)) return 0.0;
+    return spline_eval_uniform(w.coef, chi, w.chi_min, (w.chi_max - w.chi_min) / (w.n - 1), w.n);
+}
+
+struct LimberF {   // W_a W_b D^2 of Kernel._kernel_integrand (kernel.py:707-712) without the Bessel factor
+    Window a, b;
+    EpochGrid g;
+    __device__ __forceinline__ double operator()(double chi) const {
+        const double D = grid_growth(g, grid_z(g, chi));
+        return window_eval(a, chi) * window_eval(b, chi) * D * D;
+    }
+};
+
+struct LimberOut {
+    double *zbar, *dbar;       // [B]
+    double *knodes;            // [B, n_kernel]
+    double *kcoef;             // [B, 4 n_kernel]
+    double *chi_nodes;         // [B, 3, n_cosmo]
+    double *win_nodes;         // [B, 2, n_window]
+    double *win_chi;           // [B, 4]  chi_min_a, chi_max_a, chi_min_b, chi_max_b
+    double *win_coef;          // [B, 2, 4 n_window]
+    double *kchi;              // [B, 2]  kernel chi_min, chi_max
+};
+
+__host__ __device__ inline size_t limber_smem_doubles(const Cfg& cfg) {
+    const size_t nz = cfg.n_cosmo, nw = cfg.n_window, nk = cfg.n_kernel;
+    const size_t nb = 2 * nw + nz + 4;                 // max base panels + 1
+    return 3 * (3 * nz + 12 * nz) + 2 * (nw + 4 * nw) + 2 * nz /*lens sums*/ + nb /*edges*/ +
+           2 * nb * cfg.nq_limber /*chi_q, Fw_q*/ + nk + 4 * nk + 2 * (nw > nz ? (nw > nk ? nw : nk) : (nz > nk ? nz : nk)) * 9 +
+           128 /*red + misc*/;
+}
+
+__global__ void __launch_bounds__(LIMBER_THREADS)
+limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __restrict__ cosmo, LimberOut out,
+                     int32_t* __restrict__ status) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+    const int nz = cfg.n_cosmo, nw = cfg.n_window, nk = cfg.n_kernel, nq = cfg.nq_limber, nql = cfg.nq_lens;
+    const double eps = cfg.window_precision;
+    // ---- carve shared memory ------------------------------------------------------------------
+    double* p = sm;
+    EpochGrid g[3];
+    for (int i = 0; i < 3; ++i) {
+        g[i].n = nz;
+        g[i].z = p; p += nz; g[i].chi = p; p += nz; g[i].growth = p; p += nz;
+        g[i].c_chi_z = p; p += 4 * nz; g[i].c_z_chi = p; p += 4 * nz; g[i].c_g_z = p; p += 4 * nz;
+    }
+    Window win[2];
+    for (int i = 0; i < 2; ++i) { win[i].n = nw; win[i].wf = p; p += nw; win[i].coef = p; p += 4 * nw; }
+    double* lens0 = p; p += nz;       // suffix sums of  w f          over the window-cosmology panels
+    double* lens1 = p; p += nz;       //                 w f / chi'
+    const int nb_max = 2 * nw + nz + 4;
+    double* edge = p; p += nb_max;
+    double* chi_q = p; p += (size_t)nb_max * nq;
+    double* fw_q = p; p += (size_t)nb_max * nq;
+    double* kn = p; p += nk;
+    double* kc = p; p += 4 * nk;
+    const int nmax = nw > nz ? (nw > nk ? nw : nk) : (nz > nk ? nz : nk);
+    double* work = p; p += (size_t)2 * nmax * 9;
+    double* red = p; p += 64;
+    __shared__ int n_edge_s;
+    __shared__ double s_misc[8];
+
+    const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
+    // ---- redshift ranges of the three tabulations ------------------------------------------
+    // [0] the MultiEpoch handed to Kernel; [1], [2] the windows' own copies, re-gridded on
+    // their z range (kernel.py:236-240, 296-297, 372-375, 434-436)
+    g[0].z_min = cfg.zk_min < 0.0 ? 0.0 : cfg.zk_min; g[0].z_max = cfg.zk_max;
+    Dndz dist[2];
+    for (int i = 0; i < 2; ++i) {
+        dist[i].kind = cfg.dndz_kind[i];
+        dist[i].z_min = cfg.dndz_zmin[i]; dist[i].z_max = cfg.dndz_zmax[i];
+        dist[i].p0 = cfg.dndz_p[i][0]; dist[i].p1 = cfg.dndz_p[i][1]; dist[i].p2 = cfg.dndz_p[i][2];
+        dist[i].norm = 1.0;
+        double zlo = (cfg.window_kind[i] == CHOMP_WINDOW_GALAXY) ? dist[i].z_min : 0.0;
+        if (zlo < eps) zlo = eps;
+        g[1 + i].z_min = zlo; g[1 + i].z_max = dist[i].z_max;
+    }
+    const int n_grid = same_window ? 2 : 3;
+    // ---- chi(z), D(z) nodes: chi_i = chi_{i-1} + GL-8 over [z_{i-1}, z_i] ---------------------
+    const double g1 = growth_approx(c, 1.0);
+    for (int idx = tid; idx < n_grid * nz; idx += blockDim.x) {
+        const int gi = idx / nz, i = idx - gi * nz;
+        EpochGrid& G = g[gi];
+        const double zi = (i == nz - 1) ? G.z_max : G.z_min + (G.z_max - G.z_min) / (nz - 1) * i;
+        G.z[i] = zi;
+        G.growth[i] = growth_approx(c, 1.0 / (1.0 + zi)) / g1;
+        double acc = 0.0;
+        if (i == 0) {
+            for (int pnl = 0; pnl < 4; ++pnl) {
+                const double a = zi * pnl / 4.0, bb = zi * (pnl + 1) / 4.0, half = 0.5 * (bb - a);
+                for (int q = 0; q < 8; ++q) acc += half * c_glw[8][q] * inv_hubble(c, 0.5 * (a + bb) + half * c_glx[8][q]);
+            }
+        } else {
+            const double a = G.z_min + (G.z_max - G.z_min) / (nz - 1) * (i - 1), half = 0.5 * (zi - a);
+            for (int q = 0; q < 8; ++q) acc += half * c_glw[8][q] * inv_hubble(c, 0.5 * (a + zi) + half * c_glx[8][q]);
+        }
+        G.chi[i] = acc;
+    }
+    __syncthreads();
+    if (tid < n_grid) { EpochGrid& G = g[tid]; for (int i = 1; i < nz; ++i) G.chi[i] += G.chi[i - 1]; }
+    __syncthreads();
+    if (tid < 3 * n_grid) {
+        EpochGrid& G = g[tid / 3];
+        double* wk = work + (size_t)tid * 2 * nmax;
+        switch (tid % 3) {
+            case 0: spline_build(nz, G.z, G.chi, G.c_chi_z, wk); break;     // cosmology.py:795-796
+            case 1: spline_build(nz, G.chi, G.z, G.c_z_chi, wk); break;     // :797-798
+            default: spline_build(nz, G.z, G.growth, G.c_g_z, wk); break;   // :814-815
+        }
+    }
+    __syncthreads();
+    if (same_window) g[2] = g[1];
+    // ---- dN/dz normalisations (kernel.py:43-54): 16 panels x GL-8 --------------------------------
+    for (int i = 0; i < (same_window ? 1 : 2); ++i) {
+        double v = 0.0;
+        if (tid < DNDZ_PANELS * 8) {
+            const int pnl = tid >> 3, q = tid & 7;
+            const double a = dist[i].z_min + (dist[i].z_max - dist[i].z_min) * pnl / DNDZ_PANELS;
+            const double bb = dist[i].z_min + (dist[i].z_max - dist[i].z_min) * (pnl + 1) / DNDZ_PANELS;
+            const double half = 0.5 * (bb - a);
+            v = half * c_glw[8][q] * dndz_raw(dist[i], 0.5 * (a + bb) + half * c_glx[8][q]);
+        }
+        dist[i].norm = 1.0 / block_sum(v, red);
+    }
+    if (same_window) dist[1].norm = dist[0].norm;
+    // ---- window tables ---------------------------------------------------------------------------
+    for (int i = 0; i < (same_window ? 1 : 2); ++i) {
+        const EpochGrid& G = g[1 + i];
+        Window& W = win[i];
+        // kernel.py:298-305 (comoving_distance at the grid ends is the node value)
+        W.chi_min = G.chi[0] < eps ? eps : G.chi[0];
+        W.chi_max = G.chi[nz - 1];
+        const double hw = (W.chi_max - W.chi_min) / (nw - 1);
+        if (cfg.window_kind[i] == CHOMP_WINDOW_GALAXY) {
+            // W = dN/dz dz/dchi (kernel.py:382-387)
+            for (int j = tid; j < nw; j += blockDim.x) {
+                const double chi = (j == nw - 1) ? W.chi_max : W.chi_min + hw * j;
+                const double z = grid_z(G, chi);
+                W.wf[j] = dndz_eval(dist[i], z) / inv_hubble(c, z);
+            }
+        } else {
+            // lensing efficiency g(chi) = int_{max(chi, g_chi_min)}^{chi_max} dchi' f(chi') (chi' - chi)/chi'
+            // with f = dN/dz dz/dchi'  (kernel.py:443-484).  Full panels between the knots of
+            // this window's chi(z) table are summed once (suffix sums), the partial panel
+            // above each node is integrated on the spot.
+            for (int pnl = tid; pnl < nz - 1; pnl += blockDim.x) {
+                const double a = G.chi[pnl], bb = G.chi[pnl + 1], half = 0.5 * (bb - a);
+                double s0 = 0.0, s1 = 0.0;
+                for (int q = 0; q < nql; ++q) {
+                    const double x = 0.5 * (a + bb) + half * c_glx[nql][q];
+                    const double z = grid_z(G, x);
+                    const double f = half * c_glw[nql][q] * dndz_eval(dist[i], z) / inv_hubble(c, z);
+                    s0 += f; s1 += f / x;
+                }
+                lens0[pnl] = s0; lens1[pnl] = s1;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                lens0[nz - 1] = 0.0; lens1[nz - 1] = 0.0;
+                for (int k = nz - 2; k >= 0; --k) { lens0[k] += lens0[k + 1]; lens1[k] += lens1[k + 1]; }
+            }
+            __syncthreads();
+            double g_chi_min = grid_chi(G, dist[i].z_min);            // kernel.py:437-441
+            if (g_chi_min < eps) g_chi_min = eps;
+            for (int j = tid; j < nw; j += blockDim.x) {
+                const double chi = (j == nw - 1) ? W.chi_max : W.chi_min + hw * j;
+                const double a_scale = 1.0 / (1.0 + grid_z(G, chi));
+                double lo = chi < g_chi_min ? g_chi_min : chi;
+                double gl = 0.0;
+                if (lo > eps && lo < W.chi_max) {
+                    int k = search_index(lo, G.chi, nz);
+                    const double bb = G.chi[k + 1], half = 0.5 * (bb - lo);
+                    for (int q = 0; q < nql; ++q) {
+                        const double x = 0.5 * (lo + bb) + half * c_glx[nql][q];
+                        const double z = grid_z(G, x);
+                        gl += half * c_glw[nql][q] * dndz_eval(dist[i], z) / inv_hubble(c, z) * (x - chi) / x;
+                    }
+                    gl += lens0[k + 1] - chi * lens1[k + 1];
+                }
+                W.wf[j] = 1.5 * c.om * (gl * c.H0 * c.H0 * chi) / a_scale;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < (same_window ? 1 : 2)) {
+        Window& W = win[tid];
+        double* wk = work + (size_t)tid * 2 * nmax;
+        // uniform chi nodes: build with explicit abscissae
+        double* xs = wk + (size_t)4 * 2 * nmax;   // separate scratch region
+        const double hw = (W.chi_max - W.chi_min) / (nw - 1);
+        for (int j = 0; j < nw; ++j) xs[j] = (j == nw - 1) ? W.chi_max : W.chi_min + hw * j;
+        spline_build(nw, xs, W.wf, W.coef, wk);
+    }
+    __syncthreads();
+    if (same_window) win[1] = win[0];
+    // ---- kernel range, z_bar (kernel.py:594-639) -----------------------------------------------------
+    LimberF F{win[0], win[1], g[0]};
+    const double zmin_k = fmax(g[1].z_min, g[2].z_min), zmax_k = fmin(g[1].z_max, g[2].z_max);
+    const double chi_min_k = fmax(eps, grid_chi(g[0], zmin_k)), chi_max_k = grid_chi(g[0], zmax_k);
+    {
+        double best = -1e300; int besti = 0;
+        for (int j = tid; j < nk; j += blockDim.x) {
+            const double zj = (j == nk - 1) ? zmax_k : zmin_k + (zmax_k - zmin_k) / (nk - 1) * j;
+            const double v = F(grid_chi(g[0], zj));
+            if (v > best) { best = v; besti = j; }
+        }
+        // arg-max with first-index tie break (numpy.argmax)
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { red[wid] = best; red[32 + wid] = (double)besti; }
+        __syncthreads();
+        if (tid == 0) {
+            double bv = red[0]; int bi = (int)red[32];
+            for (int i = 1; i < nwarp; ++i) {
+                const int oi = (int)red[32 + i];
+                if (red[i] > bv || (red[i] == bv && oi < bi)) { bv = red[i]; bi = oi; }
+            }
+            const double zb = (bi == nk - 1) ? zmax_k : zmin_k + (zmax_k - zmin_k) / (nk - 1) * bi;
+            s_misc[0] = zb;
+            s_misc[1] = grid_growth(g[0], zb);           // Correlation.D_z, correlation.py:94
+        }
+    }
+    // ---- base panels: union of the knots of both windows and of the kernel's chi(z) table -------------
+    if (tid == 0) {
+        int cnt = 0;
+        edge[cnt++] = chi_min_k;
+        int ia = 0, ib = 0, ic = 0;
+        const double ha = (win[0].chi_max - win[0].chi_min) / (nw - 1), hb = (win[1].chi_max - win[1].chi_min) / (nw - 1);
+        const double tol = 1e-9 * chi_max_k;
+        while (true) {
+            const double xa = ia < nw ? win[0].chi_min + ha * ia : 1e300;
+            const double xb = (!same_window && ib < nw) ? win[1].chi_min + hb * ib : 1e300;
+            const double xc = ic < nz ? g[0].chi[ic] : 1e300;
+            double x = xa; int which = 0;
+            if (xb < x) { x = xb; which = 1; }
+            if (xc < x) { x = xc; which = 2; }
+            if (x >= 1e300) break;
+            if (which == 0) ++ia; else if (which == 1) ++ib; else ++ic;
+            if (x > edge[cnt - 1] + tol && x < chi_max_k - tol && cnt < nb_max - 1) edge[cnt++] = x;
+        }
+        edge[cnt++] = chi_max_k;
+        n_edge_s = cnt;
+    }
+    __syncthreads();
+    const int n_pan = n_edge_s - 1;
+    for (int idx = tid; idx < n_pan * nq; idx += blockDim.x) {
+        const int pnl = idx / nq, q = idx - pnl * nq;
+        const double a = edge[pnl], bb = edge[pnl + 1], half = 0.5 * (bb - a);
+        const double x = 0.5 * (a + bb) + half * c_glx[nq][q];
+        chi_q[idx] = x;
+        fw_q[idx] = half * c_glw[nq][q] * F(x);
+    }
+    __syncthreads();
+    // ---- K(ln k theta) nodes: one warp per node (kernel.py:678-705) ----------------------------------
+    const double x0 = log(cfg.ktheta_min), x1 = log(cfg.ktheta_max);
+    const int order = cfg.bessel_order;
+    for (int j = wid; j < nk; j += nwarp) {
+        const double lkt = (j == nk - 1) ? x1 : x0 + (x1 - x0) / (nk - 1) * j;
+        const double kt = exp(lkt);
+        double top = cfg.bessel_limit / kt;
+        if (top >= chi_max_k) top = chi_max_k;
+        double acc = 0.0;
+        for (int pnl = lane; pnl < n_pan; pnl += 32) {
+            const double a = edge[pnl];
+            if (a >= top) continue;
+            const double bfull = edge[pnl + 1];
+            const bool clipped = bfull > top;
+            const double bb = clipped ? top : bfull;
+            const int nsub = (int)fmax(1.0, ceil(kt * (bb - a) / 2.0));
+            if (!clipped && nsub == 1) {
+                for (int q = 0; q < nq; ++q) acc += fw_q[pnl * nq + q] * bessel_j(order, kt * chi_q[pnl * nq + q]);
+            } else {
+                const double d = (bb - a) / nsub, half = 0.5 * d;
+                for (int s = 0; s < nsub; ++s) {
+                    const double mid = a + d * (s + 0.5);
+                    for (int q = 0; q < nq; ++q) {
+                        const double x = mid + half * c_glx[nq][q];
+                        acc += half * c_glw[nq][q] * F(x) * bessel_j(order, kt * x);
+                    }
+                }
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) kn[j] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double* xs = work + (size_t)4 * 2 * nmax;
+        for (int j = 0; j < nk; ++j) xs[j] = (j == nk - 1) ? x1 : x0 + (x1 - x0) / (nk - 1) * j;
+        spline_build(nk, xs, kn, kc, work);               // kernel.py:645-646
+    }
+    __syncthreads();
+    // ---- write out ------------------------------------------------------------------------------------
+    if (tid == 0) {
+        out.zbar[b] = s_misc[0];
+        out.dbar[b] = s_misc[1];
+        out.kchi[2 * b] = chi_min_k; out.kchi[2 * b + 1] = chi_max_k;
+        out.win_chi[4 * b + 0] = win[0].chi_min; out.win_chi[4 * b + 1] = win[0].chi_max;
+        out.win_chi[4 * b + 2] = win[1].chi_min; out.win_chi[4 * b + 3] = win[1].chi_max;
+        int st = c.bad ? CHOMP_ST_DOMAIN : 0;
+        if (!isfinite(s_misc[1])) st |= CHOMP_ST_NONFINITE;
+        if (status && st) atomicOr(status + b, st);
+    }
+    bool bad = false;
+    for (int j = tid; j < nk; j += blockDim.x) { out.knodes[(size_t)b * nk + j] = kn[j]; if (!isfinite(kn[j])) bad = true; }
+    if (bad && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
+    for (int j = tid; j < 4 * (nk - 1); j += blockDim.x) out.kcoef[(size_t)b * 4 * nk + j] = kc[j];
+    for (int idx = tid; idx < 3 * nz; idx += blockDim.x) out.chi_nodes[(size_t)b * 3 * nz + idx] = g[idx / nz].chi[idx % nz];
+    for (int idx = tid; idx < 2 * nw; idx += blockDim.x) out.win_nodes[(size_t)b * 2 * nw + idx] = win[idx / nw].wf[idx % nw];
+    for (int idx = tid; idx < 2 * 4 * nw; idx += blockDim.x) {
+        const int i = idx / (4 * nw), j = idx % (4 * nw);
+        if (j < 4 * (nw - 1)) out.win_coef[(size_t)b * 8 * nw + idx] = win[i].coef[j];
+    }
+}
+
+}  // namespace chomp

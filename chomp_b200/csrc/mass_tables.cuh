@@ -1,0 +1,281 @@
+// Stage 2: SingleEpoch scalars, sigma(R), mass limits, nu(M) tables, Sheth-Tormen
+// normalisations.  One CTA per parameter point; one warp per sigma(R) evaluation.
+//
+// Replaces (reference): SingleEpoch._initialize_defaults cosmology.py:93-119,
+// sigma_r / _sigma_integrand cosmology.py:602-660, nu_m :687-699,
+// MassFunction._set_mass_limits / _initialize_splines / _normalize
+// mass_function.py:160-241.
+#pragma once
+#include "common.cuh"
+#include "spline.cuh"
+
+namespace chomp {
+
+#define SIG_NQ 16          // Gauss-Legendre order per sigma(R) panel
+#define SIG_XSPLIT 48.0    // beyond x = kR = 48 only the non-oscillatory part of W^2 is integrated
+#define SIG_DX 8.0         // panel width in x between 1 and SIG_XSPLIT
+#define SIG_NLOW 3         // geometric panels below x = 1
+#define SIG_NTAIL 2        // geometric panels beyond SIG_XSPLIT
+
+// squared top-hat window W^2(x), W = 3 (sin x / x^3 - cos x / x^2)   (cosmology.py:651-652)
+__device__ __forceinline__ double tophat2(double x) {
+    double W;
+    if (x < 0.1) {
+        const double x2 = x * x;
+        W = 1.0 + x2 * (-0.1 + x2 * (1.0 / 280.0 + x2 * (-1.0 / 15120.0 + x2 / 1330560.0)));
+    } else {
+        double s, c;
+        sincos(x, &s, &c);
+        W = 3.0 * (s - x * c) / (x * x * x);
+    }
+    return W * W;
+}
+
+// first-order end-point term of the oscillatory tail
+//   int F(x)/x [B cos 2x + C sin 2x] dx,  B = 9 (x^2-1) / (2 x^6),  C = -9 / x^5
+__device__ __forceinline__ double sigma_tail_edge(const PkParams& pk, double x, double R) {
+    const double k = x / R;
+    const double F = delta2(pk, k, log(k)) / x;
+    const double x2 = x * x;
+    const double B = 9.0 * (x2 - 1.0) / (2.0 * x2 * x2 * x2), C = -9.0 / (x2 * x2 * x);
+    double s, c;
+    sincos(2.0 * x, &s, &c);
+    return F * (B * s - C * c) * 0.5;
+}
+
+// sigma^2(R) = int dlnk Delta^2(k) W^2(kR) over the reference's k range
+// (cosmology.py:611-638); executed by one full warp, result in every lane.
+__device__ inline double warp_sigma2(const PkParams& pk, double R, double k_min, double k_max) {
+    // integration range rules, cosmology.py:611-629
+    double k_lo = k_min, k_hi = k_max;
+    const double need_lo = 1.0 / R / 10.0, need_hi = 1.0 / R * 14.0662;
+    if (need_lo <= k_lo) k_lo = (need_lo > k_min / 100.0) ? need_lo : k_min / 100.0;
+    if (need_hi >= k_hi) k_hi = (need_hi < k_max * 100.0) ? need_hi : k_max * 100.0;
+    const double x_lo = k_lo * R, x_hi = k_hi * R;
+    const double xs = fmin(SIG_XSPLIT, x_hi);
+    const double x_one = fmin(fmax(1.0, x_lo), xs);   // low (geometric) panels cover [x_lo, x_one]
+    int n_lin = 0;
+    if (xs > x_one) n_lin = (int)ceil((xs - x_one) / SIG_DX - 1e-9);
+    if (n_lin < 0) n_lin = 0;
+    const int n_tail = (x_hi > xs) ? SIG_NTAIL : 0;
+    const int n_pan = SIG_NLOW + n_lin + n_tail;
+    const double lnR = log(R);
+    const double l_lo = log(x_lo), l_one = log(x_one), l_s = log(xs), l_hi = log(x_hi);
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int idx = lane; idx < n_pan * SIG_NQ; idx += 32) {
+        const int p = idx / SIG_NQ, q = idx - p * SIG_NQ;
+        double a, b;
+        bool tail = false;
+        if (p < SIG_NLOW) {
+            a = l_lo + (l_one - l_lo) * p / SIG_NLOW;
+            b = l_lo + (l_one - l_lo) * (p + 1) / SIG_NLOW;
+        } else if (p < SIG_NLOW + n_lin) {
+            const int j = p - SIG_NLOW;
+            a = log(x_one + SIG_DX * j);
+            b = (j == n_lin - 1) ? l_s : log(x_one + SIG_DX * (j + 1));
+        } else {
+            const int j = p - SIG_NLOW - n_lin;
+            a = l_s + (l_hi - l_s) * j / SIG_NTAIL;
+            b = l_s + (l_hi - l_s) * (j + 1) / SIG_NTAIL;
+            tail = true;
+        }
+        const double half = 0.5 * (b - a);
+        const double lx = 0.5 * (a + b) + half * c_glx[SIG_NQ][q];
+        const double x = exp(lx);
+        const double lnk = lx - lnR;
+        double w2;
+        if (tail) {
+            const double x2 = x * x;
+            w2 = 9.0 * (1.0 + x2) / (2.0 * x2 * x2 * x2);
+        } else {
+            w2 = tophat2(x);
+        }
+        acc += half * c_glw[SIG_NQ][q] * delta2(pk, exp(lnk), lnk) * w2;
+    }
+    if (n_tail && lane == 0) acc += sigma_tail_edge(pk, x_hi, R) - sigma_tail_edge(pk, xs, R);
+    return warp_sum(acc);
+}
+
+struct MassCtx {
+    PkParams pk;
+    double delta_c, rho_bar, k_min, k_max;
+};
+
+// nu(M) = (delta_c / sigma(M))^2, warp-collective (cosmology.py:662-699)
+__device__ inline double warp_nu_m(const MassCtx& m, double mass) {
+    const double R = cbrt(3.0 * mass / (4.0 * M_PI * m.rho_bar));
+    const double s2 = warp_sigma2(m.pk, R, m.k_min, m.k_max);
+    return m.delta_c * m.delta_c / s2;
+}
+
+// Smallest j in [1, J] with pred(j) true, pred monotone (false ... false true ... true), by
+// warp-parallel multisection.  pred(j) = (nu(M0 * step^(dir*j)) compared with thr).
+// Returns -1 if pred(J) is false.  Collective over the CTA (blockDim.x / 32 warps).
+__device__ inline int walk_search(const MassCtx& m, double M0, int dir, bool want_le, double thr, int J,
+                                  double* sh_val) {
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
+    int lo = 0, hi = J;         // pred(lo) false (caller checked j = 0); pred(hi) assumed, verified in round 1
+    bool hi_known = false;
+    while (hi - lo > 1 || !hi_known) {
+        const int span = hi - lo;
+        // candidates lo < c_0 < ... <= hi, always including hi while it is unverified
+        int cand = lo + (int)(((long long)span * (w + 1) + nw - 1) / nw);
+        if (cand > hi) cand = hi;
+        if (cand <= lo) cand = lo + 1;
+        const double mass = M0 * pow(1.05, (double)(dir * cand));
+        const double nu = warp_nu_m(m, mass);
+        __syncthreads();
+        if (lane == 0) sh_val[w] = (want_le ? (nu <= thr) : (nu >= thr)) ? (double)cand : -(double)cand;
+        __syncthreads();
+        int new_hi = hi, new_lo = lo;
+        bool any_true = false;
+        for (int i = 0; i < nw; ++i) {
+            const int c = (int)fabs(sh_val[i]);
+            if (sh_val[i] > 0.0) { if (!any_true || c < new_hi) new_hi = c; any_true = true; }
+        }
+        for (int i = 0; i < nw; ++i) {
+            const int c = (int)fabs(sh_val[i]);
+            if (sh_val[i] < 0.0 && c < new_hi && c > new_lo) new_lo = c;
+        }
+        if (!any_true && !hi_known) return -1;
+        hi = new_hi; lo = new_lo; hi_known = true;
+    }
+    return hi;
+}
+
+struct MassOut {
+    double* epoch;     // [B, CHOMP_EPOCH_LEN]
+    double* lnm_nodes; // [B, n_mass]
+    double* nu_nodes;  // [B, n_mass]
+    double* c_lnm_nu;  // [B, 4 n_mass]  ln M as a function of nu
+    double* c_nu_lnm;  // [B, 4 n_mass]  nu as a function of ln M
+};
+
+__global__ void __launch_bounds__(256)
+mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const double* __restrict__ halo,
+                   const double* __restrict__ z_in, const double* __restrict__ zbar, MassOut out,
+                   int32_t* __restrict__ status) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    const int n = cfg.n_mass;
+    double* lnm = sm;            // n
+    double* nu = lnm + n;        // n
+    double* c1 = nu + n;         // 4n
+    double* c2 = c1 + 4 * n;     // 4n
+    double* work = c2 + 4 * n;   // 4n (two spline builds)
+    double* red = work + 4 * n;  // 64
+    const int tid = threadIdx.x, w = tid >> 5, nw = blockDim.x >> 5, lane = tid & 31;
+
+    const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
+    double z = z_in ? z_in[b] : zbar[b];
+    if (z < 0.0) z = 0.0;                                          // cosmology.py:40-41
+    const double* hp = halo + (size_t)b * CHOMP_N_HALO;
+    const double growth = growth_approx(c, 1.0 / (1.0 + z)) / growth_approx(c, 1.0);
+    MassCtx m;
+    m.delta_c = delta_c_z(c, z);
+    m.rho_bar = rho_bar_z(c, z);
+    m.k_min = cfg.k_min; m.k_max = cfg.k_max;
+    // sigma_norm = sigma_8 * growth / sigma_r(8) with sigma_norm = 1 (cosmology.py:118-119)
+    m.pk = make_pk(c, growth, 1.0);
+    const double s8_raw = sqrt(warp_sigma2(m.pk, 8.0, m.k_min, m.k_max));
+    const double sigma_norm = c.s8 * growth / s8_raw;
+    m.pk = make_pk(c, growth, sigma_norm);
+
+    int st = 0;
+    if (c.bad || hp[CHOMP_H_ALPHA] != -1.0) st |= CHOMP_ST_DOMAIN;
+    int walk_steps = 0;
+    // ---- mass limits (mass_function.py:160-203) -----------------------------------
+    double m_lo = 1.0e9, m_hi = 1.0e16;
+    if (cfg.mass_min > 0.0 && cfg.mass_max > 0.0) {
+        m_lo = cfg.mass_min; m_hi = cfg.mass_max;
+    } else {
+        const int J = 512;
+        // lower limit: walk until 0.095 <= nu(M) <= 0.105
+        double nu0 = warp_nu_m(m, m_lo);
+        if (0.1 * (1.0 + 0.05) < nu0) {
+            const int j = walk_search(m, m_lo, -1, true, 0.1 * (1.0 + 0.05), J, red);
+            if (j < 0) st |= CHOMP_ST_MASS_WALK; else { m_lo = m_lo * pow(1.05, -(double)j); walk_steps += j; }
+        } else if (0.1 * (1.0 - 0.05) > nu0) {
+            const int j = walk_search(m, m_lo, +1, false, 0.1 * (1.0 - 0.05), J, red);
+            if (j < 0) st |= CHOMP_ST_MASS_WALK; else { m_lo = m_lo * pow(1.05, (double)j); walk_steps += j; }
+        }
+        nu0 = warp_nu_m(m, m_hi);
+        if (50.0 * (1.0 - 0.05) > nu0) {
+            const int j = walk_search(m, m_hi, +1, false, 50.0 * (1.0 - 0.05), J, red);
+            if (j < 0) st |= CHOMP_ST_MASS_WALK; else { m_hi = m_hi * pow(1.05, (double)j); walk_steps += j; }
+        } else if (50.0 * (1.0 + 0.05) < nu0) {
+            const int j = walk_search(m, m_hi, -1, true, 50.0 * (1.0 + 0.05), J, red);
+            if (j < 0) st |= CHOMP_ST_MASS_WALK; else { m_hi = m_hi * pow(1.05, -(double)j); walk_steps += j; }
+        }
+    }
+    const double lnm_min = log(m_lo), lnm_max = log(m_hi);
+    const double hM = (lnm_max - lnm_min) / (n - 1);
+    // ---- nu at the mass nodes (mass_function.py:205-209) -----------------------------
+    __syncthreads();
+    for (int i = w; i < n; i += nw) {
+        const double lm = (i == n - 1) ? lnm_max : lnm_min + hM * i;
+        const double v = warp_nu_m(m, exp(lm));
+        if (lane == 0) { lnm[i] = lm; nu[i] = v; }
+    }
+    __syncthreads();
+    if (tid == 0) spline_build(n, lnm, nu, c2, work);          // nu(ln M)
+    if (tid == 32) spline_build(n, nu, lnm, c1, work + 2 * n);  // ln M(nu)
+    __syncthreads();
+    const double nu_min = 1.001 * nu[0], nu_max = 0.999 * nu[n - 1];  // mass_function.py:212-213
+    const double lnm_star = spline_eval_search(c1, 1.0, nu, n);        // m_star = mass(1.0), :223
+    // ---- f_norm, bias_norm (mass_function.py:225-241): int f dnu = int nu f dln nu over
+    //      [nu_min, nu_max], 8-point Gauss-Legendre on every knot interval of ln nu
+    const double stq = hp[CHOMP_H_STQ], sta = hp[CHOMP_H_ST_LITTLE_A];
+    double sf = 0.0, sfb = 0.0;
+    const double l_min = log(nu_min), l_max = log(nu_max);
+    for (int idx = tid; idx < (n - 1) * 8; idx += blockDim.x) {
+        const int i = idx >> 3, q = idx & 7;
+        const double a = (i == 0) ? l_min : log(nu[i]);
+        const double bb = (i == n - 2) ? l_max : log(nu[i + 1]);
+        const double half = 0.5 * (bb - a);
+        const double x = 0.5 * (a + bb) + half * c_glx[8][q];
+        double nf, bi;
+        st_raw(exp(x), sta, stq, m.delta_c, nf, bi);
+        const double wgt = half * c_glw[8][q];
+        sf += wgt * nf;
+        sfb += wgt * nf * bi;
+    }
+    sf = block_sum(sf, red);
+    sfb = block_sum(sfb, red + 32);
+    const double f_norm = 1.0 / sf;
+    const double b_norm = 1.0 / (f_norm * sfb);
+    // comoving distance to z (SingleEpoch._chi, cosmology.py:106-110): 8 panels x GL-8
+    double chi = 0.0;
+    if (tid < 64) {
+        const int p = tid >> 3, q = tid & 7;
+        const double a = z * p / 8.0, bb = z * (p + 1) / 8.0;
+        const double half = 0.5 * (bb - a);
+        chi = half * c_glw[8][q] * inv_hubble(c, 0.5 * (a + bb) + half * c_glx[8][q]);
+    }
+    chi = block_sum(chi, red);
+
+    // ---- write out ----------------------------------------------------------------------
+    for (int i = tid; i < n; i += blockDim.x) {
+        out.lnm_nodes[(size_t)b * n + i] = lnm[i];
+        out.nu_nodes[(size_t)b * n + i] = nu[i];
+    }
+    for (int i = tid; i < 4 * (n - 1); i += blockDim.x) {
+        out.c_lnm_nu[(size_t)b * 4 * n + i] = c1[i];
+        out.c_nu_lnm[(size_t)b * 4 * n + i] = c2[i];
+    }
+    if (tid == 0) {
+        double* e = out.epoch + (size_t)b * CHOMP_EPOCH_LEN;
+        double dv = hp[CHOMP_H_DELTA_V];
+        if (dv == -1.0) dv = delta_v_z(c, z, growth);           // mass_function.py:51-53, halo.py:73-75
+        e[EP_Z] = z; e[EP_GROWTH] = growth; e[EP_SIGMA_NORM] = sigma_norm; e[EP_DELTA_C] = m.delta_c;
+        e[EP_DELTA_V] = dv; e[EP_RHO_BAR] = m.rho_bar; e[EP_LNM_MIN] = lnm_min; e[EP_LNM_MAX] = lnm_max;
+        e[EP_NU_MIN] = nu_min; e[EP_NU_MAX] = nu_max; e[EP_F_NORM] = f_norm; e[EP_B_NORM] = b_norm;
+        e[EP_LNM_STAR] = lnm_star; e[EP_PK_AMP] = m.pk.amp; e[EP_CHI] = chi; e[EP_WALK] = (double)walk_steps;
+        if (!(isfinite(f_norm) && isfinite(b_norm) && isfinite(lnm_star))) st |= CHOMP_ST_NONFINITE;
+        if (status && st) atomicOr(status + b, st);
+    }
+}
+
+}  // namespace chomp

@@ -1,0 +1,92 @@
+// Not-a-knot interpolating cubic splines on the device.
+//
+// Every table in the reference is a scipy InterpolatedUnivariateSpline(k=3)
+// (e.g. cosmology.py:795-798, mass_function.py:215-218, halo.py:919, 960,
+// kernel.py:310, 645).  For k=3 FITPACK's interpolating spline is the
+// not-a-knot cubic, so the device builds exactly that: a tridiagonal solve for
+// the second derivatives with the third derivative continuous across x[1] and
+// x[n-2], stored as per-interval polynomial coefficients
+//     y(x) = c0 + t (c1 + t (c2 + t c3)),   t = x - x[i].
+#pragma once
+
+namespace chomp {
+
+// Build by ONE thread.  x[n], y[n] inputs; coef[4*(n-1)] output; work[2*n]
+// scratch.  n >= 4.
+__device__ inline void spline_build(int n, const double* __restrict__ x, const double* __restrict__ y,
+                                    double* __restrict__ coef, double* __restrict__ work) {
+    double* m = work;      // second derivatives
+    double* cp = work + n; // Thomas scratch (modified upper diagonal)
+    // unknowns m[1..n-2]; m[0], m[n-1] eliminated through the not-a-knot rows
+    const int last = n - 2;
+    double h0 = x[1] - x[0], h1 = x[2] - x[1];
+    double diag = h0 * (1.0 + h0 / h1) + 2.0 * (h0 + h1);
+    double up = h1 - h0 * h0 / h1;
+    double rhs = 6.0 * ((y[2] - y[1]) / h1 - (y[1] - y[0]) / h0);
+    cp[1] = up / diag;
+    m[1] = rhs / diag;
+    for (int i = 2; i <= last; ++i) {
+        const double hl = x[i] - x[i - 1], hr = x[i + 1] - x[i];
+        double lo = hl, dg = 2.0 * (hl + hr), u = hr;
+        if (i == last) {
+            // m[n-1] = (1 + hr/hl) m[n-2] - (hr/hl) m[n-3]
+            dg = hr * (1.0 + hr / hl) + 2.0 * (hl + hr);
+            lo = hl - hr * hr / hl;
+            u = 0.0;
+        }
+        const double r = 6.0 * ((y[i + 1] - y[i]) / hr - (y[i] - y[i - 1]) / hl);
+        const double den = dg - lo * cp[i - 1];
+        cp[i] = u / den;
+        m[i] = (r - lo * m[i - 1]) / den;
+    }
+    for (int i = last - 1; i >= 1; --i) m[i] -= cp[i] * m[i + 1];
+    m[0] = (1.0 + h0 / h1) * m[1] - (h0 / h1) * m[2];
+    {
+        const double hl = x[n - 2] - x[n - 3], hr = x[n - 1] - x[n - 2];
+        m[n - 1] = (1.0 + hr / hl) * m[n - 2] - (hr / hl) * m[n - 3];
+    }
+    for (int i = 0; i < n - 1; ++i) {
+        const double h = x[i + 1] - x[i];
+        coef[4 * i + 0] = y[i];
+        coef[4 * i + 1] = (y[i + 1] - y[i]) / h - h * (2.0 * m[i] + m[i + 1]) / 6.0;
+        coef[4 * i + 2] = 0.5 * m[i];
+        coef[4 * i + 3] = (m[i + 1] - m[i]) / (6.0 * h);
+    }
+}
+
+__device__ __forceinline__ double spline_poly(const double* __restrict__ coef, int i, double t) {
+    const double* c = coef + 4 * i;
+    return fma(t, fma(t, fma(t, c[3], c[2]), c[1]), c[0]);
+}
+
+// index of the interval containing v on a uniform grid x0 + i*h (clamped)
+__device__ __forceinline__ int uniform_index(double v, double x0, double inv_h, int n) {
+    int i = (int)floor((v - x0) * inv_h);
+    return i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+}
+
+// index of the interval containing v on an increasing grid (clamped)
+__device__ __forceinline__ int search_index(double v, const double* __restrict__ x, int n) {
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ double spline_eval_uniform(const double* __restrict__ coef, double v, double x0,
+                                                      double h, int n) {
+    int i = uniform_index(v, x0, 1.0 / h, n);
+    // guard against floor() landing one interval off at a knot
+    const double xi = x0 + i * h;
+    return spline_poly(coef, i, v - xi);
+}
+
+__device__ __forceinline__ double spline_eval_search(const double* __restrict__ coef, double v,
+                                                     const double* __restrict__ x, int n) {
+    const int i = search_index(v, x, n);
+    return spline_poly(coef, i, v - x[i]);
+}
+
+}  // namespace chomp

@@ -1,0 +1,302 @@
+"""Batched evaluation of the halo-model -> Limber -> Hankel path on one GPU.
+
+`Engine` owns one C-ABI handle (device scratch + configuration) and exposes the
+stages of include/chomp_b200.h on torch CUDA tensors.  `Survey` collects the
+batch-invariant set-up that the reference spreads over constructor arguments:
+the two redshift distributions / windows (kernel.py:89, 148, 372, 430), the
+MultiEpoch range and k*theta range given to Kernel (kernel.py:584), the
+angular bins of Correlation (correlation.py:65-90) and the module precision
+dictionaries (defaults.py).
+
+PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib, defaults
+
+# zeros of J0 and J2 (scipy.special.jn_zeros(order, 24)); the Limber integral stops
+# at zero number defaults.default_precision["kernel_bessel_limit"] (kernel.py:627-629, 806-807)
+_J0_ZEROS = (2.4048255576957724, 5.520078110286311, 8.653727912911013, 11.791534439014281,
+             14.930917708487787, 18.071063967910924, 21.21163662987926, 24.352471530749302,
+             27.493479132040253, 30.634606468431976, 33.77582021357357, 36.917098353664045,
+             40.05842576462824, 43.19979171317673, 46.341188371661815, 49.482609897397815,
+             52.624051841115, 55.76551075501998, 58.90698392608094, 62.048469190227166,
+             65.18996480020687, 68.3314693298568, 71.47298160359374, 74.61450064370183)
+_J2_ZEROS = (5.135622301840683, 8.417244140399866, 11.61984117214906, 14.795951782351262,
+             17.959819494987826, 21.116997053021844, 24.2701123135731, 27.420573549984557,
+             30.569204495516395, 33.7165195092227, 36.86285651128381, 40.008446733478195,
+             43.153453778371464, 46.29799667723692, 49.442164110416876, 52.58602350681596,
+             55.72962705320114, 58.87301577261216, 62.01622235921766, 65.1592731907578,
+             68.30218978418345, 71.44498986635786, 74.5876881736024, 77.7302970569789)
+
+DEG_TO_RAD = math.pi/180.0
+
+
+def bessel_limit(order, n_zeros):
+    zeros = _J0_ZEROS if order == 0 else _J2_ZEROS
+    if not 1 <= n_zeros <= len(zeros):
+        raise ValueError("kernel_bessel_limit must be in 1..%d" % len(zeros))
+    return zeros[n_zeros - 1]
+
+
+def theta_bins(theta_min_deg, theta_max_deg, bins_per_decade=5.0):
+    """Geometric bin centres in radians, exactly as Correlation.__init__ builds
+    them (correlation.py:69-90): edges at 10**(u/bpd) for integer u counted up
+    from floor(log10 theta_min)*bpd, centre = geometric mean of the two edges,
+    bins kept when theta_min <= lower edge < theta_max."""
+    lo = math.log10(theta_min_deg*DEG_TO_RAD)
+    hi = math.log10(theta_max_deg*DEG_TO_RAD)
+    if theta_min_deg == theta_max_deg:
+        return np.array([theta_min_deg*DEG_TO_RAD])
+    bpd = 1.0*bins_per_decade
+    t_lo, t_hi = np.power(10.0, lo), np.power(10.0, hi)
+    centres = []
+    u = np.floor(lo)*bins_per_decade
+    edge = np.power(10.0, u/bpd)
+    while edge < t_hi:
+        if t_lo <= edge < t_hi:
+            centres.append(10**(0.5*(np.log10(edge) + (u + 1.0)/bpd)))
+        u += 1.0
+        edge = np.power(10.0, u/bpd)
+    return np.array(centres)
+
+
+class RedshiftDistribution(object):
+    """Parameters of a dNdzGaussian / dNdzMagLim after the constructors' range
+    clipping (kernel.py:100-106, 160-175)."""
+
+    def __init__(self, kind, z_min, z_max, p):
+        self.kind, self.z_min, self.z_max, self.p = kind, float(z_min), float(z_max), tuple(p)
+
+    @classmethod
+    def gaussian(cls, z_min, z_max, z0, sigma_z):
+        z_min = max(z_min, z0 - 8.0*sigma_z)
+        z_max = min(z_max, z0 + 8.0*sigma_z)
+        return cls(_lib.DNDZ_GAUSSIAN, z_min, z_max, (z0, sigma_z, 0.0))
+
+    @classmethod
+    def maglim(cls, z_min, z_max, a, z0, b, dndz_precision=None):
+        if dndz_precision is None:
+            dndz_precision = defaults.default_precision["dNdz_precision"]
+        # the reference computes 1/b under Python 2: integer division for int b (kernel.py:164-168)
+        inv_b = (1//b) if isinstance(b, (int, np.integer)) else 1.0/b
+        cap = (-1.0*math.log(dndz_precision))**inv_b*z0
+        if cap < z_max:
+            z_max = cap
+        return cls(_lib.DNDZ_MAGLIM, z_min, z_max, (float(a), float(z0), float(b)))
+
+
+class Survey(object):
+    """Everything that is shared by all points of a batch."""
+
+    def __init__(self, dist_a, dist_b=None, window_a="galaxy", window_b=None,
+                 z_range=(0.0, 5.0), ktheta_range_deg=(1e-6, 100.0),
+                 theta_deg=(0.001, 1.0), bins_per_decade=5.0, bessel_order=0,
+                 power_spec="power_mm", hod="zheng", exclusion=False,
+                 extrapolate=False, precision=None, limits=None, quadrature=None):
+        self.dist = (dist_a, dist_b or dist_a)
+        kinds = {"galaxy": _lib.WINDOW_GALAXY, "convergence": _lib.WINDOW_CONVERGENCE}
+        self.window = (kinds[window_a], kinds[window_b or window_a])
+        self.z_range = tuple(z_range)
+        self.ktheta = (ktheta_range_deg[0]*DEG_TO_RAD, ktheta_range_deg[1]*DEG_TO_RAD)
+        self.theta = theta_bins(theta_deg[0], theta_deg[1], bins_per_decade)
+        self.bessel_order = int(bessel_order)
+        self.power_spec = power_spec
+        self.hod_kind = {"zheng": _lib.HOD_ZHENG, "mandelbaum": _lib.HOD_MANDELBAUM}[hod]
+        self.exclusion, self.extrapolate = bool(exclusion), bool(extrapolate)
+        self.precision = dict(precision or defaults.default_precision)
+        self.limits = dict(limits or defaults.default_limits)
+        self.quadrature = dict(quadrature or defaults.default_quadrature)
+
+    def config(self):
+        p, lim, q = self.precision, self.limits, self.quadrature
+        c = _lib.Config()
+        c.n_cosmo, c.n_mass, c.n_halo = p["cosmo_npoints"], p["mass_npoints"], p["halo_npoints"]
+        c.n_window, c.n_kernel = p["window_npoints"], p["kernel_npoints"]
+        c.nq_nu, c.nq_hankel, c.nq_limber, c.nq_lens = q["nu"], q["hankel"], q["limber"], q["lens"]
+        c.hod_kind, c.bessel_order = self.hod_kind, self.bessel_order
+        c.exclusion, c.extrapolate = int(self.exclusion), int(self.extrapolate)
+        for i in range(2):
+            c.window_kind[i] = self.window[i]
+            c.dndz_kind[i] = self.dist[i].kind
+            c.dndz_zmin[i], c.dndz_zmax[i] = self.dist[i].z_min, self.dist[i].z_max
+            for j in range(3):
+                c.dndz_p[i][j] = self.dist[i].p[j]
+        c.halo_precision, c.cosmo_precision = p["halo_precision"], p["cosmo_precision"]
+        c.window_precision = p["window_precision"]
+        c.k_min, c.k_max = lim["k_min"], lim["k_max"]
+        c.mass_min, c.mass_max = lim["mass_min"], lim["mass_max"]
+        c.zk_min, c.zk_max = self.z_range
+        c.ktheta_min, c.ktheta_max = self.ktheta
+        c.bessel_limit = bessel_limit(self.bessel_order, p["kernel_bessel_limit"])
+        c.corr_k_min = c.corr_k_max = -1.0
+        return c
+
+
+def pack_params(dicts, keys):
+    """[B, len(keys)] float64 array from a list of parameter dictionaries
+    (KeyError on a missing key, like the reference)."""
+    return np.array([[float(d[k]) for k in keys] for d in dicts], dtype=np.float64)
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.ChompError("chomp_b200 needs a CUDA device: there is no CPU fallback")
+    return torch
+
+
+class Engine(object):
+    """One C-ABI handle on one device."""
+
+    def __init__(self, config=None, device=None):
+        self.torch = _torch()
+        self.lib = _lib.load()
+        if device is None:
+            device = self.torch.cuda.current_device()
+        self.device = int(device)
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.chomp_b200_create(ctypes.byref(self._h), self.device))
+        self.cfg = None
+        self.n_theta = 0
+        if config is not None:
+            self.configure(config)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                self.lib.chomp_b200_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- plumbing -----------------------------------------------------------
+    def configure(self, config):
+        if isinstance(config, Survey):
+            config = config.config()
+        _lib.check(self.lib.chomp_b200_configure(self._h, ctypes.byref(config)))
+        self.cfg = config
+
+    def reserve(self, n_points):
+        _lib.check(self.lib.chomp_b200_reserve(self._h, int(n_points)))
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, a, cols=None):
+        t = self.torch
+        if not isinstance(a, t.Tensor):
+            a = t.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
+        a = a.to(device="cuda:%d" % self.device, dtype=t.float64).contiguous()
+        if cols is not None and (a.dim() != 2 or a.shape[1] != cols):
+            raise ValueError("expected a [B, %d] array, got %s" % (cols, tuple(a.shape)))
+        return a
+
+    def _new(self, *shape, dtype=None):
+        t = self.torch
+        return t.empty(shape, dtype=dtype or t.float64, device="cuda:%d" % self.device)
+
+    @staticmethod
+    def _p(tensor):
+        return ctypes.c_void_p(tensor.data_ptr()) if tensor is not None else None
+
+    # -- stages ---------------------------------------------------------------
+    def limber_tables(self, cosmo, status=None):
+        cosmo = self._dev(cosmo, _lib.N_COSMO)
+        _lib.check(self.lib.chomp_b200_limber_tables(self._h, cosmo.shape[0], self._p(cosmo),
+                                                     self._p(status), self._stream()))
+        return cosmo.shape[0]
+
+    def mass_tables(self, cosmo, halo, z=None, status=None):
+        cosmo, halo = self._dev(cosmo, _lib.N_COSMO), self._dev(halo, _lib.N_HALO)
+        zt = None if z is None else self._dev(z).reshape(-1)
+        _lib.check(self.lib.chomp_b200_mass_tables(self._h, cosmo.shape[0], self._p(cosmo), self._p(halo),
+                                                   self._p(zt), self._p(status), self._stream()))
+        return cosmo.shape[0]
+
+    def halo_tables(self, halo, hod, status=None):
+        halo, hod = self._dev(halo, _lib.N_HALO), self._dev(hod, _lib.N_HOD)
+        _lib.check(self.lib.chomp_b200_halo_tables(self._h, halo.shape[0], self._p(halo), self._p(hod),
+                                                   self._p(status), self._stream()))
+        return halo.shape[0]
+
+    def power(self, B, which, k):
+        k = self._dev(k).reshape(-1)
+        out = self._new(B, k.numel())
+        _lib.check(self.lib.chomp_b200_power(self._h, B, int(which), k.numel(), self._p(k), self._p(out),
+                                             self._stream()))
+        return out
+
+    def wtheta_stage(self, B, which, theta, status=None):
+        theta = self._dev(theta).reshape(-1)
+        out = self._new(B, theta.numel())
+        _lib.check(self.lib.chomp_b200_wtheta(self._h, B, int(which), theta.numel(), self._p(theta),
+                                              self._p(out), self._p(status), self._stream()))
+        return out
+
+    def wtheta(self, cosmo, halo, hod, theta, which, out=None, status=None):
+        """All four stages on device-resident inputs -> w [B, n_theta]."""
+        cosmo, halo = self._dev(cosmo, _lib.N_COSMO), self._dev(halo, _lib.N_HALO)
+        hod = self._dev(hod, _lib.N_HOD)
+        theta = self._dev(theta).reshape(-1)
+        B = cosmo.shape[0]
+        if out is None:
+            out = self._new(B, theta.numel())
+        _lib.check(self.lib.chomp_b200_wtheta_batch(
+            self._h, B, self._p(cosmo), self._p(halo), self._p(hod), int(which), theta.numel(),
+            self._p(theta), self._p(out), self._p(status), self._stream()))
+        return out
+
+    def wtheta_host(self, cosmo, halo, hod, theta, which):
+        """Host numpy in, host numpy out (copies inside): the end-to-end call."""
+        cosmo = np.ascontiguousarray(cosmo, dtype=np.float64)
+        halo = np.ascontiguousarray(halo, dtype=np.float64)
+        hod = np.ascontiguousarray(hod, dtype=np.float64)
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1)
+        B = cosmo.shape[0]
+        if cosmo.shape != (B, _lib.N_COSMO) or halo.shape != (B, _lib.N_HALO) or hod.shape != (B, _lib.N_HOD):
+            raise ValueError("parameter arrays must be [B,10], [B,6], [B,5]")
+        w = np.empty((B, theta.size), dtype=np.float64)
+        status = np.zeros(B, dtype=np.int32)
+        _lib.check(self.lib.chomp_b200_wtheta_batch_host(
+            self._h, B, cosmo.ctypes.data_as(ctypes.c_void_p), halo.ctypes.data_as(ctypes.c_void_p),
+            hod.ctypes.data_as(ctypes.c_void_p), int(which), theta.size,
+            theta.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p),
+            status.ctypes.data_as(ctypes.c_void_p)))
+        return w, status
+
+    # -- inspection -------------------------------------------------------------
+    def table(self, table_id, B):
+        n = ctypes.c_int(0)
+        _lib.check(self.lib.chomp_b200_copy_table(self._h, B, int(table_id), None, ctypes.byref(n), None))
+        out = self._new(B, n.value)
+        _lib.check(self.lib.chomp_b200_copy_table(self._h, B, int(table_id), self._p(out), ctypes.byref(n),
+                                                  self._stream()))
+        return out
+
+    def evaluate(self, what, x, point=0, aux=0.0):
+        x = self._dev(np.atleast_1d(np.asarray(x, dtype=np.float64))).reshape(-1)
+        out = self._new(x.numel())
+        _lib.check(self.lib.chomp_b200_eval(self._h, int(point), int(what), x.numel(), self._p(x),
+                                            float(aux), self._p(out), self._stream()))
+        return out
+
+    def dfma_peak_tflops(self, iters=20000):
+        v = ctypes.c_double(0.0)
+        _lib.check(self.lib.chomp_b200_dfma_peak(self._h, int(iters), ctypes.byref(v)))
+        return v.value
+
+    def set_timing(self, on=True):
+        _lib.check(self.lib.chomp_b200_set_timing(self._h, int(bool(on))))
+
+    def kernel_times_ms(self):
+        """Device time of each kernel of the last wtheta() call, by kernel name."""
+        ms = (ctypes.c_double*len(_lib.KERNEL_NAMES))()
+        _lib.check(self.lib.chomp_b200_get_timing(self._h, ms))
+        return dict(zip(_lib.KERNEL_NAMES, [float(v) for v in ms]))
+
+    def launch_count(self):
+        return int(self.lib.chomp_b200_launch_count(self._h))

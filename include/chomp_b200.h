@@ -1,0 +1,174 @@
+/* chomp_b200 -- C ABI of the B200-native halo-model / Limber / Hankel hot path.
+ *
+ * The reference (morriscb/chomp) is pure Python and has no FFI; its boundary is
+ * the Python class API.  This library is what the drop-in Python classes in
+ * chomp_b200/ bind through ctypes (see INTEGRATION.md for the stubs).  Each
+ * entry point names the reference code it replaces (paths relative to
+ * /root/reference).
+ *
+ * Conventions
+ *   - every array argument is FP64, row-major; "dev" pointers are device
+ *     pointers owned by the caller, "host" pointers are host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - return 0 on success, nonzero on a call-level failure (bad argument, CUDA
+ *     error; text from chomp_b200_last_error); per-point numerical trouble is
+ *     reported in `status[B]` bit flags and never aborts the batch;
+ *   - the library never frees caller memory and only synchronises the device
+ *     in create / reserve / destroy and in the *_host convenience calls.
+ */
+#ifndef CHOMP_B200_H
+#define CHOMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHOMP_B200_VERSION 100
+
+/* cosmology parameter columns: keys of defaults.default_cosmo_dict (defaults.py:6-19) */
+enum {
+    CHOMP_C_OMEGA_M0 = 0, CHOMP_C_OMEGA_B0, CHOMP_C_OMEGA_L0, CHOMP_C_OMEGA_R0,
+    CHOMP_C_CMB_TEMP, CHOMP_C_H, CHOMP_C_SIGMA_8, CHOMP_C_N_SCALAR, CHOMP_C_W0,
+    CHOMP_C_WA, CHOMP_N_COSMO
+};
+/* halo parameter columns: defaults.default_halo_dict (defaults.py:21-30) */
+enum { CHOMP_H_STQ = 0, CHOMP_H_ST_LITTLE_A, CHOMP_H_C0, CHOMP_H_BETA, CHOMP_H_ALPHA,
+       CHOMP_H_DELTA_V, CHOMP_N_HALO };
+/* HOD parameter columns (hod.py:141-186 Zheng; hod.py:232-261 Mandelbaum: log_M_0, w) */
+enum { CHOMP_HOD_ZHENG = 0, CHOMP_HOD_MANDELBAUM = 1 };
+#define CHOMP_N_HOD 5
+/* power spectra (halo.py:266, 277, 322, 391) */
+enum { CHOMP_P_LINEAR = 0, CHOMP_P_MM = 1, CHOMP_P_GM = 2, CHOMP_P_GG = 3 };
+/* redshift distributions (kernel.py:89-112, 148-179) and windows (kernel.py:360-387, 409-484) */
+enum { CHOMP_DNDZ_GAUSSIAN = 0, CHOMP_DNDZ_MAGLIM = 1 };
+enum { CHOMP_WINDOW_GALAXY = 0, CHOMP_WINDOW_CONVERGENCE = 1 };
+/* per-point status bits */
+enum {
+    CHOMP_ST_NONFINITE = 1,      /* a result is NaN/Inf                                  */
+    CHOMP_ST_MASS_WALK = 2,      /* mass-limit search left its bracket                   */
+    CHOMP_ST_NODE_OVERFLOW = 4,  /* nu-quadrature node list exceeded its capacity        */
+    CHOMP_ST_DOMAIN = 8          /* parameter outside the supported domain (w0/wa, alpha) */
+};
+
+/* Batch-invariant configuration: the reference's defaults.default_precision /
+ * default_limits (defaults.py:42-92) plus the survey set-up the reference takes
+ * as constructor arguments (kernel.py:89, 148, 372, 430, 584; correlation.py:65). */
+typedef struct chomp_b200_config {
+    /* table sizes: cosmo_npoints, mass_npoints, halo_npoints, window_npoints, kernel_npoints */
+    int32_t n_cosmo, n_mass, n_halo, n_window, n_kernel;
+    /* Gauss-Legendre orders per panel: nu mass integrals, Hankel, Limber, lensing efficiency */
+    int32_t nq_nu, nq_hankel, nq_limber, nq_lens;
+    int32_t hod_kind;         /* CHOMP_HOD_*                                             */
+    int32_t bessel_order;     /* 0: Kernel (kernel.py:559), 2: GalaxyGalaxyLensingKernel */
+    int32_t exclusion;        /* 1: HaloExclusion mass window (halo.py:1201-1233)        */
+    int32_t extrapolate;      /* Halo(extrapolate=...) (halo.py:42)                      */
+    int32_t window_kind[2];   /* CHOMP_WINDOW_* for window a, b                          */
+    int32_t dndz_kind[2];     /* CHOMP_DNDZ_*                                            */
+    int32_t reserved_i[3];
+    double halo_precision;    /* enters HODZheng.first_moment_zero (hod.py:176-179)      */
+    double cosmo_precision;   /* flat/open/closed test (cosmology.py:65-79)              */
+    double window_precision;  /* z / chi floor of the windows (kernel.py:236, 301, 612)  */
+    double k_min, k_max;      /* defaults.default_limits                                 */
+    double mass_min, mass_max;/* > 0: fixed mass limits (mass_function.py:163-171)       */
+    double zk_min, zk_max;    /* MultiEpoch(z_min, z_max) handed to Kernel               */
+    double dndz_zmin[2], dndz_zmax[2]; /* after the constructors' clipping (kernel.py:101-104, 163-174) */
+    double dndz_p[2][3];      /* Gaussian: z0, sigma_z, -; MagLim: a, z0, b              */
+    double ktheta_min, ktheta_max;     /* Kernel(ktheta_min, ktheta_max, ...)            */
+    double bessel_limit;      /* special.jn_zeros(order, kernel_bessel_limit)[-1]        */
+    double corr_k_min, corr_k_max;     /* Correlation(k_min=, k_max=); <= 0: halo limits */
+    double reserved_d[4];
+} chomp_b200_config;
+
+int chomp_b200_version(void);
+const char* chomp_b200_last_error(void);
+
+/* handle = per-device scratch + constant tables; one handle per thread/stream */
+int chomp_b200_create(void** handle, int device);
+void chomp_b200_destroy(void* handle);
+int chomp_b200_configure(void* handle, const chomp_b200_config* cfg);
+/* (re)allocate device scratch for batches of up to max_points parameter points */
+int chomp_b200_reserve(void* handle, int max_points);
+
+/* Stage 1 -- replaces MultiEpoch._initialize_splines (cosmology.py:787-817),
+ * dNdz.normalize (kernel.py:43-54), WindowFunction._initialize_spline (kernel.py:308-313),
+ * WindowFunctionConvergence.raw_window_function (kernel.py:443-477), Kernel.__init__ /
+ * _find_z_bar / raw_kernel / _initialize_spline (kernel.py:584-705, 812-839).
+ * cosmo_dev: [B, CHOMP_N_COSMO].  Leaves z_bar, D(z_bar) and the K(ln k theta) spline
+ * in the handle. */
+int chomp_b200_limber_tables(void* handle, int B, const double* cosmo_dev, int32_t* status_dev, void* stream);
+
+/* Stage 2 -- replaces SingleEpoch._initialize_defaults / sigma_r / nu_m
+ * (cosmology.py:93-119, 602-699) and MassFunction._set_mass_limits / _initialize_splines /
+ * _normalize (mass_function.py:160-241).  z_dev: [B] redshifts, or NULL to use stage 1's
+ * z_bar (what Correlation.__init__ does, correlation.py:103).  halo_dev: [B, CHOMP_N_HALO]. */
+int chomp_b200_mass_tables(void* handle, int B, const double* cosmo_dev, const double* halo_dev,
+                           const double* z_dev, int32_t* status_dev, void* stream);
+
+/* Stage 3 -- replaces Halo._calculate_n_bar, _initialize_h_m / _h_g / _pp_mm / _pp_gm / _pp_gg
+ * and y_nfw (halo.py:561-585, 674-707, 904-1086) with the HOD moments of hod.py:188-230,
+ * 262-299.  hod_dev: [B, CHOMP_N_HOD] (Zheng: log_M_min, sigma, log_M_0, log_M_1p, alpha;
+ * Mandelbaum: log_M_0, w, -, -, -). */
+int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const double* hod_dev,
+                           int32_t* status_dev, void* stream);
+
+/* Halo.linear_power / power_mm / power_gm / power_gg (halo.py:266-439) at k_dev[n_k]
+ * for every point: P_out_dev [B, n_k]. */
+int chomp_b200_power(void* handle, int B, int which, int n_k, const double* k_dev, double* P_out_dev, void* stream);
+
+/* Correlation.correlation (correlation.py:242-275): w_out_dev [B, n_theta], theta in radians. */
+int chomp_b200_wtheta(void* handle, int B, int which, int n_theta, const double* theta_dev, double* w_out_dev,
+                      int32_t* status_dev, void* stream);
+
+/* All four stages back to back on `stream` (one MCMC step per point,
+ * examples/example_script.py:141-143): inputs and outputs already on the device. */
+int chomp_b200_wtheta_batch(void* handle, int B, const double* cosmo_dev, const double* halo_dev,
+                            const double* hod_dev, int which, int n_theta, const double* theta_dev,
+                            double* w_out_dev, int32_t* status_dev, void* stream);
+
+/* Same with HOST buffers: pinned staging, H2D copies, the four stages, D2H copy, one
+ * stream synchronise.  This is the call the end-to-end benchmark times. */
+int chomp_b200_wtheta_batch_host(void* handle, int B, const double* cosmo_host, const double* halo_host,
+                                 const double* hod_host, int which, int n_theta, const double* theta_host,
+                                 double* w_out_host, int32_t* status_host);
+
+/* Element-wise evaluators behind the drop-in classes' scalar methods (point index p of the
+ * last batch): SingleEpoch.linear_power / sigma_r (cosmology.py:589, 602), MassFunction.nu /
+ * mass / f_nu / bias_nu (mass_function.py:243-346), Kernel.kernel (kernel.py:714). */
+enum { CHOMP_EVAL_LINEAR_POWER = 0, CHOMP_EVAL_SIGMA_R, CHOMP_EVAL_NU_OF_MASS, CHOMP_EVAL_MASS_OF_NU,
+       CHOMP_EVAL_F_NU, CHOMP_EVAL_BIAS_NU, CHOMP_EVAL_KERNEL, CHOMP_EVAL_WINDOW_A, CHOMP_EVAL_WINDOW_B,
+       CHOMP_EVAL_Y_NFW /* x = mass, aux = ln k */ , CHOMP_EVAL_FIRST_MOMENT, CHOMP_EVAL_SECOND_MOMENT };
+int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_dev, double aux, double* out_dev,
+                    void* stream);
+
+/* Copy one of the per-point tables of the last batch into out_dev [B, len]; *len_out
+ * receives the row length.  Table ids below. */
+enum {
+    CHOMP_T_ZBAR = 0, CHOMP_T_DBAR, CHOMP_T_KERNEL_NODES, CHOMP_T_CHI_NODES /* [3, n_cosmo]: kernel, a, b */,
+    CHOMP_T_WINDOW_NODES /* [2, n_window] */, CHOMP_T_WINDOW_CHI /* [2,2] chi_min, chi_max */,
+    CHOMP_T_EPOCH /* 16 scalars, see chomp_b200.cu */, CHOMP_T_LNM_NODES, CHOMP_T_NU_NODES,
+    CHOMP_T_HALO_NODES /* [5, n_halo]: h_m, pp_mm, h_g, pp_gm, pp_gg */, CHOMP_T_NBAR /* n_bar/rho_bar */,
+    CHOMP_T_NU_QUAD_COUNT /* number of nu quadrature nodes (as double) */
+};
+int chomp_b200_copy_table(void* handle, int B, int table, double* out_dev, int* len_out, void* stream);
+
+/* Measured FP64 FMA peak of the device (dependent-free DFMA chains on all SMs): the
+ * roofline denominator of bench.py, MEASURED_PEAKS.json carries no FP64 figure. */
+int chomp_b200_dfma_peak(void* handle, int iters, double* tflops_out);
+
+/* Per-kernel device times of the last chomp_b200_wtheta_batch on this handle, measured with
+ * CUDA events recorded on the launching stream around every kernel (order below).  With
+ * timing on, the events are recorded at every call; get_timing synchronises on the last. */
+enum { CHOMP_K_LIMBER = 0, CHOMP_K_MASS, CHOMP_K_NODES, CHOMP_K_SUMS, CHOMP_K_SPLINES, CHOMP_K_WTHETA,
+       CHOMP_N_KERNELS };
+int chomp_b200_set_timing(void* handle, int on);
+int chomp_b200_get_timing(void* handle, double* ms_out /* [CHOMP_N_KERNELS] */);
+
+/* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+long long chomp_b200_launch_count(void* handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHOMP_B200_H */

@@ -1,0 +1,82 @@
+"""Shared fixtures for the parity tests: the reference's unit-test dictionaries
+(unit_test.py:17-119) and helpers that run the same inputs through the CPU
+oracle."""
+import numpy as np
+
+from oracle import chomp_oracle as O
+from oracle.quadrature import Tight
+
+D2R = np.pi/180.0
+
+C_DICT = {"omega_m0": 0.3 - 4.15e-5/0.7**2, "omega_b0": 0.046, "omega_l0": 0.7,
+          "omega_r0": 4.15e-5/0.7**2, "cmb_temp": 2.726, "h": 0.7, "sigma_8": 0.8,
+          "n_scalar": 0.960, "w0": -1.0, "wa": 0.0}
+C_DICT_2 = dict(C_DICT, omega_m0=1.0 - 4.15e-5/0.7**2, omega_l0=0.0)
+H_DICT = {"stq": 0.3, "st_little_a": 0.707, "c0": 9., "beta": -0.13, "alpha": -1.,
+          "delta_v": -1.}
+H_DICT_2 = {"stq": 0.5, "st_little_a": 0.5, "c0": 5., "beta": -0.2, "alpha": -1,
+            "delta_v": 200.0}
+HOD_DICT = {"log_M_min": 12.14, "sigma": 0.15, "log_M_0": 12.14, "log_M_1p": 13.43,
+            "alpha": 1.0}
+HOD_DICT_2 = {"log_M_min": 14.06, "sigma": 0.71, "log_M_0": 14.06, "log_M_1p": 14.80,
+              "alpha": 1.0}
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)/np.maximum(np.abs(b), 1e-300)))
+
+
+def w_err(w, ref, floor=1e-3):
+    """Relative error of a correlation function that may cross zero: each bin
+    relative to max(|ref_i|, floor * max|ref|)  (parity
+    report)."""
+    w, ref = np.asarray(w, dtype=float), np.asarray(ref, dtype=float)
+    scale = np.maximum(np.abs(ref), floor*np.max(np.abs(ref)))
+    return float(np.max(np.abs(w - ref)/scale))
+
+
+def oracle_wtheta(cosmo, halo, hod, dist_a, dist_b=None, window_a="galaxy", window_b=None,
+                  power_spec="power_gg", bins_per_decade=10.0, prec=None, integ=None,
+                  z_range=(0.0, 5.0), theta_deg=(0.001, 1.0), bessel_order=0, hod_kind="zheng"):
+    """One parameter point through the oracle; returns a dict of every table."""
+    prec = prec or O.precision()
+    integ = integ or Tight(40)
+
+    def make_dist(spec):
+        kind, args = spec
+        cls = O.dNdzGaussian if kind == "gaussian" else O.dNdzMagLim
+        return cls(*args, prec=prec, integ=integ)
+
+    def make_window(kind, dist, cm):
+        cls = O.WindowFunctionGalaxy if kind == "galaxy" else O.WindowFunctionConvergence
+        return cls(dist, cm)
+
+    cm = O.MultiEpoch(z_range[0], z_range[1], cosmo, prec, integ)
+    da = make_dist(dist_a)
+    db = make_dist(dist_b) if dist_b is not None else da
+    wa = make_window(window_a, da, cm)
+    wb = make_window(window_b or window_a, db, cm)
+    kcls = O.Kernel if bessel_order == 0 else O.GalaxyGalaxyLensingKernel
+    kern = kcls(1e-6*D2R, 100*D2R, wa, wb, cm)
+    hod_cls = O.HODZheng if hod_kind == "zheng" else O.HODMandelbaum
+
+    def factory(z):
+        se = O.SingleEpoch(z, cosmo, prec, integ)
+        mf = O.MassFunction(se, halo)
+        return O.Halo(se, mf, hod_cls(hod, prec["halo_precision"]), halo)
+
+    corr = O.Correlation(theta_deg[0], theta_deg[1], kern, factory, power_spec,
+                         bins_per_decade=bins_per_decade)
+    w = corr.compute_correlation()
+    h = corr.halo
+    out = dict(w=w, theta=corr.theta, z_bar=kern.z_bar, D_z=corr.D_z,
+               kernel_nodes=kern.kernel_nodes, chi_nodes=cm.chi_nodes,
+               wa_nodes=kern.wa.wf_nodes, wb_nodes=kern.wb.wf_nodes,
+               nu_nodes=h.mass.nu_nodes, ln_mass_nodes=h.mass.ln_mass_nodes,
+               f_norm=h.mass.f_norm, bias_norm=h.mass.bias_norm,
+               ln_m_star=np.log(h.mass.m_star), n_bar_over_rho_bar=h.n_bar_over_rho_bar,
+               sigma_norm=h.epoch.sigma_norm, growth=h.epoch.growth, halo=h)
+    for name in ("h_m", "pp_mm", "h_g", "pp_gm", "pp_gg"):
+        out[name] = h.table(name)[0]
+    return out

@@ -1,0 +1,125 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle's
+converged ("tight") evaluation of the reference's integrands on the same node
+grids and splines.  Bar: 1e-5 relative on P(k) and w(theta) (BASELINE.json
+north_star); intermediate tables are held tighter so that a failure points at
+the stage that caused it."""
+import numpy as np
+import pytest
+
+from chomp_b200 import _lib, design, engine
+from oracle import chomp_oracle as O
+
+from common import (C_DICT, C_DICT_2, H_DICT, H_DICT_2, HOD_DICT, HOD_DICT_2, oracle_wtheta,
+                    rel_err, w_err)
+
+pytestmark = pytest.mark.gpu
+
+TOL_FINAL = 1e-5      # north_star bar, P(k) and w(theta)
+TOL_TABLE = 2e-6      # intermediate tables
+
+
+def _survey(power_spec="power_gg", **kw):
+    dist = engine.RedshiftDistribution.gaussian(0.0, 2.0, 0.5, 0.1)
+    return engine.Survey(dist, bins_per_decade=10.0, power_spec=power_spec, **kw)
+
+
+def _run_point(eng, survey, cosmo, halo, hod, which):
+    c = engine.pack_params([cosmo], _lib.COSMO_KEYS)
+    h = engine.pack_params([halo], _lib.HALO_KEYS)
+    g = np.zeros((1, _lib.N_HOD))
+    keys = _lib.HOD_ZHENG_KEYS if survey.hod_kind == _lib.HOD_ZHENG else _lib.HOD_MANDELBAUM_KEYS
+    g[0, :len(keys)] = [hod[k] for k in keys]
+    import torch
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    w = eng.wtheta(c, h, g, survey.theta, which, status=status)
+    torch.cuda.synchronize()
+    return w.cpu().numpy()[0], int(status.cpu()[0])
+
+
+CASES = [
+    ("base", C_DICT, H_DICT, HOD_DICT),
+    ("cosmo2", C_DICT_2, H_DICT, HOD_DICT),
+    ("halo2", C_DICT, H_DICT_2, HOD_DICT),
+    ("hod2", C_DICT, H_DICT, HOD_DICT_2),
+]
+
+
+@pytest.mark.parametrize("name,cosmo,halo,hod", CASES, ids=[c[0] for c in CASES])
+def test_stage_tables_against_oracle(name, cosmo, halo, hod):
+    survey = _survey()
+    eng = engine.Engine(survey)
+    w, status = _run_point(eng, survey, cosmo, halo, hod, _lib.P_GG)
+    assert status == 0
+    ref = oracle_wtheta(cosmo, halo, hod, ("gaussian", (0.0, 2.0, 0.5, 0.1)))
+    nz, nw = survey.precision["cosmo_npoints"], survey.precision["window_npoints"]
+    chi = eng.table(_lib.T_CHI_NODES, 1).cpu().numpy()[0].reshape(3, nz)
+    assert rel_err(chi[0][1:], ref["chi_nodes"][1:]) < 1e-9
+    win = eng.table(_lib.T_WINDOW_NODES, 1).cpu().numpy()[0].reshape(2, nw)
+    peak = np.max(np.abs(ref["wa_nodes"]))
+    assert np.max(np.abs(win[0] - ref["wa_nodes"]))/peak < 1e-8
+    assert abs(eng.table(_lib.T_ZBAR, 1).cpu().numpy()[0, 0] - ref["z_bar"]) < 1e-12
+    assert rel_err(eng.table(_lib.T_DBAR, 1).cpu().numpy()[0, 0], ref["D_z"]) < 1e-10
+    kn = eng.table(_lib.T_KERNEL_NODES, 1).cpu().numpy()[0]
+    assert np.max(np.abs(kn - ref["kernel_nodes"]))/np.max(np.abs(ref["kernel_nodes"])) < 1e-7
+    ep = dict(zip(_lib.EPOCH_FIELDS, eng.table(_lib.T_EPOCH, 1).cpu().numpy()[0]))
+    assert rel_err(ep["sigma_norm"], ref["sigma_norm"]) < 1e-8
+    assert rel_err(ep["growth"], ref["growth"]) < 1e-12
+    assert rel_err(eng.table(_lib.T_LNM_NODES, 1).cpu().numpy()[0], ref["ln_mass_nodes"]) < 1e-12
+    assert rel_err(eng.table(_lib.T_NU_NODES, 1).cpu().numpy()[0], ref["nu_nodes"]) < 1e-7
+    assert rel_err(ep["f_norm"], ref["f_norm"]) < 1e-7
+    assert rel_err(ep["bias_norm"], ref["bias_norm"]) < 1e-7
+    assert rel_err(ep["ln_m_star"], ref["ln_m_star"]) < 1e-8
+    assert rel_err(eng.table(_lib.T_NBAR, 1).cpu().numpy()[0, 0], ref["n_bar_over_rho_bar"]) < TOL_TABLE
+    nk = survey.precision["halo_npoints"]
+    tabs = eng.table(_lib.T_HALO_NODES, 1).cpu().numpy()[0].reshape(5, nk)
+    for i, nm in enumerate(("h_m", "pp_mm", "h_g", "pp_gm", "pp_gg")):
+        assert rel_err(tabs[i], ref[nm]) < TOL_TABLE, nm
+    assert w_err(w, ref["w"]) < TOL_FINAL
+
+
+@pytest.mark.parametrize("spec", ["linear_power", "power_mm", "power_gm", "power_gg"])
+def test_power_spectra_and_wtheta(spec):
+    survey = _survey(spec)
+    eng = engine.Engine(survey)
+    which = _lib.POWER_SPEC[spec]
+    w, status = _run_point(eng, survey, C_DICT, H_DICT, HOD_DICT, which)
+    assert status == 0
+    ref = oracle_wtheta(C_DICT, H_DICT, HOD_DICT, ("gaussian", (0.0, 2.0, 0.5, 0.1)), power_spec=spec)
+    k = np.logspace(-3.5, 2.2, 200)      # includes the k < k_min and k > k_max branches
+    P = eng.power(1, which, k).cpu().numpy()[0]
+    Pref = ref["halo"].power(spec, k)
+    assert np.all((P == 0) == (Pref == 0))
+    nz = Pref != 0
+    assert rel_err(P[nz], Pref[nz]) < TOL_FINAL
+    assert w_err(w, ref["w"]) < TOL_FINAL
+
+
+def test_named_shape_200_k_nodes():
+    """halo_npoints = 200 (the named benchmark shape) on both sides."""
+    prec = dict(O.DEFAULT_PRECISION, halo_npoints=200)
+    survey = _survey(precision=prec)
+    eng = engine.Engine(survey)
+    w, status = _run_point(eng, survey, C_DICT, H_DICT, HOD_DICT, _lib.P_GG)
+    assert status == 0
+    ref = oracle_wtheta(C_DICT, H_DICT, HOD_DICT, ("gaussian", (0.0, 2.0, 0.5, 0.1)), prec=prec)
+    assert w_err(w, ref["w"]) < TOL_FINAL
+
+
+def test_synthetic_batch_points_and_batch_invariance():
+    """Latin-hypercube points: each against the oracle, and the same point gives
+    bit-identical results whatever batch it is evaluated in."""
+    import torch
+    survey = _survey()
+    eng = engine.Engine(survey)
+    cosmo, halo, hod = design.synthetic_batch(64)
+    w = eng.wtheta(cosmo, halo, hod, survey.theta, _lib.P_GG).cpu().numpy()
+    assert np.all(np.isfinite(w))
+    for i, (cd, hd, gd) in enumerate(design.as_dicts(cosmo, halo, hod)[:4]):
+        ref = oracle_wtheta(cd, hd, gd, ("gaussian", (0.0, 2.0, 0.5, 0.1)))
+        assert w_err(w[i], ref["w"]) < TOL_FINAL, i
+    sub = slice(16, 48)
+    w2 = eng.wtheta(cosmo[sub], halo[sub], hod[sub], survey.theta, _lib.P_GG).cpu().numpy()
+    assert np.array_equal(w2, w[sub])
+    wh, status = eng.wtheta_host(cosmo, halo, hod, survey.theta, _lib.P_GG)
+    assert np.array_equal(wh, w) and not status.any()
+    torch.cuda.synchronize()
