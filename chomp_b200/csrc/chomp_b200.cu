@@ -48,13 +48,13 @@ struct Handle {
     Cfg cfg;
     int same_window = 0;
     int cap_points = 0;
-    int node_cap = 0;
+    int node_cap[N_KCLASS] = {0, 0, 0}, node_off[N_KCLASS] = {0, 0, 0}, node_cap_total = 0;
     long long launches = 0;
     // device scratch (all FP64 unless noted)
     double *zbar = nullptr, *dbar = nullptr, *knodes = nullptr, *kcoef = nullptr, *chi_nodes = nullptr,
            *win_nodes = nullptr, *win_chi = nullptr, *win_coef = nullptr, *kchi = nullptr;
     double *epoch = nullptr, *lnm_nodes = nullptr, *nu_nodes = nullptr, *c_lnm_nu = nullptr, *c_nu_lnm = nullptr;
-    double *nodes = nullptr, *nbar = nullptr, *raw = nullptr, *htab = nullptr, *hcoef = nullptr;
+    double *nodes = nullptr, *nbar = nullptr, *rv_max = nullptr, *raw = nullptr, *htab = nullptr, *hcoef = nullptr;
     int32_t* n_nodes = nullptr;
     // parameter copies of the last batch (the evaluators need them)
     double *cosmo = nullptr, *halo = nullptr, *hod = nullptr;
@@ -131,7 +131,16 @@ int check_cfg(const Cfg& c) {
 }
 
 size_t mass_smem(const Cfg& c) { return (14 * (size_t)c.n_mass + 64) * sizeof(double); }
-size_t nodes_smem(const Cfg& c) { return (10 * (size_t)c.n_mass + 2 * MAX_EXTRA_BREAKS + 64 + 8) * sizeof(double); }
+size_t nodes_smem(const Cfg& c) {
+    const size_t max_edge = (size_t)c.n_mass + MAX_EXTRA_BREAKS;
+    return (10 * (size_t)c.n_mass + max_edge + MAX_EXTRA_BREAKS + 64) * sizeof(double) +
+           ((N_KCLASS + 1) * max_edge + 8) * sizeof(int);
+}
+size_t sums_smem(const Handle* h) {
+    int m = 0;
+    for (int c = 0; c < N_KCLASS; ++c) m = h->node_cap[c] > m ? h->node_cap[c] : m;
+    return (size_t)NODE_FIELDS * m * sizeof(double);
+}
 size_t splines_smem(const Cfg& c) { return 36 * (size_t)c.n_halo * sizeof(double); }
 size_t wtheta_smem(const Cfg& c) { return (12 * (size_t)c.n_halo + 4 * (size_t)c.n_kernel + 8) * sizeof(double); }
 
@@ -218,7 +227,13 @@ int chomp_b200_reserve(void* handle, int max_points) {
     free_scratch(h);
     const Cfg& c = h->cfg;
     const size_t B = (size_t)max_points;
-    h->node_cap = (((c.n_mass - 1 + MAX_EXTRA_BREAKS) * c.nq_nu + 31) / 32) * 32;
+    h->node_cap_total = 0;
+    for (int k = 0; k < N_KCLASS; ++k) {
+        h->node_cap[k] = kclass_cap(k, c.n_mass);
+        h->node_off[k] = h->node_cap_total;
+        h->node_cap_total += h->node_cap[k];
+    }
+    CK(cudaFuncSetAttribute(halo_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem(h)));
     int rc = 0;
     rc |= dev_alloc(h, &h->zbar, B);
     rc |= dev_alloc(h, &h->dbar, B);
@@ -234,9 +249,10 @@ int chomp_b200_reserve(void* handle, int max_points) {
     rc |= dev_alloc(h, &h->nu_nodes, B * c.n_mass);
     rc |= dev_alloc(h, &h->c_lnm_nu, B * 4 * c.n_mass);
     rc |= dev_alloc(h, &h->c_nu_lnm, B * 4 * c.n_mass);
-    rc |= dev_alloc(h, &h->nodes, B * NODE_FIELDS * h->node_cap);
-    rc |= dev_alloc(h, &h->n_nodes, B);
+    rc |= dev_alloc(h, &h->nodes, B * NODE_FIELDS * h->node_cap_total);
+    rc |= dev_alloc(h, &h->n_nodes, B * N_KCLASS);
     rc |= dev_alloc(h, &h->nbar, B);
+    rc |= dev_alloc(h, &h->rv_max, B);
     rc |= dev_alloc(h, &h->raw, B * 5 * c.n_halo);
     rc |= dev_alloc(h, &h->htab, B * 5 * c.n_halo);
     rc |= dev_alloc(h, &h->hcoef, B * 20 * c.n_halo);
@@ -301,15 +317,17 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
         CK(cudaMemcpyAsync(h->halo, halo_dev, sizeof(double) * B * CHOMP_N_HALO, cudaMemcpyDeviceToDevice, s));
     if (hod_dev != h->hod)
         CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
-    NodesOut no{h->nodes, h->n_nodes, h->nbar, h->node_cap};
+    NodesOut no;
+    no.nodes = h->nodes; no.n_nodes = h->n_nodes; no.nbar = h->nbar; no.rv_max = h->rv_max;
+    for (int k = 0; k < N_KCLASS; ++k) { no.cap[k] = h->node_cap[k]; no.off[k] = h->node_off[k]; }
+    no.cap_total = h->node_cap_total;
     mark(h, CHOMP_K_NODES, s);
     nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
                                                   h->c_lnm_nu, h->c_nu_lnm, no, status_dev);
     CK(cudaGetLastError());
-    const int warps = 8;
-    dim3 grid((c.n_halo + warps - 1) / warps, B);
+    dim3 grid((c.n_halo + SUMS_K_PER_CTA - 1) / SUMS_K_PER_CTA + N_KCLASS - 1, B);
     mark(h, CHOMP_K_SUMS, s);
-    halo_sums_kernel<<<grid, warps * 32, 0, s>>>(c, B, h->nodes, h->n_nodes, h->node_cap, h->raw);
+    halo_sums_kernel<<<grid, 256, sums_smem(h), s>>>(c, B, no, h->raw);
     CK(cudaGetLastError());
     mark(h, CHOMP_K_SPLINES, s);
     halo_splines_kernel<<<B, 64, splines_smem(c), s>>>(c, B, h->raw, h->nbar, h->epoch, h->htab, h->hcoef, status_dev);
@@ -534,18 +552,18 @@ int chomp_b200_copy_table(void* handle, int B, int table, double* out_dev, int* 
         case CHOMP_T_NU_NODES: src = h->nu_nodes; len = c.n_mass; break;
         case CHOMP_T_HALO_NODES: src = h->htab; len = 5 * c.n_halo; break;
         case CHOMP_T_NBAR: src = h->nbar; len = 1; break;
-        case CHOMP_T_NU_QUAD_COUNT: len = 1; break;
+        case CHOMP_T_NU_QUAD_COUNT: len = N_KCLASS; break;
         default: FAIL("unknown table id");
     }
     if (len_out) *len_out = len;
     if (!out_dev) return 0;
     if (table == CHOMP_T_NU_QUAD_COUNT) {
-        std::vector<int32_t> tmp(B);
-        CK(cudaMemcpyAsync(tmp.data(), h->n_nodes, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        std::vector<int32_t> tmp((size_t)B * N_KCLASS);
+        CK(cudaMemcpyAsync(tmp.data(), h->n_nodes, sizeof(int32_t) * B * N_KCLASS, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
         CK(cudaStreamSynchronize((cudaStream_t)stream));
-        std::vector<double> d(B);
-        for (int i = 0; i < B; ++i) d[i] = (double)tmp[i];
-        CK(cudaMemcpyAsync(out_dev, d.data(), sizeof(double) * B, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        std::vector<double> d((size_t)B * N_KCLASS);
+        for (size_t i = 0; i < d.size(); ++i) d[i] = (double)tmp[i];
+        CK(cudaMemcpyAsync(out_dev, d.data(), sizeof(double) * B * N_KCLASS, cudaMemcpyHostToDevice, (cudaStream_t)stream));
         CK(cudaStreamSynchronize((cudaStream_t)stream));
         return 0;
     }

@@ -22,9 +22,24 @@
 
 namespace chomp {
 
-#define NODE_FIELDS 11
-enum { NF_C = 0, NF_RS, NF_INV_MK, NF_LNCP, NF_W_HM, NF_W_PMM, NF_W_HG, NF_W_GM1, NF_W_GM2, NF_W_GG1, NF_W_GG2 };
+// Per-node record (structure of arrays).  1/m(c) = 1/(ln(1+c) - c/(1+c)) is folded into the
+// weights, so the sums run over rho_k = m(c) * y directly.  The sign of W_GM / W_GG carries the
+// reference's exponent switch: negative = "moment < 1, first power of y" (halo.py:1038-1041,
+// 1084-1086), positive = second power.
+#define NODE_FIELDS 8
+enum { NF_CP = 0, NF_RS, NF_LNCP, NF_W_HM, NF_W_PMM, NF_W_HG, NF_W_GM, NF_W_GG };
 #define MAX_EXTRA_BREAKS 8
+// k classes: the panel order grows with phi = k * r_vir(M_max), the phase of the profile's
+// oscillation in mass across the table.  {smooth panels, panels inside the central-galaxy
+// erf edge log_M_min +- 3.5 sigma}
+#define N_KCLASS 3
+#define KCLASS_PHI_1 45.0
+#define KCLASS_PHI_2 180.0
+__device__ __constant__ int k_class_base[N_KCLASS] = {4, 8, 16};
+__device__ __constant__ int k_class_sharp[N_KCLASS] = {10, 10, 16};
+#define KCLASS_MAX_ORDER 16
+#define SING_MIN_ORDER 8
+#define SUMS_K_PER_CTA 32
 
 struct HodP {
     int kind;
@@ -113,11 +128,21 @@ __device__ inline double lnnu_moment_crossing(const NuTab& t, const HodP& h, int
 }
 
 struct NodesOut {
-    double* nodes;     // [B, NODE_FIELDS, cap]
-    int32_t* n_nodes;  // [B]
+    double* nodes;     // [B, cap_total * NODE_FIELDS]; class c occupies [off_c*NF, (off_c+cap_c)*NF), fields SoA
+    int32_t* n_nodes;  // [B, N_KCLASS]
     double* nbar;      // [B] n_bar / rho_bar
-    int cap;
+    double* rv_max;    // [B] r_vir at the upper end of the mass table (sets the k classes)
+    int cap[N_KCLASS];
+    int off[N_KCLASS];
+    int cap_total;
 };
+
+__host__ __device__ inline int kclass_cap(int c, int n_mass) {
+    const int base[N_KCLASS] = {4, 8, 16}, sharp[N_KCLASS] = {10, 10, 16};
+    int m = base[c] > sharp[c] ? base[c] : sharp[c];
+    if (m < SING_MIN_ORDER) m = SING_MIN_ORDER;
+    return (((n_mass - 1 + MAX_EXTRA_BREAKS) * m + 31) / 32) * 32;
+}
 
 __global__ void __launch_bounds__(128)
 nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const double* __restrict__ hod,
@@ -128,13 +153,16 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     const int b = blockIdx.x;
     if (b >= B) return;
     const int n = cfg.n_mass, tid = threadIdx.x;
+    const int max_edge = n + MAX_EXTRA_BREAKS;
     double* lnm = sm;
     double* nu = lnm + n;
     double* c1 = nu + n;
     double* c2 = c1 + 4 * n;
-    double* edge = c2 + 4 * n;                 // n + MAX_EXTRA_BREAKS
-    double* extra = edge + n + MAX_EXTRA_BREAKS;  // MAX_EXTRA_BREAKS
+    double* edge = c2 + 4 * n;                 // max_edge
+    double* extra = edge + max_edge;           // MAX_EXTRA_BREAKS
     double* red = extra + MAX_EXTRA_BREAKS;    // 64
+    int* pstart = (int*)(red + 64);            // [N_KCLASS][max_edge] first node of each panel
+    int* pknot = pstart + N_KCLASS * max_edge; // [max_edge] knot interval of the ln M(nu) spline holding the panel
     __shared__ int n_edge;
     __shared__ double x_singular;
     for (int i = tid; i < n; i += blockDim.x) { lnm[i] = g_lnm[(size_t)b * n + i]; nu[i] = g_nu[(size_t)b * n + i]; }
@@ -193,73 +221,101 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
         }
         n_edge = cnt;
         x_singular = x_sing;
+        // per panel: spline interval and, per k class, the first node index
+        // panels inside the erf edge of the central occupation get the "sharp" order
+        const double ln10 = 2.302585092994046;
+        const double sharp_lo = (h.log_M_min - 3.5 * h.sigma) * ln10, sharp_hi = (h.log_M_min + 3.5 * h.sigma) * ln10;
+        int acc[N_KCLASS] = {0, 0, 0};
+        for (int p = 0; p < cnt - 1; ++p) {
+            const double xm = 0.5 * (edge[p] + edge[p + 1]);
+            const int kn = search_index(exp(xm), nu, n);
+            pknot[p] = kn;
+            const double lm_lo = spline_poly(c1, kn, exp(edge[p]) - nu[kn]);
+            const double lm_hi = spline_poly(c1, kn, exp(edge[p + 1]) - nu[kn]);
+            const bool sharp = (h.kind == CHOMP_HOD_ZHENG) && h.sigma > 0.0 && lm_hi > sharp_lo && lm_lo < sharp_hi;
+            const bool sing = edge[p] >= x_sing - 1e-12 && edge[p] <= x_sing + 0.02;
+            for (int c = 0; c < N_KCLASS; ++c) {
+                int o = sharp ? k_class_sharp[c] : k_class_base[c];
+                if (sing && o < SING_MIN_ORDER) o = SING_MIN_ORDER;
+                pstart[c * max_edge + p] = acc[c];
+                acc[c] += o;
+            }
+        }
+        for (int c = 0; c < N_KCLASS; ++c) pstart[c * max_edge + cnt - 1] = acc[c];
     }
     __syncthreads();
     // ---- nodes ------------------------------------------------------------------------------
-    const int nq = cfg.nq_nu;
     const int n_pan = n_edge - 1;
-    const int total = n_pan * nq;
     const double* hp = halo + (size_t)b * CHOMP_N_HALO;
     const double stq = hp[CHOMP_H_STQ], sta = hp[CHOMP_H_ST_LITTLE_A], beta = hp[CHOMP_H_BETA];
     const double c0 = hp[CHOMP_H_C0] / (1.0 + e[EP_Z]);                   // halo.py:65
     const double f_norm = e[EP_F_NORM], b_norm = e[EP_B_NORM], delta_c = e[EP_DELTA_C];
     const double rho_bar = e[EP_RHO_BAR], delta_v = e[EP_DELTA_V], lnm_star = e[EP_LNM_STAR];
-    double* rec = out.nodes + (size_t)b * NODE_FIELDS * out.cap;
+    const double rv_coef = 3.0 / (4.0 * M_PI * delta_v * rho_bar);
     double nbar = 0.0;
-    if (total > out.cap) {
-        if (tid == 0 && status) atomicOr(status + b, CHOMP_ST_NODE_OVERFLOW);
-    }
-    for (int idx = tid; idx < total && idx < out.cap; idx += blockDim.x) {
-        const int p = idx / nq, q = idx - p * nq;
-        const double a = edge[p], bb = edge[p + 1];
-        double x, wq;
-        if (a >= x_singular - 1e-12 && a <= x_singular + 0.02) {
-            // x = a + (b - a) t^4 removes the (M - M0)^alpha end-point behaviour (hod.py:226-230);
-            // also applied when the panel starts just above M0 (lower limit from the forward spline)
-            const double tt = 0.5 * (c_glx[nq][q] + 1.0);
-            const double t2 = tt * tt;
-            x = a + (bb - a) * t2 * t2;
-            wq = (bb - a) * 4.0 * t2 * tt * 0.5 * c_glw[nq][q];
-        } else {
-            const double half = 0.5 * (bb - a);
-            x = 0.5 * (a + bb) + half * c_glx[nq][q];
-            wq = half * c_glw[nq][q];
+    int st = 0;
+    for (int c = 0; c < N_KCLASS; ++c) {
+        const int* ps = pstart + c * max_edge;
+        const int total = ps[n_pan];
+        const int cap = out.cap[c];
+        if (total > cap) st |= CHOMP_ST_NODE_OVERFLOW;
+        double* rec = out.nodes + ((size_t)b * out.cap_total + out.off[c]) * NODE_FIELDS;
+        // one thread per (panel, node): walk the panels with a running index
+        for (int idx = tid; idx < total && idx < cap; idx += blockDim.x) {
+            int p = 0, hi = n_pan;          // panel with ps[p] <= idx < ps[p+1]
+            while (hi - p > 1) { const int mid = (p + hi) >> 1; if (ps[mid] <= idx) p = mid; else hi = mid; }
+            const int nq = ps[p + 1] - ps[p], q = idx - ps[p];
+            const double a = edge[p], bb = edge[p + 1];
+            double x, wq;
+            if (a >= x_singular - 1e-12 && a <= x_singular + 0.02) {
+                // x = a + (b - a) t^4 removes the (M - M0)^alpha end-point behaviour (hod.py:226-230);
+                // also applied when the panel starts just above M0 (lower limit from the forward spline)
+                const double tt = 0.5 * (c_glx[nq][q] + 1.0);
+                const double t2 = tt * tt;
+                x = a + (bb - a) * t2 * t2;
+                wq = (bb - a) * 4.0 * t2 * tt * 0.5 * c_glw[nq][q];
+            } else {
+                const double half = 0.5 * (bb - a);
+                x = 0.5 * (a + bb) + half * c_glx[nq][q];
+                wq = half * c_glw[nq][q];
+            }
+            const double xmid = 0.5 * (a + bb);
+            const double v = exp(x);
+            const int kn = pknot[p];
+            const double lm = spline_poly(c1, kn, v - nu[kn]);      // MassFunction.ln_mass, mass_function.py:326
+            const double M = exp(lm);
+            double nf, bias;
+            st_raw(v, sta, stq, delta_c, nf, bias);
+            const double wt = wq * nf * f_norm;          // d ln(nu) * nu f(nu)
+            bias *= b_norm;
+            const double con = c0 * exp(beta * (lm - lnm_star));                           // halo.py:869-873
+            const double r_v = cbrt(rv_coef * M);                                          // halo.py:890-893
+            const double cp = 1.0 + con;
+            const double lncp = log(cp);
+            const double imk = 1.0 / (lncp - con / cp);                                    // halo.py:584
+            double n1, n2;
+            hod_moments(h, M, n1, n2);
+            const double in1 = (xmid > x_lo1) ? 1.0 : 0.0, in2 = (xmid > x_lo2) ? 1.0 : 0.0;
+            rec[NF_CP * cap + idx] = cp;
+            rec[NF_RS * cap + idx] = r_v / con;
+            rec[NF_LNCP * cap + idx] = lncp;
+            rec[NF_W_HM * cap + idx] = wt * bias * imk;                                     // halo.py:923-927
+            rec[NF_W_PMM * cap + idx] = wt * M / rho_bar * imk * imk;                       // halo.py:990-994, :988
+            rec[NF_W_HG * cap + idx] = in1 * wt * bias * n1 / M * imk;                      // halo.py:964-969
+            const double wgm = in1 * wt * n1;                                               // halo.py:1078-1086
+            rec[NF_W_GM * cap + idx] = (n1 < 1.0) ? -wgm * imk : wgm * imk * imk;
+            const double wgg = in2 * wt * n2 / M;                                           // halo.py:1032-1041
+            rec[NF_W_GG * cap + idx] = (n2 < 1.0) ? -wgg * imk : wgg * imk * imk;
+            if (c == N_KCLASS - 1) nbar += in1 * wt * n1 / M;                               // halo.py:704-707
         }
-        const double xmid = 0.5 * (a + bb);
-        const double v = exp(x);
-        const double lm = mass_of_nu_ln(t, v);
-        const double M = exp(lm);
-        double nf, bias;
-        st_raw(v, sta, stq, delta_c, nf, bias);
-        const double wt = wq * nf * f_norm;          // d ln(nu) * nu f(nu)
-        bias *= b_norm;
-        const double con = c0 * exp(beta * (lm - lnm_star));                           // halo.py:869-873
-        const double r_v = cbrt(3.0 * M / (4.0 * M_PI * delta_v * rho_bar));           // halo.py:890-893
-        const double cp = 1.0 + con;
-        const double lncp = log(cp);
-        double n1, n2;
-        hod_moments(h, M, n1, n2);
-        const double in1 = (xmid > x_lo1) ? 1.0 : 0.0, in2 = (xmid > x_lo2) ? 1.0 : 0.0;
-        rec[NF_C * out.cap + idx] = con;
-        rec[NF_RS * out.cap + idx] = r_v / con;
-        rec[NF_INV_MK * out.cap + idx] = 1.0 / (lncp - con / cp);
-        rec[NF_LNCP * out.cap + idx] = lncp;
-        rec[NF_W_HM * out.cap + idx] = wt * bias;                                       // halo.py:923-927
-        rec[NF_W_PMM * out.cap + idx] = wt * M / rho_bar;                               // halo.py:990-994, :919
-        rec[NF_W_HG * out.cap + idx] = in1 * wt * bias * n1 / M;                        // halo.py:964-969
-        const double wgm = in1 * wt * n1;                                               // halo.py:1078-1086
-        rec[NF_W_GM1 * out.cap + idx] = (n1 < 1.0) ? wgm : 0.0;
-        rec[NF_W_GM2 * out.cap + idx] = (n1 < 1.0) ? 0.0 : wgm;
-        const double wgg = in2 * wt * n2 / M;                                           // halo.py:1032-1041
-        rec[NF_W_GG1 * out.cap + idx] = (n2 < 1.0) ? wgg : 0.0;
-        rec[NF_W_GG2 * out.cap + idx] = (n2 < 1.0) ? 0.0 : wgg;
-        nbar += in1 * wt * n1 / M;                                                      // halo.py:704-707
+        if (tid == 0) out.n_nodes[(size_t)b * N_KCLASS + c] = total < cap ? total : cap;
     }
     nbar = block_sum(nbar, red);
     if (tid == 0) {
-        out.n_nodes[b] = total < out.cap ? total : out.cap;
         out.nbar[b] = nbar;
-        if (!isfinite(nbar) && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
+        out.rv_max[b] = cbrt(rv_coef * exp(lnm[n - 1]));
+        if (!isfinite(nbar)) st |= CHOMP_ST_NONFINITE;
+        if (status && st) atomicOr(status + b, st);
     }
 }
 
@@ -271,44 +327,89 @@ __device__ __forceinline__ double exclusion_window(const SiciTables* t, double k
     return (kR * c + kR * kR * kR * ci + (2.0 - kR * kR) * s) / (3.0 * kR);
 }
 
-// One warp per (point, ln k node); lanes stride the nu nodes.
-__global__ void __launch_bounds__(256)
-halo_sums_kernel(const Cfg cfg, int B, const double* __restrict__ nodes, const int32_t* __restrict__ n_nodes,
-                 int cap, double* __restrict__ raw /* [B, 5, n_halo] */) {
+// first ln k node index whose phi = k * rv_max reaches `phi`
+__device__ __forceinline__ int kclass_first_index(double phi, double rv_max, double l0, double hk, int nk) {
+    const double x = (log(phi / rv_max) - l0) / hk;
+    if (!(x > 0.0)) return 0;
+    if (x >= (double)nk) return nk;
+    return (int)ceil(x);
+}
+
+// grid (chunks, B): a CTA stages the node list of one k class in shared memory and its 8
+// warps take the ln k nodes of one SUMS_K_PER_CTA chunk of that class; lanes stride the nodes.
+__global__ void __launch_bounds__(256, 2)
+halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ raw /* [B, 5, n_halo] */) {
+    extern __shared__ double srec[];      // NODE_FIELDS * cap of the staged class
     __shared__ SiciTables tabs;
-    sici_tables_load(&tabs);
-    __syncthreads();
     const int b = blockIdx.y;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ik = blockIdx.x * (blockDim.x >> 5) + w;
+    if (b >= B) return;
     const int nk = cfg.n_halo;
-    if (b >= B || ik >= nk) return;
-    const double l0 = log(cfg.k_min), l1 = log(cfg.k_max);
-    const double lnk = (ik == nk - 1) ? l1 : l0 + (l1 - l0) / (nk - 1) * ik;      // halo.py:49-51
-    const double k = exp(lnk);
-    const double* __restrict__ rec = nodes + (size_t)b * NODE_FIELDS * cap;
-    const int nn = n_nodes[b];
-    double a_hm = 0.0, a_pmm = 0.0, a_hg = 0.0, a_gm = 0.0, a_gg = 0.0;
-    for (int i = lane; i < nn; i += 32) {
-        const double con = rec[NF_C * cap + i];
-        const double rs = rec[NF_RS * cap + i];
-        const double rho = nfw_rho_k(&tabs, k * rs, 1.0 + con, rec[NF_LNCP * cap + i]);
-        const double y = rho * rec[NF_INV_MK * cap + i];                            // halo.py:584-585
-        const double y2 = y * y;
-        double y2h = y;
-        if (cfg.exclusion) y2h = y * exclusion_window(&tabs, 2.0 * k * rs * con);
-        a_hm = fma(rec[NF_W_HM * cap + i], y2h, a_hm);
-        a_pmm = fma(rec[NF_W_PMM * cap + i], y2, a_pmm);
-        a_hg = fma(rec[NF_W_HG * cap + i], y2h, a_hg);
-        a_gm = fma(rec[NF_W_GM1 * cap + i], y, fma(rec[NF_W_GM2 * cap + i], y2, a_gm));
-        a_gg = fma(rec[NF_W_GG1 * cap + i], y, fma(rec[NF_W_GG2 * cap + i], y2, a_gg));
+    const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hk = (l1 - l0) / (nk - 1);
+    // which class / k range does this CTA own?
+    const double rv_max = nd.rv_max[b];
+    const int i1 = kclass_first_index(KCLASS_PHI_1, rv_max, l0, hk, nk);
+    const int i2 = max(i1, kclass_first_index(KCLASS_PHI_2, rv_max, l0, hk, nk));
+    const int first[N_KCLASS + 1] = {0, i1, i2, nk};
+    int chunk = blockIdx.x, cls = -1, k_begin = 0, k_end = 0;
+    for (int c = 0; c < N_KCLASS; ++c) {
+        const int cnt = first[c + 1] - first[c];
+        const int nch = (cnt + SUMS_K_PER_CTA - 1) / SUMS_K_PER_CTA;
+        if (chunk < nch) {
+            cls = c;
+            k_begin = first[c] + chunk * SUMS_K_PER_CTA;
+            k_end = min(first[c + 1], k_begin + SUMS_K_PER_CTA);
+            break;
+        }
+        chunk -= nch;
     }
-    a_hm = warp_sum(a_hm); a_pmm = warp_sum(a_pmm); a_hg = warp_sum(a_hg);
-    a_gm = warp_sum(a_gm); a_gg = warp_sum(a_gg);
-    if (lane == 0) {
-        double* r = raw + (size_t)b * 5 * nk;
-        r[0 * nk + ik] = a_hm; r[1 * nk + ik] = a_pmm; r[2 * nk + ik] = a_hg;
-        r[3 * nk + ik] = a_gm; r[4 * nk + ik] = a_gg;
+    if (cls < 0) return;
+    sici_tables_load(&tabs);
+    const int cap = nd.cap[cls];
+    const int nn = nd.n_nodes[(size_t)b * N_KCLASS + cls];
+    const double* __restrict__ g = nd.nodes + ((size_t)b * nd.cap_total + nd.off[cls]) * NODE_FIELDS;
+    // stage: field f of node i at srec[f * nn_pad + i]
+    const int nn_pad = (nn + 31) & ~31;
+    for (int idx = threadIdx.x; idx < NODE_FIELDS * nn_pad; idx += blockDim.x) {
+        const int f = idx / nn_pad, i = idx - f * nn_pad;
+        double v;
+        if (i < nn) v = g[(size_t)f * cap + i];
+        else v = (f >= NF_W_HM) ? 0.0 : g[(size_t)f * cap + (nn - 1)];   // padding: valid shape, zero weight
+        srec[idx] = v;
+    }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const double* __restrict__ s_cp = srec + NF_CP * nn_pad;
+    const double* __restrict__ s_rs = srec + NF_RS * nn_pad;
+    const double* __restrict__ s_ln = srec + NF_LNCP * nn_pad;
+    const double* __restrict__ s_hm = srec + NF_W_HM * nn_pad;
+    const double* __restrict__ s_pm = srec + NF_W_PMM * nn_pad;
+    const double* __restrict__ s_hg = srec + NF_W_HG * nn_pad;
+    const double* __restrict__ s_gm = srec + NF_W_GM * nn_pad;
+    const double* __restrict__ s_gg = srec + NF_W_GG * nn_pad;
+    for (int ik = k_begin + w; ik < k_end; ik += nwarp) {
+        const double lnk = (ik == nk - 1) ? l1 : l0 + hk * ik;                      // halo.py:49-51
+        const double k = exp(lnk);
+        double a_hm = 0.0, a_pmm = 0.0, a_hg = 0.0, a_gm = 0.0, a_gg = 0.0;
+        for (int i = lane; i < nn_pad; i += 32) {
+            const double cp = s_cp[i], rs = s_rs[i];
+            const double rho = nfw_rho_k_warp(&tabs, k * rs, cp, s_ln[i]);          // halo.py:574-583
+            const double rho2 = rho * rho;
+            double rho_h = rho;
+            if (cfg.exclusion) rho_h = rho * exclusion_window(&tabs, 2.0 * k * rs * (cp - 1.0));
+            a_hm = fma(s_hm[i], rho_h, a_hm);
+            a_pmm = fma(s_pm[i], rho2, a_pmm);
+            a_hg = fma(s_hg[i], rho_h, a_hg);
+            const double wgm = s_gm[i], wgg = s_gg[i];
+            a_gm = fma(fabs(wgm), (wgm < 0.0) ? rho : rho2, a_gm);
+            a_gg = fma(fabs(wgg), (wgg < 0.0) ? rho : rho2, a_gg);
+        }
+        a_hm = warp_sum(a_hm); a_pmm = warp_sum(a_pmm); a_hg = warp_sum(a_hg);
+        a_gm = warp_sum(a_gm); a_gg = warp_sum(a_gg);
+        if (lane == 0) {
+            double* r = raw + (size_t)b * 5 * nk;
+            r[0 * nk + ik] = a_hm; r[1 * nk + ik] = a_pmm; r[2 * nk + ik] = a_hg;
+            r[3 * nk + ik] = a_gm; r[4 * nk + ik] = a_gg;
+        }
     }
 }
 

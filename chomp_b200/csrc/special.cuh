@@ -124,6 +124,117 @@ __device__ __forceinline__ double nfw_rho_k(const SiciTables* t, double z, doubl
     return c1 * dci + s1 * dsi - sin_cz / z2;
 }
 
+// ---------------------------------------------------------------------------------------
+// Warp-uniform fast path.  The nu nodes are ordered by mass, so the 32 lanes of a warp
+// almost always fall into the same Si/Ci ranges; the polynomials are then evaluated with
+// the coefficients as constant-bank operands of the DFMA instructions (no loads at all).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void sici_series_c(double x, double& si, double& ci_nolog) {
+    const double xx = x * x;
+    const double s = (xx - CHOMP_SI_SMALL_MID) * CHOMP_SI_SMALL_IHALF;
+    double p = k_si_small[CHOMP_SICI_DEG_S];
+    double q = k_ci_small[CHOMP_SICI_DEG_S];
+#pragma unroll
+    for (int i = CHOMP_SICI_DEG_S - 1; i >= 0; --i) {
+        p = fma(p, s, k_si_small[i]);
+        q = fma(q, s, k_ci_small[i]);
+    }
+    si = x * p;
+    ci_nolog = fma(xx, q, CHOMP_EULER);
+}
+
+template <int R>
+__device__ __forceinline__ void sici_aux_c(double x, double sx, double cx, double& si, double& ci) {
+    const double ix = 1.0 / x;
+    const double u = ix * ix;
+    const double s = (u - k_sici_urange[R][0]) * k_sici_urange[R][1];
+    double f = k_sici_F[R][CHOMP_SICI_DEG_L];
+    double g = k_sici_G[R][CHOMP_SICI_DEG_L];
+#pragma unroll
+    for (int i = CHOMP_SICI_DEG_L - 1; i >= 0; --i) {
+        f = fma(f, s, k_sici_F[R][i]);
+        g = fma(g, s, k_sici_G[R][i]);
+    }
+    f *= ix;
+    g *= u;
+    si = CHOMP_PI_2 - f * cx - g * sx;
+    ci = f * sx - g * cx;
+}
+
+__device__ __forceinline__ int sici_range(double x) {
+    return (x >= CHOMP_SICI_X2) ? 2 : ((x >= CHOMP_SICI_X1) ? 1 : 0);
+}
+
+template <int R1, int R2>
+__device__ __forceinline__ void nfw_large_large(double z, double z2, double s1, double c1, double s2, double c2,
+                                                double& dsi, double& dci) {
+    double si1, ci1, si2, ci2;
+    sici_aux_c<R1>(z, s1, c1, si1, ci1);
+    sici_aux_c<R2>(z2, s2, c2, si2, ci2);
+    dsi = si2 - si1;
+    dci = ci2 - ci1;
+}
+template <int R2>
+__device__ __forceinline__ void nfw_small_large(double z, double z2, double s2, double c2, double& dsi, double& dci) {
+    double si1, ci1, si2, ci2;
+    sici_series_c(z, si1, ci1);
+    sici_aux_c<R2>(z2, s2, c2, si2, ci2);
+    dsi = si2 - si1;
+    dci = ci2 - (ci1 + log(z));
+}
+
+// Same value as nfw_rho_k; all 32 lanes of the warp must call it together.
+__device__ __forceinline__ double nfw_rho_k_warp(const SiciTables* t, double z, double cp, double lncp) {
+    const double z2 = cp * z;
+    double s1, c1, s2, c2;
+    sincos(z, &s1, &c1);
+    sincos(z2, &s2, &c2);
+    const double sin_cz = s2 * c1 - c2 * s1;
+    const bool small1 = z <= CHOMP_SICI_SMALL_X, small2 = z2 <= CHOMP_SICI_SMALL_X;
+    const int key = small2 ? 0 : (small1 ? 1 + sici_range(z2) : 4 + 3 * sici_range(z) + sici_range(z2));
+    const int key0 = __shfl_sync(0xffffffffu, key, 0);
+    double dsi, dci;
+    if (__all_sync(0xffffffffu, key == key0)) {
+        switch (key0) {
+            case 0: {
+                double si1, ci1, si2, ci2;
+                sici_series_c(z, si1, ci1);
+                sici_series_c(z2, si2, ci2);
+                dsi = si2 - si1;
+                dci = lncp + (ci2 - ci1);
+            } break;
+            case 1: nfw_small_large<0>(z, z2, s2, c2, dsi, dci); break;
+            case 2: nfw_small_large<1>(z, z2, s2, c2, dsi, dci); break;
+            case 3: nfw_small_large<2>(z, z2, s2, c2, dsi, dci); break;
+            case 4: nfw_large_large<0, 0>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+            case 5: nfw_large_large<0, 1>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+            case 6: nfw_large_large<0, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+            case 8: nfw_large_large<1, 1>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+            case 9: nfw_large_large<1, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+            default: nfw_large_large<2, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;   // 12
+        }
+    } else {
+        double si1, ci1, si2, ci2;
+        if (small2) {
+            sici_series(t, z, si1, ci1);
+            sici_series(t, z2, si2, ci2);
+            dsi = si2 - si1;
+            dci = lncp + (ci2 - ci1);
+        } else if (small1) {
+            sici_series(t, z, si1, ci1);
+            sici_aux(t, z2, s2, c2, si2, ci2);
+            dsi = si2 - si1;
+            dci = ci2 - (ci1 + log(z));
+        } else {
+            sici_aux(t, z, s1, c1, si1, ci1);
+            sici_aux(t, z2, s2, c2, si2, ci2);
+            dsi = si2 - si1;
+            dci = ci2 - ci1;
+        }
+    }
+    return c1 * dci + s1 * dsi - sin_cz / z2;
+}
+
 __device__ __forceinline__ double bessel_j(int order, double x) {
     return order == 0 ? j0(x) : jn(2, x);
 }
