@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchomp_b200.so")
+LIB_PATH = os.environ.get("CHOMP_B200_LIB", os.path.join(_HERE, "libchomp_b200.so"))
 
 # enums of include/chomp_b200.h
 N_COSMO, N_HALO, N_HOD = 10, 6, 5

@@ -142,7 +142,7 @@ size_t sums_smem(const Handle* h) {
     return (size_t)NODE_FIELDS * m * sizeof(double);
 }
 size_t splines_smem(const Cfg& c) { return 36 * (size_t)c.n_halo * sizeof(double); }
-size_t wtheta_smem(const Cfg& c) { return (12 * (size_t)c.n_halo + 4 * (size_t)c.n_kernel + 8) * sizeof(double); }
+size_t wtheta_smem(const Cfg& c) { return (2 * (size_t)hankel_nodes(c) + 4 * (size_t)c.n_kernel + 8) * sizeof(double); }
 
 }  // namespace
 
@@ -164,6 +164,7 @@ int chomp_b200_create(void** handle, int device) {
     for (int n = 1; n <= CHOMP_MAX_GL; ++n) gauss_legendre(n, glx[n], glw[n]);
     CK(cudaMemcpyToSymbol(c_glx, glx, sizeof glx));
     CK(cudaMemcpyToSymbol(c_glw, glw, sizeof glw));
+    CK(chomp_upload_special_tables());
     Handle* h = new Handle();
     h->device = device;
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));

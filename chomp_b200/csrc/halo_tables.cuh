@@ -144,7 +144,10 @@ __host__ __device__ inline int kclass_cap(int c, int n_mass) {
     return (((n_mass - 1 + MAX_EXTRA_BREAKS) * m + 31) / 32) * 32;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef NODES_MIN_BLOCKS
+#define NODES_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, NODES_MIN_BLOCKS)
 nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const double* __restrict__ hod,
                 const double* __restrict__ epoch, const double* __restrict__ g_lnm, const double* __restrict__ g_nu,
                 const double* __restrict__ g_c1, const double* __restrict__ g_c2, NodesOut out,
@@ -337,7 +340,10 @@ __device__ __forceinline__ int kclass_first_index(double phi, double rv_max, dou
 
 // grid (chunks, B): a CTA stages the node list of one k class in shared memory and its 8
 // warps take the ln k nodes of one SUMS_K_PER_CTA chunk of that class; lanes stride the nodes.
-__global__ void __launch_bounds__(256, 2)
+#ifndef SUMS_MIN_BLOCKS
+#define SUMS_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, SUMS_MIN_BLOCKS)
 halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ raw /* [B, 5, n_halo] */) {
     extern __shared__ double srec[];      // NODE_FIELDS * cap of the staged class
     __shared__ SiciTables tabs;

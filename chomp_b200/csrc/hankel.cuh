@@ -6,9 +6,9 @@
 //
 // The integrand is a product of splines: smooth between the ln k knots of the halo tables
 // and the (theta-shifted) ln k theta knots of the kernel table.  Each halo-table interval is
-// cut at the kernel knot that falls inside it (there is at most one as long as the halo grid
-// is finer than the kernel grid; otherwise at its midpoint) and each piece gets an
-// nq_hankel-point Gauss-Legendre rule.  One warp per (point, theta).
+// cut into pieces no wider than HANKEL_MAX_PIECE with an nq_hankel-point Gauss-Legendre rule
+// each; at that resolution the third-derivative jumps of the (much coarser) kernel spline
+// contribute < 1e-7, so the nodes are shared by all theta.
 #pragma once
 #include "common.cuh"
 #include "spline.cuh"
@@ -103,7 +103,21 @@ power_kernel(const Cfg cfg, int B, int which, int n_k, const double* __restrict_
     P_out[(size_t)b * n_k + i] = halo_power(T, pk, which, k_in[i]);
 }
 
-// grid (B), 256 threads: warps loop over theta.
+// Widest piece of a halo-table interval used by the Hankel rule: pieces this narrow make the
+// kernel-table knots (spacing ~0.38 in ln k theta) harmless, so the nodes do not depend on
+// theta and k^2 P(k) is evaluated once per node instead of once per (node, theta).
+#define HANKEL_MAX_PIECE 0.0625
+
+__host__ __device__ inline int hankel_subdiv(const Cfg& cfg) {
+    const double hP = (log(cfg.k_max) - log(cfg.k_min)) / (cfg.n_halo - 1);
+    int m = (int)ceil(hP / HANKEL_MAX_PIECE - 1e-9);
+    return m < 1 ? 1 : m;
+}
+__host__ __device__ inline int hankel_nodes(const Cfg& cfg) { return (cfg.n_halo - 1) * hankel_subdiv(cfg) * cfg.nq_hankel; }
+
+// grid (B), 256 threads.  Phase 1: G_q = w_q k^2 P(k_q) / (2 pi D^2) at the theta-independent
+// Gauss-Legendre nodes (each halo-table interval cut into `sub` equal pieces).  Phase 2: one
+// warp per theta sums G_q K(x_q + ln theta).
 __global__ void __launch_bounds__(256)
 wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __restrict__ theta,
               const double* __restrict__ cosmo, const double* __restrict__ epoch, const double* __restrict__ dbar,
@@ -115,67 +129,60 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
     if (b >= B) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
     const int nk = cfg.n_halo, nkt = cfg.n_kernel, nq = cfg.nq_hankel;
-    // stage the tables this point needs in shared memory
+    const int sub = hankel_subdiv(cfg);
+    const int total = (nk - 1) * sub * nq;
+    double* s_x = sm;                 // total
+    double* s_g = s_x + total;        // total
+    double* s_kc = s_g + total;       // 4 nkt
     int ta = 0, tb = 0, tpp = 1;
     if (which != CHOMP_P_LINEAR) which_tables(which, ta, tb, tpp);
-    double* s_a = sm;                 // 4 nk
-    double* s_b = s_a + 4 * nk;       // 4 nk
-    double* s_pp = s_b + 4 * nk;      // 4 nk
-    double* s_kc = s_pp + 4 * nk;     // 4 nkt
-    double* s_ends = s_kc + 4 * nkt;  // 8: node values needed by the branches outside the table
     const double* hc = hcoef + (size_t)b * 20 * nk;
-    for (int i = tid; i < 4 * (nk - 1); i += blockDim.x) {
-        s_a[i] = hc[(size_t)ta * 4 * nk + i];
-        s_b[i] = hc[(size_t)tb * 4 * nk + i];
-        s_pp[i] = hc[(size_t)tpp * 4 * nk + i];
-    }
+    const double* ca = hc + (size_t)ta * 4 * nk;
+    const double* cb = hc + (size_t)tb * 4 * nk;
+    const double* cpp = hc + (size_t)tpp * 4 * nk;
     for (int i = tid; i < 4 * (nkt - 1); i += blockDim.x) s_kc[i] = kcoef[(size_t)b * 4 * nkt + i];
-    if (tid == 0) s_ends[0] = knodes[(size_t)b * nkt];
-    __syncthreads();
     const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
     const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
     const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
     const double D = dbar[b];
-    const double inv_norm = 1.0 / (2.0 * M_PI * D * D);
+    const double inv_norm = 1.0 / (2.0 * M_PI * D * D);                 // correlation.py:270-275
     const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hP = (l1 - l0) / (nk - 1);
+    for (int idx = tid; idx < total; idx += blockDim.x) {
+        const int i = idx / (sub * nq), r = idx - i * (sub * nq);
+        const int s = r / nq, q = r - s * nq;
+        const double a = l0 + hP * i;
+        const double bb = (i == nk - 2) ? l1 : l0 + hP * (i + 1);
+        const double pa = a + (bb - a) * s / sub, pb = (s == sub - 1) ? bb : a + (bb - a) * (s + 1) / sub;
+        const double half = 0.5 * (pb - pa);
+        const double x = 0.5 * (pa + pb) + half * c_glx[nq][q];
+        const double k = exp(x);
+        const double dx = x - a;
+        double P = 2.0 * M_PI * M_PI * delta2(pk, k, x) / (k * k * k);
+        if (which != CHOMP_P_LINEAR)
+            P = P * spline_poly(ca, i, dx) * spline_poly(cb, i, dx) + spline_poly(cpp, i, dx);
+        s_x[idx] = x;
+        s_g[idx] = half * c_glw[nq][q] * k * k * P * inv_norm;
+    }
+    __syncthreads();
     const double x0 = log(cfg.ktheta_min), x1 = log(cfg.ktheta_max), hK = (x1 - x0) / (nkt - 1);
-    const double k_first = s_ends[0];
-    const int per_int = 2 * nq;
-    const int total = (nk - 1) * per_int;
+    const double ihK = 1.0 / hK;
+    const double k_first = knodes[(size_t)b * nkt];
     for (int it = wid; it < n_theta; it += nwarp) {
         const double lt = log(theta[it]);
         double acc = 0.0;
         for (int idx = lane; idx < total; idx += 32) {
-            const int i = idx / per_int, r = idx - i * per_int;
-            const int s = r / nq, q = r - s * nq;
-            const double a = l0 + hP * i;
-            const double bb = (i == nk - 2) ? l1 : l0 + hP * (i + 1);
-            // kernel knot inside (a, b)?
-            const double m = ceil((a + lt - x0) / hK);
-            double split = x0 + m * hK - lt;
-            const double tol = 1e-9 * hP;
-            if (!(m >= 0.0 && m <= (double)(nkt - 1) && split > a + tol && split < bb - tol)) split = 0.5 * (a + bb);
-            const double pa = s ? split : a, pb = s ? bb : split;
-            const double half = 0.5 * (pb - pa), mid = 0.5 * (pa + pb);
-            const double x = mid + half * c_glx[nq][q];
-            const double k = exp(x);
-            const double dx = x - a;
-            double P = 2.0 * M_PI * M_PI * delta2(pk, k, x) / (k * k * k);
-            if (which != CHOMP_P_LINEAR)
-                P = P * spline_poly(s_a, i, dx) * spline_poly(s_b, i, dx) + spline_poly(s_pp, i, dx);
-            // kernel table: the piece lies inside one kernel interval, pick it from the midpoint
-            const double um = mid + lt, u = x + lt;
-            double Kv;
-            if (um < x0) Kv = k_first;
-            else if (um > x1) Kv = 0.0;
+            const double u = s_x[idx] + lt;
+            double Kv;                                                   // Kernel.kernel, kernel.py:714-729
+            if (u < x0) Kv = k_first;
+            else if (u > x1) Kv = 0.0;
             else {
-                int j = (int)floor((um - x0) / hK);
-                j = j < 0 ? 0 : (j > nkt - 2 ? nkt - 2 : j);
+                int j = (int)((u - x0) * ihK);
+                j = j > nkt - 2 ? nkt - 2 : j;
                 Kv = spline_poly(s_kc, j, u - (x0 + hK * j));
             }
-            acc += half * c_glw[nq][q] * k * k * P * Kv;
+            acc = fma(s_g[idx], Kv, acc);
         }
-        acc = warp_sum(acc) * inv_norm;
+        acc = warp_sum(acc);
         if (lane == 0) {
             w_out[(size_t)b * n_theta + it] = acc;
             if (!isfinite(acc) && status) atomicOr(status + b, CHOMP_ST_NONFINITE);

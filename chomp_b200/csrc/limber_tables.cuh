@@ -19,7 +19,9 @@
 
 namespace chomp {
 
+#ifndef LIMBER_THREADS
 #define LIMBER_THREADS 128
+#endif
 #define DNDZ_PANELS 16
 
 struct EpochGrid {     // one MultiEpoch tabulation (cosmology.py:747-817)

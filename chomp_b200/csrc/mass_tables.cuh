@@ -152,7 +152,10 @@ struct MassOut {
     double* c_nu_lnm;  // [B, 4 n_mass]  nu as a function of ln M
 };
 
-__global__ void __launch_bounds__(256)
+#ifndef MASS_MIN_BLOCKS
+#define MASS_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, MASS_MIN_BLOCKS)
 mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const double* __restrict__ halo,
                    const double* __restrict__ z_in, const double* __restrict__ zbar, MassOut out,
                    int32_t* __restrict__ status) {

@@ -73,7 +73,7 @@ default_precision = {
 # counterpart: they replace the adaptive Romberg refinement).
 default_quadrature = {
     "nu": 8,        # mass integrals, per knot interval of ln M(nu)
-    "hankel": 3,    # w(theta) k-integral, per half halo-table interval
+    "hankel": 4,    # w(theta) k-integral, per piece (<= 0.0625 wide in ln k) of a halo-table interval
     "limber": 5,    # K(ln k theta) chi-integral, per knot interval
     "lens": 6,      # lensing-efficiency integral, per chi(z) knot interval
 }
