@@ -862,17 +862,20 @@ class Kernel(object):
             self.bessel_order, self.prec["kernel_bessel_limit"])[-1]
         # kernel.py:635-639
         zg = np.linspace(self.z_min, self.z_max, n)
-        self.z_bar = zg[np.argmax(self._integrand(
-            cosmo.comoving_distance(zg), 0.0))]
+        # _find_z_bar always goes through Kernel._kernel_integrand, i.e. J0 (= 1 at
+        # k theta = 0), also for the J2 kernel, which does not override it (kernel.py:635-639)
+        self.z_bar = zg[np.argmax(self._weight(cosmo.comoving_distance(zg)))]
         self._k = None
 
     def bessel(self, x):
         return special.j0(x)
 
-    def _integrand(self, chi, ktheta):                    # kernel.py:707-712
+    def _weight(self, chi):
         D = self.cosmo.growth_factor(self.cosmo.redshift(chi))
-        return (self.wa.window_function(chi)*self.wb.window_function(chi) *
-                D*D*self.bessel(ktheta*chi))
+        return self.wa.window_function(chi)*self.wb.window_function(chi)*D*D
+
+    def _integrand(self, chi, ktheta):                    # kernel.py:707-712, 834-839
+        return self._weight(chi)*self.bessel(ktheta*chi)
 
     def smooth_breaks(self, ktheta):
         if self.integ.name != "tight":

@@ -123,3 +123,58 @@ def test_synthetic_batch_points_and_batch_invariance():
     wh, status = eng.wtheta_host(cosmo, halo, hod, survey.theta, _lib.P_GG)
     assert np.array_equal(wh, w) and not status.any()
     torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------ the other BASELINE configs
+MAND = {"log_M_0": 12.3, "w": 1.2}
+CONFIGS = {
+    # config 1: matter w(theta), Gaussian dN/dz at z0 = 1
+    "cfg1_mm": dict(dist_a=("gaussian", (0.0, 2.0, 1.0, 0.2)), power_spec="power_mm", bins_per_decade=5.0),
+    # config 3: galaxy-galaxy lensing gamma_t: HODMandelbaum power_gm, galaxy x convergence, J2
+    "cfg3_gammat": dict(dist_a=("gaussian", (0.0, 2.0, 0.4, 0.1)), dist_b=("gaussian", (0.0, 2.0, 1.0, 0.2)),
+                        window_a="galaxy", window_b="convergence", bessel_order=2, hod_kind="mandelbaum",
+                        power_spec="power_gm", bins_per_decade=5.0),
+    # the unit tests' magnitude-limited lens sample (int b: Python-2 z_max cap) x convergence
+    "maglim_conv": dict(dist_a=("maglim", (0.0, 2.0, 2, 0.3, 2)), dist_b=("gaussian", (0.0, 2.0, 1.0, 0.2)),
+                        window_a="galaxy", window_b="convergence", power_spec="power_gm", bins_per_decade=5.0),
+    # float-b magnitude-limited sample, convergence x convergence (config 4's windows)
+    "maglim_shear": dict(dist_a=("maglim", (0.0, 2.0, 2.0, 0.5, 2.0)), window_a="convergence",
+                         power_spec="power_mm", bins_per_decade=5.0),
+}
+
+
+def _dist(spec):
+    kind, args = spec
+    mk = engine.RedshiftDistribution.gaussian if kind == "gaussian" else engine.RedshiftDistribution.maglim
+    return mk(*args)
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_baseline_configs_against_oracle(name):
+    import json
+    import os
+    kw = dict(CONFIGS[name])
+    hod = MAND if kw.get("hod_kind") == "mandelbaum" else HOD_DICT
+    survey = engine.Survey(_dist(kw["dist_a"]), _dist(kw["dist_b"]) if "dist_b" in kw else None,
+                           kw.get("window_a", "galaxy"), kw.get("window_b"),
+                           bins_per_decade=kw["bins_per_decade"], bessel_order=kw.get("bessel_order", 0),
+                           power_spec=kw["power_spec"], hod=kw.get("hod_kind", "zheng"))
+    eng = engine.Engine(survey)
+    which = _lib.POWER_SPEC[kw["power_spec"]]
+    w, status = _run_point(eng, survey, C_DICT, H_DICT, hod, which)
+    assert status == 0
+    ref = oracle_wtheta(C_DICT, H_DICT, hod, **kw)
+    nw = survey.precision["window_npoints"]
+    win = eng.table(_lib.T_WINDOW_NODES, 1).cpu().numpy()[0].reshape(2, nw)
+    for got, want in ((win[0], ref["wa_nodes"]), (win[1], ref["wb_nodes"])):
+        assert np.max(np.abs(got - want))/np.max(np.abs(want)) < 1e-7
+    assert abs(eng.table(_lib.T_ZBAR, 1).cpu().numpy()[0, 0] - ref["z_bar"]) < 1e-12
+    kn = eng.table(_lib.T_KERNEL_NODES, 1).cpu().numpy()[0]
+    assert np.max(np.abs(kn - ref["kernel_nodes"]))/np.max(np.abs(ref["kernel_nodes"])) < 1e-6
+    assert np.array_equal(survey.theta, ref["theta"])
+    assert w_err(w, ref["w"]) < TOL_FINAL
+    # and against the reference itself at its default tolerances (committed run), within the
+    # reference's own quadrature error
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.json")))["corr"]
+    if name in gold:
+        assert w_err(w, gold[name]["w"]) < 2e-3
