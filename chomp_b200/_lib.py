@@ -25,14 +25,18 @@ WINDOW_GALAXY, WINDOW_CONVERGENCE = 0, 1
 ST_NONFINITE, ST_MASS_WALK, ST_NODE_OVERFLOW, ST_DOMAIN = 1, 2, 4, 8
 (EVAL_LINEAR_POWER, EVAL_SIGMA_R, EVAL_NU_OF_MASS, EVAL_MASS_OF_NU, EVAL_F_NU,
  EVAL_BIAS_NU, EVAL_KERNEL, EVAL_WINDOW_A, EVAL_WINDOW_B, EVAL_Y_NFW,
- EVAL_FIRST_MOMENT, EVAL_SECOND_MOMENT) = range(12)
+ EVAL_FIRST_MOMENT, EVAL_SECOND_MOMENT, EVAL_NTH_MOMENT, EVAL_HOD_ZEROS, EVAL_CONCENTRATION,
+ EVAL_VIRIAL_RADIUS, EVAL_CHI_OF_Z, EVAL_Z_OF_CHI, EVAL_GROWTH_OF_Z, EVAL_INV_HUBBLE, EVAL_E0,
+ EVAL_GROWTH_APPROX, EVAL_DNDZ_A, EVAL_DNDZ_B) = range(24)
 (T_ZBAR, T_DBAR, T_KERNEL_NODES, T_CHI_NODES, T_WINDOW_NODES, T_WINDOW_CHI,
- T_EPOCH, T_LNM_NODES, T_NU_NODES, T_HALO_NODES, T_NBAR, T_NU_QUAD_COUNT) = range(12)
+ T_EPOCH, T_LNM_NODES, T_NU_NODES, T_HALO_NODES, T_NBAR, T_NU_QUAD_COUNT, T_KERNEL_CHI,
+ T_DNDZ_NORM) = range(14)
 KERNEL_NAMES = ("limber_tables_kernel", "mass_tables_kernel", "nu_nodes_kernel",
                 "halo_sums_kernel", "halo_splines_kernel", "wtheta_kernel")
 EPOCH_FIELDS = ("z", "growth", "sigma_norm", "delta_c", "delta_v", "rho_bar",
                 "ln_mass_min", "ln_mass_max", "nu_min", "nu_max", "f_norm",
-                "bias_norm", "ln_m_star", "pk_amp", "chi", "walk_steps")
+                "bias_norm", "ln_m_star", "pk_amp", "chi", "walk_steps", "omega_m", "omega_l", "E0",
+                "delta_v_cosmo", "rho_crit", "flat", "open", "sigma_8_z")
 
 
 class Config(ctypes.Structure):
@@ -97,6 +101,9 @@ _SIGNATURES = {
     "chomp_b200_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+    "chomp_b200_set_params": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
+    "chomp_b200_set_zbar": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "chomp_b200_copy_table": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
                                              ctypes.c_void_p]),

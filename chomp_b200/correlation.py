@@ -1,0 +1,103 @@
+"""Drop-in for the reference's correlation.Correlation (correlation.py:33-289):
+w(theta) = int dln k k^2/(2 pi) P(k)/D(z_bar)^2 K(ln k theta), all four GPU
+stages per call.  CorrelationFourier / Correlation3d are listed as next in
+SURVEY.md section 8(f)."""
+import numpy as np
+
+from . import _facade, _lib, engine, halo as halo_module
+
+deg_to_rad = np.pi/180.0
+rad_to_deg = 180.0/np.pi
+
+
+class Correlation(object):
+    def __init__(self, theta_min_deg, theta_max_deg, input_kernel, bins_per_decade=5.0, input_halo=None,
+                 power_spec=None, k_min=None, k_max=None, keep_halo_z_bar=False, **kws):
+        self.log_theta_min = np.log10(theta_min_deg*deg_to_rad)
+        self.log_theta_max = np.log10(theta_max_deg*deg_to_rad)
+        self.theta_array = engine.theta_bins(theta_min_deg, theta_max_deg, bins_per_decade)
+        self.wtheta_array = np.zeros(self.theta_array.size)
+        self.kernel = input_kernel
+        self.D_z = float(self.kernel.cosmo.growth_factor(self.kernel.z_bar))
+        if input_halo is None:
+            input_halo = halo_module.Halo(self.kernel.z_bar)
+        self.halo = input_halo
+        if not keep_halo_z_bar:
+            self.halo.set_redshift(self.kernel.z_bar)            # correlation.py:103
+        if ((k_min is not None and k_min != self.halo._k_min) or
+                (k_max is not None and k_max != self.halo._k_max)):
+            raise NotImplementedError("Correlation(k_min/k_max) different from the halo limits")
+        self._ln_k_min = np.log(self.halo._k_min)
+        self._ln_k_max = np.log(self.halo._k_max)
+        if power_spec is None:
+            power_spec = "linear_power"
+        self.set_power_spectrum(power_spec)
+
+    def get_redshift(self):
+        return self.kernel.z_bar
+
+    def set_redshift(self, redshift):
+        self.kernel.z_bar = redshift
+        self.D_z = float(self.kernel.cosmo.growth_factor(self.kernel.z_bar))
+        self.halo.set_redshift(self.kernel.z_bar)
+
+    def get_cosmology(self):
+        return self.kernel.get_cosmology()
+
+    def set_cosmology(self, cosmo_dict):
+        self.kernel.set_cosmology(cosmo_dict)
+        self.D_z = float(self.kernel.cosmo.growth_factor(self.kernel.z_bar))
+        self.halo.set_cosmology(cosmo_dict, self.kernel.z_bar)
+
+    def get_power_spectrum(self):
+        return self._power_name
+
+    def set_power_spectrum(self, powSpec):
+        if powSpec not in _lib.POWER_SPEC or not hasattr(self.halo, powSpec):
+            print("WARNING: Invalid input for power spectra variable,")
+            print("\t setting to 'linear_power'")
+            powSpec = "linear_power"
+        self._power_name = powSpec
+        self.power_spec = getattr(self.halo, powSpec)
+
+    def get_halo(self):
+        return self.halo.get_halo()
+
+    def set_halo(self, halo_dict):
+        self.halo.set_halo(halo_dict)
+
+    def get_hod(self, return_object=False):
+        return self.halo.get_hod(return_object)
+
+    def set_hod(self, hod_dict):
+        self.halo.set_hod(hod_dict)
+
+    def set_hod_object(self, input_hod):
+        self.halo.set_hod_object(input_hod)
+
+    def compute_correlation(self):
+        self.wtheta_array = np.array(self.correlation(self.theta_array), dtype=float)
+
+    def correlation(self, theta_rad):
+        """correlation.py:242-268.  The halo object holds its tables on its own handle, so the
+        Limber stage is replayed there (same configuration as the kernel object) before the
+        Hankel stage."""
+        h = self.halo
+        h._ensure()
+        cfg = self.kernel._config()
+        hc = h._gpu.eng.cfg
+        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision"):
+            setattr(cfg, name, getattr(hc, name))
+        gpu = h._gpu
+        gpu.configure(cfg)
+        gpu.eng.limber_tables(_facade.cosmo_row(self.kernel.cosmo.get_cosmology()))
+        gpu.eng.set_params(cosmo=_facade.cosmo_row(h.cosmo.cosmo_dict))
+        gpu.eng.set_zbar([self.kernel.z_bar])                   # also covers Correlation.set_redshift
+        w = gpu.eng.wtheta_stage(1, _lib.POWER_SPEC[self._power_name], _facade.flat(theta_rad))
+        return _facade.like_input(theta_rad, w.cpu().numpy()[0])
+
+    def write(self, output_file_name):
+        with open(output_file_name, "w") as f:
+            f.write("#ttype1 = theta [deg]\n#ttype2 = wtheta\n")
+            for theta, w in zip(self.theta_array, self.wtheta_array):
+                f.write("%1.10g %1.10g\n" % (theta/deg_to_rad, w))

@@ -52,7 +52,8 @@ struct Handle {
     long long launches = 0;
     // device scratch (all FP64 unless noted)
     double *zbar = nullptr, *dbar = nullptr, *knodes = nullptr, *kcoef = nullptr, *chi_nodes = nullptr,
-           *win_nodes = nullptr, *win_chi = nullptr, *win_coef = nullptr, *kchi = nullptr;
+           *win_nodes = nullptr, *win_chi = nullptr, *win_coef = nullptr, *kchi = nullptr, *grid0 = nullptr,
+           *dndz_norm = nullptr;
     double *epoch = nullptr, *lnm_nodes = nullptr, *nu_nodes = nullptr, *c_lnm_nu = nullptr, *c_nu_lnm = nullptr;
     double *nodes = nullptr, *nbar = nullptr, *rv_max = nullptr, *raw = nullptr, *htab = nullptr, *hcoef = nullptr;
     int32_t* n_nodes = nullptr;
@@ -245,6 +246,8 @@ int chomp_b200_reserve(void* handle, int max_points) {
     rc |= dev_alloc(h, &h->win_chi, B * 4);
     rc |= dev_alloc(h, &h->win_coef, B * 8 * c.n_window);
     rc |= dev_alloc(h, &h->kchi, B * 2);
+    rc |= dev_alloc(h, &h->grid0, B * 13 * c.n_cosmo);
+    rc |= dev_alloc(h, &h->dndz_norm, B * 2);
     rc |= dev_alloc(h, &h->epoch, B * CHOMP_EPOCH_LEN);
     rc |= dev_alloc(h, &h->lnm_nodes, B * c.n_mass);
     rc |= dev_alloc(h, &h->nu_nodes, B * c.n_mass);
@@ -280,7 +283,8 @@ int chomp_b200_limber_tables(void* handle, int B, const double* cosmo_dev, int32
     cudaStream_t s = (cudaStream_t)stream;
     if (cosmo_dev != h->cosmo)
         CK(cudaMemcpyAsync(h->cosmo, cosmo_dev, sizeof(double) * B * CHOMP_N_COSMO, cudaMemcpyDeviceToDevice, s));
-    LimberOut out{h->zbar, h->dbar, h->knodes, h->kcoef, h->chi_nodes, h->win_nodes, h->win_chi, h->win_coef, h->kchi};
+    LimberOut out{h->zbar, h->dbar, h->knodes, h->kcoef, h->chi_nodes, h->win_nodes, h->win_chi, h->win_coef, h->kchi,
+                  h->grid0, h->dndz_norm};
     const size_t smem = limber_smem_doubles(h->cfg) * sizeof(double);
     mark(h, CHOMP_K_LIMBER, s);
     limber_tables_kernel<<<B, LIMBER_THREADS, smem, s>>>(h->cfg, B, h->same_window, h->cosmo, out, status_dev);
@@ -435,7 +439,8 @@ int chomp_b200_wtheta_batch_host(void* handle, int B, const double* cosmo_host, 
 // ---------------------------------------------------------------------------------------------------
 namespace {
 struct EvalCtx {
-    const double *cosmo, *halo, *hod, *epoch, *lnm, *nu, *c_lnm_nu, *c_nu_lnm, *knodes, *kcoef, *win_chi, *win_coef;
+    const double *cosmo, *halo, *hod, *epoch, *lnm, *nu, *c_lnm_nu, *c_nu_lnm, *knodes, *kcoef, *win_chi, *win_coef,
+        *grid0, *dndz_norm;
 };
 
 __global__ void __launch_bounds__(128)
@@ -494,6 +499,49 @@ eval_kernel(const Cfg cfg, int what, int n, const double* __restrict__ x, double
                 hod_moments(h, v, n1, n2);
                 r = (what == CHOMP_EVAL_FIRST_MOMENT) ? n1 : n2;
             } break;
+            case CHOMP_EVAL_NTH_MOMENT: {                       // HOD.nth_moment, hod.py:68-92
+                const HodP h = load_hod(cfg.hod_kind, cx.hod, cfg.halo_precision);
+                double n1, n2;
+                hod_moments(h, v, n1, n2);
+                const int nmom = (int)aux;
+                if (nmom == 1) r = n1;
+                else if (nmom == 2) r = n2;
+                else {
+                    const double a2 = (n1 != 0.0) ? n2 / (n1 * n1) : 0.0;
+                    r = pow(n1, (double)nmom);
+                    for (int j = 0; j < nmom; ++j) r *= (j * a2 - j + 1);
+                }
+            } break;
+            case CHOMP_EVAL_HOD_ZEROS: {                        // hod.py:176-186; x = 0, 1, 2 selects the value
+                const HodP h = load_hod(cfg.hod_kind, cx.hod, cfg.halo_precision);
+                const int sel = (int)v;
+                r = sel == 0 ? h.first_zero : (sel == 1 ? h.second_zero
+                    : (cfg.hod_kind == CHOMP_HOD_ZHENG ? pow(10.0, h.log_M_min + h.sigma) : -1.0));
+            } break;
+            case CHOMP_EVAL_CONCENTRATION: case CHOMP_EVAL_VIRIAL_RADIUS: {   // halo.py:441-463
+                const double lm = log(v);
+                if (what == CHOMP_EVAL_CONCENTRATION)
+                    r = cx.halo[CHOMP_H_C0] / (1.0 + e[EP_Z]) * exp(cx.halo[CHOMP_H_BETA] * (lm - e[EP_LNM_STAR]));
+                else r = cbrt(3.0 * v / (4.0 * M_PI * e[EP_DELTA_V] * e[EP_RHO_BAR]));
+            } break;
+            case CHOMP_EVAL_CHI_OF_Z: case CHOMP_EVAL_Z_OF_CHI: case CHOMP_EVAL_GROWTH_OF_Z: {
+                const int nz = cfg.n_cosmo;
+                EpochGrid G;
+                G.n = nz; G.z_min = cfg.zk_min < 0.0 ? 0.0 : cfg.zk_min; G.z_max = cfg.zk_max;
+                G.chi = const_cast<double*>(cx.grid0); G.c_chi_z = G.chi + nz; G.c_z_chi = G.chi + 5 * nz;
+                G.c_g_z = G.chi + 9 * nz; G.z = nullptr; G.growth = nullptr;
+                r = what == CHOMP_EVAL_CHI_OF_Z ? grid_chi(G, v) : (what == CHOMP_EVAL_Z_OF_CHI ? grid_z(G, v)
+                                                                                              : grid_growth(G, v));
+            } break;
+            case CHOMP_EVAL_INV_HUBBLE: r = inv_hubble(c, v); break;             // cosmology.py:153
+            case CHOMP_EVAL_E0: r = E0(c, v); break;                             // cosmology.py:164
+            case CHOMP_EVAL_GROWTH_APPROX: r = growth_approx(c, 1.0 / (1.0 + v)) / growth_approx(c, 1.0); break;
+            case CHOMP_EVAL_DNDZ_A: case CHOMP_EVAL_DNDZ_B: {                    // kernel.py:67-86
+                const int wi = (what == CHOMP_EVAL_DNDZ_B) ? 1 : 0;
+                Dndz d{cfg.dndz_kind[wi], cfg.dndz_zmin[wi], cfg.dndz_zmax[wi], cfg.dndz_p[wi][0], cfg.dndz_p[wi][1],
+                       cfg.dndz_p[wi][2], cx.dndz_norm[wi]};
+                r = aux != 0.0 ? dndz_raw(d, v) : dndz_eval(d, v);
+            } break;
             default: r = nan("");
         }
         out[i] = r;
@@ -525,10 +573,47 @@ int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_de
     EvalCtx cx{h->cosmo + p * CHOMP_N_COSMO, h->halo + p * CHOMP_N_HALO, h->hod + p * CHOMP_N_HOD,
                h->epoch + p * CHOMP_EPOCH_LEN, h->lnm_nodes + p * c.n_mass, h->nu_nodes + p * c.n_mass,
                h->c_lnm_nu + p * 4 * c.n_mass, h->c_nu_lnm + p * 4 * c.n_mass, h->knodes + p * c.n_kernel,
-               h->kcoef + p * 4 * c.n_kernel, h->win_chi + p * 4, h->win_coef + p * 8 * c.n_window};
+               h->kcoef + p * 4 * c.n_kernel, h->win_chi + p * 4, h->win_coef + p * 8 * c.n_window,
+               h->grid0 + p * 13 * c.n_cosmo, h->dndz_norm + p * 2};
     int blocks = (what == CHOMP_EVAL_SIGMA_R) ? (n + 3) / 4 : (n + 127) / 128;
     if (blocks > 1184) blocks = 1184;
     eval_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(c, what, n, x_dev, aux, cx, out_dev);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int chomp_b200_set_params(void* handle, int B, const double* cosmo_dev, const double* halo_dev,
+                          const double* hod_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cosmo_dev) CK(cudaMemcpyAsync(h->cosmo, cosmo_dev, sizeof(double) * B * CHOMP_N_COSMO, cudaMemcpyDeviceToDevice, s));
+    if (halo_dev) CK(cudaMemcpyAsync(h->halo, halo_dev, sizeof(double) * B * CHOMP_N_HALO, cudaMemcpyDeviceToDevice, s));
+    if (hod_dev) CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+namespace {
+__global__ void set_zbar_kernel(const Cfg cfg, int B, const double* __restrict__ z_in, const double* __restrict__ grid0,
+                                double* __restrict__ zbar, double* __restrict__ dbar) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nz = cfg.n_cosmo;
+    EpochGrid G;
+    G.n = nz; G.z_min = cfg.zk_min < 0.0 ? 0.0 : cfg.zk_min; G.z_max = cfg.zk_max;
+    G.chi = const_cast<double*>(grid0) + (size_t)b * 13 * nz; G.c_chi_z = G.chi + nz; G.c_z_chi = G.chi + 5 * nz;
+    G.c_g_z = G.chi + 9 * nz; G.z = nullptr; G.growth = nullptr;
+    zbar[b] = z_in[b];
+    dbar[b] = grid_growth(G, z_in[b]);
+}
+}  // namespace
+
+int chomp_b200_set_zbar(void* handle, int B, const double* z_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    if (!z_dev) FAIL("null z_dev");
+    set_zbar_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cfg, B, z_dev, h->grid0, h->zbar, h->dbar);
     h->launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -553,6 +638,8 @@ int chomp_b200_copy_table(void* handle, int B, int table, double* out_dev, int* 
         case CHOMP_T_NU_NODES: src = h->nu_nodes; len = c.n_mass; break;
         case CHOMP_T_HALO_NODES: src = h->htab; len = 5 * c.n_halo; break;
         case CHOMP_T_NBAR: src = h->nbar; len = 1; break;
+        case CHOMP_T_KERNEL_CHI: src = h->kchi; len = 2; break;
+        case CHOMP_T_DNDZ_NORM: src = h->dndz_norm; len = 2; break;
         case CHOMP_T_NU_QUAD_COUNT: len = N_KCLASS; break;
         default: FAIL("unknown table id");
     }

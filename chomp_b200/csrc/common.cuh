@@ -14,9 +14,11 @@ __constant__ double c_glw[CHOMP_MAX_GL + 1][CHOMP_MAX_GL];
 
 typedef chomp_b200_config Cfg;
 
-#define CHOMP_EPOCH_LEN 16
+#define CHOMP_EPOCH_LEN 24
 enum { EP_Z = 0, EP_GROWTH, EP_SIGMA_NORM, EP_DELTA_C, EP_DELTA_V, EP_RHO_BAR, EP_LNM_MIN, EP_LNM_MAX, EP_NU_MIN,
-       EP_NU_MAX, EP_F_NORM, EP_B_NORM, EP_LNM_STAR, EP_PK_AMP, EP_CHI, EP_WALK };
+       EP_NU_MAX, EP_F_NORM, EP_B_NORM, EP_LNM_STAR, EP_PK_AMP, EP_CHI, EP_WALK,
+       // scalars behind SingleEpoch's accessors (cosmology.py:366-447)
+       EP_OMEGA_M, EP_OMEGA_L, EP_E0, EP_DELTA_V_COSMO, EP_RHO_CRIT, EP_FLAT, EP_OPEN, EP_SIGMA_8_Z };
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

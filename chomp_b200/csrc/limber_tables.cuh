@@ -88,6 +88,8 @@ struct LimberOut {
     double *win_chi;           // [B, 4]  chi_min_a, chi_max_a, chi_min_b, chi_max_b
     double *win_coef;          // [B, 2, 4 n_window]
     double *kchi;              // [B, 2]  kernel chi_min, chi_max
+    double *grid0;             // [B, 13 n_cosmo]  chi nodes + chi(z), z(chi), D(z) coefficients of the kernel's MultiEpoch
+    double *dndz_norm;         // [B, 2]
 };
 
 __host__ __device__ inline size_t limber_smem_doubles(const Cfg& cfg) {
@@ -381,6 +383,12 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     if (bad && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
     for (int j = tid; j < 4 * (nk - 1); j += blockDim.x) out.kcoef[(size_t)b * 4 * nk + j] = kc[j];
     for (int idx = tid; idx < 3 * nz; idx += blockDim.x) out.chi_nodes[(size_t)b * 3 * nz + idx] = g[idx / nz].chi[idx % nz];
+    for (int idx = tid; idx < 13 * nz; idx += blockDim.x) {
+        const double* src = idx < nz ? g[0].chi : (idx < 5 * nz ? g[0].c_chi_z : (idx < 9 * nz ? g[0].c_z_chi : g[0].c_g_z));
+        const int off = idx < nz ? idx : (idx < 5 * nz ? idx - nz : (idx < 9 * nz ? idx - 5 * nz : idx - 9 * nz));
+        out.grid0[(size_t)b * 13 * nz + idx] = src[off];
+    }
+    if (tid < 2) out.dndz_norm[2 * b + tid] = dist[tid].norm;
     for (int idx = tid; idx < 2 * nw; idx += blockDim.x) out.win_nodes[(size_t)b * 2 * nw + idx] = win[idx / nw].wf[idx % nw];
     for (int idx = tid; idx < 2 * 4 * nw; idx += blockDim.x) {
         const int i = idx / (4 * nw), j = idx % (4 * nw);

@@ -12,7 +12,7 @@
 namespace chomp {
 
 #define SIG_NQ 16          // Gauss-Legendre order per sigma(R) panel
-#define SIG_XSPLIT 48.0    // beyond x = kR = 48 only the non-oscillatory part of W^2 is integrated
+#define SIG_XSPLIT 48.0    // beyond x = kR = 48 (96 for R >= 8 Mpc/h) only the non-oscillatory part of W^2 is integrated
 #define SIG_DX 8.0         // panel width in x between 1 and SIG_XSPLIT
 #define SIG_NLOW 3         // geometric panels below x = 1
 #define SIG_NTAIL 2        // geometric panels beyond SIG_XSPLIT
@@ -52,7 +52,9 @@ __device__ inline double warp_sigma2(const PkParams& pk, double R, double k_min,
     if (need_lo <= k_lo) k_lo = (need_lo > k_min / 100.0) ? need_lo : k_min / 100.0;
     if (need_hi >= k_hi) k_hi = (need_hi < k_max * 100.0) ? need_hi : k_max * 100.0;
     const double x_lo = k_lo * R, x_hi = k_hi * R;
-    const double xs = fmin(SIG_XSPLIT, x_hi);
+    // large spheres: nu ~ 40 there and ln f(nu) amplifies an error in sigma 14-fold, so the
+    // oscillatory part is carried twice as far
+    const double xs = fmin(R >= 8.0 ? 2.0 * SIG_XSPLIT : SIG_XSPLIT, x_hi);
     const double x_one = fmin(fmax(1.0, x_lo), xs);   // low (geometric) panels cover [x_lo, x_one]
     int n_lin = 0;
     if (xs > x_one) n_lin = (int)ceil((xs - x_one) / SIG_DX - 1e-9);
@@ -276,6 +278,10 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         e[EP_DELTA_V] = dv; e[EP_RHO_BAR] = m.rho_bar; e[EP_LNM_MIN] = lnm_min; e[EP_LNM_MAX] = lnm_max;
         e[EP_NU_MIN] = nu_min; e[EP_NU_MAX] = nu_max; e[EP_F_NORM] = f_norm; e[EP_B_NORM] = b_norm;
         e[EP_LNM_STAR] = lnm_star; e[EP_PK_AMP] = m.pk.amp; e[EP_CHI] = chi; e[EP_WALK] = (double)walk_steps;
+        e[EP_OMEGA_M] = omega_m_z(c, z); e[EP_OMEGA_L] = c.ol / E0(c, z); e[EP_E0] = E0(c, z);
+        e[EP_DELTA_V_COSMO] = delta_v_z(c, z, growth);
+        e[EP_RHO_CRIT] = 1.879 / 1.989 * (3.086 * 3.086 * 3.086) * 1e10 * E0(c, z);
+        e[EP_FLAT] = c.flat; e[EP_OPEN] = c.open; e[EP_SIGMA_8_Z] = s8_raw * sigma_norm;
         if (!(isfinite(f_norm) && isfinite(b_norm) && isfinite(lnm_star))) st |= CHOMP_ST_NONFINITE;
         if (status && st) atomicOr(status + b, st);
     }

@@ -268,6 +268,17 @@ class Engine(object):
             status.ctypes.data_as(ctypes.c_void_p)))
         return w, status
 
+    def set_params(self, cosmo=None, halo=None, hod=None):
+        arrs = [None if a is None else self._dev(a, n) for a, n in
+                ((cosmo, _lib.N_COSMO), (halo, _lib.N_HALO), (hod, _lib.N_HOD))]
+        B = next(a.shape[0] for a in arrs if a is not None)
+        _lib.check(self.lib.chomp_b200_set_params(self._h, B, self._p(arrs[0]), self._p(arrs[1]),
+                                                  self._p(arrs[2]), self._stream()))
+
+    def set_zbar(self, z):
+        z = self._dev(np.atleast_1d(np.asarray(z, dtype=np.float64))).reshape(-1)
+        _lib.check(self.lib.chomp_b200_set_zbar(self._h, z.numel(), self._p(z), self._stream()))
+
     # -- inspection -------------------------------------------------------------
     def table(self, table_id, B):
         n = ctypes.c_int(0)

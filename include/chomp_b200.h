@@ -138,9 +138,23 @@ int chomp_b200_wtheta_batch_host(void* handle, int B, const double* cosmo_host, 
  * mass / f_nu / bias_nu (mass_function.py:243-346), Kernel.kernel (kernel.py:714). */
 enum { CHOMP_EVAL_LINEAR_POWER = 0, CHOMP_EVAL_SIGMA_R, CHOMP_EVAL_NU_OF_MASS, CHOMP_EVAL_MASS_OF_NU,
        CHOMP_EVAL_F_NU, CHOMP_EVAL_BIAS_NU, CHOMP_EVAL_KERNEL, CHOMP_EVAL_WINDOW_A, CHOMP_EVAL_WINDOW_B,
-       CHOMP_EVAL_Y_NFW /* x = mass, aux = ln k */ , CHOMP_EVAL_FIRST_MOMENT, CHOMP_EVAL_SECOND_MOMENT };
+       CHOMP_EVAL_Y_NFW /* x = mass, aux = ln k */ , CHOMP_EVAL_FIRST_MOMENT, CHOMP_EVAL_SECOND_MOMENT,
+       CHOMP_EVAL_NTH_MOMENT /* aux = n */, CHOMP_EVAL_HOD_ZEROS /* x = 0,1,2: first_moment_zero, second_moment_zero, _safe_norm */,
+       CHOMP_EVAL_CONCENTRATION, CHOMP_EVAL_VIRIAL_RADIUS /* halo.py:441-463 */,
+       CHOMP_EVAL_CHI_OF_Z, CHOMP_EVAL_Z_OF_CHI, CHOMP_EVAL_GROWTH_OF_Z /* MultiEpoch accessors, cosmology.py:873-953 */,
+       CHOMP_EVAL_INV_HUBBLE /* E(z), cosmology.py:153 */, CHOMP_EVAL_E0, CHOMP_EVAL_GROWTH_APPROX,
+       CHOMP_EVAL_DNDZ_A, CHOMP_EVAL_DNDZ_B /* dNdz.dndz (aux != 0: raw_dndz), kernel.py:56-86 */ };
 int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_dev, double aux, double* out_dev,
                     void* stream);
+
+/* Store parameter rows in the handle without running a stage (NULL = leave as is): lets the
+ * HOD / cosmology closed forms be evaluated through chomp_b200_eval on their own. */
+int chomp_b200_set_params(void* handle, int B, const double* cosmo_dev, const double* halo_dev,
+                          const double* hod_dev, void* stream);
+
+/* Correlation.set_redshift (correlation.py:144-153): force z_bar, D(z_bar) follows from the
+ * kernel cosmology's growth spline of the last chomp_b200_limber_tables. */
+int chomp_b200_set_zbar(void* handle, int B, const double* z_dev, void* stream);
 
 /* Copy one of the per-point tables of the last batch into out_dev [B, len]; *len_out
  * receives the row length.  Table ids below. */
@@ -149,7 +163,8 @@ enum {
     CHOMP_T_WINDOW_NODES /* [2, n_window] */, CHOMP_T_WINDOW_CHI /* [2,2] chi_min, chi_max */,
     CHOMP_T_EPOCH /* 16 scalars, see chomp_b200.cu */, CHOMP_T_LNM_NODES, CHOMP_T_NU_NODES,
     CHOMP_T_HALO_NODES /* [5, n_halo]: h_m, pp_mm, h_g, pp_gm, pp_gg */, CHOMP_T_NBAR /* n_bar/rho_bar */,
-    CHOMP_T_NU_QUAD_COUNT /* number of nu quadrature nodes (as double) */
+    CHOMP_T_NU_QUAD_COUNT /* number of nu quadrature nodes per k class (as double) */,
+    CHOMP_T_KERNEL_CHI /* Kernel.chi_min, chi_max */, CHOMP_T_DNDZ_NORM /* dNdz.norm of both distributions */
 };
 int chomp_b200_copy_table(void* handle, int B, int table, double* out_dev, int* len_out, void* stream);
 
