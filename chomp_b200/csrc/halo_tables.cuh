@@ -48,7 +48,7 @@ struct HodP {
     double first_zero, second_zero; // hod.py:176-185; -1 for Mandelbaum
 };
 
-__device__ inline HodP load_hod(int kind, const double* __restrict__ p, double halo_precision) {
+__device__ __noinline__ HodP load_hod(int kind, const double* __restrict__ p, double halo_precision) {
     HodP h;
     h.kind = kind;
     if (kind == CHOMP_HOD_ZHENG) {
@@ -67,7 +67,7 @@ __device__ inline HodP load_hod(int kind, const double* __restrict__ p, double h
 }
 
 // <N>, <N(N-1)>  (hod.py:188-230 Zheng, 262-299 Mandelbaum)
-__device__ __forceinline__ void hod_moments(const HodP& h, double M, double& n1, double& n2) {
+__device__ __noinline__ void hod_moments(const HodP& h, double M, double& n1, double& n2) {
     const double lg = log10(M);
     double nc, ns;
     if (h.kind == CHOMP_HOD_ZHENG) {
@@ -102,10 +102,16 @@ __device__ inline double lnnu_of_lnm_inverse(const NuTab& t, double lnm_t, doubl
     if (!(mass_of_nu_ln(t, nu_min) < lnm_t) || !(mass_of_nu_ln(t, nu_max) > lnm_t)) return nan("");
     int i = 0;
     while (i < t.n - 2 && t.lnm[i + 1] <= lnm_t) ++i;       // node values bracket the root
+    // regula falsi (Illinois variant) on the monotone cubic of this interval
     double lo = t.nu[i], hi = t.nu[i + 1];
-    for (int it = 0; it < 64; ++it) {
-        const double mid = 0.5 * (lo + hi);
-        if (spline_poly(t.c_lnm_nu, i, mid - t.nu[i]) < lnm_t) lo = mid; else hi = mid;
+    double flo = t.lnm[i] - lnm_t, fhi = t.lnm[i + 1] - lnm_t;
+    if (flo == 0.0) return log(lo);
+    for (int it = 0; it < 60 && hi - lo > 4e-16 * hi; ++it) {
+        double mid = (lo * fhi - hi * flo) / (fhi - flo);
+        if (!(mid > lo && mid < hi)) mid = 0.5 * (lo + hi);
+        const double fm = spline_poly(t.c_lnm_nu, i, mid - t.nu[i]) - lnm_t;
+        if (fm == 0.0) { lo = hi = mid; break; }
+        if (fm < 0.0) { lo = mid; flo = fm; fhi *= 0.5; } else { hi = mid; fhi = fm; flo *= 0.5; }
     }
     return log(0.5 * (lo + hi));
 }
@@ -118,8 +124,16 @@ __device__ inline double lnnu_moment_crossing(const NuTab& t, const HodP& h, int
     if (!((which == 1 ? n1 : n2) < 1.0)) return nan("");
     hod_moments(h, exp(mass_of_nu_ln(t, exp(b))), n1, n2);
     if ((which == 1 ? n1 : n2) < 1.0) return nan("");
+    // first narrow the bracket to one knot interval (the moments are monotone in mass), then
+    // bisect; a step-function HOD converges onto the step
     double lo = a, hi = b;
-    for (int it = 0; it < 64; ++it) {
+    for (int i = 1; i < t.n - 1; ++i) {
+        const double x = log(t.nu[i]);
+        if (x <= lo || x >= hi) continue;
+        hod_moments(h, exp(t.lnm[i]), n1, n2);
+        if ((which == 1 ? n1 : n2) < 1.0) lo = x; else { hi = x; break; }
+    }
+    for (int it = 0; it < 50 && hi - lo > 1e-15 * fabs(hi); ++it) {
         const double mid = 0.5 * (lo + hi);
         hod_moments(h, exp(mass_of_nu_ln(t, exp(mid))), n1, n2);
         if ((which == 1 ? n1 : n2) < 1.0) lo = mid; else hi = mid;

@@ -14,7 +14,7 @@ namespace chomp {
 #define SIG_NQ 16          // Gauss-Legendre order per sigma(R) panel
 #define SIG_XSPLIT 48.0    // beyond x = kR = 48 (96 for R >= 8 Mpc/h) only the non-oscillatory part of W^2 is integrated
 #define SIG_DX 8.0         // panel width in x between 1 and SIG_XSPLIT
-#define SIG_NLOW 3         // geometric panels below x = 1
+#define SIG_NLOW 4         // geometric panels below x = 1 (4 + 6 + 2 panels x 16 nodes = 6 full warp passes)
 #define SIG_NTAIL 2        // geometric panels beyond SIG_XSPLIT
 
 // squared top-hat window W^2(x), W = 3 (sin x / x^3 - cos x / x^2)   (cosmology.py:651-652)
@@ -45,7 +45,11 @@ __device__ __forceinline__ double sigma_tail_edge(const PkParams& pk, double x, 
 
 // sigma^2(R) = int dlnk Delta^2(k) W^2(kR) over the reference's k range
 // (cosmology.py:611-638); executed by one full warp, result in every lane.
-__device__ inline double warp_sigma2(const PkParams& pk, double R, double k_min, double k_max) {
+// Partial sum (this thread's share) of
+//   sigma^2(R) = int dlnk Delta^2(k) W^2(kR) over the reference's k range (cosmology.py:611-638).
+// `rank` / `size`: position of the thread in the group (a warp or a slice of the CTA) that
+// evaluates this sigma together; the caller reduces over the group.
+__device__ __noinline__ double sigma2_partial(const PkParams& pk, double R, double k_min, double k_max, int rank, int size) {
     // integration range rules, cosmology.py:611-629
     double k_lo = k_min, k_hi = k_max;
     const double need_lo = 1.0 / R / 10.0, need_hi = 1.0 / R * 14.0662;
@@ -63,40 +67,79 @@ __device__ inline double warp_sigma2(const PkParams& pk, double R, double k_min,
     const int n_pan = SIG_NLOW + n_lin + n_tail;
     const double lnR = log(R);
     const double l_lo = log(x_lo), l_one = log(x_one), l_s = log(xs), l_hi = log(x_hi);
-    const int lane = threadIdx.x & 31;
+    const int n_nodes = n_pan * SIG_NQ;
     double acc = 0.0;
-    for (int idx = lane; idx < n_pan * SIG_NQ; idx += 32) {
+    // the two end-point terms of the oscillatory tail ride along as virtual nodes
+    for (int idx = rank; idx < n_nodes + (n_tail ? 2 : 0); idx += size) {
+        if (idx >= n_nodes) {
+            acc += (idx == n_nodes) ? sigma_tail_edge(pk, x_hi, R) : -sigma_tail_edge(pk, xs, R);
+            continue;
+        }
         const int p = idx / SIG_NQ, q = idx - p * SIG_NQ;
-        double a, b;
-        bool tail = false;
-        if (p < SIG_NLOW) {
-            a = l_lo + (l_one - l_lo) * p / SIG_NLOW;
-            b = l_lo + (l_one - l_lo) * (p + 1) / SIG_NLOW;
-        } else if (p < SIG_NLOW + n_lin) {
-            const int j = p - SIG_NLOW;
-            a = log(x_one + SIG_DX * j);
-            b = (j == n_lin - 1) ? l_s : log(x_one + SIG_DX * (j + 1));
-        } else {
-            const int j = p - SIG_NLOW - n_lin;
-            a = l_s + (l_hi - l_s) * j / SIG_NTAIL;
-            b = l_s + (l_hi - l_s) * (j + 1) / SIG_NTAIL;
-            tail = true;
-        }
-        const double half = 0.5 * (b - a);
-        const double lx = 0.5 * (a + b) + half * c_glx[SIG_NQ][q];
-        const double x = exp(lx);
-        const double lnk = lx - lnR;
-        double w2;
-        if (tail) {
-            const double x2 = x * x;
-            w2 = 9.0 * (1.0 + x2) / (2.0 * x2 * x2 * x2);
-        } else {
+        const double t = c_glx[SIG_NQ][q], wq = c_glw[SIG_NQ][q];
+        double x, lnk, wgt, w2;
+        if (p >= SIG_NLOW && p < SIG_NLOW + n_lin) {
+            // Gauss-Legendre in x on [x_one + 8 j, x_one + 8 (j + 1)]: dlnk = dx / x
+            const int jp = p - SIG_NLOW;
+            const double a = x_one + SIG_DX * jp;
+            const double b = (jp == n_lin - 1) ? xs : a + SIG_DX;
+            const double half = 0.5 * (b - a);
+            x = 0.5 * (a + b) + half * t;
+            lnk = log(x) - lnR;
+            wgt = half * wq / x;
             w2 = tophat2(x);
+        } else {
+            double a, b;
+            const bool tail = p >= SIG_NLOW;
+            if (!tail) {
+                a = l_lo + (l_one - l_lo) * p / SIG_NLOW;
+                b = l_lo + (l_one - l_lo) * (p + 1) / SIG_NLOW;
+            } else {
+                const int jp = p - SIG_NLOW - n_lin;
+                a = l_s + (l_hi - l_s) * jp / SIG_NTAIL;
+                b = l_s + (l_hi - l_s) * (jp + 1) / SIG_NTAIL;
+            }
+            const double half = 0.5 * (b - a);
+            const double lx = 0.5 * (a + b) + half * t;
+            x = exp(lx);
+            lnk = lx - lnR;
+            wgt = half * wq;
+            if (tail) {
+                const double x2 = x * x;
+                w2 = 9.0 * (1.0 + x2) / (2.0 * x2 * x2 * x2);
+            } else {
+                w2 = tophat2(x);
+            }
         }
-        acc += half * c_glw[SIG_NQ][q] * delta2(pk, exp(lnk), lnk) * w2;
+        acc += wgt * delta2(pk, x / R, lnk) * w2;
     }
-    if (n_tail && lane == 0) acc += sigma_tail_edge(pk, x_hi, R) - sigma_tail_edge(pk, xs, R);
-    return warp_sum(acc);
+    return acc;
+}
+
+// one full warp; result in every lane
+__device__ inline double warp_sigma2(const PkParams& pk, double R, double k_min, double k_max) {
+    return warp_sum(sigma2_partial(pk, R, k_min, k_max, threadIdx.x & 31, 32));
+}
+
+// A "team" is one half of the 256-thread CTA (4 warps) with its own named barrier, so that
+// the two mass-limit walks run side by side.
+struct Team {
+    int id, rank;        // 0 / 1, thread rank inside the team
+    double* red;         // 8 doubles of shared scratch per team
+};
+#define TEAM_SIZE 128
+__device__ __forceinline__ void team_sync(const Team& t) {
+    asm volatile("bar.sync %0, %1;" ::"r"(t.id + 1), "r"(TEAM_SIZE) : "memory");
+}
+__device__ inline double team_sum(const Team& t, double v) {
+    v = warp_sum(v);
+    team_sync(t);
+    if ((t.rank & 31) == 0) t.red[t.rank >> 5] = v;
+    team_sync(t);
+    return (t.red[0] + t.red[1]) + (t.red[2] + t.red[3]);
+}
+__device__ inline double team_sigma2(const Team& t, const PkParams& pk, double R, double k_min, double k_max) {
+    return team_sum(t, sigma2_partial(pk, R, k_min, k_max, t.rank, TEAM_SIZE));
 }
 
 struct MassCtx {
@@ -110,40 +153,59 @@ __device__ inline double warp_nu_m(const MassCtx& m, double mass) {
     const double s2 = warp_sigma2(m.pk, R, m.k_min, m.k_max);
     return m.delta_c * m.delta_c / s2;
 }
+// same, team-collective
+__device__ inline double team_nu_m(const Team& t, const MassCtx& m, double mass) {
+    const double R = cbrt(3.0 * mass / (4.0 * M_PI * m.rho_bar));
+    const double s2 = team_sigma2(t, m.pk, R, m.k_min, m.k_max);
+    return m.delta_c * m.delta_c / s2;
+}
 
-// Smallest j in [1, J] with pred(j) true, pred monotone (false ... false true ... true), by
-// warp-parallel multisection.  pred(j) = (nu(M0 * step^(dir*j)) compared with thr).
-// Returns -1 if pred(J) is false.  Collective over the CTA (blockDim.x / 32 warps).
-__device__ inline int walk_search(const MassCtx& m, double M0, int dir, bool want_le, double thr, int J,
-                                  double* sh_val) {
-    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
-    int lo = 0, hi = J;         // pred(lo) false (caller checked j = 0); pred(hi) assumed, verified in round 1
-    bool hi_known = false;
-    while (hi - lo > 1 || !hi_known) {
-        const int span = hi - lo;
-        // candidates lo < c_0 < ... <= hi, always including hi while it is unverified
-        int cand = lo + (int)(((long long)span * (w + 1) + nw - 1) / nw);
-        if (cand > hi) cand = hi;
-        if (cand <= lo) cand = lo + 1;
-        const double mass = M0 * pow(1.05, (double)(dir * cand));
-        const double nu = warp_nu_m(m, mass);
-        __syncthreads();
-        if (lane == 0) sh_val[w] = (want_le ? (nu <= thr) : (nu >= thr)) ? (double)cand : -(double)cand;
-        __syncthreads();
-        int new_hi = hi, new_lo = lo;
-        bool any_true = false;
-        for (int i = 0; i < nw; ++i) {
-            const int c = (int)fabs(sh_val[i]);
-            if (sh_val[i] > 0.0) { if (!any_true || c < new_hi) new_hi = c; any_true = true; }
-        }
-        for (int i = 0; i < nw; ++i) {
-            const int c = (int)fabs(sh_val[i]);
-            if (sh_val[i] < 0.0 && c < new_hi && c > new_lo) new_lo = c;
-        }
-        if (!any_true && !hi_known) return -1;
-        hi = new_hi; lo = new_lo; hi_known = true;
+// The reference walks a mass limit in factors of 1.05 until nu(M) enters a window
+// (mass_function.py:172-194).  nu(M) is monotone, so the walk stops at the first step j whose
+// mass passes the window edge `thr`; that step is found here by solving ln nu(M0 e^t) = ln thr
+// with the secant method (ln nu is almost linear in ln M) and then checking the two
+// neighbouring steps with the reference's own comparison.  Team-collective (every sigma(R) is
+// spread over 128 threads: the walk is a serial chain, so latency is what counts); returns the
+// number of steps (0 = already inside), or -1 if no step within +-J satisfies it.
+__device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scale, double M0, double nu0,
+                                double lo_edge, double hi_edge, int J, double* mass_out) {
+    *mass_out = M0;
+    int dir;          // +1: multiply by 1.05, -1: divide
+    double thr;
+    bool want_le;
+    if (hi_edge < nu0) { dir = -1; thr = hi_edge; want_le = true; }        // "too high": M /= 1.05 until nu <= hi_edge
+    else if (lo_edge > nu0) { dir = +1; thr = lo_edge; want_le = false; }  // "too low":  M *= 1.05 until nu >= lo_edge
+    else return 0;
+    const double ln_step = log(1.05), target = log(thr);
+    // secant on g(t) = ln nu(M0 e^t) - target
+    double t0 = 0.0, g0 = log(nu0) - target;
+    double t1 = -g0 / 0.35;                       // d ln nu / d ln M is 0.15 ... 0.7
+    double g1 = 0.0;
+    const double t_max = J * ln_step;
+    // sigma(R) carries quadrature noise of ~1e-9, and only the step index is needed: stop early
+    for (int it = 0; it < 10; ++it) {
+        t1 = fmax(-t_max, fmin(t_max, t1));
+        g1 = log(team_nu_m(tm, m, M0 * exp(t1)) * nu_scale) - target;
+        if (fabs(g1) < 2e-8 || fabs(t1 - t0) < 1e-7) break;
+        const double t2 = t1 - g1 * (t1 - t0) / (g1 - g0);
+        t0 = t1; g0 = g1; t1 = t2;
     }
-    return hi;
+    int j = (int)ceil(fabs(t1) / ln_step - 1e-7);
+    if (j < 1) j = 1;
+    // settle on the first step that passes, exactly as the sequential walk would
+    for (int guard = 0; guard < 8; ++guard) {
+        if (j > J) return -1;
+        const double nu_j = team_nu_m(tm, m, M0 * pow(1.05, (double)(dir * j))) * nu_scale;
+        const bool ok_j = want_le ? (nu_j <= thr) : (nu_j >= thr);
+        if (!ok_j) { ++j; continue; }
+        if (j == 1) break;
+        const double nu_p = team_nu_m(tm, m, M0 * pow(1.05, (double)(dir * (j - 1)))) * nu_scale;
+        const bool ok_p = want_le ? (nu_p <= thr) : (nu_p >= thr);
+        if (ok_p) { --j; continue; }
+        break;
+    }
+    *mass_out = M0 * pow(1.05, (double)(dir * j));
+    return j;
 }
 
 struct MassOut {
@@ -182,38 +244,38 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     m.delta_c = delta_c_z(c, z);
     m.rho_bar = rho_bar_z(c, z);
     m.k_min = cfg.k_min; m.k_max = cfg.k_max;
-    // sigma_norm = sigma_8 * growth / sigma_r(8) with sigma_norm = 1 (cosmology.py:118-119)
+    // Every sigma(R) is evaluated with sigma_norm = 1; nu scales as 1 / sigma_norm^2
+    // (cosmology.py:118-119, 574-587).  Round 0: sigma_8, nu(1e9) and nu(1e16) on three warps.
     m.pk = make_pk(c, growth, 1.0);
-    const double s8_raw = sqrt(warp_sigma2(m.pk, 8.0, m.k_min, m.k_max));
+    double m_lo = 1.0e9, m_hi = 1.0e16;
+    const bool fixed_limits = cfg.mass_min > 0.0 && cfg.mass_max > 0.0;
+    if (fixed_limits) { m_lo = cfg.mass_min; m_hi = cfg.mass_max; }
+    if (w == 0) { const double v = warp_sigma2(m.pk, 8.0, m.k_min, m.k_max); if (lane == 0) red[0] = v; }
+    if (w == 1 && !fixed_limits) { const double v = warp_nu_m(m, m_lo); if (lane == 0) red[1] = v; }
+    if (w == 2 && !fixed_limits) { const double v = warp_nu_m(m, m_hi); if (lane == 0) red[2] = v; }
+    __syncthreads();
+    const double s8_raw = sqrt(red[0]);
     const double sigma_norm = c.s8 * growth / s8_raw;
-    m.pk = make_pk(c, growth, sigma_norm);
+    const double nu_scale = 1.0 / (sigma_norm * sigma_norm);
 
     int st = 0;
     if (c.bad || hp[CHOMP_H_ALPHA] != -1.0) st |= CHOMP_ST_DOMAIN;
     int walk_steps = 0;
-    // ---- mass limits (mass_function.py:160-203) -----------------------------------
-    double m_lo = 1.0e9, m_hi = 1.0e16;
-    if (cfg.mass_min > 0.0 && cfg.mass_max > 0.0) {
-        m_lo = cfg.mass_min; m_hi = cfg.mass_max;
-    } else {
-        const int J = 512;
-        // lower limit: walk until 0.095 <= nu(M) <= 0.105
-        double nu0 = warp_nu_m(m, m_lo);
-        if (0.1 * (1.0 + 0.05) < nu0) {
-            const int j = walk_search(m, m_lo, -1, true, 0.1 * (1.0 + 0.05), J, red);
-            if (j < 0) st |= CHOMP_ST_MASS_WALK; else { m_lo = m_lo * pow(1.05, -(double)j); walk_steps += j; }
-        } else if (0.1 * (1.0 - 0.05) > nu0) {
-            const int j = walk_search(m, m_lo, +1, false, 0.1 * (1.0 - 0.05), J, red);
-            if (j < 0) st |= CHOMP_ST_MASS_WALK; else { m_lo = m_lo * pow(1.05, (double)j); walk_steps += j; }
-        }
-        nu0 = warp_nu_m(m, m_hi);
-        if (50.0 * (1.0 - 0.05) > nu0) {
-            const int j = walk_search(m, m_hi, +1, false, 50.0 * (1.0 - 0.05), J, red);
-            if (j < 0) st |= CHOMP_ST_MASS_WALK; else { m_hi = m_hi * pow(1.05, (double)j); walk_steps += j; }
-        } else if (50.0 * (1.0 + 0.05) < nu0) {
-            const int j = walk_search(m, m_hi, -1, true, 50.0 * (1.0 + 0.05), J, red);
-            if (j < 0) st |= CHOMP_ST_MASS_WALK; else { m_hi = m_hi * pow(1.05, -(double)j); walk_steps += j; }
-        }
+    // ---- mass limits (mass_function.py:160-203): the two walks are independent -------------
+    if (!fixed_limits) {
+        const double nu_lo0 = red[1] * nu_scale, nu_hi0 = red[2] * nu_scale;
+        __syncthreads();
+        Team tm{tid / TEAM_SIZE, tid % TEAM_SIZE, red + 16 + 8 * (tid / TEAM_SIZE)};
+        double mm;
+        int j;
+        if (tm.id == 0) j = team_walk(tm, m, nu_scale, m_lo, nu_lo0, 0.1 * (1.0 - 0.05), 0.1 * (1.0 + 0.05), 512, &mm);
+        else j = team_walk(tm, m, nu_scale, m_hi, nu_hi0, 50.0 * (1.0 - 0.05), 50.0 * (1.0 + 0.05), 512, &mm);
+        if (tm.rank == 0) { red[4 + 2 * tm.id] = mm; red[5 + 2 * tm.id] = (double)j; }
+        __syncthreads();
+        m_lo = red[4]; m_hi = red[6];
+        if (red[5] < 0.0 || red[7] < 0.0) st |= CHOMP_ST_MASS_WALK;
+        walk_steps = (int)(fmax(red[5], 0.0) + fmax(red[7], 0.0));
+        __syncthreads();
     }
     const double lnm_min = log(m_lo), lnm_max = log(m_hi);
     const double hM = (lnm_max - lnm_min) / (n - 1);
@@ -221,7 +283,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     __syncthreads();
     for (int i = w; i < n; i += nw) {
         const double lm = (i == n - 1) ? lnm_max : lnm_min + hM * i;
-        const double v = warp_nu_m(m, exp(lm));
+        const double v = warp_nu_m(m, exp(lm)) * nu_scale;
         if (lane == 0) { lnm[i] = lm; nu[i] = v; }
     }
     __syncthreads();
@@ -277,7 +339,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         e[EP_Z] = z; e[EP_GROWTH] = growth; e[EP_SIGMA_NORM] = sigma_norm; e[EP_DELTA_C] = m.delta_c;
         e[EP_DELTA_V] = dv; e[EP_RHO_BAR] = m.rho_bar; e[EP_LNM_MIN] = lnm_min; e[EP_LNM_MAX] = lnm_max;
         e[EP_NU_MIN] = nu_min; e[EP_NU_MAX] = nu_max; e[EP_F_NORM] = f_norm; e[EP_B_NORM] = b_norm;
-        e[EP_LNM_STAR] = lnm_star; e[EP_PK_AMP] = m.pk.amp; e[EP_CHI] = chi; e[EP_WALK] = (double)walk_steps;
+        e[EP_LNM_STAR] = lnm_star; e[EP_PK_AMP] = m.pk.amp * sigma_norm * sigma_norm; e[EP_CHI] = chi; e[EP_WALK] = (double)walk_steps;
         e[EP_OMEGA_M] = omega_m_z(c, z); e[EP_OMEGA_L] = c.ol / E0(c, z); e[EP_E0] = E0(c, z);
         e[EP_DELTA_V_COSMO] = delta_v_z(c, z, growth);
         e[EP_RHO_CRIT] = 1.879 / 1.989 * (3.086 * 3.086 * 3.086) * 1e10 * E0(c, z);

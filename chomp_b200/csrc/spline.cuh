@@ -13,7 +13,7 @@ namespace chomp {
 
 // Build by ONE thread.  x[n], y[n] inputs; coef[4*(n-1)] output; work[2*n]
 // scratch.  n >= 4.
-__device__ inline void spline_build(int n, const double* __restrict__ x, const double* __restrict__ y,
+__device__ __noinline__ void spline_build(int n, const double* __restrict__ x, const double* __restrict__ y,
                                     double* __restrict__ coef, double* __restrict__ work) {
     double* m = work;      // second derivatives
     double* cp = work + n; // Thomas scratch (modified upper diagonal)

@@ -74,6 +74,6 @@ default_precision = {
 default_quadrature = {
     "nu": 8,        # mass integrals, per knot interval of ln M(nu)
     "hankel": 4,    # w(theta) k-integral, per piece (<= 0.0625 wide in ln k) of a halo-table interval
-    "limber": 5,    # K(ln k theta) chi-integral, per knot interval
+    "limber": 4,    # K(ln k theta) chi-integral, per knot interval
     "lens": 6,      # lensing-efficiency integral, per chi(z) knot interval
 }
