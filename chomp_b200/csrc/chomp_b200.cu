@@ -142,7 +142,6 @@ size_t sums_smem(const Handle* h) {
     for (int c = 0; c < N_KCLASS; ++c) m = h->node_cap[c] > m ? h->node_cap[c] : m;
     return (size_t)NODE_FIELDS * m * sizeof(double);
 }
-size_t splines_smem(const Cfg& c) { return 36 * (size_t)c.n_halo * sizeof(double); }
 size_t wtheta_smem(const Cfg& c) { return (2 * (size_t)hankel_nodes(c) + 4 * (size_t)c.n_kernel + 8) * sizeof(double); }
 
 }  // namespace
@@ -208,7 +207,8 @@ int chomp_b200_configure(void* handle, const chomp_b200_config* cfg) {
     // opt in to > 48 KB dynamic shared memory where a stage needs it
     CK(cudaFuncSetAttribute(limber_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(limber_smem_doubles(h->cfg) * sizeof(double))));
-    CK(cudaFuncSetAttribute(halo_splines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)splines_smem(h->cfg)));
+    CK(cudaFuncSetAttribute(halo_splines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(15 * (size_t)h->cfg.n_halo * sizeof(double))));
     CK(cudaFuncSetAttribute(wtheta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wtheta_smem(h->cfg)));
     if (resize && h->cap_points > 0) {
         const int n = h->cap_points;
@@ -335,7 +335,8 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
     halo_sums_kernel<<<grid, 256, sums_smem(h), s>>>(c, B, no, h->raw);
     CK(cudaGetLastError());
     mark(h, CHOMP_K_SPLINES, s);
-    halo_splines_kernel<<<B, 64, splines_smem(c), s>>>(c, B, h->raw, h->nbar, h->epoch, h->htab, h->hcoef, status_dev);
+    halo_splines_kernel<<<B, 160, 15 * (size_t)c.n_halo * sizeof(double), s>>>(c, B, h->raw, h->nbar, h->epoch, h->htab, h->hcoef,
+                                                                          status_dev);
     mark(h, CHOMP_K_SPLINES + 1, s);
     CK(cudaGetLastError());
     h->launches += 3;

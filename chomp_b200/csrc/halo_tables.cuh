@@ -133,10 +133,18 @@ __device__ inline double lnnu_moment_crossing(const NuTab& t, const HodP& h, int
         hod_moments(h, exp(t.lnm[i]), n1, n2);
         if ((which == 1 ? n1 : n2) < 1.0) lo = x; else { hi = x; break; }
     }
-    for (int it = 0; it < 50 && hi - lo > 1e-15 * fabs(hi); ++it) {
-        const double mid = 0.5 * (lo + hi);
+    // Illinois regula falsi on g = moment - 1 (smooth and monotone between the breaks); a
+    // step in the moment degrades it to bisection, which still converges onto the step
+    hod_moments(h, exp(mass_of_nu_ln(t, exp(lo))), n1, n2);
+    double glo = (which == 1 ? n1 : n2) - 1.0;
+    hod_moments(h, exp(mass_of_nu_ln(t, exp(hi))), n1, n2);
+    double ghi = (which == 1 ? n1 : n2) - 1.0;
+    for (int it = 0; it < 64 && hi - lo > 1e-15 * fabs(hi); ++it) {
+        double mid = (lo * ghi - hi * glo) / (ghi - glo);
+        if (!(mid > lo && mid < hi) || (it & 3) == 3) mid = 0.5 * (lo + hi);
         hod_moments(h, exp(mass_of_nu_ln(t, exp(mid))), n1, n2);
-        if ((which == 1 ? n1 : n2) < 1.0) lo = mid; else hi = mid;
+        const double gm = (which == 1 ? n1 : n2) - 1.0;
+        if (gm < 0.0) { lo = mid; glo = gm; ghi *= 0.5; } else { hi = mid; ghi = gm; glo *= 0.5; }
     }
     return hi;   // first abscissa on the ">= 1" side
 }
@@ -433,35 +441,72 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ raw /* 
     }
 }
 
-// Normalise (halo.py:919, 958, 988, 1028, 1074) and spline the five tables in ln k.
-__global__ void __launch_bounds__(64)
+// Normalise (halo.py:919, 958, 988, 1028, 1074) and spline the five tables in ln k
+// (uniform knots).  One CTA of five warps per point, one warp per table: loads, second
+// differences, coefficients and stores are lane-parallel and coalesced; only the two sweeps of
+// the tridiagonal solve (a serial chain) run on lane 0, in shared memory.
+__global__ void __launch_bounds__(160)
 halo_splines_kernel(const Cfg cfg, int B, const double* __restrict__ raw, const double* __restrict__ nbar,
                     const double* __restrict__ epoch, double* __restrict__ tab /* [B,5,n_halo] */,
                     double* __restrict__ coef /* [B,5,4 n_halo] */, int32_t* __restrict__ status) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     if (b >= B) return;
-    const int nk = cfg.n_halo, tid = threadIdx.x;
-    double* x = sm;              // nk
-    double* y = x + nk;          // 5 nk
-    double* cf = y + 5 * nk;     // 5 * 4 nk
-    double* work = cf + 20 * nk; // 5 * 2 nk
-    const double l0 = log(cfg.k_min), l1 = log(cfg.k_max);
+    const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = cfg.n_halo;
+    double* sy = sm + (size_t)t * 3 * n;   // node values
+    double* sm2 = sy + n;                  // rhs -> second derivatives m
+    double* scp = sm2 + n;                 // modified upper diagonal
+    const double h = (log(cfg.k_max) - log(cfg.k_min)) / (n - 1), ih = 1.0 / h;
     const double nb = nbar[b], rho_bar = epoch[(size_t)b * CHOMP_EPOCH_LEN + EP_RHO_BAR];
-    const double scale[5] = {1.0, 1.0, 1.0 / nb, 1.0 / (nb * rho_bar), 1.0 / (nb * nb * rho_bar)};
-    for (int i = tid; i < nk; i += blockDim.x) x[i] = (i == nk - 1) ? l1 : l0 + (l1 - l0) / (nk - 1) * i;
+    const double scale = t < 2 ? 1.0 : (t == 2 ? 1.0 / nb : (t == 3 ? 1.0 / (nb * rho_bar) : 1.0 / (nb * nb * rho_bar)));
+    const double* __restrict__ y_in = raw + ((size_t)b * 5 + t) * n;
+    double* __restrict__ y_out = tab + ((size_t)b * 5 + t) * n;
+    double* __restrict__ c = coef + ((size_t)b * 5 + t) * 4 * n;
     bool bad = false;
-    for (int i = tid; i < 5 * nk; i += blockDim.x) {
-        const double v = raw[(size_t)b * 5 * nk + i] * scale[i / nk];
-        y[i] = v;
-        tab[(size_t)b * 5 * nk + i] = v;
+    for (int i = lane; i < n; i += 32) {
+        const double v = y_in[i] * scale;
+        sy[i] = v;
+        y_out[i] = v;
         if (!isfinite(v)) bad = true;
     }
     if (bad && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
-    __syncthreads();
-    if (tid < 5) spline_build(nk, x, y + tid * nk, cf + tid * 4 * nk, work + tid * 2 * nk);
-    __syncthreads();
-    for (int i = tid; i < 20 * nk; i += blockDim.x) coef[(size_t)b * 20 * nk + i] = cf[i];
+    __syncwarp();
+    for (int i = 1 + lane; i <= n - 2; i += 32) sm2[i] = 6.0 * ((sy[i + 1] - sy[i]) - (sy[i] - sy[i - 1])) * ih;
+    __syncwarp();
+    if (lane == 0) {
+        // not-a-knot with equal spacing: rows 1 and n-2 reduce to 6 h m_i = rhs_i (see spline.cuh)
+        const double i6h = 1.0 / (6.0 * h);
+        double cp_prev = 0.0, m_prev = sm2[1] * i6h;
+        sm2[1] = m_prev;
+        scp[1] = 0.0;
+        for (int i = 2; i <= n - 3; ++i) {
+            const double inv = 1.0 / (4.0 * h - h * cp_prev);
+            cp_prev = h * inv;
+            m_prev = (sm2[i] - h * m_prev) * inv;
+            scp[i] = cp_prev;
+            sm2[i] = m_prev;
+        }
+        double m_next = sm2[n - 2] * i6h;
+        sm2[n - 2] = m_next;
+        for (int i = n - 3; i >= 2; --i) {
+            m_next = sm2[i] - scp[i] * m_next;
+            sm2[i] = m_next;
+        }
+        sm2[0] = 2.0 * sm2[1] - sm2[2];
+        sm2[n - 1] = 2.0 * sm2[n - 2] - sm2[n - 3];
+    }
+    __syncwarp();
+    for (int idx = lane; idx < 4 * (n - 1); idx += 32) {
+        const int i = idx >> 2, k = idx & 3;
+        const double mi = sm2[i], mn = sm2[i + 1];
+        double v;
+        if (k == 0) v = sy[i];
+        else if (k == 1) v = (sy[i + 1] - sy[i]) * ih - h * (2.0 * mi + mn) / 6.0;
+        else if (k == 2) v = 0.5 * mi;
+        else v = (mn - mi) / (6.0 * h);
+        c[idx] = v;
+    }
 }
 
 }  // namespace chomp
