@@ -97,7 +97,7 @@ __host__ __device__ inline size_t limber_smem_doubles(const Cfg& cfg) {
     const size_t nb = 2 * nw + nz + 4;                 // max base panels + 1
     return 3 * (3 * nz + 12 * nz) + 2 * (nw + 4 * nw) + 2 * nz /*lens sums*/ + nb /*edges*/ +
            2 * nb * cfg.nq_limber /*chi_q, Fw_q*/ + nk + 4 * nk + 2 * (nw > nz ? (nw > nk ? nw : nk) : (nz > nk ? nz : nk)) * 9 +
-           128 /*red + misc*/;
+           128 /*red + misc*/ + (LIMBER_THREADS / 32) * (nb / 2 + 2) /*per-warp int prefix sums*/;
 }
 
 __global__ void __launch_bounds__(LIMBER_THREADS)
@@ -130,6 +130,7 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     const int nmax = nw > nz ? (nw > nk ? nw : nk) : (nz > nk ? nz : nk);
     double* work = p; p += (size_t)2 * nmax * 9;
     double* red = p; p += 64;
+    int* pfx_all = (int*)p;           // (LIMBER_THREADS / 32) x (nb_max + 1) ints
     __shared__ int n_edge_s;
     __shared__ double s_misc[8];
 
@@ -331,31 +332,59 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     // ---- K(ln k theta) nodes: one warp per node (kernel.py:678-705) ----------------------------------
     const double x0 = log(cfg.ktheta_min), x1 = log(cfg.ktheta_max);
     const int order = cfg.bessel_order;
+    // widest base panel: below kt * width <= 2 no panel needs sub-division
+    double wmax = 0.0;
+    for (int pnl = 0; pnl < n_pan; ++pnl) wmax = fmax(wmax, edge[pnl + 1] - edge[pnl]);
+    int* pfx = pfx_all + wid * (nb_max + 1);     // per-warp prefix sums of node counts
     for (int j = wid; j < nk; j += nwarp) {
         const double lkt = (j == nk - 1) ? x1 : x0 + (x1 - x0) / (nk - 1) * j;
         const double kt = exp(lkt);
         double top = cfg.bessel_limit / kt;
         if (top >= chi_max_k) top = chi_max_k;
         double acc = 0.0;
-        for (int pnl = lane; pnl < n_pan; pnl += 32) {
-            const double a = edge[pnl];
-            if (a >= top) continue;
-            const double bfull = edge[pnl + 1];
-            const bool clipped = bfull > top;
-            const double bb = clipped ? top : bfull;
-            const int nsub = (int)fmax(1.0, ceil(kt * (bb - a) / 2.0));
-            if (!clipped && nsub == 1) {
-                for (int q = 0; q < nq; ++q) acc += fw_q[pnl * nq + q] * bessel_j(order, kt * chi_q[pnl * nq + q]);
-            } else {
-                const double d = (bb - a) / nsub, half = 0.5 * d;
-                for (int s = 0; s < nsub; ++s) {
-                    const double mid = a + d * (s + 0.5);
-                    for (int q = 0; q < nq; ++q) {
-                        const double x = mid + half * c_glx[nq][q];
-                        acc += half * c_glw[nq][q] * F(x) * bessel_j(order, kt * x);
-                    }
+        if (top >= chi_max_k && kt * wmax <= 2.0) {
+            // every panel whole and un-divided: W_a W_b D^2 was tabulated at these nodes
+            for (int idx = lane; idx < n_pan * nq; idx += 32) acc += fw_q[idx] * bessel_j(order, kt * chi_q[idx]);
+        } else {
+            // clipped at the Bessel-zero limit and / or sub-divided: spread all (panel, piece,
+            // node) triples evenly over the lanes
+            const int per = (n_pan + 31) / 32;
+            const int p_begin = lane * per, p_end = min(n_pan, (lane + 1) * per);
+            auto count = [&](int pnl) -> int {
+                const double a = edge[pnl];
+                if (!(a < top)) return 0;
+                const double bb = fmin(edge[pnl + 1], top);
+                return (int)fmax(1.0, ceil(kt * (bb - a) / 2.0)) * nq;
+            };
+            int mine = 0;
+            for (int pnl = p_begin; pnl < p_end; ++pnl) mine += count(pnl);
+            int incl = mine;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int run = incl - mine;
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int pnl = p_begin; pnl < p_end; ++pnl) { pfx[pnl] = run; run += count(pnl); }
+            if (lane == 31) pfx[n_pan] = total;
+            __syncwarp();
+            for (int idx = lane; idx < total; idx += 32) {
+                int lo = 0, hi = n_pan;            // panel with pfx[lo] <= idx < pfx[lo + 1]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= idx) lo = mid; else hi = mid; }
+                const int pnl = lo, local = idx - pfx[pnl];
+                const int nsub = (pfx[pnl + 1] - pfx[pnl]) / nq;
+                const int sidx = local / nq, q = local - sidx * nq;
+                const double a = edge[pnl], bfull = edge[pnl + 1];
+                if (nsub == 1 && bfull <= top) {
+                    acc += fw_q[pnl * nq + q] * bessel_j(order, kt * chi_q[pnl * nq + q]);
+                } else {
+                    const double bb = fmin(bfull, top);
+                    const double d = (bb - a) / nsub, half = 0.5 * d;
+                    const double x = a + d * (sidx + 0.5) + half * c_glx[nq][q];
+                    acc += half * c_glw[nq][q] * F(x) * bessel_j(order, kt * x);
                 }
             }
+            __syncwarp();
         }
         acc = warp_sum(acc);
         if (lane == 0) kn[j] = acc;

@@ -17,38 +17,49 @@ __device__ __noinline__ void spline_build(int n, const double* __restrict__ x, c
                                     double* __restrict__ coef, double* __restrict__ work) {
     double* m = work;      // second derivatives
     double* cp = work + n; // Thomas scratch (modified upper diagonal)
-    // unknowns m[1..n-2]; m[0], m[n-1] eliminated through the not-a-knot rows
+    // unknowns m[1..n-2]; m[0], m[n-1] eliminated through the not-a-knot rows.  The chord slopes
+    // are kept in coef[4 i + 1] so that every interval costs one division in the sweep and one
+    // in the coefficient pass.
     const int last = n - 2;
-    double h0 = x[1] - x[0], h1 = x[2] - x[1];
-    double diag = h0 * (1.0 + h0 / h1) + 2.0 * (h0 + h1);
-    double up = h1 - h0 * h0 / h1;
-    double rhs = 6.0 * ((y[2] - y[1]) / h1 - (y[1] - y[0]) / h0);
-    cp[1] = up / diag;
-    m[1] = rhs / diag;
-    for (int i = 2; i <= last; ++i) {
-        const double hl = x[i] - x[i - 1], hr = x[i + 1] - x[i];
+    const double h0 = x[1] - x[0], h1 = x[2] - x[1];
+    double slope_prev = (y[1] - y[0]) / h0;
+    coef[1] = slope_prev;
+    double hl = h0;
+    for (int i = 1; i <= last; ++i) {
+        const double hr = x[i + 1] - x[i];
+        const double slope = (y[i + 1] - y[i]) / hr;
+        coef[4 * i + 1] = slope;
         double lo = hl, dg = 2.0 * (hl + hr), u = hr;
+        if (i == 1) {
+            // m[0] = (1 + h0/h1) m[1] - (h0/h1) m[2]
+            dg = hl * (1.0 + hl / hr) + 2.0 * (hl + hr);
+            u = hr - hl * hl / hr;
+            lo = 0.0;
+        }
         if (i == last) {
             // m[n-1] = (1 + hr/hl) m[n-2] - (hr/hl) m[n-3]
             dg = hr * (1.0 + hr / hl) + 2.0 * (hl + hr);
             lo = hl - hr * hr / hl;
             u = 0.0;
         }
-        const double r = 6.0 * ((y[i + 1] - y[i]) / hr - (y[i] - y[i - 1]) / hl);
-        const double den = dg - lo * cp[i - 1];
-        cp[i] = u / den;
-        m[i] = (r - lo * m[i - 1]) / den;
+        const double r = 6.0 * (slope - slope_prev);
+        const double cprev = (i == 1) ? 0.0 : cp[i - 1], mprev = (i == 1) ? 0.0 : m[i - 1];
+        const double inv = 1.0 / (dg - lo * cprev);
+        cp[i] = u * inv;
+        m[i] = (r - lo * mprev) * inv;
+        slope_prev = slope;
+        hl = hr;
     }
     for (int i = last - 1; i >= 1; --i) m[i] -= cp[i] * m[i + 1];
     m[0] = (1.0 + h0 / h1) * m[1] - (h0 / h1) * m[2];
     {
-        const double hl = x[n - 2] - x[n - 3], hr = x[n - 1] - x[n - 2];
-        m[n - 1] = (1.0 + hr / hl) * m[n - 2] - (hr / hl) * m[n - 3];
+        const double hl2 = x[n - 2] - x[n - 3], hr2 = x[n - 1] - x[n - 2];
+        m[n - 1] = (1.0 + hr2 / hl2) * m[n - 2] - (hr2 / hl2) * m[n - 3];
     }
     for (int i = 0; i < n - 1; ++i) {
         const double h = x[i + 1] - x[i];
         coef[4 * i + 0] = y[i];
-        coef[4 * i + 1] = (y[i + 1] - y[i]) / h - h * (2.0 * m[i] + m[i + 1]) / 6.0;
+        coef[4 * i + 1] = coef[4 * i + 1] - h * (2.0 * m[i] + m[i + 1]) * (1.0 / 6.0);
         coef[4 * i + 2] = 0.5 * m[i];
         coef[4 * i + 3] = (m[i + 1] - m[i]) / (6.0 * h);
     }
