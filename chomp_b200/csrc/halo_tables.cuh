@@ -222,13 +222,16 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
         }
         extra[tid] = x;
     }
+    // ln(nu) of the knots, in parallel (staged in the tail of the edge array)
+    double* lognu = edge + MAX_EXTRA_BREAKS;     // edge has n + MAX_EXTRA_BREAKS slots; the merge below
+    for (int i = tid; i < n; i += blockDim.x) lognu[i] = log(nu[i]);   // writes edge[k] only for k <= i + extras so far
     __syncthreads();
     if (tid == 0) {
         int cnt = 0;
         edge[cnt++] = l_min;
         for (int i = 1; i < n - 1; ++i) {
-            const double x = log(nu[i]);
-            if (x > l_min && x < l_max) edge[cnt++] = x;
+            const double x = lognu[i];
+            if (x > l_min && x < l_max) edge[cnt++] = x;      // cnt <= i < i + MAX_EXTRA_BREAKS: never overtakes lognu
         }
         edge[cnt++] = l_max;
         double x_sing = nan("");
@@ -246,27 +249,34 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
         }
         n_edge = cnt;
         x_singular = x_sing;
-        // per panel: spline interval and, per k class, the first node index
-        // panels inside the erf edge of the central occupation get the "sharp" order
+    }
+    __syncthreads();
+    // per panel (in parallel): spline interval and the Gauss-Legendre order in each k class;
+    // panels inside the erf edge of the central occupation get the "sharp" order
+    {
         const double ln10 = 2.302585092994046;
         const double sharp_lo = (h.log_M_min - 3.5 * h.sigma) * ln10, sharp_hi = (h.log_M_min + 3.5 * h.sigma) * ln10;
-        int acc[N_KCLASS] = {0, 0, 0};
-        for (int p = 0; p < cnt - 1; ++p) {
+        for (int p = tid; p < n_edge - 1; p += blockDim.x) {
             const double xm = 0.5 * (edge[p] + edge[p + 1]);
             const int kn = search_index(exp(xm), nu, n);
             pknot[p] = kn;
             const double lm_lo = spline_poly(c1, kn, exp(edge[p]) - nu[kn]);
             const double lm_hi = spline_poly(c1, kn, exp(edge[p + 1]) - nu[kn]);
             const bool sharp = (h.kind == CHOMP_HOD_ZHENG) && h.sigma > 0.0 && lm_hi > sharp_lo && lm_lo < sharp_hi;
-            const bool sing = edge[p] >= x_sing - 1e-12 && edge[p] <= x_sing + 0.02;
+            const bool sing = edge[p] >= x_singular - 1e-12 && edge[p] <= x_singular + 0.02;
             for (int c = 0; c < N_KCLASS; ++c) {
                 int o = sharp ? k_class_sharp[c] : k_class_base[c];
                 if (sing && o < SING_MIN_ORDER) o = SING_MIN_ORDER;
-                pstart[c * max_edge + p] = acc[c];
-                acc[c] += o;
+                pstart[c * max_edge + p] = o;
             }
         }
-        for (int c = 0; c < N_KCLASS; ++c) pstart[c * max_edge + cnt - 1] = acc[c];
+    }
+    __syncthreads();
+    if (tid < N_KCLASS) {        // exclusive prefix sums, one class per thread
+        int acc = 0;
+        int* ps = pstart + tid * max_edge;
+        for (int p = 0; p < n_edge - 1; ++p) { const int o = ps[p]; ps[p] = acc; acc += o; }
+        ps[n_edge - 1] = acc;
     }
     __syncthreads();
     // ---- nodes ------------------------------------------------------------------------------
