@@ -47,6 +47,7 @@ def base_config(**kw):
     c.bessel_order = 0
     c.bessel_limit = engine.bessel_limit(0, p["kernel_bessel_limit"])
     c.corr_k_min = c.corr_k_max = -1.0
+    c.tri_moment = -1
     for name, value in kw.items():
         setattr(c, name, value)
     return c

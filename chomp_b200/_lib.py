@@ -18,6 +18,7 @@ HOD_ZHENG_KEYS = ("log_M_min", "sigma", "log_M_0", "log_M_1p", "alpha")
 HOD_MANDELBAUM_KEYS = ("log_M_0", "w")
 HOD_ZHENG, HOD_MANDELBAUM = 0, 1
 P_LINEAR, P_MM, P_GM, P_GG = 0, 1, 2, 3
+TRISPECTRUM_MOMENT = {"power_mmmm": 0, "power_gmmm": 1, "power_ggmm": 2, "power_gggm": 3, "power_gggg": 4}
 POWER_SPEC = {"linear_power": P_LINEAR, "power_mm": P_MM, "power_gm": P_GM,
               "power_mg": P_GM, "power_gg": P_GG}
 DNDZ_GAUSSIAN, DNDZ_MAGLIM = 0, 1
@@ -50,7 +51,7 @@ class Config(ctypes.Structure):
         ("hod_kind", ctypes.c_int32), ("bessel_order", ctypes.c_int32),
         ("exclusion", ctypes.c_int32), ("extrapolate", ctypes.c_int32),
         ("window_kind", ctypes.c_int32*2), ("dndz_kind", ctypes.c_int32*2),
-        ("reserved_i", ctypes.c_int32*3),
+        ("tri_moment", ctypes.c_int32), ("reserved_i", ctypes.c_int32*2),
         ("halo_precision", ctypes.c_double), ("cosmo_precision", ctypes.c_double),
         ("window_precision", ctypes.c_double),
         ("k_min", ctypes.c_double), ("k_max", ctypes.c_double),
@@ -101,6 +102,9 @@ _SIGNATURES = {
     "chomp_b200_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+    "chomp_b200_trispectrum_1h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "chomp_b200_trispectrum_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "chomp_b200_set_params": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]),
     "chomp_b200_set_zbar": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),

@@ -18,6 +18,7 @@
 #include "mass_tables.cuh"
 #include "special.cuh"
 #include "spline.cuh"
+#include "trispectrum.cuh"
 
 using namespace chomp;
 
@@ -48,13 +49,15 @@ struct Handle {
     Cfg cfg;
     int same_window = 0;
     int cap_points = 0;
-    int node_cap[N_KCLASS] = {0, 0, 0}, node_off[N_KCLASS] = {0, 0, 0}, node_cap_total = 0;
+    int node_cap[N_NODE_LISTS] = {0, 0, 0, 0}, node_off[N_NODE_LISTS] = {0, 0, 0, 0}, node_cap_total = 0;
     long long launches = 0;
     // device scratch (all FP64 unless noted)
     double *zbar = nullptr, *dbar = nullptr, *knodes = nullptr, *kcoef = nullptr, *chi_nodes = nullptr,
            *win_nodes = nullptr, *win_chi = nullptr, *win_coef = nullptr, *kchi = nullptr, *grid0 = nullptr,
            *dndz_norm = nullptr;
     double *epoch = nullptr, *lnm_nodes = nullptr, *nu_nodes = nullptr, *c_lnm_nu = nullptr, *c_nu_lnm = nullptr;
+    double *tri_w = nullptr, *tri_A = nullptr, *tri_T = nullptr;   // 1-halo trispectrum (tri_A / tri_T allocated on first use)
+    int tri_points = 0;
     double *nodes = nullptr, *nbar = nullptr, *rv_max = nullptr, *raw = nullptr, *htab = nullptr, *hcoef = nullptr;
     int32_t* n_nodes = nullptr;
     // parameter copies of the last batch (the evaluators need them)
@@ -109,6 +112,7 @@ void free_scratch(Handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     h->allocs.clear();
     h->cap_points = 0;
+    h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0;
 }
 
 int check_cfg(const Cfg& c) {
@@ -135,11 +139,11 @@ size_t mass_smem(const Cfg& c) { return (14 * (size_t)c.n_mass + 64) * sizeof(do
 size_t nodes_smem(const Cfg& c) {
     const size_t max_edge = (size_t)c.n_mass + MAX_EXTRA_BREAKS;
     return (10 * (size_t)c.n_mass + max_edge + MAX_EXTRA_BREAKS + 64) * sizeof(double) +
-           ((N_KCLASS + 1) * max_edge + 8) * sizeof(int);
+           ((N_NODE_LISTS + 1) * max_edge + 8) * sizeof(int);
 }
 size_t sums_smem(const Handle* h) {
     int m = 0;
-    for (int c = 0; c < N_KCLASS; ++c) m = h->node_cap[c] > m ? h->node_cap[c] : m;
+    for (int c = 0; c < N_KCLASS; ++c) m = h->node_cap[c] > m ? h->node_cap[c] : m;   // the sums kernel stages lists 0..2 only
     return (size_t)NODE_FIELDS * m * sizeof(double);
 }
 size_t wtheta_smem(const Cfg& c) { return (2 * (size_t)hankel_nodes(c) + 4 * (size_t)c.n_kernel + 8) * sizeof(double); }
@@ -197,7 +201,8 @@ int chomp_b200_configure(void* handle, const chomp_b200_config* cfg) {
     CK(cudaSetDevice(h->device));
     const bool resize = !h->configured || h->cfg.n_cosmo != cfg->n_cosmo || h->cfg.n_mass != cfg->n_mass ||
                         h->cfg.n_halo != cfg->n_halo || h->cfg.n_window != cfg->n_window ||
-                        h->cfg.n_kernel != cfg->n_kernel || h->cfg.nq_nu != cfg->nq_nu;
+                        h->cfg.n_kernel != cfg->n_kernel || h->cfg.nq_nu != cfg->nq_nu ||
+                        (h->cfg.tri_moment >= 0) != (cfg->tri_moment >= 0);
     h->cfg = *cfg;
     h->same_window = (cfg->window_kind[0] == cfg->window_kind[1] && cfg->dndz_kind[0] == cfg->dndz_kind[1] &&
                       cfg->dndz_zmin[0] == cfg->dndz_zmin[1] && cfg->dndz_zmax[0] == cfg->dndz_zmax[1] &&
@@ -230,8 +235,8 @@ int chomp_b200_reserve(void* handle, int max_points) {
     const Cfg& c = h->cfg;
     const size_t B = (size_t)max_points;
     h->node_cap_total = 0;
-    for (int k = 0; k < N_KCLASS; ++k) {
-        h->node_cap[k] = kclass_cap(k, c.n_mass);
+    for (int k = 0; k < N_NODE_LISTS; ++k) {
+        h->node_cap[k] = kclass_cap(k, c.n_mass, c.tri_moment >= 0);
         h->node_off[k] = h->node_cap_total;
         h->node_cap_total += h->node_cap[k];
     }
@@ -254,9 +259,11 @@ int chomp_b200_reserve(void* handle, int max_points) {
     rc |= dev_alloc(h, &h->c_lnm_nu, B * 4 * c.n_mass);
     rc |= dev_alloc(h, &h->c_nu_lnm, B * 4 * c.n_mass);
     rc |= dev_alloc(h, &h->nodes, B * NODE_FIELDS * h->node_cap_total);
-    rc |= dev_alloc(h, &h->n_nodes, B * N_KCLASS);
+    rc |= dev_alloc(h, &h->n_nodes, B * N_NODE_LISTS);
     rc |= dev_alloc(h, &h->nbar, B);
     rc |= dev_alloc(h, &h->rv_max, B);
+    rc |= dev_alloc(h, &h->tri_w, B * h->node_cap[TRI_LIST]);
+    h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0;
     rc |= dev_alloc(h, &h->raw, B * 5 * c.n_halo);
     rc |= dev_alloc(h, &h->htab, B * 5 * c.n_halo);
     rc |= dev_alloc(h, &h->hcoef, B * 20 * c.n_halo);
@@ -312,6 +319,8 @@ int chomp_b200_mass_tables(void* handle, int B, const double* cosmo_dev, const d
     return 0;
 }
 
+static NodesOut nodes_view(Handle* h);
+
 int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const double* hod_dev,
                            int32_t* status_dev, void* stream) {
     Handle* h = (Handle*)handle;
@@ -322,10 +331,7 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
         CK(cudaMemcpyAsync(h->halo, halo_dev, sizeof(double) * B * CHOMP_N_HALO, cudaMemcpyDeviceToDevice, s));
     if (hod_dev != h->hod)
         CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
-    NodesOut no;
-    no.nodes = h->nodes; no.n_nodes = h->n_nodes; no.nbar = h->nbar; no.rv_max = h->rv_max;
-    for (int k = 0; k < N_KCLASS; ++k) { no.cap[k] = h->node_cap[k]; no.off[k] = h->node_off[k]; }
-    no.cap_total = h->node_cap_total;
+    NodesOut no = nodes_view(h);
     mark(h, CHOMP_K_NODES, s);
     nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
                                                   h->c_lnm_nu, h->c_nu_lnm, no, status_dev);
@@ -584,6 +590,62 @@ int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_de
     return 0;
 }
 
+static NodesOut nodes_view(Handle* h) {
+    NodesOut no;
+    no.nodes = h->nodes; no.n_nodes = h->n_nodes; no.nbar = h->nbar; no.rv_max = h->rv_max; no.tri_w = h->tri_w;
+    for (int k = 0; k < N_NODE_LISTS; ++k) { no.cap[k] = h->node_cap[k]; no.off[k] = h->node_off[k]; }
+    no.cap_total = h->node_cap_total;
+    return no;
+}
+
+int chomp_b200_trispectrum_1h(void* handle, int B, double* T_out_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    const Cfg& c = h->cfg;
+    if (c.tri_moment < 0) FAIL("the trispectrum node list is disabled: configure with tri_moment >= 0");
+    const int cap = h->node_cap[TRI_LIST];
+    if (B > h->tri_points) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaMalloc((void**)&h->tri_A, sizeof(double) * (size_t)B * c.n_halo * cap));
+        CK(cudaMalloc((void**)&h->tri_T, sizeof(double) * (size_t)B * c.n_halo * c.n_halo));
+        h->allocs.push_back(h->tri_A);
+        h->allocs.push_back(h->tri_T);
+        h->tri_points = B;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    NodesOut no = nodes_view(h);
+    dim3 g1((c.n_halo + 7) / 8, B);
+    tri_profile_kernel<<<g1, 256, 0, s>>>(c, B, no, h->tri_A);
+    CK(cudaGetLastError());
+    const int nt = (c.n_halo + 63) / 64;
+    dim3 g2(nt * (nt + 1) / 2, B);
+    tri_gram_kernel<<<g2, 256, 0, s>>>(c, B, cap, h->tri_A, h->tri_w, h->tri_T);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    if (T_out_dev)
+        CK(cudaMemcpyAsync(T_out_dev, h->tri_T, sizeof(double) * (size_t)B * c.n_halo * c.n_halo, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int chomp_b200_trispectrum_eval(void* handle, int point, int n, const double* k1_dev, const double* k2_dev,
+                                double* out_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (!h || !h->configured || !h->tri_T) FAIL("run chomp_b200_trispectrum_1h first");
+    if (point < 0 || point >= h->tri_points) FAIL("point index out of range");
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const Cfg& c = h->cfg;
+    double* scratch = nullptr;
+    CK(cudaMalloc((void**)&scratch, sizeof(double) * (size_t)n * 9 * c.n_halo));
+    tri_eval_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(c, n, k1_dev, k2_dev,
+                                                                    h->tri_T + (size_t)point * c.n_halo * c.n_halo, scratch, out_dev);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    CK(cudaFree(scratch));
+    return 0;
+}
+
 int chomp_b200_set_params(void* handle, int B, const double* cosmo_dev, const double* halo_dev,
                           const double* hod_dev, void* stream) {
     Handle* h = (Handle*)handle;
@@ -641,18 +703,18 @@ int chomp_b200_copy_table(void* handle, int B, int table, double* out_dev, int* 
         case CHOMP_T_NBAR: src = h->nbar; len = 1; break;
         case CHOMP_T_KERNEL_CHI: src = h->kchi; len = 2; break;
         case CHOMP_T_DNDZ_NORM: src = h->dndz_norm; len = 2; break;
-        case CHOMP_T_NU_QUAD_COUNT: len = N_KCLASS; break;
+        case CHOMP_T_NU_QUAD_COUNT: len = N_NODE_LISTS; break;
         default: FAIL("unknown table id");
     }
     if (len_out) *len_out = len;
     if (!out_dev) return 0;
     if (table == CHOMP_T_NU_QUAD_COUNT) {
-        std::vector<int32_t> tmp((size_t)B * N_KCLASS);
-        CK(cudaMemcpyAsync(tmp.data(), h->n_nodes, sizeof(int32_t) * B * N_KCLASS, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        std::vector<int32_t> tmp((size_t)B * N_NODE_LISTS);
+        CK(cudaMemcpyAsync(tmp.data(), h->n_nodes, sizeof(int32_t) * B * N_NODE_LISTS, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
         CK(cudaStreamSynchronize((cudaStream_t)stream));
-        std::vector<double> d((size_t)B * N_KCLASS);
+        std::vector<double> d((size_t)B * N_NODE_LISTS);
         for (size_t i = 0; i < d.size(); ++i) d[i] = (double)tmp[i];
-        CK(cudaMemcpyAsync(out_dev, d.data(), sizeof(double) * B * N_KCLASS, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        CK(cudaMemcpyAsync(out_dev, d.data(), sizeof(double) * B * N_NODE_LISTS, cudaMemcpyHostToDevice, (cudaStream_t)stream));
         CK(cudaStreamSynchronize((cudaStream_t)stream));
         return 0;
     }

@@ -35,8 +35,13 @@ enum { NF_CP = 0, NF_RS, NF_LNCP, NF_W_HM, NF_W_PMM, NF_W_HG, NF_W_GM, NF_W_GG }
 #define N_KCLASS 3
 #define KCLASS_PHI_1 45.0
 #define KCLASS_PHI_2 180.0
-__device__ __constant__ int k_class_base[N_KCLASS] = {4, 8, 16};
-__device__ __constant__ int k_class_sharp[N_KCLASS] = {10, 10, 16};
+// A fourth node list serves the 1-halo trispectrum only (built when cfg.tri_moment >= 0): its
+// M^3 weighting moves the integrand to high masses, where y(k, M) oscillates fastest, so every
+// panel is cut in two halves of order 16 ("32").
+#define N_NODE_LISTS 4
+#define TRI_LIST 3
+__device__ __constant__ int k_class_base[N_NODE_LISTS] = {4, 8, 16, 32};
+__device__ __constant__ int k_class_sharp[N_NODE_LISTS] = {10, 10, 16, 32};
 #define KCLASS_MAX_ORDER 16
 #define SING_MIN_ORDER 8
 #define SUMS_K_PER_CTA 32
@@ -151,16 +156,18 @@ __device__ inline double lnnu_moment_crossing(const NuTab& t, const HodP& h, int
 
 struct NodesOut {
     double* nodes;     // [B, cap_total * NODE_FIELDS]; class c occupies [off_c*NF, (off_c+cap_c)*NF), fields SoA
-    int32_t* n_nodes;  // [B, N_KCLASS]
+    int32_t* n_nodes;  // [B, N_NODE_LISTS]
     double* nbar;      // [B] n_bar / rho_bar
     double* rv_max;    // [B] r_vir at the upper end of the mass table (sets the k classes)
-    int cap[N_KCLASS];
-    int off[N_KCLASS];
+    double* tri_w;     // [B, cap of the last class] weights of the 1-halo trispectrum integral (0-padded)
+    int cap[N_NODE_LISTS];
+    int off[N_NODE_LISTS];
     int cap_total;
 };
 
-__host__ __device__ inline int kclass_cap(int c, int n_mass) {
-    const int base[N_KCLASS] = {4, 8, 16}, sharp[N_KCLASS] = {10, 10, 16};
+__host__ __device__ inline int kclass_cap(int c, int n_mass, bool with_trispectrum) {
+    const int base[N_NODE_LISTS] = {4, 8, 16, 32}, sharp[N_NODE_LISTS] = {10, 10, 16, 32};
+    if (c == TRI_LIST && !with_trispectrum) return 32;
     int m = base[c] > sharp[c] ? base[c] : sharp[c];
     if (m < SING_MIN_ORDER) m = SING_MIN_ORDER;
     return (((n_mass - 1 + MAX_EXTRA_BREAKS) * m + 31) / 32) * 32;
@@ -186,8 +193,8 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     double* edge = c2 + 4 * n;                 // max_edge
     double* extra = edge + max_edge;           // MAX_EXTRA_BREAKS
     double* red = extra + MAX_EXTRA_BREAKS;    // 64
-    int* pstart = (int*)(red + 64);            // [N_KCLASS][max_edge] first node of each panel
-    int* pknot = pstart + N_KCLASS * max_edge; // [max_edge] knot interval of the ln M(nu) spline holding the panel
+    int* pstart = (int*)(red + 64);            // [N_NODE_LISTS][max_edge] first node of each panel
+    int* pknot = pstart + N_NODE_LISTS * max_edge; // [max_edge] knot interval of the ln M(nu) spline holding the panel
     __shared__ int n_edge;
     __shared__ double x_singular;
     for (int i = tid; i < n; i += blockDim.x) { lnm[i] = g_lnm[(size_t)b * n + i]; nu[i] = g_nu[(size_t)b * n + i]; }
@@ -264,7 +271,7 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
             const double lm_hi = spline_poly(c1, kn, exp(edge[p + 1]) - nu[kn]);
             const bool sharp = (h.kind == CHOMP_HOD_ZHENG) && h.sigma > 0.0 && lm_hi > sharp_lo && lm_lo < sharp_hi;
             const bool sing = edge[p] >= x_singular - 1e-12 && edge[p] <= x_singular + 0.02;
-            for (int c = 0; c < N_KCLASS; ++c) {
+            for (int c = 0; c < N_NODE_LISTS; ++c) {
                 int o = sharp ? k_class_sharp[c] : k_class_base[c];
                 if (sing && o < SING_MIN_ORDER) o = SING_MIN_ORDER;
                 pstart[c * max_edge + p] = o;
@@ -272,7 +279,7 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
         }
     }
     __syncthreads();
-    if (tid < N_KCLASS) {        // exclusive prefix sums, one class per thread
+    if (tid < N_NODE_LISTS) {    // exclusive prefix sums, one list per thread
         int acc = 0;
         int* ps = pstart + tid * max_edge;
         for (int p = 0; p < n_edge - 1; ++p) { const int o = ps[p]; ps[p] = acc; acc += o; }
@@ -289,7 +296,8 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     const double rv_coef = 3.0 / (4.0 * M_PI * delta_v * rho_bar);
     double nbar = 0.0;
     int st = 0;
-    for (int c = 0; c < N_KCLASS; ++c) {
+    const int n_lists = cfg.tri_moment >= 0 ? N_NODE_LISTS : N_KCLASS;
+    for (int c = 0; c < n_lists; ++c) {
         const int* ps = pstart + c * max_edge;
         const int total = ps[n_pan];
         const int cap = out.cap[c];
@@ -299,10 +307,17 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
         for (int idx = tid; idx < total && idx < cap; idx += blockDim.x) {
             int p = 0, hi = n_pan;          // panel with ps[p] <= idx < ps[p+1]
             while (hi - p > 1) { const int mid = (p + hi) >> 1; if (ps[mid] <= idx) p = mid; else hi = mid; }
-            const int nq = ps[p + 1] - ps[p], q = idx - ps[p];
-            const double a = edge[p], bb = edge[p + 1];
+            int nq = ps[p + 1] - ps[p], q = idx - ps[p];
+            double a = edge[p], bb = edge[p + 1];
+            const double xmid = 0.5 * (a + bb);
+            const bool sing_panel = a >= x_singular - 1e-12 && a <= x_singular + 0.02;
+            if (nq == 32) {          // two halves of order 16 (trispectrum list)
+                const double mid2 = 0.5 * (a + bb);
+                if (q < 16) bb = mid2; else { a = mid2; q -= 16; }
+                nq = 16;
+            }
             double x, wq;
-            if (a >= x_singular - 1e-12 && a <= x_singular + 0.02) {
+            if (sing_panel && a == edge[p]) {
                 // x = a + (b - a) t^4 removes the (M - M0)^alpha end-point behaviour (hod.py:226-230);
                 // also applied when the panel starts just above M0 (lower limit from the forward spline)
                 const double tt = 0.5 * (c_glx[nq][q] + 1.0);
@@ -314,7 +329,6 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
                 x = 0.5 * (a + bb) + half * c_glx[nq][q];
                 wq = half * c_glw[nq][q];
             }
-            const double xmid = 0.5 * (a + bb);
             const double v = exp(x);
             const int kn = pknot[p];
             const double lm = spline_poly(c1, kn, v - nu[kn]);      // MassFunction.ln_mass, mass_function.py:326
@@ -342,8 +356,23 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
             const double wgg = in2 * wt * n2 / M;                                           // halo.py:1032-1041
             rec[NF_W_GG * cap + idx] = (n2 < 1.0) ? -wgg * imk : wgg * imk * imk;
             if (c == N_KCLASS - 1) nbar += in1 * wt * n1 / M;                               // halo.py:704-707
+            if (c == TRI_LIST) {
+                // d ln(nu) nu f(nu) M^3 <moment> / rho_bar^3 (halo_trispectrum.py:131-151); full nu range
+                double mom = 1.0;
+                if (cfg.tri_moment == 1) mom = n1;
+                else if (cfg.tri_moment == 2) mom = n2;
+                else if (cfg.tri_moment >= 3) {
+                    const double a2 = (n1 != 0.0) ? n2 / (n1 * n1) : 0.0;       // HOD.nth_moment, hod.py:68-92
+                    mom = pow(n1, (double)cfg.tri_moment);
+                    for (int jm = 0; jm < cfg.tri_moment; ++jm) mom *= (jm * a2 - jm + 1);
+                }
+                const double mr = M / rho_bar;
+                out.tri_w[(size_t)b * cap + idx] = wt * mr * mr * mr * mom;
+            }
         }
-        if (tid == 0) out.n_nodes[(size_t)b * N_KCLASS + c] = total < cap ? total : cap;
+        if (c == TRI_LIST)
+            for (int idx = total + tid; idx < cap; idx += blockDim.x) out.tri_w[(size_t)b * cap + idx] = 0.0;
+        if (tid == 0) out.n_nodes[(size_t)b * N_NODE_LISTS + c] = total < cap ? total : cap;
     }
     nbar = block_sum(nbar, red);
     if (tid == 0) {
@@ -403,7 +432,7 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ raw /* 
     if (cls < 0) return;
     sici_tables_load(&tabs);
     const int cap = nd.cap[cls];
-    const int nn = nd.n_nodes[(size_t)b * N_KCLASS + cls];
+    const int nn = nd.n_nodes[(size_t)b * N_NODE_LISTS + cls];
     const double* __restrict__ g = nd.nodes + ((size_t)b * nd.cap_total + nd.off[cls]) * NODE_FIELDS;
     // stage: field f of node i at srec[f * nn_pad + i]
     const int nn_pad = (nn + 31) & ~31;

@@ -133,6 +133,7 @@ class Survey(object):
         c.ktheta_min, c.ktheta_max = self.ktheta
         c.bessel_limit = bessel_limit(self.bessel_order, p["kernel_bessel_limit"])
         c.corr_k_min = c.corr_k_max = -1.0
+        c.tri_moment = -1          # >= 0 also builds the 1-halo trispectrum's node list
         return c
 
 
@@ -267,6 +268,20 @@ class Engine(object):
             theta.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p),
             status.ctypes.data_as(ctypes.c_void_p)))
         return w, status
+
+    def trispectrum_1h(self, B):
+        """[B, n_halo, n_halo] table of the 1-halo trispectrum (after mass_tables + halo_tables)."""
+        out = self._new(B, self.cfg.n_halo, self.cfg.n_halo)
+        _lib.check(self.lib.chomp_b200_trispectrum_1h(self._h, int(B), self._p(out), self._stream()))
+        return out
+
+    def trispectrum_eval(self, k1, k2, point=0):
+        k1 = self._dev(np.atleast_1d(np.asarray(k1, dtype=np.float64))).reshape(-1)
+        k2 = self._dev(np.atleast_1d(np.asarray(k2, dtype=np.float64))).reshape(-1)
+        out = self._new(k1.numel())
+        _lib.check(self.lib.chomp_b200_trispectrum_eval(self._h, int(point), k1.numel(), self._p(k1), self._p(k2),
+                                                        self._p(out), self._stream()))
+        return out
 
     def set_params(self, cosmo=None, halo=None, hod=None):
         arrs = [None if a is None else self._dev(a, n) for a, n in

@@ -61,7 +61,8 @@ class Halo(object):
         if not self._dirty:
             return
         cfg = _facade.base_config(hod_kind=self.local_hod._kind, exclusion=self._exclusion,
-                                  extrapolate=int(bool(self._extrapolate)))
+                                  extrapolate=int(bool(self._extrapolate)),
+                                  tri_moment=int(getattr(self, "_tri_moment", -1)))
         cfg.halo_precision = getattr(self.local_hod, "_halo_precision", cfg.halo_precision)
         # first_moment_zero was fixed when the HOD object was built (hod.py:176-179)
         self._gpu.configure(cfg)

@@ -66,7 +66,9 @@ typedef struct chomp_b200_config {
     int32_t extrapolate;      /* Halo(extrapolate=...) (halo.py:42)                      */
     int32_t window_kind[2];   /* CHOMP_WINDOW_* for window a, b                          */
     int32_t dndz_kind[2];     /* CHOMP_DNDZ_*                                            */
-    int32_t reserved_i[3];
+    int32_t tri_moment;       /* HaloTrispectrumOneHalo power_spec: 0 mmmm, 1 gmmm, 2 ggmm, 3 gggm, 4 gggg;
+                                 -1: no trispectrum (its node list is then not built)              */
+    int32_t reserved_i[2];
     double halo_precision;    /* enters HODZheng.first_moment_zero (hod.py:176-179)      */
     double cosmo_precision;   /* flat/open/closed test (cosmology.py:65-79)              */
     double window_precision;  /* z / chi floor of the windows (kernel.py:236, 301, 612)  */
@@ -146,6 +148,17 @@ enum { CHOMP_EVAL_LINEAR_POWER = 0, CHOMP_EVAL_SIGMA_R, CHOMP_EVAL_NU_OF_MASS, C
        CHOMP_EVAL_DNDZ_A, CHOMP_EVAL_DNDZ_B /* dNdz.dndz (aux != 0: raw_dndz), kernel.py:56-86 */ };
 int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_dev, double aux, double* out_dev,
                     void* stream);
+
+/* HaloTrispectrumOneHalo._initialize_i_0_4 (halo_trispectrum.py:58-140): the 1-halo trispectrum
+ * I^0_4(k_i, k_i, k_j, k_j) on the n_halo x n_halo grid of ln k nodes, T_out_dev [B, n_halo, n_halo].
+ * Needs stages 2 and 3 (chomp_b200_mass_tables, chomp_b200_halo_tables) of the same batch.
+ * The (k x nu)(nu x k) contraction runs on the FP64 tensor-core path (DMMA m8n8k4). */
+int chomp_b200_trispectrum_1h(void* handle, int B, double* T_out_dev, void* stream);
+/* HaloTrispectrumOneHalo.trispectrum_parallelogram (halo_trispectrum.py:53-57, 100-107) for
+ * point `point` of the last chomp_b200_trispectrum_1h: bicubic not-a-knot interpolation of the
+ * table (RectBivariateSpline kx = ky = 3, s = 0), k clamped below k_min, 0 above k_max. */
+int chomp_b200_trispectrum_eval(void* handle, int point, int n, const double* k1_dev, const double* k2_dev,
+                                double* out_dev, void* stream);
 
 /* Store parameter rows in the handle without running a stage (NULL = leave as is): lets the
  * HOD / cosmology closed forms be evaluated through chomp_b200_eval on their own. */

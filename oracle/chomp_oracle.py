@@ -981,3 +981,60 @@ class Correlation(object):
     def compute_correlation(self):                        # correlation.py:234
         self.wtheta = self.correlation(self.theta)
         return self.wtheta
+
+
+# ----------------------------------------------------------------------------
+# halo_trispectrum.HaloTrispectrumOneHalo  (halo_trispectrum.py:13-151)
+# ----------------------------------------------------------------------------
+TRISPECTRUM_MOMENT = {"power_mmmm": 0, "power_gmmm": 1, "power_ggmm": 2, "power_gggm": 3, "power_gggg": 4}
+
+
+class HaloTrispectrumOneHalo(Halo):
+    """I^0_4(k1, k1, k2, k2) = rho_bar^-3 int dln nu  nu f(nu) M^3 y(k1)^2 y(k2)^2 <moment>(M)
+    on the n_k x n_k grid of ln k nodes.  The reference always integrates over the full
+    [nu_min, nu_max] (the HOD-limited nu_min it computes is not used, Q18)."""
+
+    def __init__(self, epoch, mass, hod, halo=None, power_spec="power_mmmm", **kw):
+        Halo.__init__(self, epoch, mass, hod, halo, **kw)
+        self.power_spec = power_spec
+
+    def _moment(self, M):                                 # halo_trispectrum.py:141-151
+        n = TRISPECTRUM_MOMENT.get(self.power_spec, 0)
+        if n == 0:
+            return np.ones(np.shape(M))
+        return self.hod.nth_moment(M, n)
+
+    def _i04_integrand(self, ln_nu, ln_k1, ln_k2):        # halo_trispectrum.py:131-140
+        nu = np.exp(ln_nu)
+        M = self.mass.mass(nu)
+        y1, y2 = self.y(ln_k1, M), self.y(ln_k2, M)
+        return nu*self.mass.f_nu(nu)*y1*y1*y2*y2*M*M*M*self._moment(M)
+
+    def i_0_4(self, ln_k1, ln_k2):                        # halo_trispectrum.py:58-98
+        lo, hi = np.log(self.mass.nu_min), np.log(self.mass.nu_max)
+        br, sg = self._panel_hints(lo, hi)
+        if TRISPECTRUM_MOMENT.get(self.power_spec, 0) == 0:
+            sg = ()
+        return self.integ(self._i04_integrand, lo, hi, self.prec["halo_precision"], breaks=br,
+                          singular=sg, args=(ln_k1, ln_k2))/self.rho_bar**3
+
+    def table_i04(self):                                  # halo_trispectrum.py:108-129
+        n = self.ln_k_nodes.size
+        T = np.empty((n, n))
+        for i in range(n):
+            for j in range(i, n):
+                T[i, j] = T[j, i] = self.i_0_4(self.ln_k_nodes[i], self.ln_k_nodes[j])
+        self._i04 = T
+        return T
+
+    def trispectrum_parallelogram(self, k1, k2):          # halo_trispectrum.py:53-57, 100-107
+        from scipy.interpolate import RectBivariateSpline
+        if not hasattr(self, "_i04"):
+            self.table_i04()
+        sp = RectBivariateSpline(self.ln_k_nodes, self.ln_k_nodes, self._i04, kx=3, ky=3, s=0)
+        k1 = np.atleast_1d(np.asarray(k1, dtype=float))
+        k2 = np.atleast_1d(np.asarray(k2, dtype=float))
+        a = np.where(k1 < self.k_min, self.k_min, k1)
+        b = np.where(k2 < self.k_min, self.k_min, k2)
+        val = sp(np.log(a), np.log(b), grid=False)
+        return np.where((a <= self.k_max) & (b <= self.k_max), val, 0.0)

@@ -96,6 +96,19 @@ def main():
                                  kernel.WindowFunctionGalaxy, kernel.WindowFunctionConvergence, kernel.Kernel,
                                  hod.HODZheng(HOD_DICT), "power_gm", 5.0),
     }
+    # ---- 1-halo trispectrum (config 5's table; halo_trispectrum.py:58-140) ------------------------
+    tri_mod = R["halo_trispectrum"]
+    out["trispectrum"] = {}
+    kq1 = np.array([1e-4, 0.01, 0.5, 3.0, 30.0, 200.0])
+    kq2 = np.array([0.02, 0.02, 7.0, 50.0, 30.0, 1.0])
+    for spec, gd in (("power_mmmm", HOD_DICT), ("power_ggmm", HOD_DICT)):
+        cs = cosmology.SingleEpoch(0.0, cosmo_dict=C_DICT)
+        mf = mass_function.MassFunction(0.0, cs, H_DICT)
+        tri = tri_mod.HaloTrispectrumOneHalo(0.0, cs, mf, None, H_DICT, hod.HODZheng(gd), spec)
+        tri._initialize_i_0_4()
+        out["trispectrum"][spec] = {
+            "table": arr(tri._i_0_4_array), "k1": arr(kq1), "k2": arr(kq2),
+            "parallelogram": [float(tri.trispectrum_parallelogram(a, b)) for a, b in zip(kq1, kq2)]}
     path = os.path.join(HERE, "reference_outputs.json")
     with open(path, "w") as f:
         json.dump(out, f)

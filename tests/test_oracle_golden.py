@@ -211,3 +211,21 @@ def test_tight_strategy_is_within_reference_quadrature_error():
     assert rel_err(h.table("pp_mm")[0], gh["pp_mm"]) < 5e-5
     assert rel_err(h.table("pp_gm")[0], gh["pp_gm"]) < 2e-3
     assert rel_err(h.mass.nu_nodes, gh["nu_nodes"]) < 1e-6
+
+
+# ---------------------------------------------------------------- 1-halo trispectrum
+@pytest.mark.parametrize("spec", ["power_mmmm", "power_ggmm"])
+def test_trispectrum_matches_reference_run(spec):
+    g = GOLD["trispectrum"][spec]
+    prec = O.precision()
+    se = O.SingleEpoch(0.0, C_DICT, prec, Romberg())
+    tri = O.HaloTrispectrumOneHalo(se, O.MassFunction(se, H_DICT), O.HODZheng(HOD_DICT), H_DICT, power_spec=spec)
+    n = tri.ln_k_nodes.size
+    ref = np.array(g["table"]).reshape(n, n)
+    # a sample of rows keeps the CPU suite short; every entry is an independent integral
+    for i in (0, 7, 23, 38, 49):
+        row = np.array([tri.i_0_4(tri.ln_k_nodes[i], x) for x in tri.ln_k_nodes])
+        assert rel_err(row, ref[i]) < 1e-11
+    tri._i04 = ref
+    got = tri.trispectrum_parallelogram(np.array(g["k1"]), np.array(g["k2"]))
+    assert np.allclose(got, g["parallelogram"], rtol=1e-12, atol=0)
