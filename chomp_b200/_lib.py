@@ -32,6 +32,8 @@ ST_NONFINITE, ST_MASS_WALK, ST_NODE_OVERFLOW, ST_DOMAIN = 1, 2, 4, 8
 (T_ZBAR, T_DBAR, T_KERNEL_NODES, T_CHI_NODES, T_WINDOW_NODES, T_WINDOW_CHI,
  T_EPOCH, T_LNM_NODES, T_NU_NODES, T_HALO_NODES, T_NBAR, T_NU_QUAD_COUNT, T_KERNEL_CHI,
  T_DNDZ_NORM) = range(14)
+HALOFIT_FIELDS = ("k_s", "n_eff", "C", "a_n", "b_n", "c_n", "gamma_n", "alpha_n", "beta_n", "mu_n", "nu_n",
+                  "f_1", "f_2", "f_3", "omega_l", "fit_z")
 KERNEL_NAMES = ("limber_tables_kernel", "mass_tables_kernel", "nu_nodes_kernel",
                 "halo_sums_kernel", "halo_splines_kernel", "wtheta_kernel")
 EPOCH_FIELDS = ("z", "growth", "sigma_norm", "delta_c", "delta_v", "rho_bar",
@@ -51,7 +53,7 @@ class Config(ctypes.Structure):
         ("hod_kind", ctypes.c_int32), ("bessel_order", ctypes.c_int32),
         ("exclusion", ctypes.c_int32), ("extrapolate", ctypes.c_int32),
         ("window_kind", ctypes.c_int32*2), ("dndz_kind", ctypes.c_int32*2),
-        ("tri_moment", ctypes.c_int32), ("reserved_i", ctypes.c_int32*2),
+        ("tri_moment", ctypes.c_int32), ("use_halofit", ctypes.c_int32), ("reserved_i", ctypes.c_int32*1),
         ("halo_precision", ctypes.c_double), ("cosmo_precision", ctypes.c_double),
         ("window_precision", ctypes.c_double),
         ("k_min", ctypes.c_double), ("k_max", ctypes.c_double),
@@ -102,6 +104,10 @@ _SIGNATURES = {
     "chomp_b200_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+    "chomp_b200_halofit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "chomp_b200_cl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p]),
     "chomp_b200_trispectrum_1h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "chomp_b200_trispectrum_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

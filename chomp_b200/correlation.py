@@ -82,22 +82,64 @@ class Correlation(object):
         """correlation.py:242-268.  The halo object holds its tables on its own handle, so the
         Limber stage is replayed there (same configuration as the kernel object) before the
         Hankel stage."""
+        gpu = self._stage_on_halo_handle()                      # also covers Correlation.set_redshift
+        w = gpu.eng.wtheta_stage(1, _lib.POWER_SPEC[self._power_name], _facade.flat(theta_rad))
+        return _facade.like_input(theta_rad, w.cpu().numpy()[0])
+
+    def _stage_on_halo_handle(self):
+        """Replay the Limber stage on the handle that holds the halo's tables and pin z_bar."""
         h = self.halo
         h._ensure()
         cfg = self.kernel._config()
         hc = h._gpu.eng.cfg
-        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision"):
+        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "tri_moment"):
             setattr(cfg, name, getattr(hc, name))
         gpu = h._gpu
         gpu.configure(cfg)
         gpu.eng.limber_tables(_facade.cosmo_row(self.kernel.cosmo.get_cosmology()))
         gpu.eng.set_params(cosmo=_facade.cosmo_row(h.cosmo.cosmo_dict))
-        gpu.eng.set_zbar([self.kernel.z_bar])                   # also covers Correlation.set_redshift
-        w = gpu.eng.wtheta_stage(1, _lib.POWER_SPEC[self._power_name], _facade.flat(theta_rad))
-        return _facade.like_input(theta_rad, w.cpu().numpy()[0])
+        gpu.eng.set_zbar([self.kernel.z_bar])
+        return gpu
 
     def write(self, output_file_name):
         with open(output_file_name, "w") as f:
             f.write("#ttype1 = theta [deg]\n#ttype2 = wtheta\n")
             for theta, w in zip(self.theta_array, self.wtheta_array):
                 f.write("%1.10g %1.10g\n" % (theta/deg_to_rad, w))
+
+
+class CorrelationFourier(Correlation):
+    """C(l) = int dchi P(l/chi)/D(z_bar)^2 W_a W_b D^2 / chi^2 (correlation.py:297-405).
+    On the GPU path for the smooth spectra: ``linear_power`` and HaloFit ``power_mm``."""
+
+    def __init__(self, l_min, l_max, input_kernel, input_halo=None, powSpec=None, **kws):
+        from . import defaults
+        self.log_l_min = np.log10(l_min)
+        self.log_l_max = np.log10(l_max)
+        self.l_array = np.logspace(self.log_l_min, self.log_l_max, defaults.default_precision["corr_npoints"])
+        if l_min == l_max:
+            self.l_array = np.array([l_min])
+        self.power_array = np.zeros(self.l_array.size, dtype="float64")
+        self.kernel = input_kernel
+        self.D_z = float(self.kernel.cosmo.growth_factor(self.kernel.z_bar))
+        if input_halo is None:
+            input_halo = halo_module.Halo(self.kernel.z_bar)
+        self.halo = input_halo
+        self.halo.set_redshift(self.kernel.z_bar)               # correlation.py:342
+        if powSpec is None:
+            powSpec = "linear_power"
+        self.set_power_spectrum(powSpec)
+
+    def compute_correlation(self):
+        self.power_array = np.array(self.correlation(self.l_array), dtype=float)
+
+    def correlation(self, l):
+        gpu = self._stage_on_halo_handle()
+        out = gpu.eng.cl(1, _lib.POWER_SPEC[self._power_name], _facade.flat(l))
+        return _facade.like_input(l, out.cpu().numpy()[0])
+
+    def write(self, output_file_name):
+        with open(output_file_name, "w") as f:
+            f.write("#ttype1 = l [deg]\n#ttype2 = power\n")
+            for l, power in zip(self.l_array, self.power_array):
+                f.write("%1.10f %1.10f\n" % (l, power))

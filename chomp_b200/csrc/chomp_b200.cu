@@ -13,6 +13,7 @@
 #include "../../include/chomp_b200.h"
 #include "common.cuh"
 #include "halo_tables.cuh"
+#include "halofit.cuh"
 #include "hankel.cuh"
 #include "limber_tables.cuh"
 #include "mass_tables.cuh"
@@ -54,7 +55,10 @@ struct Handle {
     // device scratch (all FP64 unless noted)
     double *zbar = nullptr, *dbar = nullptr, *knodes = nullptr, *kcoef = nullptr, *chi_nodes = nullptr,
            *win_nodes = nullptr, *win_chi = nullptr, *win_coef = nullptr, *kchi = nullptr, *grid0 = nullptr,
-           *dndz_norm = nullptr;
+           *dndz_norm = nullptr, *edges = nullptr, *hfit = nullptr, *hf_ls2 = nullptr;
+    int32_t* n_edges = nullptr;
+    int edge_stride = 0;
+    bool halofit_ready = false;
     double *epoch = nullptr, *lnm_nodes = nullptr, *nu_nodes = nullptr, *c_lnm_nu = nullptr, *c_nu_lnm = nullptr;
     double *tri_w = nullptr, *tri_A = nullptr, *tri_T = nullptr;   // 1-halo trispectrum (tri_A / tri_T allocated on first use)
     int tri_points = 0;
@@ -253,6 +257,11 @@ int chomp_b200_reserve(void* handle, int max_points) {
     rc |= dev_alloc(h, &h->kchi, B * 2);
     rc |= dev_alloc(h, &h->grid0, B * 13 * c.n_cosmo);
     rc |= dev_alloc(h, &h->dndz_norm, B * 2);
+    h->edge_stride = 2 * c.n_window + c.n_cosmo + 4;
+    rc |= dev_alloc(h, &h->edges, B * h->edge_stride);
+    rc |= dev_alloc(h, &h->n_edges, B);
+    rc |= dev_alloc(h, &h->hfit, B * HF_LEN);
+    rc |= dev_alloc(h, &h->hf_ls2, B * c.n_halo);
     rc |= dev_alloc(h, &h->epoch, B * CHOMP_EPOCH_LEN);
     rc |= dev_alloc(h, &h->lnm_nodes, B * c.n_mass);
     rc |= dev_alloc(h, &h->nu_nodes, B * c.n_mass);
@@ -291,7 +300,7 @@ int chomp_b200_limber_tables(void* handle, int B, const double* cosmo_dev, int32
     if (cosmo_dev != h->cosmo)
         CK(cudaMemcpyAsync(h->cosmo, cosmo_dev, sizeof(double) * B * CHOMP_N_COSMO, cudaMemcpyDeviceToDevice, s));
     LimberOut out{h->zbar, h->dbar, h->knodes, h->kcoef, h->chi_nodes, h->win_nodes, h->win_chi, h->win_coef, h->kchi,
-                  h->grid0, h->dndz_norm};
+                  h->grid0, h->dndz_norm, h->edges, h->n_edges};
     const size_t smem = limber_smem_doubles(h->cfg) * sizeof(double);
     mark(h, CHOMP_K_LIMBER, s);
     limber_tables_kernel<<<B, LIMBER_THREADS, smem, s>>>(h->cfg, B, h->same_window, h->cosmo, out, status_dev);
@@ -356,7 +365,7 @@ int chomp_b200_power(void* handle, int B, int which, int n_k, const double* k_de
     if (n_k <= 0) FAIL("n_k must be positive");
     dim3 grid((n_k + 255) / 256, B);
     power_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->cfg, B, which, n_k, k_dev, h->cosmo, h->epoch, h->htab,
-                                                        h->hcoef, P_out_dev);
+                                                        h->hcoef, h->cfg.use_halofit ? h->hfit : nullptr, P_out_dev);
     h->launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -371,7 +380,7 @@ int chomp_b200_wtheta(void* handle, int B, int which, int n_theta, const double*
     mark(h, CHOMP_K_WTHETA, (cudaStream_t)stream);
     wtheta_kernel<<<B, 256, wtheta_smem(h->cfg), (cudaStream_t)stream>>>(
         h->cfg, B, which, n_theta, theta_dev, h->cosmo, h->epoch, h->dbar, h->htab, h->hcoef, h->knodes, h->kcoef,
-        w_out_dev, status_dev);
+        h->cfg.use_halofit ? h->hfit : nullptr, w_out_dev, status_dev);
     mark(h, CHOMP_K_WTHETA + 1, (cudaStream_t)stream);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -585,6 +594,36 @@ int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_de
     int blocks = (what == CHOMP_EVAL_SIGMA_R) ? (n + 3) / 4 : (n + 127) / 128;
     if (blocks > 1184) blocks = 1184;
     eval_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(c, what, n, x_dev, aux, cx, out_dev);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int chomp_b200_halofit(void* handle, int B, double fit_z, double* params_out_dev, int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    const Cfg& c = h->cfg;
+    const size_t smem = (2 * HF_PANELS * HF_NQ + 8 * (size_t)c.n_halo + 11 * (size_t)c.n_halo + 16) * sizeof(double);
+    CK(cudaFuncSetAttribute(halofit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    halofit_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(c, B, fit_z, h->cosmo, h->epoch, h->hfit, h->hf_ls2, status_dev);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    if (params_out_dev)
+        CK(cudaMemcpyAsync(params_out_dev, h->hfit, sizeof(double) * (size_t)B * HF_LEN, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+    return 0;
+}
+
+int chomp_b200_cl(void* handle, int B, int which, int n_ell, const double* ell_dev, double* cl_out_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    if (n_ell <= 0) FAIL("n_ell must be positive");
+    const bool hf = h->cfg.use_halofit != 0;
+    if (!(which == CHOMP_P_LINEAR || (hf && which == CHOMP_P_MM)))
+        FAIL("C(l) is implemented for linear_power and HaloFit power_mm (table-based spectra: next)");
+    cl_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(h->cfg, B, hf && which == CHOMP_P_MM, n_ell, ell_dev, h->cosmo, h->epoch,
+                                                   h->dbar, h->hfit, h->grid0, h->win_chi, h->win_coef, h->edges,
+                                                   h->n_edges, h->edge_stride, cl_out_dev);
     h->launches += 1;
     CK(cudaGetLastError());
     return 0;

@@ -11,6 +11,7 @@
 // contribute < 1e-7, so the nodes are shared by all theta.
 #pragma once
 #include "common.cuh"
+#include "halofit.cuh"
 #include "spline.cuh"
 
 namespace chomp {
@@ -22,6 +23,7 @@ struct HaloTabs {          // per-point views
     const double* tab;      // [5, nk] node values
     const double* coef;     // [5, 4 nk]
     int extrapolate;
+    const double* hf;       // HALOFIT parameters of the point, or nullptr (halo.py:1236)
 };
 
 __device__ __forceinline__ void which_tables(int which, int& a, int& b, int& pp) {
@@ -38,6 +40,20 @@ __device__ __forceinline__ double tab_at(const HaloTabs& T, int t, int i, double
 
 // Halo.power_xx(k) for any k (halo.py:277-439)
 __device__ inline double halo_power(const HaloTabs& T, const PkParams& pk, int which, double k) {
+    if (T.hf) {
+        // HaloFit: power_mm is the closed form; gm / gg are P_halofit h h + pp with the table
+        // wrappers returning 0 outside [k_min, k_max] (halo.py:1325-1412, 649-672)
+        if (which == CHOMP_P_LINEAR) return linear_power(pk, k);
+        const double pm = halofit_power(T.hf, pk, k);
+        if (which == CHOMP_P_MM) return pm;
+        if (!(k >= T.k_min && k <= T.k_max)) return 0.0;
+        int a, b, pp;
+        which_tables(which, a, b, pp);
+        const double x = log(k);
+        const int i = uniform_index(x, T.l0, 1.0 / T.h, T.nk);
+        const double dx = x - (T.l0 + T.h * i);
+        return pm * tab_at(T, a, i, dx) * tab_at(T, b, i, dx) + tab_at(T, pp, i, dx);
+    }
     const double pl = linear_power(pk, k);
     if (which == CHOMP_P_LINEAR) return pl;
     int a, b, pp;
@@ -89,7 +105,8 @@ __device__ __forceinline__ double kernel_eval(const KernelTab& K, double u) {
 __global__ void __launch_bounds__(256)
 power_kernel(const Cfg cfg, int B, int which, int n_k, const double* __restrict__ k_in,
              const double* __restrict__ cosmo, const double* __restrict__ epoch,
-             const double* __restrict__ htab, const double* __restrict__ hcoef, double* __restrict__ P_out) {
+             const double* __restrict__ htab, const double* __restrict__ hcoef, const double* __restrict__ hfit,
+             double* __restrict__ P_out) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B || i >= n_k) return;
@@ -100,6 +117,7 @@ power_kernel(const Cfg cfg, int B, int which, int n_k, const double* __restrict_
     T.nk = cfg.n_halo; T.l0 = log(cfg.k_min); T.l1 = log(cfg.k_max); T.h = (T.l1 - T.l0) / (T.nk - 1);
     T.k_min = cfg.k_min; T.k_max = cfg.k_max; T.extrapolate = cfg.extrapolate;
     T.tab = htab + (size_t)b * 5 * T.nk; T.coef = hcoef + (size_t)b * 20 * T.nk;
+    T.hf = hfit ? hfit + (size_t)b * HF_LEN : nullptr;
     P_out[(size_t)b * n_k + i] = halo_power(T, pk, which, k_in[i]);
 }
 
@@ -122,7 +140,7 @@ __global__ void __launch_bounds__(256)
 wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __restrict__ theta,
               const double* __restrict__ cosmo, const double* __restrict__ epoch, const double* __restrict__ dbar,
               const double* __restrict__ htab, const double* __restrict__ hcoef,
-              const double* __restrict__ knodes, const double* __restrict__ kcoef,
+              const double* __restrict__ knodes, const double* __restrict__ kcoef, const double* __restrict__ hfit,
               double* __restrict__ w_out, int32_t* __restrict__ status) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
@@ -130,6 +148,7 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
     const int nk = cfg.n_halo, nkt = cfg.n_kernel, nq = cfg.nq_hankel;
     const int sub = hankel_subdiv(cfg);
+    const double* hf = hfit ? hfit + (size_t)b * HF_LEN : nullptr;
     const int total = (nk - 1) * sub * nq;
     double* s_x = sm;                 // total
     double* s_g = s_x + total;        // total
@@ -158,8 +177,11 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
         const double k = exp(x);
         const double dx = x - a;
         double P = 2.0 * M_PI * M_PI * delta2(pk, k, x) / (k * k * k);
-        if (which != CHOMP_P_LINEAR)
-            P = P * spline_poly(ca, i, dx) * spline_poly(cb, i, dx) + spline_poly(cpp, i, dx);
+        if (which != CHOMP_P_LINEAR) {
+            if (hf) P = halofit_power(hf, pk, k);
+            if (!(hf && which == CHOMP_P_MM))
+                P = P * spline_poly(ca, i, dx) * spline_poly(cb, i, dx) + spline_poly(cpp, i, dx);
+        }
         s_x[idx] = x;
         s_g[idx] = half * c_glw[nq][q] * k * k * P * inv_norm;
     }

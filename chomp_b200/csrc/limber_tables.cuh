@@ -90,6 +90,8 @@ struct LimberOut {
     double *kchi;              // [B, 2]  kernel chi_min, chi_max
     double *grid0;             // [B, 13 n_cosmo]  chi nodes + chi(z), z(chi), D(z) coefficients of the kernel's MultiEpoch
     double *dndz_norm;         // [B, 2]
+    double *edges;             // [B, 2 n_window + n_cosmo + 4] base panel edges of the chi integrals
+    int32_t *n_edges;          // [B]
 };
 
 __host__ __device__ inline size_t limber_smem_doubles(const Cfg& cfg) {
@@ -418,6 +420,8 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
         out.grid0[(size_t)b * 13 * nz + idx] = src[off];
     }
     if (tid < 2) out.dndz_norm[2 * b + tid] = dist[tid].norm;
+    for (int idx = tid; idx < n_edge_s; idx += blockDim.x) out.edges[(size_t)b * nb_max + idx] = edge[idx];
+    if (tid == 0) out.n_edges[b] = n_edge_s;
     for (int idx = tid; idx < 2 * nw; idx += blockDim.x) out.win_nodes[(size_t)b * 2 * nw + idx] = win[idx / nw].wf[idx % nw];
     for (int idx = tid; idx < 2 * 4 * nw; idx += blockDim.x) {
         const int i = idx / (4 * nw), j = idx % (4 * nw);

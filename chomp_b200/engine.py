@@ -269,6 +269,20 @@ class Engine(object):
             status.ctypes.data_as(ctypes.c_void_p)))
         return w, status
 
+    def halofit(self, B, fit_z=-1.0, status=None):
+        """HALOFIT parameters [B, 16] for the epochs of the last mass_tables call."""
+        out = self._new(B, len(_lib.HALOFIT_FIELDS))
+        _lib.check(self.lib.chomp_b200_halofit(self._h, int(B), float(fit_z), self._p(out), self._p(status),
+                                               self._stream()))
+        return out
+
+    def cl(self, B, which, ell):
+        ell = self._dev(ell).reshape(-1)
+        out = self._new(B, ell.numel())
+        _lib.check(self.lib.chomp_b200_cl(self._h, int(B), int(which), ell.numel(), self._p(ell), self._p(out),
+                                          self._stream()))
+        return out
+
     def trispectrum_1h(self, B):
         """[B, n_halo, n_halo] table of the 1-halo trispectrum (after mass_tables + halo_tables)."""
         out = self._new(B, self.cfg.n_halo, self.cfg.n_halo)

@@ -16,6 +16,7 @@ from . import _facade, _lib, cosmology, defaults, hod as hod_module, mass_functi
 
 class Halo(object):
     _exclusion = 0
+    _halofit = False
 
     def __init__(self, redshift=0.0, input_hod=None, cosmo_single_epoch=None, mass_func=None,
                  halo_dict=None, extrapolate=False, **kws):
@@ -62,7 +63,8 @@ class Halo(object):
             return
         cfg = _facade.base_config(hod_kind=self.local_hod._kind, exclusion=self._exclusion,
                                   extrapolate=int(bool(self._extrapolate)),
-                                  tri_moment=int(getattr(self, "_tri_moment", -1)))
+                                  tri_moment=int(getattr(self, "_tri_moment", -1)),
+                                  use_halofit=int(self._halofit))
         cfg.halo_precision = getattr(self.local_hod, "_halo_precision", cfg.halo_precision)
         # first_moment_zero was fixed when the HOD object was built (hod.py:176-179)
         self._gpu.configure(cfg)
@@ -70,6 +72,10 @@ class Halo(object):
         hrow = _facade.halo_row(self.mass.halo_dict, self._profile)
         eng.mass_tables(_facade.cosmo_row(self.cosmo.cosmo_dict), hrow, [self._redshift])
         eng.halo_tables(hrow, _facade.hod_row(self.local_hod._kind, self.local_hod._params()))
+        if self._halofit:
+            fit = eng.halofit(1, fit_z=self._fit_redshift).cpu().numpy()[0]
+            for name, value in zip(_lib.HALOFIT_FIELDS, fit):
+                setattr(self, "_" + name, float(value))
         self.n_bar_over_rho_bar = float(self._gpu.table(_lib.T_NBAR)[0])
         self.n_bar = self.n_bar_over_rho_bar*self.rho_bar
         self._dirty = False
@@ -212,3 +218,21 @@ class HaloExclusion(Halo):
     def __init__(self, redshift=0.0, input_hod=None, cosmo_single_epoch=None, mass_func=None,
                  halo_dict=None, **kws):
         Halo.__init__(self, redshift, input_hod, cosmo_single_epoch, mass_func, halo_dict, **kws)
+
+
+class HaloFit(Halo):
+    """HALOFIT matter power spectrum (Smith et al. 2003, Takahashi et al. 2012 coefficients);
+    power_gm / power_gg are the halo-model tables on top of it (halo.py:1236-1412).
+
+    As in the reference, ``extrapolate`` is not forwarded (halo.py:1254-1259), power_mm has no
+    k-range guards, and Omega_m(z), Omega_L(z) inside f_1..f_3 are those of the *construction*
+    redshift (halo.py:1261-1266 runs once; Correlation* moving the halo to z_bar does not redo
+    it).  Deviation: after ``set_cosmology`` the reference keeps the construction cosmology in
+    f_1..f_3 as well; here they follow the new cosmology at the construction redshift."""
+    _halofit = True
+
+    def __init__(self, redshift=0.0, input_hod=None, cosmo_single_epoch=None, mass_func=None,
+                 halo_dict=None, **kws):
+        self._fit_redshift = float(redshift)
+        Halo.__init__(self, redshift, input_hod, cosmo_single_epoch, mass_func, halo_dict)
+        self._initialized_sigma_spline = False

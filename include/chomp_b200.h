@@ -68,7 +68,8 @@ typedef struct chomp_b200_config {
     int32_t dndz_kind[2];     /* CHOMP_DNDZ_*                                            */
     int32_t tri_moment;       /* HaloTrispectrumOneHalo power_spec: 0 mmmm, 1 gmmm, 2 ggmm, 3 gggm, 4 gggg;
                                  -1: no trispectrum (its node list is then not built)              */
-    int32_t reserved_i[2];
+    int32_t use_halofit;      /* 1: HaloFit two-halo spectrum (halo.py:1236-1412); run chomp_b200_halofit first */
+    int32_t reserved_i[1];
     double halo_precision;    /* enters HODZheng.first_moment_zero (hod.py:176-179)      */
     double cosmo_precision;   /* flat/open/closed test (cosmology.py:65-79)              */
     double window_precision;  /* z / chi floor of the windows (kernel.py:236, 301, 612)  */
@@ -148,6 +149,18 @@ enum { CHOMP_EVAL_LINEAR_POWER = 0, CHOMP_EVAL_SIGMA_R, CHOMP_EVAL_NU_OF_MASS, C
        CHOMP_EVAL_DNDZ_A, CHOMP_EVAL_DNDZ_B /* dNdz.dndz (aux != 0: raw_dndz), kernel.py:56-86 */ };
 int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_dev, double aux, double* out_dev,
                     void* stream);
+
+/* HaloFit._initialize_halo_fit / _initialize_sigma_spline (halo.py:1261-1319) for the epochs of
+ * the last chomp_b200_mass_tables: k_s, n_eff, C and the Takahashi et al. (2012) coefficients,
+ * params_out_dev [B, 16] (may be NULL).  fit_z: redshift at which Omega_m(z), Omega_L(z) enter
+ * f_1..f_3 -- the reference evaluates them once at construction (z = 0 for halo.HaloFit());
+ * < 0: the epoch's own redshift.  With cfg.use_halofit = 1, chomp_b200_power / _wtheta / _cl use
+ * the HALOFIT spectrum as power_mm and as the two-halo spectrum of power_gm / power_gg. */
+int chomp_b200_halofit(void* handle, int B, double fit_z, double* params_out_dev, int32_t* status_dev, void* stream);
+
+/* CorrelationFourier.correlation (correlation.py:360-392): C(l) = int dchi P(l/chi)/D(z_bar)^2
+ * W_a W_b D^2 / chi^2, cl_out_dev [B, n_ell]; linear_power and HaloFit power_mm. */
+int chomp_b200_cl(void* handle, int B, int which, int n_ell, const double* ell_dev, double* cl_out_dev, void* stream);
 
 /* HaloTrispectrumOneHalo._initialize_i_0_4 (halo_trispectrum.py:58-140): the 1-halo trispectrum
  * I^0_4(k_i, k_i, k_j, k_j) on the n_halo x n_halo grid of ln k nodes, T_out_dev [B, n_halo, n_halo].

@@ -1038,3 +1038,110 @@ class HaloTrispectrumOneHalo(Halo):
         b = np.where(k2 < self.k_min, self.k_min, k2)
         val = sp(np.log(a), np.log(b), grid=False)
         return np.where((a <= self.k_max) & (b <= self.k_max), val, 0.0)
+
+
+# ----------------------------------------------------------------------------
+# halo.HaloFit  (halo.py:1236-1412)
+# ----------------------------------------------------------------------------
+class HaloFit(Halo):
+    """Takahashi et al. (2012) HALOFIT for power_mm; gm / gg use the halo-model
+    tables with the HALOFIT spectrum as the 2-halo spectrum.  ``extrapolate`` is
+    dropped by the reference's constructor (halo.py:1254-1259, Q17)."""
+
+    def __init__(self, epoch, mass, hod, halo=None, fit_epoch=None, **kw):
+        """``fit_epoch``: the SingleEpoch whose Omega_m(z), Omega_L(z) enter f_1..f_3.  The
+        reference evaluates them once, in the constructor (halo.py:1261-1266), and never
+        again -- not when Correlation*.__init__ moves the halo to z_bar -- so in the
+        reference's own flow they belong to the construction redshift (z = 0 for
+        ``halo.HaloFit()``, examples/shear_shear_spectrum.py:81)."""
+        kw.pop("extrapolate", None)
+        Halo.__init__(self, epoch, mass, hod, halo, **kw)
+        epoch = fit_epoch or epoch
+        om = epoch.omega_m()                                   # halo.py:1261-1266
+        self.f1, self.f2, self.f3 = om**-0.0307, om**-0.0585, om**0.0743
+        self.omega_l = epoch.omega_l()
+        self.w = -1.0
+        self._fit = None
+
+    def _sigma2_integrand(self, ln_k, R):                      # halo.py:1321-1323
+        k = np.exp(ln_k)
+        return self.epoch.delta_k(k)*np.exp(-k*k*R*R)
+
+    def _fit_params(self):                                     # halo.py:1268-1319
+        if self._fit is not None:
+            return self._fit
+        n = self.prec["halo_npoints"]
+        ln_R = np.linspace(np.log(0.1), np.log(10.0), n)
+        lk0, lk1 = np.log(self.k_min), np.log(self.k_max)
+        breaks = np.linspace(lk0, lk1, 33)
+        ln_s2 = np.array([np.log(self.integ(self._sigma2_integrand, lk0, lk1, self.prec["halo_precision"],
+                                            breaks=breaks, args=(np.exp(x),))) for x in ln_R])
+        self.ln_R_nodes, self.ln_sigma2_nodes = ln_R, ln_s2
+        k_s = 1.0/np.exp(_IUS(ln_s2[::-1], ln_R[::-1], k=3)(0.0))
+        quintic = _IUS(ln_R, ln_s2, k=5)
+        d1, d2 = quintic.derivatives(np.log(1.0/k_s))[1:3]
+        ne, C = -d1 - 3.0, -d2
+        ow = self.omega_l*(1 + self.w)
+        self._fit = dict(
+            k_s=k_s, n_eff=ne, C=C,
+            a_n=10**(1.5222 + 2.8553*ne + 2.3706*ne*ne + 0.9903*ne**3 + 0.2250*ne**4 - 0.6038*C + 0.1749*ow),
+            b_n=10**(-0.5642 + 0.5864*ne + 0.5716*ne*ne - 1.5474*C + 0.2279*ow),
+            c_n=10**(0.3698 + 2.0404*ne + 0.8161*ne*ne + 0.5869*C),
+            gamma_n=0.1971 - 0.0843*ne + 0.8460*C,
+            alpha_n=np.fabs(6.0835 + 1.3373*ne - 0.1959*ne*ne - 5.5274*C),
+            beta_n=2.0379 - 0.7354*ne + 0.3157*ne*ne + 1.2490*ne**3 + 0.3980*ne**4 - 0.1682*C,
+            mu_n=0.0, nu_n=10**(5.2105 + 3.6902*ne))
+        return self._fit
+
+    def power_mm(self, k):                                     # halo.py:1325-1365
+        p = self._fit_params()
+        k = np.asarray(k, dtype=float)
+        dk = self.epoch.delta_k(k)
+        y = k/p["k_s"]
+        dq = dk*(np.power(1 + dk, p["beta_n"])/(1 + p["alpha_n"]*dk)*np.exp(-(y/4.0 + y*y/8.0)))
+        dh = (p["a_n"]*np.power(y, 3.0*self.f1)/(1.0 + p["b_n"]*np.power(y, self.f2) +
+                                                 np.power(p["c_n"]*self.f3*y, 3.0 - p["gamma_n"])))
+        dh = dh/(1.0 + p["mu_n"]/y + p["nu_n"]/(y*y))
+        return 2.0*np.pi*np.pi/np.power(k, 3)*(dq + dh)
+
+    def power_gm(self, k):                                     # halo.py:1367-1387
+        return self.power_mm(k)*self._tab("h_g", k)*self._tab("h_m", k) + self._tab("pp_gm", k)
+
+    def power_gg(self, k):                                     # halo.py:1400-1412
+        return self.power_mm(k)*self._tab("h_g", k)*self._tab("h_g", k) + self._tab("pp_gg", k)
+
+
+# ----------------------------------------------------------------------------
+# correlation.CorrelationFourier  (correlation.py:297-405)
+# ----------------------------------------------------------------------------
+class CorrelationFourier(object):
+    def __init__(self, kernel, halo_factory, power_spec="linear_power", prec=None, integ=None):
+        self.prec = prec or kernel.prec
+        self.integ = integ or kernel.integ
+        self.kernel = kernel
+        self.D_z = float(kernel.cosmo.growth_factor(kernel.z_bar))
+        self.halo = halo_factory(kernel.z_bar)
+        self.power_spec = power_spec
+
+    def _integrand(self, chi, ell):                            # correlation.py:387-392
+        k = self.kernel
+        D = k.cosmo.growth_factor(k.cosmo.redshift(chi))
+        return (self.halo.power(self.power_spec, ell/chi)/(self.D_z*self.D_z) *
+                k.wa.window_function(chi)*k.wb.window_function(chi)*D*D/(chi*chi))
+
+    def correlation(self, ell):                                # correlation.py:360-385
+        ell = np.atleast_1d(np.asarray(ell, dtype=float))
+        k = self.kernel
+        out = np.empty(ell.size)
+        for i, l in enumerate(ell):
+            breaks = ()
+            if self.integ.name == "tight":
+                marks = [k.wa.chi_nodes, k.wb.chi_nodes, k.cosmo.chi_nodes]
+                if self.power_spec != "linear_power" and not isinstance(self.halo, HaloFit):
+                    marks.append(l/np.exp(self.halo.ln_k_nodes))
+                elif self.power_spec in ("power_gm", "power_gg"):
+                    marks.append(l/np.exp(self.halo.ln_k_nodes))
+                breaks = np.concatenate([np.asarray(m, dtype=float) for m in marks])
+            out[i] = self.integ(self._integrand, k.chi_min, k.chi_max, self.prec["corr_precision"],
+                                breaks=breaks, args=(l,))
+        return out

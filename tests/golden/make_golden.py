@@ -96,6 +96,23 @@ def main():
                                  kernel.WindowFunctionGalaxy, kernel.WindowFunctionConvergence, kernel.Kernel,
                                  hod.HODZheng(HOD_DICT), "power_gm", 5.0),
     }
+    # ---- config 4: HaloFit shear-shear C(l), magnitude-limited dN/dz (examples/shear_shear_spectrum.py) ----
+    cm = cosmology.MultiEpoch(0.0, 5.0, cosmo_dict=C_DICT)
+    win = kernel.WindowFunctionConvergence(kernel.dNdzMagLim(0.0, 2.0, 2.0, 0.5, 2.0), cm)
+    kern = kernel.Kernel(1e-6*D2R, 100.0*D2R, win, win, cm)
+    hf = halo.HaloFit(input_hod=hod.HODZheng(HOD_DICT), cosmo_single_epoch=cosmology.SingleEpoch(0.0, cosmo_dict=C_DICT),
+                      halo_dict=H_DICT)
+    cf = correlation.CorrelationFourier(10, 1e5, kern, input_halo=hf, powSpec="power_mm")
+    ell = np.logspace(1, 5, 30)
+    cl = [float(cf.correlation(l)) for l in ell]
+    out["cfg4_halofit"] = {
+        "ell": arr(ell), "cl": cl, "z_bar": float(kern.z_bar), "k": arr(k),
+        "power_mm": arr(hf.power_mm(k)), "power_gm": arr(hf.power_gm(k)), "power_gg": arr(hf.power_gg(k)),
+        "fit": {n: float(getattr(hf, "_" + n)) for n in ("k_s", "n_eff", "C", "a_n", "b_n", "c_n", "gamma_n",
+                                                        "alpha_n", "beta_n", "nu_n", "f_1", "f_2", "f_3")}}
+    cf_lin = correlation.CorrelationFourier(10, 1e5, kern, input_halo=hf, powSpec="linear_power")
+    out["cfg4_halofit"]["cl_linear"] = [float(cf_lin.correlation(l)) for l in ell]
+
     # ---- 1-halo trispectrum (config 5's table; halo_trispectrum.py:58-140) ------------------------
     tri_mod = R["halo_trispectrum"]
     out["trispectrum"] = {}

@@ -229,3 +229,28 @@ def test_trispectrum_matches_reference_run(spec):
     tri._i04 = ref
     got = tri.trispectrum_parallelogram(np.array(g["k1"]), np.array(g["k2"]))
     assert np.allclose(got, g["parallelogram"], rtol=1e-12, atol=0)
+
+
+# ---------------------------------------------------------------- HaloFit + C(l) (config 4)
+def test_halofit_and_cl_match_reference_run():
+    g = GOLD["cfg4_halofit"]
+    prec, integ = O.precision(), Romberg()
+    cm = O.MultiEpoch(0.0, 5.0, C_DICT, prec, integ)
+    win = O.WindowFunctionConvergence(O.dNdzMagLim(0.0, 2.0, 2.0, 0.5, 2.0, prec, integ), cm)
+    kern = O.Kernel(1e-6*D2R, 100.0*D2R, win, win, cm)
+    fit_epoch = O.SingleEpoch(0.0, C_DICT, prec, integ)
+
+    def factory(z):
+        se = O.SingleEpoch(z, C_DICT, prec, integ)
+        return O.HaloFit(se, O.MassFunction(se, H_DICT), O.HODZheng(HOD_DICT), H_DICT, fit_epoch=fit_epoch)
+    cf = O.CorrelationFourier(kern, factory, "power_mm")
+    assert kern.z_bar == pytest.approx(g["z_bar"], abs=1e-13)
+    h = cf.halo
+    k = np.array(g["k"])
+    assert rel_err(h.power_mm(k), g["power_mm"]) < 1e-12
+    assert rel_err(h.power_gm(k), g["power_gm"]) < 1e-10
+    for name, want in g["fit"].items():
+        key = {"f_1": "f1", "f_2": "f2", "f_3": "f3"}.get(name)
+        got = getattr(h, key) if key else h._fit[name]
+        assert got == pytest.approx(want, rel=1e-12), name
+    assert rel_err(cf.correlation(np.array(g["ell"])[::3]), np.array(g["cl"])[::3]) < 1e-11
