@@ -60,6 +60,11 @@ def main():
                        ("pp_gm", h._pp_gm_spline), ("pp_gg", h._pp_gg_spline)):
             entry[nm] = arr(sp(h._ln_k_array))
         out["halo"][name] = entry
+    cs = cosmology.SingleEpoch(0.0, cosmo_dict=C_DICT)
+    hx = halo.HaloExclusion(input_hod=hod.HODZheng(HOD_DICT), cosmo_single_epoch=cs, halo_dict=H_DICT)
+    out["halo"]["exclusion"] = {"power_mm": arr(hx.power_mm(k)), "power_gm": arr(hx.power_gm(k)),
+                                "power_gg": arr(hx.power_gg(k)), "h_m": arr(hx._h_m_spline(hx._ln_k_array)),
+                                "h_g": arr(hx._h_g_spline(hx._ln_k_array))}
     z = hod.HODZheng(HOD_DICT)
     out["hod_zheng"] = {"first": arr(z.first_moment(M)), "second": arr(z.second_moment(M)),
                         "third": arr(z.nth_moment(M, 3))}

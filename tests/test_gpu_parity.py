@@ -178,3 +178,33 @@ def test_baseline_configs_against_oracle(name):
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.json")))["corr"]
     if name in gold:
         assert w_err(w, gold[name]["w"]) < 2e-3
+
+
+def test_halo_exclusion_against_oracle_and_reference_run():
+    """HaloExclusion (halo.py:1201-1233): the mass window multiplies the h_m and h_g integrands."""
+    import json
+    import os
+    from oracle.quadrature import Tight
+    survey = _survey("power_gm", exclusion=True)
+    eng = engine.Engine(survey)
+    c = engine.pack_params([C_DICT], _lib.COSMO_KEYS)
+    h = engine.pack_params([H_DICT], _lib.HALO_KEYS)
+    g = engine.pack_params([HOD_DICT], _lib.HOD_ZHENG_KEYS)
+    eng.mass_tables(c, h, [0.0])
+    eng.halo_tables(h, g)
+    se = O.SingleEpoch(0.0, C_DICT, O.precision(), Tight(40))
+    ref = O.HaloExclusion(se, O.MassFunction(se, H_DICT), O.HODZheng(HOD_DICT), H_DICT)
+    tabs = eng.table(_lib.T_HALO_NODES, 1).cpu().numpy()[0].reshape(5, -1)
+    for i, nm in enumerate(("h_m", "pp_mm", "h_g", "pp_gm", "pp_gg")):
+        want = ref.table(nm)[0]        # h_m, h_g oscillate through zero at high k: relative to the peak
+        assert np.max(np.abs(tabs[i] - want))/np.max(np.abs(want)) < TOL_TABLE, nm
+    k = np.logspace(-3, 2, 200)
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.json")))["halo"]["exclusion"]
+    for spec in ("power_mm", "power_gm", "power_gg"):
+        P = eng.power(1, _lib.POWER_SPEC[spec], k).cpu().numpy()[0]
+        assert rel_err(P, ref.power(spec, k)) < TOL_FINAL, spec
+        assert rel_err(P, gold[spec]) < 1e-3, spec        # the reference's own Romberg error
+    from chomp_b200 import cosmology, halo, hod
+    hx = halo.HaloExclusion(input_hod=hod.HODZheng(HOD_DICT), cosmo_single_epoch=cosmology.SingleEpoch(0.0, C_DICT),
+                            halo_dict=H_DICT)
+    assert rel_err(hx.power_gm(k), ref.power_gm(k)) < TOL_FINAL

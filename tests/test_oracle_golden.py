@@ -254,3 +254,15 @@ def test_halofit_and_cl_match_reference_run():
         got = getattr(h, key) if key else h._fit[name]
         assert got == pytest.approx(want, rel=1e-12), name
     assert rel_err(cf.correlation(np.array(g["ell"])[::3]), np.array(g["cl"])[::3]) < 1e-11
+
+
+def test_halo_exclusion_matches_reference_run():
+    g = GOLD["halo"]["exclusion"]
+    se = O.SingleEpoch(0.0, C_DICT, O.precision(), Romberg())
+    h = O.HaloExclusion(se, O.MassFunction(se, H_DICT), O.HODZheng(HOD_DICT), H_DICT)
+    # with the exclusion window h_m, h_g oscillate through zero at high k: errors relative to the peak
+    for nm in ("h_m", "h_g"):
+        assert np.max(np.abs(h.table(nm)[0] - np.array(g[nm])))/np.max(np.abs(g[nm])) < 1e-13
+    k = np.array(GOLD["k"])
+    for spec in ("power_mm", "power_gm", "power_gg"):
+        assert rel_err(h.power(spec, k), g[spec]) < 1e-10
