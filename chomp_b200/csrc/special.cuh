@@ -124,6 +124,52 @@ __device__ __forceinline__ double nfw_rho_k(const SiciTables* t, double z, doubl
     return c1 * dci + s1 * dsi - sin_cz / z2;
 }
 
+// sin and cos for 0 <= x < 1e5: three-term Cody-Waite reduction by pi/2 with FMAs, then the
+// classic degree-13 / degree-14 minimax kernels on |r| <= pi/4 (max abs error 1.2e-16, checked
+// against mpmath in tools/gen_special.py's companion test).  The arguments k r_s (1 + c) of the
+// halo tables stay below ~1e3, so the large-argument machinery of the library routine (and its
+// register / instruction footprint in the hot loop) is not needed.
+__device__ __forceinline__ void sincos_reduced(double x, double& s, double& c) {
+    const double n = rint(x * 0.63661977236758134308);
+    double r = fma(-n, 1.5707963267948966, x);
+    r = fma(-n, 6.123233995736766e-17, r);
+    r = fma(-n, -1.4973849048591698e-33, r);
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double sr = fma(r * z, ps, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int q = (int)n;
+    const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
+    s = (q & 2) ? -a : a;
+    c = ((q + 1) & 2) ? -b : b;
+}
+
+// x <= CHOMP_SICI_TINY_X: same series, degree CHOMP_SICI_DEG_T
+__device__ __forceinline__ void sici_series_tiny_c(double x, double& si, double& ci_nolog) {
+    const double xx = x * x;
+    const double s = (xx - CHOMP_SI_TINY_MID) * CHOMP_SI_TINY_IHALF;
+    double p = k_si_tiny[CHOMP_SICI_DEG_T];
+    double q = k_ci_tiny[CHOMP_SICI_DEG_T];
+#pragma unroll
+    for (int i = CHOMP_SICI_DEG_T - 1; i >= 0; --i) {
+        p = fma(p, s, k_si_tiny[i]);
+        q = fma(q, s, k_ci_tiny[i]);
+    }
+    si = x * p;
+    ci_nolog = fma(xx, q, CHOMP_EULER);
+}
+
 // ---------------------------------------------------------------------------------------
 // Warp-uniform fast path.  The nu nodes are ordered by mass, so the 32 lanes of a warp
 // almost always fall into the same Si/Ci ranges; the polynomials are then evaluated with
@@ -187,11 +233,12 @@ __device__ __forceinline__ void nfw_small_large(double z, double z2, double s2, 
 __device__ __forceinline__ double nfw_rho_k_warp(const SiciTables* t, double z, double cp, double lncp) {
     const double z2 = cp * z;
     double s1, c1, s2, c2;
-    sincos(z, &s1, &c1);
-    sincos(z2, &s2, &c2);
+    sincos_reduced(z, s1, c1);
+    sincos_reduced(z2, s2, c2);
     const double sin_cz = s2 * c1 - c2 * s1;
     const bool small1 = z <= CHOMP_SICI_SMALL_X, small2 = z2 <= CHOMP_SICI_SMALL_X;
-    const int key = small2 ? 0 : (small1 ? 1 + sici_range(z2) : 4 + 3 * sici_range(z) + sici_range(z2));
+    const int key = (z2 <= CHOMP_SICI_TINY_X) ? 13
+                    : (small2 ? 0 : (small1 ? 1 + sici_range(z2) : 4 + 3 * sici_range(z) + sici_range(z2)));
     const int key0 = __shfl_sync(0xffffffffu, key, 0);
     double dsi, dci;
     if (__all_sync(0xffffffffu, key == key0)) {
@@ -200,6 +247,13 @@ __device__ __forceinline__ double nfw_rho_k_warp(const SiciTables* t, double z, 
                 double si1, ci1, si2, ci2;
                 sici_series_c(z, si1, ci1);
                 sici_series_c(z2, si2, ci2);
+                dsi = si2 - si1;
+                dci = lncp + (ci2 - ci1);
+            } break;
+            case 13: {
+                double si1, ci1, si2, ci2;
+                sici_series_tiny_c(z, si1, ci1);
+                sici_series_tiny_c(z2, si2, ci2);
                 dsi = si2 - si1;
                 dci = lncp + (ci2 - ci1);
             } break;

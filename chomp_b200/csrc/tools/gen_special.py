@@ -125,13 +125,20 @@ def emit(f, name, c):
 def main():
     tabs = {}
     SMALL = 4.0
-    DEG_S = 14
+    DEG_S = 10
     tabs["SI_SMALL"] = cheb_fit(si_small, 0.0, SMALL**2, DEG_S)
     tabs["CI_SMALL"] = cheb_fit(ci_small, 0.0, SMALL**2, DEG_S)
     check("si_small", *tabs["SI_SMALL"], si_small, 0.0, SMALL**2)
     check("ci_small", *tabs["CI_SMALL"], ci_small, 0.0, SMALL**2)
+    # x <= 1: most (k, M) pairs of the halo tables live here; degree 6 is already exact to rounding
+    TINY = 1.0
+    DEG_T = 6
+    tabs["SI_TINY"] = cheb_fit(si_small, 0.0, TINY**2, DEG_T)
+    tabs["CI_TINY"] = cheb_fit(ci_small, 0.0, TINY**2, DEG_T)
+    check("si_tiny", *tabs["SI_TINY"], si_small, 0.0, TINY**2)
+    check("ci_tiny", *tabs["CI_TINY"], ci_small, 0.0, TINY**2)
     ranges = [(4.0, 7.0), (7.0, 14.0), (14.0, None)]
-    DEG_L = 15
+    DEG_L = 12
     fg = []
     for i, (a, b) in enumerate(ranges):
         ulo = 0.0 if b is None else 1.0/b**2
@@ -146,11 +153,12 @@ def main():
         f.write("// Chebyshev-derived monomial coefficients (variable s in "
                 "[-1,1]) for Si/Ci.\n#pragma once\n\n")
         f.write("#define CHOMP_SICI_SMALL_X %r\n" % SMALL)
+        f.write("#define CHOMP_SICI_TINY_X %r\n#define CHOMP_SICI_DEG_T %d\n" % (TINY, DEG_T))
         f.write("#define CHOMP_SICI_DEG_S %d\n#define CHOMP_SICI_DEG_L %d\n"
                 % (DEG_S, DEG_L))
         f.write("#define CHOMP_SICI_X1 %r\n#define CHOMP_SICI_X2 %r\n"
                 % (ranges[1][0], ranges[2][0]))
-        for nm in ("SI_SMALL", "CI_SMALL"):
+        for nm in ("SI_SMALL", "CI_SMALL", "SI_TINY", "CI_TINY"):
             c, mid, half = tabs[nm]
             f.write("#define CHOMP_%s_MID %r\n#define CHOMP_%s_IHALF %r\n"
                     % (nm, mid, nm, 1.0/half))
@@ -171,6 +179,8 @@ static inline cudaError_t chomp_upload_special_tables() {
     cudaError_t e;
     if ((e = cudaMemcpyToSymbol(k_si_small, h_k_si_small, sizeof h_k_si_small)) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(k_ci_small, h_k_ci_small, sizeof h_k_ci_small)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(k_si_tiny, h_k_si_tiny, sizeof h_k_si_tiny)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(k_ci_tiny, h_k_ci_tiny, sizeof h_k_ci_tiny)) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(k_sici_urange, h_k_sici_urange, sizeof h_k_sici_urange)) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(k_sici_F, h_k_sici_F, sizeof h_k_sici_F)) != cudaSuccess) return e;
     return cudaMemcpyToSymbol(k_sici_G, h_k_sici_G, sizeof h_k_sici_G);
