@@ -215,7 +215,7 @@ int chomp_b200_configure(void* handle, const chomp_b200_config* cfg) {
     h->configured = true;
     // opt in to > 48 KB dynamic shared memory where a stage needs it
     CK(cudaFuncSetAttribute(limber_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(limber_smem_doubles(h->cfg) * sizeof(double))));
+                            (int)(limber_smem_doubles(h->cfg, h->same_window) * sizeof(double))));
     CK(cudaFuncSetAttribute(halo_splines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(15 * (size_t)h->cfg.n_halo * sizeof(double))));
     CK(cudaFuncSetAttribute(wtheta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wtheta_smem(h->cfg)));
@@ -301,7 +301,7 @@ int chomp_b200_limber_tables(void* handle, int B, const double* cosmo_dev, int32
         CK(cudaMemcpyAsync(h->cosmo, cosmo_dev, sizeof(double) * B * CHOMP_N_COSMO, cudaMemcpyDeviceToDevice, s));
     LimberOut out{h->zbar, h->dbar, h->knodes, h->kcoef, h->chi_nodes, h->win_nodes, h->win_chi, h->win_coef, h->kchi,
                   h->grid0, h->dndz_norm, h->edges, h->n_edges};
-    const size_t smem = limber_smem_doubles(h->cfg) * sizeof(double);
+    const size_t smem = limber_smem_doubles(h->cfg, h->same_window) * sizeof(double);
     mark(h, CHOMP_K_LIMBER, s);
     limber_tables_kernel<<<B, LIMBER_THREADS, smem, s>>>(h->cfg, B, h->same_window, h->cosmo, out, status_dev);
     mark(h, CHOMP_K_LIMBER + 1, s);

@@ -103,7 +103,7 @@ __device__ __forceinline__ double nu_of_lnm(const NuTab& t, double lnm) {
 }
 
 // ln(nu) at which exp(ln_mass(nu)) equals the target mass; NaN if outside (nu_min, nu_max).
-__device__ inline double lnnu_of_lnm_inverse(const NuTab& t, double lnm_t, double nu_min, double nu_max) {
+__device__ __noinline__ double lnnu_of_lnm_inverse(const NuTab& t, double lnm_t, double nu_min, double nu_max) {
     if (!(mass_of_nu_ln(t, nu_min) < lnm_t) || !(mass_of_nu_ln(t, nu_max) > lnm_t)) return nan("");
     int i = 0;
     while (i < t.n - 2 && t.lnm[i + 1] <= lnm_t) ++i;       // node values bracket the root
@@ -123,7 +123,7 @@ __device__ inline double lnnu_of_lnm_inverse(const NuTab& t, double lnm_t, doubl
 
 // ln(nu) in (a, b) where moment(mass(nu)) crosses 1 (which = 1: <N>, 2: <N(N-1)>); NaN if none.
 // Both moments are non-decreasing in mass.
-__device__ inline double lnnu_moment_crossing(const NuTab& t, const HodP& h, int which, double a, double b) {
+__device__ __noinline__ double lnnu_moment_crossing(const NuTab& t, const HodP& h, int which, double a, double b) {
     double n1, n2;
     hod_moments(h, exp(mass_of_nu_ln(t, exp(a))), n1, n2);
     if (!((which == 1 ? n1 : n2) < 1.0)) return nan("");
@@ -212,22 +212,22 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     double x_lo1 = l_min, x_lo2 = l_min;
     if (h.first_zero > -1.0 && h.first_zero > exp(e[EP_LNM_MIN])) x_lo1 = log(nu_of_lnm(t, log(h.first_zero)));
     if (h.second_zero > -1.0 && h.second_zero > exp(e[EP_LNM_MIN])) x_lo2 = log(nu_of_lnm(t, log(h.second_zero)));
-    // ---- break points, one per thread -----------------------------------------------------
-    if (tid < MAX_EXTRA_BREAKS) {
-        double x = nan("");
-        switch (tid) {
-            case 0: x = x_lo1; break;
-            case 1: x = x_lo2; break;
-            case 2: x = lnnu_of_lnm_inverse(t, log(h.M0), nu_min, nu_max); break;          // satellite turn-on / central step
-            case 3:   // Mandelbaum satellite slope change at 3 M_0; Zheng central step when sigma <= 0
-                if (h.kind == CHOMP_HOD_MANDELBAUM || h.sigma <= 0.0)
-                    x = lnnu_of_lnm_inverse(t, log(h.Mmin), nu_min, nu_max);
-                break;
-            case 4: x = lnnu_moment_crossing(t, h, 1, fmax(x_lo1, l_min), l_max); break;   // halo.py:1084-1086
-            case 5: x = lnnu_moment_crossing(t, h, 2, fmax(x_lo2, l_min), l_max); break;   // halo.py:1038-1041
-            default: break;
+    // ---- break points: the two expensive root finders on warps of their own (lanes of one warp
+    //      would run the different searches one after the other) ------------------------------
+    {
+        const int wid = tid >> 5, lane = tid & 31;
+        if (wid == 0 && lane < 4) {
+            double x = nan("");
+            if (lane == 0) x = x_lo1;
+            else if (lane == 1) x = x_lo2;
+            else if (lane == 2) x = lnnu_of_lnm_inverse(t, log(h.M0), nu_min, nu_max);   // satellite turn-on / central step
+            else if (h.kind == CHOMP_HOD_MANDELBAUM || h.sigma <= 0.0)
+                x = lnnu_of_lnm_inverse(t, log(h.Mmin), nu_min, nu_max);   // Mandelbaum slope change at 3 M_0; Zheng step
+            extra[lane] = x;
         }
-        extra[tid] = x;
+        if (wid == 1 && lane == 0) extra[4] = lnnu_moment_crossing(t, h, 1, fmax(x_lo1, l_min), l_max);   // halo.py:1084-1086
+        if (wid == 2 && lane == 0) extra[5] = lnnu_moment_crossing(t, h, 2, fmax(x_lo2, l_min), l_max);   // halo.py:1038-1041
+        if (wid == 3 && lane < 2) extra[6 + lane] = nan("");
     }
     // ln(nu) of the knots, in parallel (staged in the tail of the edge array)
     double* lognu = edge + MAX_EXTRA_BREAKS;     // edge has n + MAX_EXTRA_BREAKS slots; the merge below

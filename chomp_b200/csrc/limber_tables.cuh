@@ -94,11 +94,20 @@ struct LimberOut {
     int32_t *n_edges;          // [B]
 };
 
-__host__ __device__ inline size_t limber_smem_doubles(const Cfg& cfg) {
+__host__ __device__ inline size_t limber_work_doubles(const Cfg& cfg) {
+    // 9 concurrent table splines (2 n each), then 2 window splines (2 n + n abscissae each), then
+    // the K spline (2 n + n)
+    size_t a = 18 * (size_t)cfg.n_cosmo, b = 6 * (size_t)cfg.n_window, c = 3 * (size_t)cfg.n_kernel;
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
+}
+__host__ __device__ inline size_t limber_edge_cap(const Cfg& cfg, int same_window) {
+    return (same_window ? 1 : 2) * (size_t)cfg.n_window + cfg.n_cosmo + 4;     // max base panels + 1
+}
+__host__ __device__ inline size_t limber_smem_doubles(const Cfg& cfg, int same_window) {
     const size_t nz = cfg.n_cosmo, nw = cfg.n_window, nk = cfg.n_kernel;
-    const size_t nb = 2 * nw + nz + 4;                 // max base panels + 1
+    const size_t nb = limber_edge_cap(cfg, same_window);
     return 3 * (3 * nz + 12 * nz) + 2 * (nw + 4 * nw) + 2 * nz /*lens sums*/ + nb /*edges*/ +
-           2 * nb * cfg.nq_limber /*chi_q, Fw_q*/ + nk + 4 * nk + 2 * (nw > nz ? (nw > nk ? nw : nk) : (nz > nk ? nz : nk)) * 9 +
+           2 * nb * cfg.nq_limber /*chi_q, Fw_q*/ + nk + 4 * nk + limber_work_doubles(cfg) +
            128 /*red + misc*/ + (LIMBER_THREADS / 32) * (nb / 2 + 2) /*per-warp int prefix sums*/;
 }
 
@@ -123,14 +132,14 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     for (int i = 0; i < 2; ++i) { win[i].n = nw; win[i].wf = p; p += nw; win[i].coef = p; p += 4 * nw; }
     double* lens0 = p; p += nz;       // suffix sums of  w f          over the window-cosmology panels
     double* lens1 = p; p += nz;       //                 w f / chi'
-    const int nb_max = 2 * nw + nz + 4;
+    const int nb_max = (int)limber_edge_cap(cfg, same_window);
+    const int edge_stride = 2 * nw + nz + 4;      // row length of the global copy
     double* edge = p; p += nb_max;
     double* chi_q = p; p += (size_t)nb_max * nq;
     double* fw_q = p; p += (size_t)nb_max * nq;
     double* kn = p; p += nk;
     double* kc = p; p += 4 * nk;
-    const int nmax = nw > nz ? (nw > nk ? nw : nk) : (nz > nk ? nz : nk);
-    double* work = p; p += (size_t)2 * nmax * 9;
+    double* work = p; p += limber_work_doubles(cfg);
     double* red = p; p += 64;
     int* pfx_all = (int*)p;           // (LIMBER_THREADS / 32) x (nb_max + 1) ints
     __shared__ int n_edge_s;
@@ -177,7 +186,7 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     __syncthreads();
     if (tid < 3 * n_grid) {
         EpochGrid& G = g[tid / 3];
-        double* wk = work + (size_t)tid * 2 * nmax;
+        double* wk = work + (size_t)tid * 2 * nz;
         switch (tid % 3) {
             case 0: spline_build(nz, G.z, G.chi, G.c_chi_z, wk); break;     // cosmology.py:795-796
             case 1: spline_build(nz, G.chi, G.z, G.c_z_chi, wk); break;     // :797-798
@@ -260,9 +269,9 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     }
     if (tid < (same_window ? 1 : 2)) {
         Window& W = win[tid];
-        double* wk = work + (size_t)tid * 2 * nmax;
+        double* wk = work + (size_t)tid * 3 * nw;
         // uniform chi nodes: build with explicit abscissae
-        double* xs = wk + (size_t)4 * 2 * nmax;   // separate scratch region
+        double* xs = wk + 2 * nw;
         const double hw = (W.chi_max - W.chi_min) / (nw - 1);
         for (int j = 0; j < nw; ++j) xs[j] = (j == nw - 1) ? W.chi_max : W.chi_min + hw * j;
         spline_build(nw, xs, W.wf, W.coef, wk);
@@ -393,7 +402,7 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     }
     __syncthreads();
     if (tid == 0) {
-        double* xs = work + (size_t)4 * 2 * nmax;
+        double* xs = work + 2 * nk;
         for (int j = 0; j < nk; ++j) xs[j] = (j == nk - 1) ? x1 : x0 + (x1 - x0) / (nk - 1) * j;
         spline_build(nk, xs, kn, kc, work);               // kernel.py:645-646
     }
@@ -420,7 +429,7 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
         out.grid0[(size_t)b * 13 * nz + idx] = src[off];
     }
     if (tid < 2) out.dndz_norm[2 * b + tid] = dist[tid].norm;
-    for (int idx = tid; idx < n_edge_s; idx += blockDim.x) out.edges[(size_t)b * nb_max + idx] = edge[idx];
+    for (int idx = tid; idx < n_edge_s; idx += blockDim.x) out.edges[(size_t)b * edge_stride + idx] = edge[idx];
     if (tid == 0) out.n_edges[b] = n_edge_s;
     for (int idx = tid; idx < 2 * nw; idx += blockDim.x) out.win_nodes[(size_t)b * 2 * nw + idx] = win[idx / nw].wf[idx % nw];
     for (int idx = tid; idx < 2 * 4 * nw; idx += blockDim.x) {
