@@ -139,7 +139,7 @@ int check_cfg(const Cfg& c) {
     return 0;
 }
 
-size_t mass_smem(const Cfg& c) { return (14 * (size_t)c.n_mass + 64) * sizeof(double); }
+size_t mass_smem(const Cfg& c) { return (14 * (size_t)c.n_mass + 64 + D2_TABLE_N) * sizeof(double); }
 size_t nodes_smem(const Cfg& c) {
     const size_t max_edge = (size_t)c.n_mass + MAX_EXTRA_BREAKS;
     return (10 * (size_t)c.n_mass + max_edge + MAX_EXTRA_BREAKS + 64) * sizeof(double) +

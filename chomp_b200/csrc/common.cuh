@@ -125,13 +125,16 @@ __device__ inline PkParams make_pk(const Cosmo& c, double growth, double sigma_n
 }
 
 __device__ __forceinline__ double transfer_eh(const PkParams& p, double k) {
+    // cosmology.py:466-472 with the two nested quotients cleared (two divisions instead of four):
+    //   q = k theta / (Omega_m h (alpha + (1 - alpha) / t^4)),  T = L0 / (L0 + C0 q^2),
+    //   C0 = 14.2 + 731 / (1 + 62.5 q)
     const double t = 1.0 + 0.43 * k * p.s;
-    const double t2 = t * t;
-    const double gamma = p.omh * (p.alpha + (1.0 - p.alpha) / (t2 * t2));
-    const double q = k * p.theta / gamma;
+    const double t2 = t * t, t4 = t2 * t2;
+    const double q = k * p.theta * t4 / (p.omh * fma(p.alpha, t4, 1.0 - p.alpha));
     const double L0 = log(2.0 * M_E + 1.8 * q);
-    const double C0 = 14.2 + 731.0 / (1.0 + 62.5 * q);
-    return L0 / (L0 + C0 * q * q);
+    const double u = fma(62.5, q, 1.0);
+    const double L0u = L0 * u;
+    return L0u / fma(fma(14.2, u, 731.0), q * q, L0u);
 }
 
 // Delta^2(k) = k^3 P(k) / (2 pi^2)
