@@ -1,0 +1,109 @@
+"""Edge cases and error behaviour of the C ABI / batch interface: ragged batch sizes, single
+points, per-point status flags instead of aborts (or the reference's infinite loops), call-level
+errors for bad arguments, determinism."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from chomp_b200 import ChompError, _lib, design, engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _survey(**kw):
+    return engine.Survey(engine.RedshiftDistribution.gaussian(0.0, 2.0, 0.5, 0.1), bins_per_decade=10.0,
+                         power_spec="power_gg", **kw)
+
+
+def test_ragged_batch_sizes_and_determinism():
+    import torch
+    survey = _survey()
+    eng = engine.Engine(survey)
+    cosmo, halo, hod = design.synthetic_batch(37)
+    full = eng.wtheta(cosmo, halo, hod, survey.theta, _lib.P_GG).cpu().numpy()
+    assert full.shape == (37, 30) and np.all(np.isfinite(full))
+    for n in (1, 2, 31, 33):
+        part = eng.wtheta(cosmo[:n], halo[:n], hod[:n], survey.theta, _lib.P_GG).cpu().numpy()
+        assert np.array_equal(part, full[:n]), n
+    again = eng.wtheta(cosmo, halo, hod, survey.theta, _lib.P_GG).cpu().numpy()
+    assert np.array_equal(again, full)                         # bit-reproducible
+    one_theta = eng.wtheta(cosmo, halo, hod, survey.theta[7:8], _lib.P_GG).cpu().numpy()
+    assert np.array_equal(one_theta[:, 0], full[:, 7])
+    # a second handle (another "rank") gives the same bits
+    eng2 = engine.Engine(survey)
+    assert np.array_equal(eng2.wtheta(cosmo[20:], halo[20:], hod[20:], survey.theta, _lib.P_GG).cpu().numpy(), full[20:])
+    torch.cuda.synchronize()
+
+
+def test_status_flags_instead_of_aborts():
+    import torch
+    survey = _survey()
+    eng = engine.Engine(survey)
+    cosmo, halo, hod = design.synthetic_batch(6)
+    cosmo[1, 8] = -0.9            # w0 != -1: outside the supported domain
+    halo[2, 4] = -1.5             # non-NFW profile slope
+    cosmo[3, 6] = np.nan          # sigma_8 = NaN
+    status = torch.zeros(6, dtype=torch.int32, device="cuda")
+    w = eng.wtheta(cosmo, halo, hod, survey.theta, _lib.P_GG, status=status).cpu().numpy()
+    st = status.cpu().numpy()
+    assert st[0] == 0 and st[4] == 0 and st[5] == 0
+    assert st[1] & _lib.ST_DOMAIN and st[2] & _lib.ST_DOMAIN
+    assert st[3] & _lib.ST_NONFINITE and not np.all(np.isfinite(w[3]))
+    assert np.all(np.isfinite(w[[0, 4, 5]]))
+    # the good points are unaffected by their neighbours
+    cosmo2, halo2, hod2 = design.synthetic_batch(6)
+    ref = eng.wtheta(cosmo2, halo2, hod2, survey.theta, _lib.P_GG).cpu().numpy()
+    assert np.array_equal(w[[0, 4, 5]], ref[[0, 4, 5]])
+
+
+def test_unreachable_mass_limit_is_flagged_not_an_infinite_loop():
+    """At z >~ 1.9 nu(M) = 0.1 cannot be reached: the reference's while-loop never ends
+    (mass_function.py:172-194); the kernel sets CHOMP_ST_MASS_WALK."""
+    import torch
+    eng = engine.Engine(_survey())
+    cosmo, halo, _ = design.synthetic_batch(2)
+    status = torch.zeros(2, dtype=torch.int32, device="cuda")
+    eng.mass_tables(cosmo, halo, z=[0.5, 3.0], status=status)
+    st = status.cpu().numpy()
+    assert st[0] == 0 and st[1] & _lib.ST_MASS_WALK
+
+
+def test_call_level_errors():
+    survey = _survey()
+    eng = engine.Engine(survey)
+    cosmo, halo, hod = design.synthetic_batch(4)
+    with pytest.raises(ValueError):
+        eng.wtheta(cosmo[:, :9], halo, hod, survey.theta, _lib.P_GG)        # wrong column count
+    with pytest.raises(ChompError):
+        eng.power(4, 7, [0.1])                                             # unknown spectrum id
+    bad = survey.config()
+    bad.n_halo = 3
+    with pytest.raises(ChompError):
+        engine.Engine(bad)
+    bad = survey.config()
+    bad.nq_nu = 99
+    with pytest.raises(ChompError):
+        engine.Engine(bad)
+    bad = survey.config()
+    bad.corr_k_max = 1e3
+    with pytest.raises(ChompError, match="not supported"):
+        engine.Engine(bad)
+    with pytest.raises(ChompError):
+        eng.trispectrum_1h(4)                                              # tri_moment < 0: list not built
+    lib = _lib.load()
+    assert lib.chomp_b200_reserve(None, 4) != 0 and lib.chomp_b200_last_error()
+    h = ctypes.c_void_p()
+    assert lib.chomp_b200_create(ctypes.byref(h), 9999) != 0                # no such device
+
+
+def test_large_batch_and_reserve_growth():
+    survey = _survey()
+    eng = engine.Engine(survey)
+    cosmo, halo, hod = design.synthetic_batch(3000)
+    small = eng.wtheta(cosmo[:8], halo[:8], hod[:8], survey.theta, _lib.P_GG).cpu().numpy()
+    big = eng.wtheta(cosmo, halo, hod, survey.theta, _lib.P_GG).cpu().numpy()      # forces a re-reserve
+    assert big.shape == (3000, 30) and np.all(np.isfinite(big))
+    assert np.array_equal(big[:8], small)
+    wh, st = eng.wtheta_host(cosmo, halo, hod, survey.theta, _lib.P_GG)
+    assert np.array_equal(wh, big) and not st.any()
