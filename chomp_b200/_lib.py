@@ -31,7 +31,7 @@ ST_NONFINITE, ST_MASS_WALK, ST_NODE_OVERFLOW, ST_DOMAIN = 1, 2, 4, 8
  EVAL_GROWTH_APPROX, EVAL_DNDZ_A, EVAL_DNDZ_B) = range(24)
 (T_ZBAR, T_DBAR, T_KERNEL_NODES, T_CHI_NODES, T_WINDOW_NODES, T_WINDOW_CHI,
  T_EPOCH, T_LNM_NODES, T_NU_NODES, T_HALO_NODES, T_NBAR, T_NU_QUAD_COUNT, T_KERNEL_CHI,
- T_DNDZ_NORM) = range(14)
+ T_DNDZ_NORM, T_KNG, T_ZBAR_NG, T_D_NG, T_KNG_MIN, T_PROJECTED) = range(19)
 HALOFIT_FIELDS = ("k_s", "n_eff", "C", "a_n", "b_n", "c_n", "gamma_n", "alpha_n", "beta_n", "mu_n", "nu_n",
                   "f_1", "f_2", "f_3", "omega_l", "fit_z")
 KERNEL_NAMES = ("limber_tables_kernel", "mass_tables_kernel", "nu_nodes_kernel",
@@ -65,6 +65,18 @@ class Config(ctypes.Structure):
         ("bessel_limit", ctypes.c_double),
         ("corr_k_min", ctypes.c_double), ("corr_k_max", ctypes.c_double),
         ("reserved_d", ctypes.c_double*4),
+    ]
+
+
+class CovParams(ctypes.Structure):
+    """Mirror of ``chomp_b200_cov_params``."""
+    _fields_ = [
+        ("n_bins", ctypes.c_int32), ("which", ctypes.c_int32), ("nongaussian", ctypes.c_int32),
+        ("poisson_only", ctypes.c_int32), ("nq_osc", ctypes.c_int32), ("zero_last_ka", ctypes.c_int32),
+        ("reserved_i", ctypes.c_int32*2),
+        ("theta_min_rad", ctypes.c_double), ("theta_max_rad", ctypes.c_double), ("area_sr", ctypes.c_double),
+        ("poisson", ctypes.c_double*6), ("shot_wt", ctypes.c_double*2), ("bessel_limit", ctypes.c_double),
+        ("osc_phase", ctypes.c_double), ("reserved_d", ctypes.c_double*3),
     ]
 
 
@@ -122,6 +134,10 @@ _SIGNATURES = {
     "chomp_b200_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "chomp_b200_get_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "chomp_b200_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
+    "chomp_b200_cov_kernel_ng": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(CovParams),
+                                                ctypes.c_void_p, ctypes.c_void_p]),
+    "chomp_b200_covariance": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(CovParams)] +
+                              [ctypes.c_void_p]*10),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

@@ -12,6 +12,7 @@
 
 #include "../../include/chomp_b200.h"
 #include "common.cuh"
+#include "covariance.cuh"
 #include "halo_tables.cuh"
 #include "halofit.cuh"
 #include "hankel.cuh"
@@ -76,6 +77,11 @@ struct Handle {
     bool timing = false;
     cudaEvent_t ev[CHOMP_N_KERNELS + 1] = {};
     std::vector<void*> allocs;
+    // covariance scratch (allocated on first use, released with the rest in free_scratch)
+    CovOut cov = {};
+    TriScratch cov_tri = {};
+    int cov_points = 0, cov_bins = 0, cov_chunk = 0;
+    bool kng_ready = false;
 };
 
 void gauss_legendre(int n, double* x, double* w) {
@@ -117,6 +123,7 @@ void free_scratch(Handle* h) {
     h->allocs.clear();
     h->cap_points = 0;
     h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0;
+    h->cov = CovOut{}; h->cov_tri = TriScratch{}; h->cov_points = 0; h->cov_bins = 0; h->cov_chunk = 0; h->kng_ready = false;
 }
 
 int check_cfg(const Cfg& c) {
@@ -743,6 +750,14 @@ int chomp_b200_copy_table(void* handle, int B, int table, double* out_dev, int* 
         case CHOMP_T_KERNEL_CHI: src = h->kchi; len = 2; break;
         case CHOMP_T_DNDZ_NORM: src = h->dndz_norm; len = 2; break;
         case CHOMP_T_NU_QUAD_COUNT: len = N_NODE_LISTS; break;
+        case CHOMP_T_KNG: case CHOMP_T_ZBAR_NG: case CHOMP_T_D_NG: case CHOMP_T_KNG_MIN: case CHOMP_T_PROJECTED:
+            if (!h->cov.kng || B > h->cov_points) FAIL("no covariance tables on this handle");
+            if (table == CHOMP_T_KNG) { src = h->cov.kng; len = c.n_kernel * c.n_kernel; }
+            else if (table == CHOMP_T_ZBAR_NG) { src = h->cov.zbar_ng; len = 1; }
+            else if (table == CHOMP_T_D_NG) { src = h->cov.d_ng; len = 1; }
+            else if (table == CHOMP_T_KNG_MIN) { src = h->cov.kng_min; len = 1; }
+            else { src = h->cov.proj; len = c.n_kernel; }
+            break;
         default: FAIL("unknown table id");
     }
     if (len_out) *len_out = len;
@@ -755,6 +770,11 @@ int chomp_b200_copy_table(void* handle, int B, int table, double* out_dev, int* 
         for (size_t i = 0; i < d.size(); ++i) d[i] = (double)tmp[i];
         CK(cudaMemcpyAsync(out_dev, d.data(), sizeof(double) * B * N_NODE_LISTS, cudaMemcpyHostToDevice, (cudaStream_t)stream));
         CK(cudaStreamSynchronize((cudaStream_t)stream));
+        return 0;
+    }
+    if (table == CHOMP_T_PROJECTED) {
+        CK(cudaMemcpy2DAsync(out_dev, sizeof(double) * len, src, sizeof(double) * 2 * len, sizeof(double) * len, (size_t)B,
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         return 0;
     }
     CK(cudaMemcpyAsync(out_dev, src, sizeof(double) * (size_t)B * len, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -814,6 +834,149 @@ int chomp_b200_get_timing(void* handle, double* ms_out) {
         CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
         ms_out[i] = ms;
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// covariance
+// ---------------------------------------------------------------------------------------------------
+namespace {
+int check_cov(const Handle* h, const CovP& p) {
+    const Cfg& c = h->cfg;
+    if (p.n_bins < 1 || p.n_bins > COV_MAX_COLS) FAIL("n_bins must be in 1..128");
+    if (c.n_kernel > COV_MAX_COLS) FAIL("covariance needs kernel_npoints <= 128");
+    if (c.bessel_order != 0) FAIL("covariance is defined for the J0 kernel");
+    if (p.which < CHOMP_P_LINEAR || p.which > CHOMP_P_GG) FAIL("unknown power spectrum");
+    if (p.nq_osc < 1 || p.nq_osc > CHOMP_MAX_GL) FAIL("nq_osc out of range 1..16");
+    if (!(p.osc_phase > 0)) FAIL("osc_phase must be positive");
+    if (!(p.theta_min_rad > 0 && p.theta_max_rad > p.theta_min_rad)) FAIL("bad theta range");
+    if (!(p.area_sr > 0)) FAIL("survey area must be positive");
+    if ((size_t)(h->edge_stride) > COV_MAX_EDGES) FAIL("window / cosmology tables too fine for the covariance kernels");
+    return 0;
+}
+
+int cov_reserve(Handle* h, int B, int n_bins) {
+    const Cfg& c = h->cfg;
+    if (B > h->cov_points) {
+        // tables per point
+        CK(cudaDeviceSynchronize());
+        const size_t nk2 = (size_t)c.n_kernel * c.n_kernel;
+        int rc = 0;
+        rc |= dev_alloc(h, &h->cov.kng, (size_t)B * nk2);
+        rc |= dev_alloc(h, &h->cov.lkng, (size_t)B * nk2);
+        rc |= dev_alloc(h, &h->cov.mkng, (size_t)B * nk2);
+        rc |= dev_alloc(h, &h->cov.kng_min, (size_t)B);
+        rc |= dev_alloc(h, &h->cov.zbar_ng, (size_t)B);
+        rc |= dev_alloc(h, &h->cov.d_ng, (size_t)B);
+        rc |= dev_alloc(h, &h->cov.proj, (size_t)B * 2 * c.n_kernel);
+        if (rc) return rc;
+        h->cov_points = B;
+        h->cov_bins = 0;
+        const int chunk = B < 256 ? B : 256;
+        const size_t nh = c.n_halo, nk = c.n_kernel, ntot = (size_t)hankel_nodes(c);
+        rc |= dev_alloc(h, &h->cov_tri.mcol, (size_t)chunk * nh * nh);
+        rc |= dev_alloc(h, &h->cov_tri.r, (size_t)chunk * nk * nh);
+        rc |= dev_alloc(h, &h->cov_tri.m2, (size_t)chunk * nk * nh);
+        rc |= dev_alloc(h, &h->cov_tri.tw, (size_t)chunk * nk * ntot);
+        if (rc) return rc;
+        h->cov_chunk = chunk;
+    }
+    if (n_bins > h->cov_bins) {
+        if (int rc = dev_alloc(h, &h->cov.parts, (size_t)h->cov_points * 3 * n_bins * n_bins)) return rc;
+        h->cov_bins = n_bins;
+    }
+    return 0;
+}
+
+LimberIn limber_view(const Handle* h) {
+    return LimberIn{h->grid0, h->win_chi, h->win_coef, h->kchi, h->edges, h->zbar, h->dbar, h->n_edges, h->edge_stride};
+}
+}  // namespace
+
+int chomp_b200_cov_kernel_ng(void* handle, int B, const chomp_b200_cov_params* p, int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    if (!p) FAIL("null covariance parameters");
+    if (int rc = check_cov(h, *p)) return rc;
+    if (int rc = cov_reserve(h, B, p->n_bins)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Cfg& c = h->cfg;
+    const size_t smem = limber_stage_doubles(c) * sizeof(double);
+    CK(cudaFuncSetAttribute(cov_kng_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(c.n_kernel, B);
+    cov_kng_kernel<<<grid, COV_THREADS, smem, s>>>(c, *p, B, limber_view(h), h->cov);
+    CK(cudaGetLastError());
+    cov_kng_spline_kernel<<<B, COV_THREADS, 0, s>>>(c, *p, B, h->cov, status_dev);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    h->kng_ready = true;
+    return 0;
+}
+
+int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, const double* bin_center_dev,
+                          const double* bin_delta_dev, const double* tri_z_dev, const double* cosmo_dev,
+                          const double* halo_dev, const double* hod_dev, double* cov_out_dev, double* parts_out_dev,
+                          int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    if (!p || !bin_center_dev || !bin_delta_dev || !cov_out_dev) FAIL("null argument");
+    if (int rc = check_cov(h, *p)) return rc;
+    const Cfg& c = h->cfg;
+    const bool want_ng = p->nongaussian && !p->poisson_only;
+    if (want_ng && c.tri_moment < 0) FAIL("the non-Gaussian term needs the trispectrum: configure with tri_moment >= 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = p->n_bins;
+    if (status_dev) CK(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * (size_t)B, s));
+    if (int rc = cov_reserve(h, B, nb)) return rc;
+    CK(cudaMemsetAsync(h->cov.parts, 0, sizeof(double) * (size_t)B * 3 * nb * nb, s));
+    if (int rc = chomp_b200_limber_tables(handle, B, cosmo_dev, status_dev, stream)) return rc;
+    if (!p->poisson_only) {
+        if (want_ng) {
+            if (int rc = chomp_b200_cov_kernel_ng(handle, B, p, status_dev, stream)) return rc;
+            // the trispectrum lives at its own redshift (covariance.py:258)
+            if (int rc = chomp_b200_mass_tables(handle, B, h->cosmo, halo_dev, tri_z_dev ? tri_z_dev : h->cov.zbar_ng,
+                                                status_dev, stream)) return rc;
+            if (hod_dev != h->hod)
+                CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
+            NodesOut no = nodes_view(h);
+            nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
+                                                          h->c_lnm_nu, h->c_nu_lnm, no, status_dev);
+            CK(cudaGetLastError());
+            h->launches += 1;
+            if (int rc = chomp_b200_trispectrum_1h(handle, B, nullptr, stream)) return rc;
+        }
+        if (int rc = chomp_b200_mass_tables(handle, B, h->cosmo, halo_dev, nullptr, status_dev, stream)) return rc;
+        if (int rc = chomp_b200_halo_tables(handle, B, h->halo, hod_dev, status_dev, stream)) return rc;
+        const size_t smem = limber_stage_doubles(c) * sizeof(double);
+        cov_projected_kernel<<<B, 128, smem, s>>>(c, *p, B, limber_view(h), h->cosmo, h->epoch, h->htab, h->hcoef,
+                                                  c.use_halofit ? h->hfit : nullptr, h->cov, status_dev);
+        CK(cudaGetLastError());
+        dim3 gg(nb, B);
+        cov_g_kernel<<<gg, COV_THREADS, 0, s>>>(c, *p, B, limber_view(h), bin_center_dev, h->cov);
+        CK(cudaGetLastError());
+        h->launches += 2;
+        if (want_ng) {
+            const int ntot = hankel_nodes(c);
+            const size_t ng_smem = (2 * (size_t)c.n_kernel * c.n_kernel + ntot + 2 * (size_t)nb * c.n_kernel + c.n_kernel) * sizeof(double);
+            if (ng_smem > 200 * 1024) FAIL("covariance: n_bins x kernel_npoints too large for the non-Gaussian kernel");
+            CK(cudaFuncSetAttribute(cov_ng_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ng_smem));
+            for (int b0 = 0; b0 < B; b0 += h->cov_chunk) {
+                const int n = (B - b0 < h->cov_chunk) ? B - b0 : h->cov_chunk;
+                cov_tri_nodes_kernel<<<n, COV_THREADS, 0, s>>>(c, *p, b0, n, h->tri_T, h->cov.d_ng, h->cov_tri);
+                CK(cudaGetLastError());
+                dim3 gn(nb, n);
+                cov_ng_kernel<<<gn, COV_THREADS, ng_smem, s>>>(c, *p, b0, n, bin_center_dev, h->cov_tri.tw, h->cov);
+                CK(cudaGetLastError());
+                h->launches += 2;
+            }
+        }
+    }
+    const size_t tot = (size_t)B * nb * nb;
+    cov_finish_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(*p, B, bin_center_dev, bin_delta_dev, h->cov, cov_out_dev, status_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    if (parts_out_dev)
+        CK(cudaMemcpyAsync(parts_out_dev, h->cov.parts, sizeof(double) * (size_t)B * 3 * nb * nb, cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 

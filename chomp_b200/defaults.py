@@ -76,4 +76,6 @@ default_quadrature = {
     "hankel": 4,    # w(theta) k-integral, per piece (<= 0.0625 wide in ln k) of a halo-table interval
     "limber": 4,    # K(ln k theta) chi-integral, per knot interval
     "lens": 6,      # lensing-efficiency integral, per chi(z) knot interval
+    "cov_osc": 4,   # J0 J0 integrals of the covariance (K_NG table, Gaussian term), per piece
+    "cov_phase": 3.0,  # largest phase advance of the faster Bessel factor over one such piece
 }

@@ -137,6 +137,67 @@ class Survey(object):
         return c
 
 
+def annular_bins(theta_min_deg, theta_max_deg, bins_per_decade=5.0):
+    """(inner, outer, center, delta) of the AnnulusBin list Covariance.__init__ builds
+    (covariance.py:53-74, 1085-1103), radians, shape [n_bins, 4]."""
+    lo = np.log10(theta_min_deg*DEG_TO_RAD)
+    hi = np.log10(theta_max_deg*DEG_TO_RAD)
+    u = np.floor(lo)*bins_per_decade
+    t = np.power(10.0, u/(1.0*bins_per_decade))
+    rows = []
+    while t < np.power(10.0, hi):
+        if t >= np.power(10.0, lo) and t < np.power(10.0, hi):
+            outer = np.power(10.0, (u + 1.0)/(1.0*bins_per_decade))
+            rows.append((t, outer, np.power(10.0, 0.5*(np.log10(t) + np.log10(outer))), outer - t))
+        u += 1.0
+        t = np.power(10.0, u/(1.0*bins_per_decade))
+    return np.array(rows, dtype=np.float64).reshape(-1, 4)
+
+
+class CovarianceSetup(object):
+    """Batch-invariant arguments of covariance.Covariance (covariance.py:47-191) for
+    ``input_correlation_a is input_correlation_b``: the annular bins, the survey, the shot-noise
+    bookkeeping of ``equal_windows`` / ``density`` / ``cosmic_shear`` (covariance.py:100-123, 194-205)."""
+
+    def __init__(self, survey, theta_deg=(0.001, 1.0), bins_per_decade=5.0, survey_area_deg2=20.0, n_a=1.0e4,
+                 n_b=1.0e4, variance=1.0, nongaussian_cov=True, power_spec="power_mm", poisson_noise_only=False):
+        self.bins = annular_bins(theta_deg[0], theta_deg[1], bins_per_decade)
+        p = _lib.CovParams()
+        p.n_bins = self.bins.shape[0]
+        p.which = _lib.POWER_SPEC.get("linear_power" if power_spec is None else power_spec, _lib.P_LINEAR)
+        p.nongaussian, p.poisson_only = int(bool(nongaussian_cov)), int(bool(poisson_noise_only))
+        q = survey.quadrature
+        p.nq_osc, p.osc_phase = q.get("cov_osc", 4), q.get("cov_phase", 3.0)
+        lim = survey.limits
+        ln_k = np.linspace(np.log(lim["k_min"]), np.log(lim["k_max"]), survey.precision["kernel_npoints"])
+        p.zero_last_ka = int(np.exp(ln_k[-1]) > lim["k_max"])       # halo_trispectrum.py:100-107 in numpy arithmetic
+        p.theta_min_rad = np.power(10.0, np.log10(theta_deg[0]*DEG_TO_RAD))     # covariance.py:93-97
+        p.theta_max_rad = np.power(10.0, np.log10(theta_deg[1]*DEG_TO_RAD))
+        self.area = survey_area_deg2*DEG_TO_RAD*DEG_TO_RAD
+        p.area_sr = self.area
+
+        def pair(n):
+            try:
+                return float(n[0]), float(n[1])
+            except (TypeError, IndexError):
+                return float(n), float(n)
+        n_a1, n_a2 = pair(n_a)
+        n_b1, n_b2 = pair(n_b)
+        # a1 == b1 and a2 == b2 are the same objects; the two windows of one Kernel never compare
+        # equal (kernel.py:248-259, 592-593: their cosmology copies differ)
+        self.equal_windows = [False, False, False, False, True, True]
+        self.density = [n_a1/self.area, n_a2/self.area, n_b1/self.area, n_b2/self.area, n_a1/self.area, n_a2/self.area]
+        self.variance = variance
+        for i in range(6):
+            p.poisson[i] = variance*variance/self.density[i] if self.equal_windows[i] else 0.0
+        conv = [w == _lib.WINDOW_CONVERGENCE for w in survey.window]
+        shear = [conv[0], conv[1], conv[0], conv[1]]
+        self.cosmic_shear = [bool(shear[0]*shear[1] or shear[2]*shear[3]), bool(shear[0]*shear[3] or shear[1]*shear[2])]
+        p.shot_wt[0], p.shot_wt[1] = 1.0 + self.cosmic_shear[0], 1.0 + self.cosmic_shear[1]
+        p.bessel_limit = bessel_limit(0, survey.precision["kernel_bessel_limit"])
+        self.params = p
+
+
 def pack_params(dicts, keys):
     """[B, len(keys)] float64 array from a list of parameter dictionaries
     (KeyError on a missing key, like the reference)."""
@@ -296,6 +357,29 @@ class Engine(object):
         _lib.check(self.lib.chomp_b200_trispectrum_eval(self._h, int(point), k1.numel(), self._p(k1), self._p(k2),
                                                         self._p(out), self._stream()))
         return out
+
+    def cov_kernel_ng(self, B, setup, status=None):
+        """K_NG table [B, n_kernel, n_kernel], z_bar_NG [B], D(z_bar_NG) [B] after limber_tables."""
+        _lib.check(self.lib.chomp_b200_cov_kernel_ng(self._h, int(B), ctypes.byref(setup.params), self._p(status),
+                                                     self._stream()))
+        nk = self.cfg.n_kernel
+        return (self.table(_lib.T_KNG, B).reshape(B, nk, nk), self.table(_lib.T_ZBAR_NG, B).reshape(B),
+                self.table(_lib.T_D_NG, B).reshape(B))
+
+    def covariance(self, cosmo, halo, hod, setup, tri_z=None, status=None, parts=False):
+        """Covariance.get_covariance for every point: [B, n_bins, n_bins] (and [B, 3, n, n] = P, G, NG)."""
+        cosmo, halo = self._dev(cosmo, _lib.N_COSMO), self._dev(halo, _lib.N_HALO)
+        hod = self._dev(hod, _lib.N_HOD)
+        B, nb = cosmo.shape[0], setup.bins.shape[0]
+        centre = self._dev(np.ascontiguousarray(setup.bins[:, 2]))
+        delta = self._dev(np.ascontiguousarray(setup.bins[:, 3]))
+        zt = None if tri_z is None else self._dev(np.broadcast_to(np.asarray(tri_z, dtype=np.float64), (B,)).copy())
+        out = self._new(B, nb, nb)
+        pt = self._new(B, 3, nb, nb) if parts else None
+        _lib.check(self.lib.chomp_b200_covariance(
+            self._h, B, ctypes.byref(setup.params), self._p(centre), self._p(delta), self._p(zt), self._p(cosmo),
+            self._p(halo), self._p(hod), self._p(out), self._p(pt), self._p(status), self._stream()))
+        return (out, pt) if parts else out
 
     def set_params(self, cosmo=None, halo=None, hod=None):
         arrs = [None if a is None else self._dev(a, n) for a, n in

@@ -190,7 +190,10 @@ enum {
     CHOMP_T_EPOCH /* 16 scalars, see chomp_b200.cu */, CHOMP_T_LNM_NODES, CHOMP_T_NU_NODES,
     CHOMP_T_HALO_NODES /* [5, n_halo]: h_m, pp_mm, h_g, pp_gm, pp_gg */, CHOMP_T_NBAR /* n_bar/rho_bar */,
     CHOMP_T_NU_QUAD_COUNT /* number of nu quadrature nodes per k class (as double) */,
-    CHOMP_T_KERNEL_CHI /* Kernel.chi_min, chi_max */, CHOMP_T_DNDZ_NORM /* dNdz.norm of both distributions */
+    CHOMP_T_KERNEL_CHI /* Kernel.chi_min, chi_max */, CHOMP_T_DNDZ_NORM /* dNdz.norm of both distributions */,
+    /* covariance tables (after chomp_b200_cov_kernel_ng / chomp_b200_covariance) */
+    CHOMP_T_KNG /* [n_kernel, n_kernel] K_NG */, CHOMP_T_ZBAR_NG, CHOMP_T_D_NG, CHOMP_T_KNG_MIN,
+    CHOMP_T_PROJECTED /* [n_kernel] projected spectrum nodes (covariance.py:455-543) */
 };
 int chomp_b200_copy_table(void* handle, int B, int table, double* out_dev, int* len_out, void* stream);
 
@@ -205,6 +208,43 @@ enum { CHOMP_K_LIMBER = 0, CHOMP_K_MASS, CHOMP_K_NODES, CHOMP_K_SUMS, CHOMP_K_SP
        CHOMP_N_KERNELS };
 int chomp_b200_set_timing(void* handle, int on);
 int chomp_b200_get_timing(void* handle, double* ms_out /* [CHOMP_N_KERNELS] */);
+
+/* ---- covariance of w(theta): covariance.Covariance (covariance.py:23-683) over kernel.KernelCovariance
+ * (kernel.py:864-1111) and HaloTrispectrumOneHalo, for input_correlation_a is input_correlation_b
+ * (``matching_corrs``, covariance.py:60-63: the case of BASELINE config 5). ------------------------ */
+typedef struct chomp_b200_cov_params {
+    int32_t n_bins;          /* annular bins (covariance.py:53-74), <= 128                          */
+    int32_t which;           /* CHOMP_P_*: Covariance(power_spec=), the projected spectrum          */
+    int32_t nongaussian;     /* nongaussian_cov                                                      */
+    int32_t poisson_only;    /* poisson_noise_only                                                   */
+    int32_t nq_osc;          /* Gauss-Legendre order of the pieces of the J0 J0 integrals            */
+    int32_t zero_last_ka;    /* outcome of exp(ln k_max) > k_max in the caller's arithmetic: the
+                                reference's last ln k_a node then sees T = 0 (halo_trispectrum.py:100-107) */
+    int32_t reserved_i[2];
+    double theta_min_rad, theta_max_rad; /* 10**log_theta_min/max of the correlation (covariance.py:93-97) */
+    double area_sr;          /* survey_area_deg2 * deg2_to_strad                                     */
+    double poisson[6];       /* proj_power_poisson(window_pair = 0..5), covariance.py:352-357        */
+    double shot_wt[2];       /* 1 + cosmic_shear[0], 1 + cosmic_shear[1], covariance.py:336-347      */
+    double bessel_limit;     /* special.jn_zeros(0, kernel_bessel_limit)[-1]                         */
+    double osc_phase;        /* largest phase advance of the fast Bessel factor over one piece      */
+    double reserved_d[3];
+} chomp_b200_cov_params;
+
+/* KernelCovariance._find_z_bar / _initialize_NG_spline (kernel.py:961-972, 1016-1068) for the batch of
+ * the last chomp_b200_limber_tables: z_bar_NG, D(z_bar_NG), the K_NG table and its log-space bicubic. */
+int chomp_b200_cov_kernel_ng(void* handle, int B, const chomp_b200_cov_params* p, int32_t* status_dev, void* stream);
+
+/* Covariance.get_covariance (covariance.py:276-321) for every point: Limber tables, K_NG, the 1-halo
+ * trispectrum at tri_z_dev[B] (NULL: z_bar_NG, what Covariance.set_cosmology does, covariance.py:258;
+ * needs cfg.tri_moment >= 0), the halo tables at z_bar, the projected spectra, then the Poisson,
+ * Gaussian and non-Gaussian terms.  bin_center_dev / bin_delta_dev: [n_bins] AnnulusBin.center / .delta
+ * in radians, ascending.  cov_out_dev [B, n_bins, n_bins]; parts_out_dev [B, 3, n_bins, n_bins] (P, G,
+ * NG; may be NULL).  On return the handle holds the same state as after stages 1-3 of the w(theta) path
+ * at z_bar, so chomp_b200_wtheta / chomp_b200_power may follow. */
+int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, const double* bin_center_dev,
+                          const double* bin_delta_dev, const double* tri_z_dev, const double* cosmo_dev,
+                          const double* halo_dev, const double* hod_dev, double* cov_out_dev, double* parts_out_dev,
+                          int32_t* status_dev, void* stream);
 
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 long long chomp_b200_launch_count(void* handle);

@@ -80,3 +80,37 @@ def oracle_wtheta(cosmo, halo, hod, dist_a, dist_b=None, window_a="galaxy", wind
     for name in ("h_m", "pp_mm", "h_g", "pp_gm", "pp_gg"):
         out[name] = h.table(name)[0]
     return out
+
+
+def oracle_covariance(cosmo, halo, hod, dist=("gaussian", (0.0, 2.0, 0.5, 0.1)), theta_deg=(0.01, 1.0),
+                      bins_per_decade=5.0, tri_spec="power_gggg", cov_spec="power_gg", tri_z=None,
+                      area_deg2=25.0, n_a=(1e10, 1e10), n_b=(1e10, 1e10), variance=1.0, prec=None, integ=None,
+                      corr_bins_per_decade=5.0):
+    """Config 5 through the oracle: galaxy x galaxy Limber kernel, Correlation, HaloTrispectrumOneHalo at
+    ``tri_z`` (None: z_bar_NG, what Covariance.set_cosmology does) and Covariance of the correlation with itself."""
+    from oracle import covariance_oracle as CO
+    prec = prec or O.precision()
+    integ = integ or Tight(16)
+    kind, args = dist
+    dcls = O.dNdzGaussian if kind == "gaussian" else O.dNdzMagLim
+    cm = O.MultiEpoch(0.0, 5.0, cosmo, prec, integ)
+    d = dcls(*args, prec=prec, integ=integ)
+    wa, wb = O.WindowFunctionGalaxy(d, cm), O.WindowFunctionGalaxy(d, cm)
+    kern = O.Kernel(1e-6*D2R, 100*D2R, wa, wb, cm)
+
+    def factory(z, cls=O.Halo, **kw):
+        se = O.SingleEpoch(z, cosmo, prec, integ)
+        return cls(se, O.MassFunction(se, halo), O.HODZheng(hod, prec["halo_precision"]), halo, **kw)
+
+    corr = O.Correlation(theta_deg[0], theta_deg[1], kern, factory, cov_spec, bins_per_decade=corr_bins_per_decade)
+    cov = CO.Covariance(corr, theta_deg, bins_per_decade, area_deg2, n_a, n_b, variance, True, None, cov_spec)
+    cov.tri = factory(cov.kernel.z_bar_NG if tri_z is None else tri_z, O.HaloTrispectrumOneHalo, power_spec=tri_spec)
+    return cov
+
+
+def cov_err(got, ref):
+    """Relative error of a covariance block: each element relative to the geometric mean of the
+    reference's diagonal (parity report)."""
+    got, ref = np.asarray(got, dtype=float), np.asarray(ref, dtype=float)
+    d = np.sqrt(np.abs(np.outer(np.diag(ref), np.diag(ref))))
+    return float(np.max(np.abs(got - ref)/np.where(d > 0, d, 1.0)))
