@@ -1,0 +1,154 @@
+"""Drop-in for the reference's covariance.Covariance (covariance.py:23-683) and AnnulusBin
+(:1085-1103): Poisson + Gaussian + 1-halo non-Gaussian covariance of w(theta) between annular bins,
+computed for all bin pairs by one call of the batched C-ABI entry point (a batch of one point).
+
+Supported: ``input_correlation_a is input_correlation_b`` (the reference's ``matching_corrs``,
+the case of its examples and of BASELINE config 5), J0 kernels, the trispectrum object sharing
+the correlation's cosmology / halo / HOD parameters (its redshift and moment kind are its own).
+Super-sample covariance (``ssc_cov``) and CovarianceMulti are listed as next in SURVEY.md 8(f)."""
+import numpy as np
+
+from . import _facade, _lib, defaults, engine, halo_trispectrum
+
+deg_to_rad = np.pi/180.0
+rad_to_deg = 180.0/np.pi
+deg2_to_strad = deg_to_rad*deg_to_rad
+strad_to_deg2 = rad_to_deg*rad_to_deg
+
+
+class AnnulusBin(object):
+    """covariance.py:1085-1103."""
+
+    def __init__(self, inner, outer):
+        self.inner = inner
+        self.outer = outer
+        self.center = np.power(10.0, 0.5*(np.log10(inner) + np.log10(outer)))
+        self.delta = outer - inner
+
+
+class _Setup(object):
+    pass
+
+
+class Covariance(object):
+    def __init__(self, input_correlation_a, input_correlation_b, bins_per_decade=5.0, survey_area_deg2=20,
+                 n_a=1.0e4, n_b=1.0e4, variance=1.0, nongaussian_cov=True, input_halo_trispectrum=None,
+                 power_spec="power_mm", poisson_noise_only=False, ssc_cov=False, **kws):
+        if input_correlation_a is not input_correlation_b:
+            raise NotImplementedError("Covariance of two different correlations is not on the GPU path yet")
+        if ssc_cov:
+            raise NotImplementedError("super-sample covariance is not on the GPU path yet")
+        self.corr_a = self.corr_b = input_correlation_a
+        self.matching_corrs = True
+        self.log_theta_min = input_correlation_a.log_theta_min
+        self.log_theta_max = input_correlation_a.log_theta_max
+        self.bins_per_decade = bins_per_decade
+        theta_deg = (np.power(10.0, self.log_theta_min)*rad_to_deg, np.power(10.0, self.log_theta_max)*rad_to_deg)
+        self._theta_deg = theta_deg
+        rows = engine.annular_bins(theta_deg[0], theta_deg[1], bins_per_decade)
+        self.annular_bins = [AnnulusBin(r[0], r[1]) for r in rows]
+        self.area = survey_area_deg2*deg2_to_strad
+        self._survey_area_deg2 = survey_area_deg2
+        self._n_a, self._n_b = n_a, n_b
+        self.variance = variance
+        self.nongaussian_cov = nongaussian_cov
+        self.poisson_noise_only = poisson_noise_only
+        self.ssc_cov = False
+        self.halo_a = self.halo_b = input_correlation_a.halo
+        if input_halo_trispectrum is None:
+            input_halo_trispectrum = halo_trispectrum.HaloTrispectrumOneHalo()
+        self.halo_tri = input_halo_trispectrum
+        if power_spec is None:
+            power_spec = "linear_power"
+        if power_spec not in _lib.POWER_SPEC or not hasattr(self.halo_a, power_spec):
+            print("WARNING: Invalid input for power spectra variable,")      # covariance.py:184-191
+            print("\t setting to linear_power")
+            power_spec = "linear_power"
+        self.power_spec = power_spec
+        self._gpu = _facade.OnePoint()
+        self._parts = None
+
+    # ---- the reference's setters -----------------------------------------------------------------
+    def set_cosmology(self, cosmo_dict):
+        """covariance.py:241-262: both correlations and the trispectrum (moved to z_bar_NG) follow."""
+        self.corr_a.set_cosmology(cosmo_dict)
+        self.halo_a = self.halo_b = self.corr_a.halo
+        self._tri_follows_z_bar_ng = True
+        self.halo_tri.cosmo_dict = cosmo_dict
+        self._parts = None
+
+    def get_cosmology(self):
+        return self.corr_a.kernel.get_cosmology()
+
+    # ---- evaluation ---------------------------------------------------------------------------------
+    def _evaluate(self):
+        if self._parts is not None:
+            return
+        corr, h = self.corr_a, self.corr_a.halo
+        h._ensure()
+        cfg = corr.kernel._config()
+        hc = h._gpu.eng.cfg
+        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit"):
+            setattr(cfg, name, getattr(hc, name))
+        if cfg.use_halofit:
+            raise NotImplementedError("Covariance with a HaloFit halo is not on the GPU path yet")
+        cfg.tri_moment = _lib.TRISPECTRUM_MOMENT.get(self.halo_tri.power_spec, 0)
+        tri = self.halo_tri
+        if (tri.local_hod._kind != h.local_hod._kind or tri.local_hod._params() != h.local_hod._params() or
+                dict(tri.mass.halo_dict) != dict(h.mass.halo_dict)):
+            raise NotImplementedError("the trispectrum object must share the correlation's halo / HOD parameters")
+        self._gpu.configure(cfg)
+        survey = _Setup()
+        survey.quadrature = dict(defaults.default_quadrature)
+        survey.limits = dict(defaults.default_limits)
+        survey.precision = dict(defaults.default_precision)
+        survey.window = (cfg.window_kind[0], cfg.window_kind[1])
+        setup = engine.CovarianceSetup(survey, self._theta_deg, self.bins_per_decade, self._survey_area_deg2,
+                                       self._n_a, self._n_b, self.variance, self.nongaussian_cov, self.power_spec,
+                                       self.poisson_noise_only)
+        # the theta range is the correlation's own log10 values (covariance.py:93-97)
+        setup.params.theta_min_rad = np.power(10.0, self.log_theta_min)
+        setup.params.theta_max_rad = np.power(10.0, self.log_theta_max)
+        self.equal_windows, self.density, self.cosmic_shear = setup.equal_windows, setup.density, setup.cosmic_shear
+        tri_z = None if getattr(self, "_tri_follows_z_bar_ng", False) else [float(tri._redshift)]
+        eng = self._gpu.eng
+        out, parts = eng.covariance(_facade.cosmo_row(corr.kernel.cosmo.get_cosmology()),
+                                    _facade.halo_row(h.mass.halo_dict, h._profile),
+                                    _facade.hod_row(h.local_hod._kind, h.local_hod._params()), setup, tri_z=tri_z,
+                                    parts=True)
+        self.covar = out.cpu().numpy()[0]
+        self._parts = parts.cpu().numpy()[0]
+        self.D_z_NG = float(eng.table(_lib.T_D_NG, 1)[0, 0]) if setup.params.nongaussian and not setup.params.poisson_only else None
+        self._centers = np.array([b.center for b in self.annular_bins])
+
+    def get_covariance(self):
+        """covariance.py:276-295."""
+        self._evaluate()
+        return self.covar
+
+    def _index(self, theta):
+        self._evaluate()
+        i = int(np.argmin(np.abs(np.log(self._centers) - np.log(theta))))
+        if abs(self._centers[i] - theta) > 1e-9*theta:
+            raise NotImplementedError("covariance terms are tabulated at this object's annular bins only")
+        return i
+
+    def covariance(self, annular_bin_a, annular_bin_b):
+        """covariance.py:297-321."""
+        return float(self.covar[self._index(annular_bin_a.center), self._index(annular_bin_b.center)])
+
+    def covariance_P(self, delta, theta, window_1=0, window_2=1):
+        i = self._index(theta)
+        return float(self._parts[0][i, i])
+
+    def covariance_G(self, theta_a, theta_b, delta_a=None, delta_b=None):
+        return float(self._parts[1][self._index(theta_a), self._index(theta_b)])
+
+    def covariance_NG(self, theta_a_rad, theta_b_rad):
+        return float(self._parts[2][self._index(theta_a_rad), self._index(theta_b_rad)])
+
+    def write(self, output_file_name):
+        cov = np.asarray(self.get_covariance(), dtype=float)
+        with open(output_file_name, "w") as f:
+            for row in cov:
+                f.write(" ".join("%1.10g" % v for v in row) + "\n")

@@ -134,3 +134,38 @@ def test_flags_and_errors():
     from chomp_b200 import ChompError
     with pytest.raises(ChompError, match="trispectrum"):
         eng2.covariance(c, h, g, setup)
+
+
+def test_drop_in_covariance_class():
+    """covariance.Covariance built exactly as the golden generator builds the reference's
+    (tests/golden/make_golden_cov.py), compared with that run."""
+    from chomp_b200 import correlation, cosmology, covariance, halo, halo_trispectrum, hod, kernel, mass_function
+    from common import D2R
+    gold = GOLD["cases"]["power_gggg"]
+    n = len(gold["bins_center"])
+    cm = cosmology.MultiEpoch(0.0, 5.0, cosmo_dict=C_DICT)
+    dist = kernel.dNdzGaussian(0.0, 2.0, 0.5, 0.1)
+    wa, wb = kernel.WindowFunctionGalaxy(dist, cm), kernel.WindowFunctionGalaxy(dist, cm)
+    kern = kernel.Kernel(1e-6*D2R, 100.0*D2R, wa, wb, cm)
+    cs = cosmology.SingleEpoch(0.0, cosmo_dict=C_DICT)
+    h = halo.Halo(input_hod=hod.HODZheng(HOD_DICT), cosmo_single_epoch=cs, halo_dict=H_DICT)
+    corr = correlation.Correlation(THETA[0], THETA[1], kern, bins_per_decade=5.0, input_halo=h, power_spec="power_gg")
+    cs_t = cosmology.SingleEpoch(GOLD["tri_z"], cosmo_dict=C_DICT)
+    tri = halo_trispectrum.HaloTrispectrumOneHalo(GOLD["tri_z"], cs_t, mass_function.MassFunction(GOLD["tri_z"], cs_t, H_DICT),
+                                                  None, H_DICT, hod.HODZheng(HOD_DICT), "power_gggg")
+    cov = covariance.Covariance(corr, corr, bins_per_decade=5.0, survey_area_deg2=GOLD["area_deg2"], n_a=GOLD["n_a"],
+                                n_b=GOLD["n_b"], variance=GOLD["variance"], nongaussian_cov=True,
+                                input_halo_trispectrum=tri, power_spec="power_gg")
+    assert len(cov.annular_bins) == n
+    assert rel_err([b.center for b in cov.annular_bins], gold["bins_center"]) < 1e-14
+    assert rel_err([b.delta for b in cov.annular_bins], gold["bins_delta"]) < 1e-13
+    total = cov.get_covariance()
+    assert cov.equal_windows == gold["equal_windows"] and cov.cosmic_shear == gold["cosmic_shear"]
+    assert cov_err(total, np.array(gold["cov"]).reshape(n, n)) < 3e-4
+    a, b = cov.annular_bins[2], cov.annular_bins[6]
+    ref_ng = np.array(gold["cov_NG"]).reshape(n, n)
+    assert cov.covariance(a, b) == total[2, 6]
+    assert cov.covariance_NG(a.center, b.center) == pytest.approx(ref_ng[2, 6], rel=2e-3)
+    assert cov.covariance_P(a.delta, a.center) == pytest.approx(np.array(gold["cov_P"]).reshape(n, n)[2, 2], rel=1e-12)
+    with pytest.raises(NotImplementedError):
+        covariance.Covariance(corr, correlation.Correlation(THETA[0], THETA[1], kern, input_halo=h), input_halo_trispectrum=tri)
