@@ -28,7 +28,7 @@ ST_NONFINITE, ST_MASS_WALK, ST_NODE_OVERFLOW, ST_DOMAIN = 1, 2, 4, 8
  EVAL_BIAS_NU, EVAL_KERNEL, EVAL_WINDOW_A, EVAL_WINDOW_B, EVAL_Y_NFW,
  EVAL_FIRST_MOMENT, EVAL_SECOND_MOMENT, EVAL_NTH_MOMENT, EVAL_HOD_ZEROS, EVAL_CONCENTRATION,
  EVAL_VIRIAL_RADIUS, EVAL_CHI_OF_Z, EVAL_Z_OF_CHI, EVAL_GROWTH_OF_Z, EVAL_INV_HUBBLE, EVAL_E0,
- EVAL_GROWTH_APPROX, EVAL_DNDZ_A, EVAL_DNDZ_B) = range(24)
+ EVAL_GROWTH_APPROX, EVAL_DNDZ_A, EVAL_DNDZ_B, EVAL_SIGMA_OF_NU, EVAL_BIAS_2_NU) = range(26)
 (T_ZBAR, T_DBAR, T_KERNEL_NODES, T_CHI_NODES, T_WINDOW_NODES, T_WINDOW_CHI,
  T_EPOCH, T_LNM_NODES, T_NU_NODES, T_HALO_NODES, T_NBAR, T_NU_QUAD_COUNT, T_KERNEL_CHI,
  T_DNDZ_NORM, T_KNG, T_ZBAR_NG, T_D_NG, T_KNG_MIN, T_PROJECTED) = range(19)
@@ -116,6 +116,8 @@ _SIGNATURES = {
     "chomp_b200_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+    "chomp_b200_mass_second_order": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_void_p]),
     "chomp_b200_halofit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p]),
     "chomp_b200_cl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,

@@ -110,7 +110,7 @@ class Correlation(object):
 
 class CorrelationFourier(Correlation):
     """C(l) = int dchi P(l/chi)/D(z_bar)^2 W_a W_b D^2 / chi^2 (correlation.py:297-405).
-    On the GPU path for the smooth spectra: ``linear_power`` and HaloFit ``power_mm``."""
+    Any of the spectra: closed-form (linear_power, HaloFit power_mm) or table-based."""
 
     def __init__(self, l_min, l_max, input_kernel, input_halo=None, powSpec=None, **kws):
         from . import defaults

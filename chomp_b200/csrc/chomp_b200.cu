@@ -17,6 +17,7 @@
 #include "halofit.cuh"
 #include "hankel.cuh"
 #include "limber_tables.cuh"
+#include "mass_second.cuh"
 #include "mass_tables.cuh"
 #include "special.cuh"
 #include "spline.cuh"
@@ -61,6 +62,7 @@ struct Handle {
     int edge_stride = 0;
     bool halofit_ready = false;
     double *epoch = nullptr, *lnm_nodes = nullptr, *nu_nodes = nullptr, *c_lnm_nu = nullptr, *c_nu_lnm = nullptr;
+    double *sig_coef = nullptr, *b2_norm = nullptr;   // MassFunctionSecondOrder
     double *tri_w = nullptr, *tri_A = nullptr, *tri_T = nullptr;   // 1-halo trispectrum (tri_A / tri_T allocated on first use)
     int tri_points = 0;
     double *nodes = nullptr, *nbar = nullptr, *rv_max = nullptr, *raw = nullptr, *htab = nullptr, *hcoef = nullptr;
@@ -274,6 +276,8 @@ int chomp_b200_reserve(void* handle, int max_points) {
     rc |= dev_alloc(h, &h->nu_nodes, B * c.n_mass);
     rc |= dev_alloc(h, &h->c_lnm_nu, B * 4 * c.n_mass);
     rc |= dev_alloc(h, &h->c_nu_lnm, B * 4 * c.n_mass);
+    rc |= dev_alloc(h, &h->sig_coef, B * 4 * c.n_mass);
+    rc |= dev_alloc(h, &h->b2_norm, B);
     rc |= dev_alloc(h, &h->nodes, B * NODE_FIELDS * h->node_cap_total);
     rc |= dev_alloc(h, &h->n_nodes, B * N_NODE_LISTS);
     rc |= dev_alloc(h, &h->nbar, B);
@@ -463,7 +467,7 @@ int chomp_b200_wtheta_batch_host(void* handle, int B, const double* cosmo_host, 
 namespace {
 struct EvalCtx {
     const double *cosmo, *halo, *hod, *epoch, *lnm, *nu, *c_lnm_nu, *c_nu_lnm, *knodes, *kcoef, *win_chi, *win_coef,
-        *grid0, *dndz_norm;
+        *grid0, *dndz_norm, *sig_coef, *b2_norm;
 };
 
 __global__ void __launch_bounds__(128)
@@ -498,6 +502,11 @@ eval_kernel(const Cfg cfg, int what, int n, const double* __restrict__ x, double
                 st_raw(v, cx.halo[CHOMP_H_ST_LITTLE_A], cx.halo[CHOMP_H_STQ], e[EP_DELTA_C], nf, bi);
                 r = (what == CHOMP_EVAL_F_NU) ? nf * e[EP_F_NORM] / v : bi * e[EP_B_NORM];
             } break;
+            case CHOMP_EVAL_SIGMA_OF_NU: r = spline_eval_search(cx.sig_coef, v, cx.nu, nm); break;   // mass_function.py:389
+            case CHOMP_EVAL_BIAS_2_NU:                                                              // mass_function.py:423-430
+                r = cx.b2_norm[0] + bias2_raw(v, spline_eval_search(cx.sig_coef, v, cx.nu, nm), cx.halo[CHOMP_H_ST_LITTLE_A],
+                                              cx.halo[CHOMP_H_STQ], e[EP_DELTA_C], e[EP_B_NORM]);
+                break;
             case CHOMP_EVAL_KERNEL: {
                 KernelTab K{cfg.n_kernel, log(cfg.ktheta_min), log(cfg.ktheta_max),
                             (log(cfg.ktheta_max) - log(cfg.ktheta_min)) / (cfg.n_kernel - 1), cx.knodes, cx.kcoef};
@@ -597,12 +606,25 @@ int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_de
                h->epoch + p * CHOMP_EPOCH_LEN, h->lnm_nodes + p * c.n_mass, h->nu_nodes + p * c.n_mass,
                h->c_lnm_nu + p * 4 * c.n_mass, h->c_nu_lnm + p * 4 * c.n_mass, h->knodes + p * c.n_kernel,
                h->kcoef + p * 4 * c.n_kernel, h->win_chi + p * 4, h->win_coef + p * 8 * c.n_window,
-               h->grid0 + p * 13 * c.n_cosmo, h->dndz_norm + p * 2};
+               h->grid0 + p * 13 * c.n_cosmo, h->dndz_norm + p * 2, h->sig_coef + p * 4 * c.n_mass, h->b2_norm + p};
     int blocks = (what == CHOMP_EVAL_SIGMA_R) ? (n + 3) / 4 : (n + 127) / 128;
     if (blocks > 1184) blocks = 1184;
     eval_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(c, what, n, x_dev, aux, cx, out_dev);
     h->launches += 1;
     CK(cudaGetLastError());
+    return 0;
+}
+
+int chomp_b200_mass_second_order(void* handle, int B, double* b2_norm_out_dev, int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    const Cfg& c = h->cfg;
+    mass_second_order_kernel<<<B, 64, 8 * (size_t)c.n_mass * sizeof(double), (cudaStream_t)stream>>>(
+        c, B, h->halo, h->epoch, h->nu_nodes, h->sig_coef, h->b2_norm, status_dev);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    if (b2_norm_out_dev)
+        CK(cudaMemcpyAsync(b2_norm_out_dev, h->b2_norm, sizeof(double) * (size_t)B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 
@@ -626,8 +648,19 @@ int chomp_b200_cl(void* handle, int B, int which, int n_ell, const double* ell_d
     if (int rc = ensure(h, B)) return rc;
     if (n_ell <= 0) FAIL("n_ell must be positive");
     const bool hf = h->cfg.use_halofit != 0;
-    if (!(which == CHOMP_P_LINEAR || (hf && which == CHOMP_P_MM)))
-        FAIL("C(l) is implemented for linear_power and HaloFit power_mm (table-based spectra: next)");
+    if (which < CHOMP_P_LINEAR || which > CHOMP_P_GG) FAIL("unknown power spectrum");
+    if (!(which == CHOMP_P_LINEAR || (hf && which == CHOMP_P_MM))) {
+        // table-based spectra: pieces no wider than 0.0625 in ln chi, split where the spectrum changes branch
+        if ((size_t)h->edge_stride > COV_MAX_EDGES) FAIL("window / cosmology tables too fine for the C(l) kernel");
+        const size_t smem = limber_stage_doubles(h->cfg) * sizeof(double);
+        cl_table_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(
+            h->cfg, which, B, n_ell, ell_dev,
+            LimberIn{h->grid0, h->win_chi, h->win_coef, h->kchi, h->edges, h->zbar, h->dbar, h->n_edges, h->edge_stride},
+            h->cosmo, h->epoch, h->htab, h->hcoef, hf ? h->hfit : nullptr, cl_out_dev, nullptr);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+    }
     cl_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(h->cfg, B, hf && which == CHOMP_P_MM, n_ell, ell_dev, h->cosmo, h->epoch,
                                                    h->dbar, h->hfit, h->grid0, h->win_chi, h->win_coef, h->edges,
                                                    h->n_edges, h->edge_stride, cl_out_dev);

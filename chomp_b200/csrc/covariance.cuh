@@ -405,6 +405,76 @@ cov_projected_kernel(const Cfg cfg, const CovP cp, int B, LimberIn in, const dou
     if (bad && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
 }
 
+// C(l) = int dchi P(l / chi) / D(z_bar)^2  W_a W_b D^2 / chi^2 over the kernel's chi range for any of the
+// spectra (CorrelationFourier.correlation, correlation.py:360-392): the same integrand as the projected
+// spectrum above without the clipping; every piece is split at chi = l / k_max and l / k_min, where the
+// halo-model spectra change branch (halo.py:277-439).  grid (B), 128 threads, one warp per l.
+__global__ void __launch_bounds__(128)
+cl_table_kernel(const Cfg cfg, int which, int B, int n_ell, const double* __restrict__ ell, LimberIn in,
+                const double* __restrict__ cosmo, const double* __restrict__ epoch, const double* __restrict__ htab,
+                const double* __restrict__ hcoef, const double* __restrict__ hfit, double* __restrict__ out,
+                int32_t* __restrict__ status) {
+    extern __shared__ double dyn[];
+    __shared__ double pe[PROJ_MAX_PIECES + 1];
+    __shared__ int n_piece_s;
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+    const int nq = cfg.nq_limber;
+    LimberF F = limber_stage(cfg, in, b, dyn);
+    const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
+    const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
+    const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    HaloTabs T;
+    T.nk = cfg.n_halo; T.l0 = log(cfg.k_min); T.l1 = log(cfg.k_max); T.h = (T.l1 - T.l0) / (T.nk - 1);
+    T.k_min = cfg.k_min; T.k_max = cfg.k_max; T.extrapolate = cfg.extrapolate;
+    T.tab = htab + (size_t)b * 5 * T.nk; T.coef = hcoef + (size_t)b * 20 * T.nk;
+    T.hf = hfit ? hfit + (size_t)b * HF_LEN : nullptr;
+    const double* ed = in.edges + (size_t)b * in.edge_stride;
+    const int n_pan = in.n_edges[b] - 1;
+    if (tid == 0) {
+        int cnt = 0;
+        bool over = false;
+        pe[cnt++] = ed[0];
+        for (int p = 0; p < n_pan; ++p) {
+            const double a = ed[p], bb = ed[p + 1];
+            int ns = (int)ceil(log(bb / a) / COV_PIECE - 1e-9);
+            if (ns < 1) ns = 1;
+            if (cnt + ns > PROJ_MAX_PIECES) { ns = 1; over = true; }
+            const double r = log(bb / a) / ns;
+            for (int k2 = 1; k2 < ns; ++k2) pe[cnt++] = a * exp(r * k2);
+            pe[cnt++] = bb;
+        }
+        n_piece_s = cnt - 1;
+        if (over && status) atomicOr(status + b, CHOMP_ST_NODE_OVERFLOW);
+    }
+    __syncthreads();
+    const int n_piece = n_piece_s;
+    const double D = in.dbar[b], inv_d2 = 1.0 / (D * D);
+    for (int il = wid; il < n_ell; il += nwarp) {
+        const double l = ell[il];
+        const double c_lo = l / cfg.k_max, c_hi = l / cfg.k_min;
+        double acc = 0.0;
+        for (int idx = lane; idx < n_piece * 3 * nq; idx += 32) {
+            const int p = idx / (3 * nq), r = idx - p * 3 * nq;
+            const int reg = r / nq, q = r - reg * nq;
+            const double r_lo = reg == 0 ? -1e300 : (reg == 1 ? c_lo : c_hi);
+            const double r_hi = reg == 0 ? c_lo : (reg == 1 ? c_hi : 1e300);
+            const double a = fmax(pe[p], r_lo), bb = fmin(pe[p + 1], r_hi);
+            if (bb > a) {
+                const double half = 0.5 * (bb - a);
+                const double chi = 0.5 * (a + bb) + half * c_glx[nq][q];
+                acc += half * c_glw[nq][q] * halo_power(T, pk, which, l / chi) * F(chi) / (chi * chi);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            out[(size_t)b * n_ell + il] = acc * inv_d2;
+            if (!isfinite(acc) && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Gaussian term.  grid (n_bins, B): row = the wider bin theta_b (index n_bins - 1 - blockIdx.x),
 // columns a <= b.  covariance.py:359-453 with matching correlations: both two-point terms

@@ -330,6 +330,12 @@ class Engine(object):
             status.ctypes.data_as(ctypes.c_void_p)))
         return w, status
 
+    def mass_second_order(self, B, status=None):
+        """bias_2_norm [B] of MassFunctionSecondOrder for the epochs of the last mass_tables call."""
+        out = self._new(B)
+        _lib.check(self.lib.chomp_b200_mass_second_order(self._h, int(B), self._p(out), self._p(status), self._stream()))
+        return out
+
     def halofit(self, B, fit_z=-1.0, status=None):
         """HALOFIT parameters [B, 16] for the epochs of the last mass_tables call."""
         out = self._new(B, len(_lib.HALOFIT_FIELDS))

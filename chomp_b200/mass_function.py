@@ -1,6 +1,6 @@
 """Drop-in for the reference's mass_function.MassFunction (Sheth-Tormen;
-mass_function.py:25-363).  MassFunctionSecondOrder and TinkerMassFunction are
-outside the hot path and are not provided."""
+mass_function.py:25-363) and MassFunctionSecondOrder (:365-433).  TinkerMassFunction is
+outside the hot path and is not provided."""
 import numpy as np
 
 from . import _facade, _lib, cosmology, defaults
@@ -94,3 +94,18 @@ class MassFunction(object):
             fn, bn = self.f_nu(self._nu_array), self.bias_nu(self._nu_array)
             for lm, nu, a, b in zip(self._ln_mass_array, self._nu_array, fn, bn):
                 f.write("%1.10f %1.10f %1.10f %1.10f\n" % (np.exp(lm), nu, a, b))
+
+
+class MassFunctionSecondOrder(MassFunction):
+    """mass_function.py:365-433: adds the sigma(nu) spline and the second-order bias b_2(nu)."""
+
+    def _refresh(self):
+        MassFunction._refresh(self)
+        self.bias_2_norm = float(self._gpu.eng.mass_second_order(1).cpu().numpy()[0])
+        self._sigma_array = self.delta_c/np.sqrt(self._nu_array)
+
+    def bias_2_nu(self, nu):
+        return _facade.like_input(nu, self._gpu.ev(_lib.EVAL_BIAS_2_NU, nu))
+
+    def bias_2_mass(self, mass):
+        return self.bias_2_nu(self.nu(mass))

@@ -146,9 +146,15 @@ enum { CHOMP_EVAL_LINEAR_POWER = 0, CHOMP_EVAL_SIGMA_R, CHOMP_EVAL_NU_OF_MASS, C
        CHOMP_EVAL_CONCENTRATION, CHOMP_EVAL_VIRIAL_RADIUS /* halo.py:441-463 */,
        CHOMP_EVAL_CHI_OF_Z, CHOMP_EVAL_Z_OF_CHI, CHOMP_EVAL_GROWTH_OF_Z /* MultiEpoch accessors, cosmology.py:873-953 */,
        CHOMP_EVAL_INV_HUBBLE /* E(z), cosmology.py:153 */, CHOMP_EVAL_E0, CHOMP_EVAL_GROWTH_APPROX,
-       CHOMP_EVAL_DNDZ_A, CHOMP_EVAL_DNDZ_B /* dNdz.dndz (aux != 0: raw_dndz), kernel.py:56-86 */ };
+       CHOMP_EVAL_DNDZ_A, CHOMP_EVAL_DNDZ_B /* dNdz.dndz (aux != 0: raw_dndz), kernel.py:56-86 */,
+       CHOMP_EVAL_SIGMA_OF_NU, CHOMP_EVAL_BIAS_2_NU /* MassFunctionSecondOrder, mass_function.py:389, 423-430;
+                                                       after chomp_b200_mass_second_order */ };
 int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_dev, double aux, double* out_dev,
                     void* stream);
+
+/* MassFunctionSecondOrder._initialize_splines / _normalize (mass_function.py:371-421) on top of the last
+ * chomp_b200_mass_tables: the sigma(nu) spline and bias_2_norm, b2_norm_out_dev [B] (may be NULL). */
+int chomp_b200_mass_second_order(void* handle, int B, double* b2_norm_out_dev, int32_t* status_dev, void* stream);
 
 /* HaloFit._initialize_halo_fit / _initialize_sigma_spline (halo.py:1261-1319) for the epochs of
  * the last chomp_b200_mass_tables: k_s, n_eff, C and the Takahashi et al. (2012) coefficients,
@@ -159,7 +165,7 @@ int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_de
 int chomp_b200_halofit(void* handle, int B, double fit_z, double* params_out_dev, int32_t* status_dev, void* stream);
 
 /* CorrelationFourier.correlation (correlation.py:360-392): C(l) = int dchi P(l/chi)/D(z_bar)^2
- * W_a W_b D^2 / chi^2, cl_out_dev [B, n_ell]; linear_power and HaloFit power_mm. */
+ * W_a W_b D^2 / chi^2, cl_out_dev [B, n_ell], for any CHOMP_P_* spectrum (HaloFit when cfg.use_halofit). */
 int chomp_b200_cl(void* handle, int B, int which, int n_ell, const double* ell_dev, double* cl_out_dev, void* stream);
 
 /* HaloTrispectrumOneHalo._initialize_i_0_4 (halo_trispectrum.py:58-140): the 1-halo trispectrum

@@ -352,6 +352,28 @@ class MassFunction(object):
         return np.exp(self._lnm_of_nu(nu))
 
 
+class MassFunctionSecondOrder(MassFunction):               # mass_function.py:365-433
+    def _tabulate(self):                                  # mass_function.py:371-393
+        MassFunction._tabulate(self)
+        # sigma_m(M) at the nodes; nu = (delta_c / sigma)^2 there
+        self.sigma_nodes = self.delta_c/np.sqrt(self.nu_nodes)
+        self._sigma_of_nu = _spline(self.nu_nodes, self.sigma_nodes)
+
+    def normalize(self):                                  # mass_function.py:395-421
+        MassFunction.normalize(self)
+        self.bias_2_norm = 0.0
+        breaks = np.geomspace(self.nu_min, self.nu_max, 12)
+        self.bias_2_norm = -self.integ(lambda v: self.f_nu(v)*self.bias_2_nu(v), self.nu_min, self.nu_max,
+                                       self.prec["mass_precision"], breaks=breaks)
+
+    def bias_2_nu(self, nu):                              # mass_function.py:423-430
+        sigma = self._sigma_of_nu(nu)
+        nup = nu*self.sta
+        return self.bias_2_norm + (
+            8.0/21.0*(self.bias_nu(nu) - 1.0) + (nu - 3.0)/(sigma*sigma) +
+            2.0*self.stq/(self.delta_c**2*(1.0 + nup**self.stq))*(2.0*self.stq + 2*nup - 1.0))
+
+
 # ----------------------------------------------------------------------------
 # hod.HODZheng / hod.HODMandelbaum  (hod.py:141-299)
 # ----------------------------------------------------------------------------
