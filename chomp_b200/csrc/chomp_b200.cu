@@ -154,10 +154,19 @@ size_t nodes_smem(const Cfg& c) {
     return (10 * (size_t)c.n_mass + max_edge + MAX_EXTRA_BREAKS + 64) * sizeof(double) +
            ((N_NODE_LISTS + 1) * max_edge + 8) * sizeof(int);
 }
-size_t sums_smem(const Handle* h) {
+// doubles of dynamic shared memory the sums kernel may use for records, series coefficients and
+// moments (the halo-exclusion Si/Ci tables come on top)
+int sums_doubles(const Handle* h) {
     int m = 0;
     for (int c = 0; c < N_KCLASS; ++c) m = h->node_cap[c] > m ? h->node_cap[c] : m;   // the sums kernel stages lists 0..2 only
-    return (size_t)NODE_FIELDS * m * sizeof(double);
+    // node records of the largest list and the moment scratch; anything beyond that holds the series
+    // coefficients of the two coarse lists.  9 000 doubles (+ 3.6 KB static) keeps three CTAs per SM
+    int d = (NODE_FIELDS + 1) * m + SUMS_EXTRA_DOUBLES;
+    if (d < 9000) d = 9000;
+    return d;
+}
+size_t sums_smem(const Handle* h) {
+    return (size_t)sums_doubles(h) * sizeof(double) + (h->cfg.exclusion ? sizeof(SiciTables) : 0);
 }
 size_t wtheta_smem(const Cfg& c) { return (2 * (size_t)hankel_nodes(c) + 4 * (size_t)c.n_kernel + 8) * sizeof(double); }
 
@@ -182,6 +191,8 @@ int chomp_b200_create(void** handle, int device) {
     CK(cudaMemcpyToSymbol(c_glx, glx, sizeof glx));
     CK(cudaMemcpyToSymbol(c_glw, glw, sizeof glw));
     CK(chomp_upload_special_tables());
+    CK(chomp_upload_sincos_table());
+    CK(chomp_upload_nfw_tables());
     Handle* h = new Handle();
     h->device = device;
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -253,7 +264,8 @@ int chomp_b200_reserve(void* handle, int max_points) {
         h->node_off[k] = h->node_cap_total;
         h->node_cap_total += h->node_cap[k];
     }
-    CK(cudaFuncSetAttribute(halo_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem(h)));
+    CK(cudaFuncSetAttribute(halo_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(sums_doubles(h) * sizeof(double) + sizeof(SiciTables))));
     int rc = 0;
     rc |= dev_alloc(h, &h->zbar, B);
     rc |= dev_alloc(h, &h->dbar, B);
@@ -358,7 +370,7 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
     CK(cudaGetLastError());
     dim3 grid((c.n_halo + SUMS_K_PER_CTA - 1) / SUMS_K_PER_CTA + N_KCLASS - 1, B);
     mark(h, CHOMP_K_SUMS, s);
-    halo_sums_kernel<<<grid, 256, sums_smem(h), s>>>(c, B, no, h->raw);
+    halo_sums_kernel<<<grid, 256, sums_smem(h), s>>>(c, B, no, sums_doubles(h), h->raw);
     CK(cudaGetLastError());
     mark(h, CHOMP_K_SPLINES, s);
     halo_splines_kernel<<<B, 160, 15 * (size_t)c.n_halo * sizeof(double), s>>>(c, B, h->raw, h->nbar, h->epoch, h->htab, h->hcoef,

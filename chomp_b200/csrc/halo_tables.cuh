@@ -44,7 +44,9 @@ __device__ __constant__ int k_class_base[N_NODE_LISTS] = {4, 8, 16, 32};
 __device__ __constant__ int k_class_sharp[N_NODE_LISTS] = {10, 10, 16, 32};
 #define KCLASS_MAX_ORDER 16
 #define SING_MIN_ORDER 8
+#ifndef SUMS_K_PER_CTA
 #define SUMS_K_PER_CTA 32
+#endif
 
 struct HodP {
     int kind;
@@ -170,7 +172,9 @@ __host__ __device__ inline int kclass_cap(int c, int n_mass, bool with_trispectr
     if (c == TRI_LIST && !with_trispectrum) return 32;
     int m = base[c] > sharp[c] ? base[c] : sharp[c];
     if (m < SING_MIN_ORDER) m = SING_MIN_ORDER;
-    return (((n_mass - 1 + MAX_EXTRA_BREAKS) * m + 31) / 32) * 32;
+    // at most six of the MAX_EXTRA_BREAKS slots are ever filled (two lower limits, M_0, the step /
+    // slope change, two moment crossings)
+    return (((n_mass - 1 + 6) * m + 31) / 32) * 32;
 }
 
 #ifndef NODES_MIN_BLOCKS
@@ -399,15 +403,56 @@ __device__ __forceinline__ int kclass_first_index(double phi, double rv_max, dou
     return (int)ceil(x);
 }
 
+// ---- small-argument series of the NFW profile numerator ---------------------------------------
+// rho(k, M) = int_0^c dx x/(1+x)^2 j0(k r_s x)  (the integral halo.py:574-583 is the closed form of)
+//           = sum_n a_n(c) t^n,   t = (k r_s c)^2 = (k r_vir)^2,
+//   a_n(c) = (-1)^n J_{2n+1}(c) / ((2n+1)! c^{2n}),   J_m(c) = int_0^c x^m / (1+x)^2 dx.
+// J_m / c^m follows the stable (for c >= 1) forward recurrence  j_m = (l_{m-1} - j_{m-1}) / c,
+// l_m = 1/m - l_{m-1} / c  with  l_0 = ln(1+c), j_0 = c / (1+c).  With t <= SER_X^2 and degree
+// SER_DEG the truncation error is below 4e-15 (scratch/series_check.py).
+// Because every k-independent factor of the five integrands is already folded into the node
+// weights, the part of each sum that comes from nodes with k r_vir <= SER_X for EVERY k of a CTA's
+// chunk collapses into 5 (SER_DEG + 1) moments  S[s][n] = sum_i w_s(i) coef_n(i) (k_hi r_vir,i)^2n
+// (coef = a for the sums linear in rho, a*a for the quadratic ones), evaluated per k as a
+// polynomial in (k / k_hi)^2: those (k, node) pairs are never visited.
+#ifndef SER_DEG
+#define SER_DEG 9
+#endif
+#ifndef SER_X
+#define SER_X 2.0
+#endif
+#define SER_NC (SER_DEG + 1)
+#define SER_MIN_C 1.0          // the recurrence is run forward: nodes with c < 1 take the general path
+
+__device__ __forceinline__ void nfw_series_coeffs(double c, double cp, double lncp, double (&a)[SER_NC]) {
+    const double ic = 1.0 / c;
+    double l = lncp, j = c / cp, fact = 1.0;
+#pragma unroll
+    for (int m = 1; m <= 2 * SER_DEG + 1; ++m) {
+        const double jn = (l - j) * ic;
+        l = 1.0 / (double)m - l * ic;
+        j = jn;
+        fact *= (double)m;
+        if (m & 1) {
+            const int n = (m - 1) >> 1;
+            a[n] = ((n & 1) ? -j : j) * c / fact;
+        }
+    }
+}
+
 // grid (chunks, B): a CTA stages the node list of one k class in shared memory and its 8
 // warps take the ln k nodes of one SUMS_K_PER_CTA chunk of that class; lanes stride the nodes.
 #ifndef SUMS_MIN_BLOCKS
 #define SUMS_MIN_BLOCKS 3
 #endif
+#define SER_ROUNDS ((SER_NC + 2) / 3)     // moment orders are reduced three at a time
+#define SER_MOM (16 * SER_ROUNDS)          // moment of order n, sum s at [16 (n / 3) + 5 (n % 3) + s]
+#define SUMS_EXTRA_DOUBLES (SER_MOM + 8 * SER_MOM)   // moments + per-warp partial moments
 __global__ void __launch_bounds__(256, SUMS_MIN_BLOCKS)
-halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ raw /* [B, 5, n_halo] */) {
-    extern __shared__ double srec[];      // NODE_FIELDS * cap of the staged class
-    __shared__ SiciTables tabs;
+halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __restrict__ raw /* [B, 5, n_halo] */) {
+    extern __shared__ double srec[];      // (NODE_FIELDS + 1) * nn_pad records | series coefficients | moments
+    __shared__ NfwTables ntab;
+    __shared__ int s_first_bad;
     const int b = blockIdx.y;
     if (b >= B) return;
     const int nk = cfg.n_halo;
@@ -430,7 +475,10 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ raw /* 
         chunk -= nch;
     }
     if (cls < 0) return;
-    sici_tables_load(&tabs);
+    // halo-exclusion window only: its Si/Ci tables sit at the end of the dynamic shared memory
+    SiciTables* tabs = (SiciTables*)(srec + smem_doubles);
+    if (cfg.exclusion) sici_tables_load(tabs);
+    nfw_tables_load(&ntab);
     const int cap = nd.cap[cls];
     const int nn = nd.n_nodes[(size_t)b * N_NODE_LISTS + cls];
     const double* __restrict__ g = nd.nodes + ((size_t)b * nd.cap_total + nd.off[cls]) * NODE_FIELDS;
@@ -443,7 +491,8 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ raw /* 
         else v = (f >= NF_W_HM) ? 0.0 : g[(size_t)f * cap + (nn - 1)];   // padding: valid shape, zero weight
         srec[idx] = v;
     }
-    __syncthreads();
+    double* s_lr = srec + NODE_FIELDS * nn_pad;                       // ln r_s (for ln z = ln k + ln r_s)
+    for (int i = threadIdx.x; i < nn_pad; i += blockDim.x) s_lr[i] = log(g[(size_t)NF_RS * cap + (i < nn ? i : nn - 1)]);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const double* __restrict__ s_cp = srec + NF_CP * nn_pad;
     const double* __restrict__ s_rs = srec + NF_RS * nn_pad;
@@ -453,16 +502,113 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ raw /* 
     const double* __restrict__ s_hg = srec + NF_W_HG * nn_pad;
     const double* __restrict__ s_gm = srec + NF_W_GM * nn_pad;
     const double* __restrict__ s_gg = srec + NF_W_GG * nn_pad;
+    // ---- series region ---------------------------------------------------------------------
+    // ser_n leading nodes get series coefficients (as many as the shared memory left over holds);
+    // i_lo of them satisfy k r_vir <= SER_X for the largest k of the chunk and go into the moments.
+    double* s_a = srec + (NODE_FIELDS + 1) * nn_pad;                  // [SER_NC][ser_n]
+    int ser_n = (smem_doubles - (NODE_FIELDS + 1) * nn_pad - SUMS_EXTRA_DOUBLES) / SER_NC;
+    ser_n = cfg.exclusion ? 0 : min(nn_pad, ser_n & ~31);
+    if (ser_n < 0) ser_n = 0;
+    double* s_mom = s_a + SER_NC * ser_n;                              // [SER_MOM]
+    double* s_part = s_mom + SER_MOM;                                  // [8 warps][SER_MOM]
+    const double k_hi = exp((k_end - 1 == nk - 1) ? l1 : l0 + hk * (k_end - 1));
+    const double k_lo = exp(l0 + hk * k_begin);
+    if (threadIdx.x == 0) s_first_bad = ser_n;
+    __syncthreads();
+    int i_lo = 0;
+    if (ser_n > 0) {
+        // pass 1: coefficients for every node some k of the chunk can use, and the end of the prefix
+        for (int i = threadIdx.x; i < ser_n; i += blockDim.x) {
+            const double cp = s_cp[i], c = cp - 1.0, q = s_rs[i] * c;
+            const bool ok = c >= SER_MIN_C;
+            if (!(ok && q * k_hi <= SER_X)) atomicMin(&s_first_bad, i);
+            if (ok && q * k_lo <= SER_X) {
+                double a[SER_NC];
+                nfw_series_coeffs(c, cp, s_ln[i], a);
+#pragma unroll
+                for (int n = 0; n < SER_NC; ++n) s_a[n * ser_n + i] = a[n];
+            } else {
+                s_a[i] = nan("");          // a_0 = NaN marks "no series for this node"
+            }
+        }
+        __syncthreads();
+        i_lo = s_first_bad;
+        // pass 2: moments of the prefix [0, i_lo).  Three orders x five sums at a time go through
+        // one 16-value warp fold (node order inside a warp, then warp order: bit-reproducible).
+        for (int idx = lane; idx < SER_MOM; idx += 32) s_part[w * SER_MOM + idx] = 0.0;
+        __syncwarp();
+        for (int base = 0; base < i_lo; base += blockDim.x) {      // uniform trip count
+            const int i = base + threadIdx.x;
+            const bool in = i < i_lo;
+            const int ii = in ? i : 0;
+            if (base + 32 * w < i_lo) {                             // warp-uniform: this warp has nodes
+                double a[SER_NC];
+#pragma unroll
+                for (int n = 0; n < SER_NC; ++n) a[n] = s_a[n * ser_n + ii];
+                const double q = s_rs[ii] * (s_cp[ii] - 1.0) * k_hi, u = q * q;
+                const double whm = in ? s_hm[ii] : 0.0, wpm = in ? s_pm[ii] : 0.0, whg = in ? s_hg[ii] : 0.0;
+                const double wgm = in ? s_gm[ii] : 0.0, wgg = in ? s_gg[ii] : 0.0;
+                const double agm = fabs(wgm), agg = fabs(wgg);
+                double pw = 1.0;
+#pragma unroll
+                for (int r = 0; r < SER_ROUNDS; ++r) {
+                    double v[16];
+                    v[15] = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) {
+                        const int n = 3 * r + m;
+                        double an = 0.0, bn = 0.0;
+                        if (n < SER_NC) {
+#pragma unroll
+                            for (int j = 0; j <= n; ++j) bn = fma(a[j], a[n - j], bn);
+                            an = a[n] * pw;
+                            bn *= pw;
+                            pw *= u;
+                        }
+                        v[5 * m + 0] = whm * an;
+                        v[5 * m + 1] = wpm * bn;
+                        v[5 * m + 2] = whg * an;
+                        v[5 * m + 3] = agm * ((wgm < 0.0) ? an : bn);
+                        v[5 * m + 4] = agg * ((wgg < 0.0) ? an : bn);
+                    }
+                    const double tot = warp_fold16(v);
+                    if ((lane & 1) == 0) s_part[w * SER_MOM + 16 * r + (lane >> 1)] += tot;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < SER_MOM) {
+            double v = 0.0;
+            for (int ww = 0; ww < nwarp; ++ww) v += s_part[ww * SER_MOM + threadIdx.x];
+            s_mom[threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    const double ik_hi = 1.0 / k_hi;
     for (int ik = k_begin + w; ik < k_end; ik += nwarp) {
         const double lnk = (ik == nk - 1) ? l1 : l0 + hk * ik;                      // halo.py:49-51
         const double k = exp(lnk);
         double a_hm = 0.0, a_pmm = 0.0, a_hg = 0.0, a_gm = 0.0, a_gg = 0.0;
-        for (int i = lane; i < nn_pad; i += 32) {
+        for (int base = i_lo; base < nn_pad; base += 32) {      // warp-uniform trip count (collectives inside)
+            const bool valid = base + lane < nn_pad;
+            const int i = valid ? base + lane : nn_pad - 1;
             const double cp = s_cp[i], rs = s_rs[i];
-            const double rho = nfw_rho_k_warp(&tabs, k * rs, cp, s_ln[i]);          // halo.py:574-583
+            const double z = k * rs;
+            const double zc = z * (cp - 1.0);
+            double rho = 0.0;
+            bool ser = !valid;                                   // lanes past the end: nothing to do, rho = 0
+            if (valid && i < ser_n && zc <= SER_X) {
+                double p = s_a[SER_DEG * ser_n + i];
+                ser = s_a[i] == s_a[i];
+                const double t = zc * zc;
+#pragma unroll
+                for (int n = SER_DEG - 1; n >= 0; --n) p = fma(p, t, s_a[n * ser_n + i]);
+                if (ser) rho = p;
+            }
+            if (!ser) rho = nfw_rho_tab(&ntab, z, cp, lnk + s_lr[i]);               // halo.py:574-583
             const double rho2 = rho * rho;
             double rho_h = rho;
-            if (cfg.exclusion) rho_h = rho * exclusion_window(&tabs, 2.0 * k * rs * (cp - 1.0));
+            if (cfg.exclusion) rho_h = rho * exclusion_window(tabs, 2.0 * z * (cp - 1.0));
             a_hm = fma(s_hm[i], rho_h, a_hm);
             a_pmm = fma(s_pm[i], rho2, a_pmm);
             a_hg = fma(s_hg[i], rho_h, a_hg);
@@ -472,10 +618,16 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ raw /* 
         }
         a_hm = warp_sum(a_hm); a_pmm = warp_sum(a_pmm); a_hg = warp_sum(a_hg);
         a_gm = warp_sum(a_gm); a_gg = warp_sum(a_gg);
-        if (lane == 0) {
-            double* r = raw + (size_t)b * 5 * nk;
-            r[0 * nk + ik] = a_hm; r[1 * nk + ik] = a_pmm; r[2 * nk + ik] = a_hg;
-            r[3 * nk + ik] = a_gm; r[4 * nk + ik] = a_gg;
+        if (lane < 5) {
+            double v = (lane == 0) ? a_hm : (lane == 1) ? a_pmm : (lane == 2) ? a_hg : (lane == 3) ? a_gm : a_gg;
+            if (i_lo > 0) {
+                const double r = k * ik_hi, sc = r * r;
+                double p = s_mom[16 * (SER_DEG / 3) + 5 * (SER_DEG % 3) + lane];
+#pragma unroll
+                for (int n = SER_DEG - 1; n >= 0; --n) p = fma(p, sc, s_mom[16 * (n / 3) + 5 * (n % 3) + lane]);
+                v += p;
+            }
+            raw[((size_t)b * 5 + lane) * nk + ik] = v;
         }
     }
 }

@@ -11,6 +11,7 @@
 #pragma once
 #include <math.h>
 #include "special_coeffs.cuh"
+#include "nfw_coeffs.cuh"
 
 namespace chomp {
 
@@ -128,26 +129,34 @@ __device__ __forceinline__ double nfw_rho_k(const SiciTables* t, double z, doubl
 // classic degree-13 / degree-14 minimax kernels on |r| <= pi/4 (max abs error 1.2e-16, checked
 // against mpmath in tools/gen_special.py's companion test).  The arguments k r_s (1 + c) of the
 // halo tables stay below ~1e3, so the large-argument machinery of the library routine (and its
-// register / instruction footprint in the hot loop) is not needed.
+// register / instruction footprint in the hot loop) is not needed.  The constants live in a
+// __constant__ array filled at create(): literals would be materialised with two UMOVs per DFMA,
+// constant-bank operands cost no issue slot.
+enum { SC_2_PI = 0, SC_PIO2_1, SC_PIO2_2, SC_PIO2_3, SC_S0, SC_C0 = SC_S0 + 6, SC_N = SC_C0 + 6 };
+static const double h_k_sincos[SC_N] = {
+    0.63661977236758134308, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+__constant__ double k_sincos[SC_N];
+static inline cudaError_t chomp_upload_sincos_table() {
+    return cudaMemcpyToSymbol(k_sincos, h_k_sincos, sizeof h_k_sincos);
+}
+
 __device__ __forceinline__ void sincos_reduced(double x, double& s, double& c) {
-    const double n = rint(x * 0.63661977236758134308);
-    double r = fma(-n, 1.5707963267948966, x);
-    r = fma(-n, 6.123233995736766e-17, r);
-    r = fma(-n, -1.4973849048591698e-33, r);
+    const double n = rint(x * k_sincos[SC_2_PI]);
+    double r = fma(-n, k_sincos[SC_PIO2_1], x);
+    r = fma(-n, k_sincos[SC_PIO2_2], r);
+    r = fma(-n, k_sincos[SC_PIO2_3], r);
     const double z = r * r;
-    double ps = 1.58969099521155010221e-10;
-    ps = fma(ps, z, -2.50507602534068634195e-08);
-    ps = fma(ps, z, 2.75573137070700676789e-06);
-    ps = fma(ps, z, -1.98412698298579493134e-04);
-    ps = fma(ps, z, 8.33333333332248946124e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);
+    double ps = k_sincos[SC_S0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) ps = fma(ps, z, k_sincos[SC_S0 + i]);
     const double sr = fma(r * z, ps, r);
-    double pc = -1.13596475577881948265e-11;
-    pc = fma(pc, z, 2.08757232129817482790e-09);
-    pc = fma(pc, z, -2.75573143513906633035e-07);
-    pc = fma(pc, z, 2.48015872894767294178e-05);
-    pc = fma(pc, z, -1.38888888888741095749e-03);
-    pc = fma(pc, z, 4.16666666666666019037e-02);
+    double pc = k_sincos[SC_C0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) pc = fma(pc, z, k_sincos[SC_C0 + i]);
     const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
     const int q = (int)n;
     const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
@@ -229,64 +238,130 @@ __device__ __forceinline__ void nfw_small_large(double z, double z2, double s2, 
     dci = ci2 - (ci1 + log(z));
 }
 
-// Same value as nfw_rho_k; all 32 lanes of the warp must call it together.
-__device__ __forceinline__ double nfw_rho_k_warp(const SiciTables* t, double z, double cp, double lncp) {
-    const double z2 = cp * z;
+// Same value as nfw_rho_k; all 32 lanes of the warp must call it together.  Lanes with
+// `skip` set get 0 back and cost nothing.  The lanes of a warp hold neighbouring masses, so they
+// fall into one or two Si/Ci range combinations ("keys"); the warp walks the distinct keys that
+// are present and evaluates each with the coefficients as constant-bank operands, the lanes of
+// the other keys masked off.
+__device__ __forceinline__ double nfw_rho_k_warp(double z, double cp, double lncp, bool skip = false) {
+    double z2 = cp * z;
     double s1, c1, s2, c2;
     sincos_reduced(z, s1, c1);
     sincos_reduced(z2, s2, c2);
     const double sin_cz = s2 * c1 - c2 * s1;
     const bool small1 = z <= CHOMP_SICI_SMALL_X, small2 = z2 <= CHOMP_SICI_SMALL_X;
-    const int key = (z2 <= CHOMP_SICI_TINY_X) ? 13
-                    : (small2 ? 0 : (small1 ? 1 + sici_range(z2) : 4 + 3 * sici_range(z) + sici_range(z2)));
-    const int key0 = __shfl_sync(0xffffffffu, key, 0);
-    double dsi, dci;
-    if (__all_sync(0xffffffffu, key == key0)) {
-        switch (key0) {
-            case 0: {
-                double si1, ci1, si2, ci2;
-                sici_series_c(z, si1, ci1);
-                sici_series_c(z2, si2, ci2);
-                dsi = si2 - si1;
-                dci = lncp + (ci2 - ci1);
-            } break;
-            case 13: {
-                double si1, ci1, si2, ci2;
-                sici_series_tiny_c(z, si1, ci1);
-                sici_series_tiny_c(z2, si2, ci2);
-                dsi = si2 - si1;
-                dci = lncp + (ci2 - ci1);
-            } break;
-            case 1: nfw_small_large<0>(z, z2, s2, c2, dsi, dci); break;
-            case 2: nfw_small_large<1>(z, z2, s2, c2, dsi, dci); break;
-            case 3: nfw_small_large<2>(z, z2, s2, c2, dsi, dci); break;
-            case 4: nfw_large_large<0, 0>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-            case 5: nfw_large_large<0, 1>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-            case 6: nfw_large_large<0, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-            case 8: nfw_large_large<1, 1>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-            case 9: nfw_large_large<1, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-            default: nfw_large_large<2, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;   // 12
+    const int key = skip ? -1
+                         : ((z2 <= CHOMP_SICI_TINY_X)
+                                ? 13
+                                : (small2 ? 0 : (small1 ? 1 + sici_range(z2) : 4 + 3 * sici_range(z) + sici_range(z2))));
+    double dsi = 0.0, dci = 0.0;
+    unsigned rem = __ballot_sync(0xffffffffu, !skip);
+    while (rem) {
+        const int key0 = __shfl_sync(0xffffffffu, key, __ffs(rem) - 1);
+        const bool mine = key == key0;
+        if (mine) {
+            // the arguments are made opaque here: everything below is loop-invariant and free of
+            // side effects, and the compiler would otherwise hoist ALL cases out of the loop
+            asm volatile("" : "+d"(z), "+d"(z2));
+            switch (key0) {
+                case 0: {
+                    double si1, ci1, si2, ci2;
+                    sici_series_c(z, si1, ci1);
+                    sici_series_c(z2, si2, ci2);
+                    dsi = si2 - si1;
+                    dci = lncp + (ci2 - ci1);
+                } break;
+                case 13: {
+                    double si1, ci1, si2, ci2;
+                    sici_series_tiny_c(z, si1, ci1);
+                    sici_series_tiny_c(z2, si2, ci2);
+                    dsi = si2 - si1;
+                    dci = lncp + (ci2 - ci1);
+                } break;
+                case 1: nfw_small_large<0>(z, z2, s2, c2, dsi, dci); break;
+                case 2: nfw_small_large<1>(z, z2, s2, c2, dsi, dci); break;
+                case 3: nfw_small_large<2>(z, z2, s2, c2, dsi, dci); break;
+                case 4: nfw_large_large<0, 0>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+                case 5: nfw_large_large<0, 1>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+                case 6: nfw_large_large<0, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+                case 8: nfw_large_large<1, 1>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+                case 9: nfw_large_large<1, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;
+                default: nfw_large_large<2, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;   // 12
+            }
         }
-    } else {
-        double si1, ci1, si2, ci2;
-        if (small2) {
-            sici_series(t, z, si1, ci1);
-            sici_series(t, z2, si2, ci2);
-            dsi = si2 - si1;
-            dci = lncp + (ci2 - ci1);
-        } else if (small1) {
-            sici_series(t, z, si1, ci1);
-            sici_aux(t, z2, s2, c2, si2, ci2);
-            dsi = si2 - si1;
-            dci = ci2 - (ci1 + log(z));
-        } else {
-            sici_aux(t, z, s1, c1, si1, ci1);
-            sici_aux(t, z2, s2, c2, si2, ci2);
-            dsi = si2 - si1;
-            dci = ci2 - ci1;
-        }
+        rem &= ~__ballot_sync(0xffffffffu, mine);
     }
-    return c1 * dci + s1 * dsi - sin_cz / z2;
+    return skip ? 0.0 : c1 * dci + s1 * dsi - sin_cz / z2;
+}
+
+// ---------------------------------------------------------------------------------------
+// Branch-free NFW profile numerator for the hot loops (tables from tools/gen_nfw_tables.py).
+//   N(z, c) = g(z) - g(z2) cos(c z) + [f(z2) - 1/z2] sin(c z),   z2 = (1 + c) z
+// (f, g: auxiliary functions of Si/Ci; derivation in the generator's header).  One sine/cosine
+// pair, f and g at z2 and g at z, each a degree-NFW_DEG polynomial whose coefficients a lane
+// fetches from shared memory by range index: lanes in different ranges read neighbouring
+// 16-byte slots of one 128-byte row, so nothing diverges and no bank conflicts arise.
+// ---------------------------------------------------------------------------------------
+struct NfwTables {
+    double2 A[NFW_DEG + 2][NFW_NSLOT];
+    double2 B[NFW_DEG + 2][NFW_NSLOT];
+};
+__device__ inline void nfw_tables_load(NfwTables* t) {
+    const double2* a = (const double2*)&k_nfw_A[0][0][0];
+    const double2* b = (const double2*)&k_nfw_B[0][0][0];
+    for (int i = threadIdx.x; i < (NFW_DEG + 2) * NFW_NSLOT; i += blockDim.x) {
+        (&t->A[0][0])[i] = a[i];
+        (&t->B[0][0])[i] = b[i];
+    }
+}
+// range of x >= 2 from the exponent of x^2: [4,8) [8,16) [16,32) [32,64) [64,256) [256,inf)
+__device__ __forceinline__ int nfw_range_large(double x2) {
+    const int e = (__double2hiint(x2) >> 20) - 1025;
+    return e < 4 ? e : (e < 6 ? 4 : 5);
+}
+// lnz = ln(z).  Any z > 0; z2 < 2 (both arguments small) takes the power series of Si and Ci,
+// which the callers' own small-argument series make rare on the hot path.
+__device__ __forceinline__ double nfw_rho_tab(const NfwTables* t, double z, double cp, double lnz) {
+    const double z2 = cp * z;
+    if (z2 < 2.0) {
+        double s1, c1, s2, c2, si1, ci1, si2, ci2;
+        sincos_reduced(z, s1, c1);
+        sincos_reduced(z2, s2, c2);
+        sici_series_c(z, si1, ci1);
+        sici_series_c(z2, si2, ci2);
+        return c1 * (log(cp) + (ci2 - ci1)) + s1 * (si2 - si1) - (s2 * c1 - c2 * s1) / z2;
+    }
+    const double iz2 = 1.0 / z2, iz = iz2 * cp, u2 = iz2 * iz2;
+    double sc, cc;
+    sincos_reduced(z2 - z, sc, cc);
+    // f and g at z2
+    const int ra = nfw_range_large(z2 * z2);
+    const double2 ma = t->A[NFW_DEG + 1][ra];
+    const double sa = (u2 - ma.x) * ma.y;
+    double2 cf = t->A[NFW_DEG][ra];
+    double ft = cf.x, g2 = cf.y;
+#pragma unroll
+    for (int j = NFW_DEG - 1; j >= 0; --j) {
+        cf = t->A[j][ra];
+        ft = fma(ft, sa, cf.x);
+        g2 = fma(g2, sa, cf.y);
+    }
+    // g at z
+    const bool small = z < 2.0;
+    const double u1 = iz * iz;
+    const int rb = small ? (z < 1.0 ? 0 : 1) : NFW_NSMALL + nfw_range_large(z * z);
+    const double2 mb = t->B[NFW_DEG + 1][rb];
+    const double sb = ((small ? z : u1) - mb.x) * mb.y;
+    cf = t->B[NFW_DEG][rb];
+    double p1 = cf.x, p2 = cf.y;
+#pragma unroll
+    for (int j = NFW_DEG - 1; j >= 0; --j) {
+        cf = t->B[j][rb];
+        p1 = fma(p1, sb, cf.x);
+        p2 = fma(p2, sb, cf.y);
+    }
+    const double g1 = small ? fma(-lnz, p2, p1) : u1 * p1;
+    return g1 - u2 * (g2 * cc - ft * iz2 * sc);
 }
 
 __device__ __forceinline__ double bessel_j(int order, double x) {

@@ -17,8 +17,8 @@ namespace chomp {
 // grid (ceil(n_k / 8), B), 256 threads: warp w handles ln k node blockIdx.x * 8 + w
 __global__ void __launch_bounds__(256, 3)
 tri_profile_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ A /* [B, n_k, cap_last] */) {
-    __shared__ SiciTables tabs;
-    sici_tables_load(&tabs);
+    __shared__ NfwTables ntab;
+    nfw_tables_load(&ntab);
     __syncthreads();
     const int b = blockIdx.y;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -40,7 +40,7 @@ tri_profile_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ A /* 
             const int ii = i < nn ? i : nn - 1;
             const double cp = g[(size_t)NF_CP * cap + ii], rs = g[(size_t)NF_RS * cap + ii];
             const double lncp = g[(size_t)NF_LNCP * cap + ii];
-            const double rho = nfw_rho_k_warp(&tabs, k * rs, cp, lncp);
+            const double rho = nfw_rho_tab(&ntab, k * rs, cp, lnk + log(rs));
             const double y = rho / (lncp - (cp - 1.0) / cp);                   // halo.py:584-585
             v = i < nn ? y * y : 0.0;
         }
