@@ -39,6 +39,14 @@ __device__ __forceinline__ void warp_fold_step(double* v, int off) {
         v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
 }
+// eight values: lanes 4j .. 4j + 3 return the warp total of input index j
+__device__ __forceinline__ double warp_fold8(double (&v)[8]) {
+    warp_fold_step<4>(v, 16);
+    warp_fold_step<2>(v, 8);
+    warp_fold_step<1>(v, 4);
+    double t = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
+    return t + __shfl_xor_sync(0xffffffffu, t, 1);
+}
 __device__ __forceinline__ double warp_fold16(double (&v)[16]) {
     warp_fold_step<8>(v, 16);
     warp_fold_step<4>(v, 8);

@@ -45,7 +45,7 @@ __device__ __constant__ int k_class_sharp[N_NODE_LISTS] = {10, 10, 16, 32};
 #define KCLASS_MAX_ORDER 16
 #define SING_MIN_ORDER 8
 #ifndef SUMS_K_PER_CTA
-#define SUMS_K_PER_CTA 32
+#define SUMS_K_PER_CTA 128
 #endif
 
 struct HodP {
@@ -484,13 +484,14 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
     const double* __restrict__ g = nd.nodes + ((size_t)b * nd.cap_total + nd.off[cls]) * NODE_FIELDS;
     // stage: field f of node i at srec[f * nn_pad + i]
     const int nn_pad = (nn + 31) & ~31;
-    for (int idx = threadIdx.x; idx < NODE_FIELDS * nn_pad; idx += blockDim.x) {
-        const int f = idx / nn_pad, i = idx - f * nn_pad;
-        double v;
-        if (i < nn) v = g[(size_t)f * cap + i];
-        else v = (f >= NF_W_HM) ? 0.0 : g[(size_t)f * cap + (nn - 1)];   // padding: valid shape, zero weight
-        srec[idx] = v;
-    }
+#pragma unroll
+    for (int f = 0; f < NODE_FIELDS; ++f)
+        for (int i = threadIdx.x; i < nn_pad; i += blockDim.x) {
+            double v;
+            if (i < nn) v = g[(size_t)f * cap + i];
+            else v = (f >= NF_W_HM) ? 0.0 : g[(size_t)f * cap + (nn - 1)];   // padding: valid shape, zero weight
+            srec[f * nn_pad + i] = v;
+        }
     double* s_lr = srec + NODE_FIELDS * nn_pad;                       // ln r_s (for ln z = ln k + ln r_s)
     for (int i = threadIdx.x; i < nn_pad; i += blockDim.x) s_lr[i] = log(g[(size_t)NF_RS * cap + (i < nn ? i : nn - 1)]);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -616,18 +617,18 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
             a_gm = fma(fabs(wgm), (wgm < 0.0) ? rho : rho2, a_gm);
             a_gg = fma(fabs(wgg), (wgg < 0.0) ? rho : rho2, a_gg);
         }
-        a_hm = warp_sum(a_hm); a_pmm = warp_sum(a_pmm); a_hg = warp_sum(a_hg);
-        a_gm = warp_sum(a_gm); a_gg = warp_sum(a_gg);
-        if (lane < 5) {
-            double v = (lane == 0) ? a_hm : (lane == 1) ? a_pmm : (lane == 2) ? a_hg : (lane == 3) ? a_gm : a_gg;
+        double v8[8] = {a_hm, a_pmm, a_hg, a_gm, a_gg, 0.0, 0.0, 0.0};
+        double v = warp_fold8(v8);                               // lane 4 s holds sum s
+        if ((lane & 3) == 0 && lane < 20) {
+            const int s5 = lane >> 2;
             if (i_lo > 0) {
                 const double r = k * ik_hi, sc = r * r;
-                double p = s_mom[16 * (SER_DEG / 3) + 5 * (SER_DEG % 3) + lane];
+                double p = s_mom[16 * (SER_DEG / 3) + 5 * (SER_DEG % 3) + s5];
 #pragma unroll
-                for (int n = SER_DEG - 1; n >= 0; --n) p = fma(p, sc, s_mom[16 * (n / 3) + 5 * (n % 3) + lane]);
+                for (int n = SER_DEG - 1; n >= 0; --n) p = fma(p, sc, s_mom[16 * (n / 3) + 5 * (n % 3) + s5]);
                 v += p;
             }
-            raw[((size_t)b * 5 + lane) * nk + ik] = v;
+            raw[((size_t)b * 5 + s5) * nk + ik] = v;
         }
     }
 }
