@@ -193,6 +193,7 @@ int chomp_b200_create(void** handle, int device) {
     CK(chomp_upload_special_tables());
     CK(chomp_upload_sincos_table());
     CK(chomp_upload_nfw_tables());
+    CK(chomp_upload_sigma_tables(glx[SIG_NQ], glw[SIG_NQ]));
     Handle* h = new Handle();
     h->device = device;
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));

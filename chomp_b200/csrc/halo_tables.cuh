@@ -123,35 +123,50 @@ __device__ __noinline__ double lnnu_of_lnm_inverse(const NuTab& t, double lnm_t,
     return log(0.5 * (lo + hi));
 }
 
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 // ln(nu) in (a, b) where moment(mass(nu)) crosses 1 (which = 1: <N>, 2: <N(N-1)>); NaN if none.
-// Both moments are non-decreasing in mass.
+// Both moments are non-decreasing in mass.  Warp-collective (all 32 lanes, result in every lane):
+// the knots of the ln M(nu) table are tested in parallel to find the knot interval, which is then
+// cut into 33 pieces per round, every lane testing one cut, until the bracket has closed to
+// rounding.  A step in the moment (sigma <= 0, Mandelbaum centrals) converges onto the step.
 __device__ __noinline__ double lnnu_moment_crossing(const NuTab& t, const HodP& h, int which, double a, double b) {
+    const int lane = threadIdx.x & 31;
     double n1, n2;
-    hod_moments(h, exp(mass_of_nu_ln(t, exp(a))), n1, n2);
-    if (!((which == 1 ? n1 : n2) < 1.0)) return nan("");
-    hod_moments(h, exp(mass_of_nu_ln(t, exp(b))), n1, n2);
-    if ((which == 1 ? n1 : n2) < 1.0) return nan("");
-    // first narrow the bracket to one knot interval (the moments are monotone in mass), then
-    // bisect; a step-function HOD converges onto the step
+    // the two ends, on lanes 0 and 1
+    hod_moments(h, exp(mass_of_nu_ln(t, exp(lane == 0 ? a : b))), n1, n2);
+    const bool lt_end = (which == 1 ? n1 : n2) < 1.0;
+    const unsigned ends = __ballot_sync(0xffffffffu, lt_end);
+    if (!(ends & 1u) || (ends & 2u)) return nan("");
     double lo = a, hi = b;
-    for (int i = 1; i < t.n - 1; ++i) {
-        const double x = log(t.nu[i]);
-        if (x <= lo || x >= hi) continue;
-        hod_moments(h, exp(t.lnm[i]), n1, n2);
-        if ((which == 1 ? n1 : n2) < 1.0) lo = x; else { hi = x; break; }
+    for (int base = 1; base < t.n - 1; base += 32) {              // interior knots
+        const int i = base + lane;
+        const bool have = i < t.n - 1;
+        const int ii = have ? i : 1;
+        const double x = log(t.nu[ii]);
+        hod_moments(h, exp(t.lnm[ii]), n1, n2);
+        const bool inside = have && x > a && x < b;
+        const bool lt = (which == 1 ? n1 : n2) < 1.0;
+        lo = fmax(lo, warp_max(inside && lt ? x : a));
+        hi = fmin(hi, warp_min(inside && !lt ? x : b));
     }
-    // Illinois regula falsi on g = moment - 1 (smooth and monotone between the breaks); a
-    // step in the moment degrades it to bisection, which still converges onto the step
-    hod_moments(h, exp(mass_of_nu_ln(t, exp(lo))), n1, n2);
-    double glo = (which == 1 ? n1 : n2) - 1.0;
-    hod_moments(h, exp(mass_of_nu_ln(t, exp(hi))), n1, n2);
-    double ghi = (which == 1 ? n1 : n2) - 1.0;
-    for (int it = 0; it < 64 && hi - lo > 1e-15 * fabs(hi); ++it) {
-        double mid = (lo * ghi - hi * glo) / (ghi - glo);
-        if (!(mid > lo && mid < hi) || (it & 3) == 3) mid = 0.5 * (lo + hi);
-        hod_moments(h, exp(mass_of_nu_ln(t, exp(mid))), n1, n2);
-        const double gm = (which == 1 ? n1 : n2) - 1.0;
-        if (gm < 0.0) { lo = mid; glo = gm; ghi *= 0.5; } else { hi = mid; ghi = gm; glo *= 0.5; }
+    const int kn = search_index(exp(0.5 * (lo + hi)), t.nu, t.n);
+    for (int round = 0; round < 16 && hi - lo > 1e-15 * fabs(hi); ++round) {
+        const double x = lo + (hi - lo) * ((lane + 1) * (1.0 / 33.0));
+        const double v = exp(x);
+        hod_moments(h, exp(spline_poly(t.c_lnm_nu, kn, v - t.nu[kn])), n1, n2);
+        const bool lt = (which == 1 ? n1 : n2) < 1.0;
+        const double nlo = warp_max(lt ? x : lo), nhi = warp_min(lt ? hi : x);
+        lo = nlo; hi = nhi;
     }
     return hi;   // first abscissa on the ">= 1" side
 }
@@ -229,8 +244,14 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
                 x = lnnu_of_lnm_inverse(t, log(h.Mmin), nu_min, nu_max);   // Mandelbaum slope change at 3 M_0; Zheng step
             extra[lane] = x;
         }
-        if (wid == 1 && lane == 0) extra[4] = lnnu_moment_crossing(t, h, 1, fmax(x_lo1, l_min), l_max);   // halo.py:1084-1086
-        if (wid == 2 && lane == 0) extra[5] = lnnu_moment_crossing(t, h, 2, fmax(x_lo2, l_min), l_max);   // halo.py:1038-1041
+        if (wid == 1) {                                                                // halo.py:1084-1086
+            const double x = lnnu_moment_crossing(t, h, 1, fmax(x_lo1, l_min), l_max);
+            if (lane == 0) extra[4] = x;
+        }
+        if (wid == 2) {                                                                // halo.py:1038-1041
+            const double x = lnnu_moment_crossing(t, h, 2, fmax(x_lo2, l_min), l_max);
+            if (lane == 0) extra[5] = x;
+        }
         if (wid == 3 && lane < 2) extra[6 + lane] = nan("");
     }
     // ln(nu) of the knots, in parallel (staged in the tail of the edge array)

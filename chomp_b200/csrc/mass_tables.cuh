@@ -32,6 +32,27 @@ __device__ __forceinline__ double tophat2(double x) {
     return W * W;
 }
 
+// The Gauss-Legendre nodes of the full-width panels [1 + 8 j, 9 + 8 j] in x = k R do not depend on
+// R (nor on the parameter point): ln x and  W^2(x) dx/x  at those nodes are tabulated once, at
+// create().  Only Delta^2(x / R) is left to evaluate per node.
+#define SIG_LIN_MAX 12     // panels up to x = 97 (2 SIG_XSPLIT)
+__device__ double g_sig_lnx[SIG_LIN_MAX * SIG_NQ];
+__device__ double g_sig_w2w[SIG_LIN_MAX * SIG_NQ];
+static inline cudaError_t chomp_upload_sigma_tables(const double* glx16, const double* glw16) {
+    static double lnx[SIG_LIN_MAX * SIG_NQ], w2w[SIG_LIN_MAX * SIG_NQ];
+    for (int j = 0; j < SIG_LIN_MAX; ++j)
+        for (int q = 0; q < SIG_NQ; ++q) {
+            const double a = 1.0 + SIG_DX * j, half = 0.5 * SIG_DX;
+            const double x = a + half + half * glx16[q];
+            const double W = 3.0 * (sin(x) - x * cos(x)) / (x * x * x);
+            lnx[j * SIG_NQ + q] = log(x);
+            w2w[j * SIG_NQ + q] = W * W * half * glw16[q] / x;
+        }
+    cudaError_t e = cudaMemcpyToSymbol(g_sig_lnx, lnx, sizeof lnx);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(g_sig_w2w, w2w, sizeof w2w);
+}
+
 // Delta^2(k) providers for the sigma(R) integrals.  The mass-tables kernel evaluates ~14 000
 // quadrature nodes per parameter point; it tabulates ln Delta^2 once on a fine uniform ln k grid
 // in shared memory and interpolates (4-point Lagrange, error 0.0234 h^4 |d4f| < 3e-10 at
@@ -40,6 +61,7 @@ __device__ __forceinline__ double tophat2(double x) {
 struct D2Direct {
     PkParams pk;
     __device__ __forceinline__ double operator()(double k, double lnk) const { return delta2(pk, k, lnk); }
+    __device__ __forceinline__ double at_lnk(double lnk) const { return delta2(pk, exp(lnk), lnk); }
 };
 struct D2Table {
     const double* tab;       // ln Delta^2 at l0 + j h
@@ -54,6 +76,7 @@ struct D2Table {
                          tab[j + 1] * (-0.5 * um * u * u2) + tab[j + 2] * ((1.0 / 6.0) * um * u * u1);
         return exp(f);
     }
+    __device__ __forceinline__ double at_lnk(double lnk) const { return (*this)(0.0, lnk); }
 };
 
 // first-order end-point term of the oscillatory tail
@@ -92,8 +115,19 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
     if (n_lin < 0) n_lin = 0;
     const int n_tail = (x_hi > xs) ? SIG_NTAIL : 0;
     const int n_pan = SIG_NLOW + n_lin + n_tail;
-    const double lnR = log(R);
-    const double l_lo = log(x_lo), l_one = log(x_one), l_s = log(xs), l_hi = log(x_hi);
+    // five logarithms, one per lane, handed round by shuffles (callers are whole warps)
+    double lnR, l_lo, l_one, l_s, l_hi;
+    {
+        const int sub = threadIdx.x & 7;
+        const double lg = log(sub == 0 ? R : (sub == 1 ? x_lo : (sub == 2 ? x_one : (sub == 3 ? xs : x_hi))));
+        const int base = threadIdx.x & 24;
+        lnR = __shfl_sync(0xffffffffu, lg, base);
+        l_lo = __shfl_sync(0xffffffffu, lg, base + 1);
+        l_one = __shfl_sync(0xffffffffu, lg, base + 2);
+        l_s = __shfl_sync(0xffffffffu, lg, base + 3);
+        l_hi = __shfl_sync(0xffffffffu, lg, base + 4);
+    }
+    const bool lattice = x_one == 1.0;     // the linear panels sit on the tabulated lattice
     const int n_nodes = n_pan * SIG_NQ;
     double acc = 0.0;
     // the two end-point terms of the oscillatory tail ride along as virtual nodes
@@ -108,6 +142,11 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
         if (p >= SIG_NLOW && p < SIG_NLOW + n_lin) {
             // Gauss-Legendre in x on [x_one + 8 j, x_one + 8 (j + 1)]: dlnk = dx / x
             const int jp = p - SIG_NLOW;
+            if (lattice && jp < n_lin - 1 && jp < SIG_LIN_MAX) {
+                const double lk = g_sig_lnx[jp * SIG_NQ + q] - lnR;
+                acc += g_sig_w2w[jp * SIG_NQ + q] * pk.at_lnk(lk);
+                continue;
+            }
             const double a = x_one + SIG_DX * jp;
             const double b = (jp == n_lin - 1) ? xs : a + SIG_DX;
             const double half = 0.5 * (b - a);
@@ -249,7 +288,7 @@ struct MassOut {
 };
 
 #ifndef MASS_MIN_BLOCKS
-#define MASS_MIN_BLOCKS 4
+#define MASS_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(256, MASS_MIN_BLOCKS)
 mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const double* __restrict__ halo,
