@@ -148,7 +148,7 @@ int check_cfg(const Cfg& c) {
     return 0;
 }
 
-size_t mass_smem(const Cfg& c) { return (14 * (size_t)c.n_mass + 64 + D2_TABLE_N) * sizeof(double); }
+size_t mass_smem(const Cfg& c) { return (20 * (size_t)c.n_mass + 64 + D2_TABLE_N) * sizeof(double); }
 size_t nodes_smem(const Cfg& c) {
     const size_t max_edge = (size_t)c.n_mass + MAX_EXTRA_BREAKS;
     return (10 * (size_t)c.n_mass + max_edge + MAX_EXTRA_BREAKS + 64) * sizeof(double) +
@@ -193,6 +193,7 @@ int chomp_b200_create(void** handle, int device) {
     CK(chomp_upload_special_tables());
     CK(chomp_upload_sincos_table());
     CK(chomp_upload_nfw_tables());
+    CK(chomp_upload_bessel_tables());
     CK(chomp_upload_sigma_tables(glx[SIG_NQ], glw[SIG_NQ]));
     Handle* h = new Handle();
     h->device = device;

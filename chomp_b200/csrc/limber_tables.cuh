@@ -95,9 +95,9 @@ struct LimberOut {
 };
 
 __host__ __device__ inline size_t limber_work_doubles(const Cfg& cfg) {
-    // 9 concurrent table splines (2 n each), then 2 window splines (2 n + n abscissae each), then
-    // the K spline (2 n + n)
-    size_t a = 18 * (size_t)cfg.n_cosmo, b = 6 * (size_t)cfg.n_window, c = 3 * (size_t)cfg.n_kernel;
+    // warp-built splines (5 n scratch each): one table spline per warp at a time, then 2 window
+    // splines (+ n abscissae each), then the K spline (+ n)
+    size_t a = 5 * (size_t)cfg.n_cosmo * (LIMBER_THREADS / 32), b = 12 * (size_t)cfg.n_window, c = 6 * (size_t)cfg.n_kernel;
     return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 __host__ __device__ inline size_t limber_edge_cap(const Cfg& cfg, int same_window) {
@@ -111,7 +111,10 @@ __host__ __device__ inline size_t limber_smem_doubles(const Cfg& cfg, int same_w
            128 /*red + misc*/ + (LIMBER_THREADS / 32) * (nb / 2 + 2) /*per-warp int prefix sums*/;
 }
 
-__global__ void __launch_bounds__(LIMBER_THREADS)
+#ifndef LIMBER_MIN_BLOCKS
+#define LIMBER_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(LIMBER_THREADS, LIMBER_MIN_BLOCKS)
 limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __restrict__ cosmo, LimberOut out,
                      int32_t* __restrict__ status) {
     extern __shared__ double sm[];
@@ -184,13 +187,13 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     __syncthreads();
     if (tid < n_grid) { EpochGrid& G = g[tid]; for (int i = 1; i < nz; ++i) G.chi[i] += G.chi[i - 1]; }
     __syncthreads();
-    if (tid < 3 * n_grid) {
-        EpochGrid& G = g[tid / 3];
-        double* wk = work + (size_t)tid * 2 * nz;
-        switch (tid % 3) {
-            case 0: spline_build(nz, G.z, G.chi, G.c_chi_z, wk); break;     // cosmology.py:795-796
-            case 1: spline_build(nz, G.chi, G.z, G.c_z_chi, wk); break;     // :797-798
-            default: spline_build(nz, G.z, G.growth, G.c_g_z, wk); break;   // :814-815
+    for (int sp = wid; sp < 3 * n_grid; sp += nwarp) {      // one spline per warp at a time
+        EpochGrid& G = g[sp / 3];
+        double* wk = work + (size_t)wid * 5 * nz;
+        switch (sp % 3) {
+            case 0: spline_build_warp(nz, G.z, G.chi, G.c_chi_z, wk); break;     // cosmology.py:795-796
+            case 1: spline_build_warp(nz, G.chi, G.z, G.c_z_chi, wk); break;     // :797-798
+            default: spline_build_warp(nz, G.z, G.growth, G.c_g_z, wk); break;   // :814-815
         }
     }
     __syncthreads();
@@ -267,14 +270,15 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
         }
         __syncthreads();
     }
-    if (tid < (same_window ? 1 : 2)) {
-        Window& W = win[tid];
-        double* wk = work + (size_t)tid * 3 * nw;
+    if (wid < (same_window ? 1 : 2)) {
+        Window& W = win[wid];
+        double* wk = work + (size_t)wid * 6 * nw;
         // uniform chi nodes: build with explicit abscissae
-        double* xs = wk + 2 * nw;
+        double* xs = wk + 5 * nw;
         const double hw = (W.chi_max - W.chi_min) / (nw - 1);
-        for (int j = 0; j < nw; ++j) xs[j] = (j == nw - 1) ? W.chi_max : W.chi_min + hw * j;
-        spline_build(nw, xs, W.wf, W.coef, wk);
+        for (int j = lane; j < nw; j += 32) xs[j] = (j == nw - 1) ? W.chi_max : W.chi_min + hw * j;
+        __syncwarp();
+        spline_build_warp(nw, xs, W.wf, W.coef, wk);
     }
     __syncthreads();
     if (same_window) win[1] = win[0];
@@ -401,10 +405,11 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
         if (lane == 0) kn[j] = acc;
     }
     __syncthreads();
-    if (tid == 0) {
-        double* xs = work + 2 * nk;
-        for (int j = 0; j < nk; ++j) xs[j] = (j == nk - 1) ? x1 : x0 + (x1 - x0) / (nk - 1) * j;
-        spline_build(nk, xs, kn, kc, work);               // kernel.py:645-646
+    if (wid == 0) {
+        double* xs = work + 5 * nk;
+        for (int j = lane; j < nk; j += 32) xs[j] = (j == nk - 1) ? x1 : x0 + (x1 - x0) / (nk - 1) * j;
+        __syncwarp();
+        spline_build_warp(nk, xs, kn, kc, work);          // kernel.py:645-646
     }
     __syncthreads();
     // ---- write out ------------------------------------------------------------------------------------

@@ -302,8 +302,8 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     double* nu = lnm + n;        // n
     double* c1 = nu + n;         // 4n
     double* c2 = c1 + 4 * n;     // 4n
-    double* work = c2 + 4 * n;   // 4n (two spline builds)
-    double* red = work + 4 * n;  // 64
+    double* work = c2 + 4 * n;   // 10n (two warp-built splines)
+    double* red = work + 10 * n; // 64
     double* d2tab = red + 64;    // D2_TABLE_N
     const int tid = threadIdx.x, w = tid >> 5, nw = blockDim.x >> 5, lane = tid & 31;
 
@@ -370,8 +370,8 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         if (lane == 0) { lnm[i] = lm; nu[i] = v; }
     }
     __syncthreads();
-    if (tid == 0) spline_build(n, lnm, nu, c2, work);          // nu(ln M)
-    if (tid == 32) spline_build(n, nu, lnm, c1, work + 2 * n);  // ln M(nu)
+    if (w == 0) spline_build_warp(n, lnm, nu, c2, work);          // nu(ln M)
+    if (w == 1) spline_build_warp(n, nu, lnm, c1, work + 5 * n);  // ln M(nu)
     __syncthreads();
     const double nu_min = 1.001 * nu[0], nu_max = 0.999 * nu[n - 1];  // mass_function.py:212-213
     const double lnm_star = spline_eval_search(c1, 1.0, nu, n);        // m_star = mass(1.0), :223

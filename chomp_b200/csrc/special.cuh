@@ -12,6 +12,7 @@
 #include <math.h>
 #include "special_coeffs.cuh"
 #include "nfw_coeffs.cuh"
+#include "bessel_coeffs.cuh"
 
 namespace chomp {
 
@@ -364,7 +365,19 @@ __device__ __forceinline__ double nfw_rho_tab(const NfwTables* t, double z, doub
     return g1 - u2 * (g2 * cc - ft * iz2 * sc);
 }
 
+// J0 / J2 for x >= 0: piecewise degree-12 polynomials below x = 28 (tools/gen_bessel_tables.py;
+// the Limber integrals stop at the 8th zero, j_{0,8} = 24.35 / j_{2,8} = 27.42), the library
+// routines beyond.
 __device__ __forceinline__ double bessel_j(int order, double x) {
+    if (x < BESSEL_NR * BESSEL_WIDTH) {
+        const int r = (int)(x * (1.0 / BESSEL_WIDTH));
+        const double s = fma(x, 2.0 / BESSEL_WIDTH, -(2.0 * r + 1.0));
+        const double* __restrict__ c = &g_bessel_tab[order ? 1 : 0][0][r];
+        double p = __ldg(c + BESSEL_DEG * BESSEL_NR);
+#pragma unroll
+        for (int j = BESSEL_DEG - 1; j >= 0; --j) p = fma(p, s, __ldg(c + j * BESSEL_NR));
+        return p;
+    }
     return order == 0 ? j0(x) : jn(2, x);
 }
 

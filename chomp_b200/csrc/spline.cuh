@@ -65,6 +65,65 @@ __device__ __noinline__ void spline_build(int n, const double* __restrict__ x, c
     }
 }
 
+// Same spline, built by one WARP (all 32 lanes must call it; work[5*n] scratch in shared memory).
+// Spacings, chord slopes, the tridiagonal rows and the coefficient pass are lane-parallel; only
+// the two sweeps of the Thomas algorithm -- a serial chain of one reciprocal per row -- run on
+// lane 0, with everything they need already in shared memory.
+__device__ __noinline__ void spline_build_warp(int n, const double* __restrict__ x, const double* __restrict__ y,
+                                               double* __restrict__ coef, double* __restrict__ work) {
+    const int lane = threadIdx.x & 31;
+    double* m = work;          // second derivatives (right-hand side first)
+    double* cp = work + n;     // modified upper diagonal
+    double* lo = work + 2 * n; // sub-diagonal
+    double* dg = work + 3 * n; // diagonal
+    double* up = work + 4 * n; // super-diagonal
+    const int last = n - 2;
+    for (int i = lane; i < n - 1; i += 32) coef[4 * i + 1] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+    __syncwarp();
+    for (int i = 1 + lane; i <= last; i += 32) {
+        const double hl = x[i] - x[i - 1], hr = x[i + 1] - x[i];
+        double l = hl, d = 2.0 * (hl + hr), u = hr;
+        if (i == 1) {               // m[0] = (1 + h0/h1) m[1] - (h0/h1) m[2]
+            d = hl * (1.0 + hl / hr) + 2.0 * (hl + hr);
+            u = hr - hl * hl / hr;
+            l = 0.0;
+        }
+        if (i == last) {            // m[n-1] = (1 + hr/hl) m[n-2] - (hr/hl) m[n-3]
+            d = hr * (1.0 + hr / hl) + 2.0 * (hl + hr);
+            l = hl - hr * hr / hl;
+            u = 0.0;
+        }
+        lo[i] = l; dg[i] = d; up[i] = u;
+        m[i] = 6.0 * (coef[4 * i + 1] - coef[4 * (i - 1) + 1]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double cprev = 0.0, mprev = 0.0;
+        for (int i = 1; i <= last; ++i) {
+            const double l = lo[i];
+            const double inv = 1.0 / (dg[i] - l * cprev);
+            cprev = up[i] * inv;
+            mprev = (m[i] - l * mprev) * inv;
+            cp[i] = cprev;
+            m[i] = mprev;
+        }
+        for (int i = last - 1; i >= 1; --i) { mprev = m[i] - cp[i] * mprev; m[i] = mprev; }
+        const double h0 = x[1] - x[0], h1 = x[2] - x[1];
+        m[0] = (1.0 + h0 / h1) * m[1] - (h0 / h1) * m[2];
+        const double hl2 = x[n - 2] - x[n - 3], hr2 = x[n - 1] - x[n - 2];
+        m[n - 1] = (1.0 + hr2 / hl2) * m[n - 2] - (hr2 / hl2) * m[n - 3];
+    }
+    __syncwarp();
+    for (int i = lane; i < n - 1; i += 32) {
+        const double h = x[i + 1] - x[i];
+        coef[4 * i + 0] = y[i];
+        coef[4 * i + 1] = coef[4 * i + 1] - h * (2.0 * m[i] + m[i + 1]) * (1.0 / 6.0);
+        coef[4 * i + 2] = 0.5 * m[i];
+        coef[4 * i + 3] = (m[i + 1] - m[i]) / (6.0 * h);
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ double spline_poly(const double* __restrict__ coef, int i, double t) {
     const double* c = coef + 4 * i;
     return fma(t, fma(t, fma(t, c[3], c[2]), c[1]), c[0]);
