@@ -496,25 +496,33 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
         chunk -= nch;
     }
     if (cls < 0) return;
+    const int cap = nd.cap[cls];
+    const int nn = nd.n_nodes[(size_t)b * N_NODE_LISTS + cls];
+    const double* __restrict__ g = nd.nodes + ((size_t)b * nd.cap_total + nd.off[cls]) * NODE_FIELDS;
+    // stage: field f of node i at srec[f * nn_pad + i].  Asynchronous copies (no register round
+    // trip): the coefficient tables are loaded while the records are in flight.
+    const int nn_pad = (nn + 31) & ~31;
+#pragma unroll
+    for (int f = 0; f < NODE_FIELDS; ++f)
+        for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(srec + f * nn_pad + i);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g + (size_t)f * cap + i) : "memory");
+        }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // halo-exclusion window only: its Si/Ci tables sit at the end of the dynamic shared memory
     SiciTables* tabs = (SiciTables*)(srec + smem_doubles);
     if (cfg.exclusion) sici_tables_load(tabs);
     nfw_tables_load(&ntab);
-    const int cap = nd.cap[cls];
-    const int nn = nd.n_nodes[(size_t)b * N_NODE_LISTS + cls];
-    const double* __restrict__ g = nd.nodes + ((size_t)b * nd.cap_total + nd.off[cls]) * NODE_FIELDS;
-    // stage: field f of node i at srec[f * nn_pad + i]
-    const int nn_pad = (nn + 31) & ~31;
-#pragma unroll
-    for (int f = 0; f < NODE_FIELDS; ++f)
-        for (int i = threadIdx.x; i < nn_pad; i += blockDim.x) {
-            double v;
-            if (i < nn) v = g[(size_t)f * cap + i];
-            else v = (f >= NF_W_HM) ? 0.0 : g[(size_t)f * cap + (nn - 1)];   // padding: valid shape, zero weight
-            srec[f * nn_pad + i] = v;
-        }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     double* s_lr = srec + NODE_FIELDS * nn_pad;                       // ln r_s (for ln z = ln k + ln r_s)
-    for (int i = threadIdx.x; i < nn_pad; i += blockDim.x) s_lr[i] = log(g[(size_t)NF_RS * cap + (i < nn ? i : nn - 1)]);
+    for (int i = threadIdx.x; i < nn_pad; i += blockDim.x) {
+        if (i >= nn) {                                                // padding: valid shape, zero weight
+#pragma unroll
+            for (int f = 0; f < NODE_FIELDS; ++f) srec[f * nn_pad + i] = (f >= NF_W_HM) ? 0.0 : srec[f * nn_pad + nn - 1];
+        }
+        s_lr[i] = log(srec[NF_RS * nn_pad + (i < nn ? i : nn - 1)]);
+    }
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const double* __restrict__ s_cp = srec + NF_CP * nn_pad;
     const double* __restrict__ s_rs = srec + NF_RS * nn_pad;
