@@ -194,7 +194,8 @@ int chomp_b200_create(void** handle, int device) {
     CK(chomp_upload_sincos_table());
     CK(chomp_upload_nfw_tables());
     CK(chomp_upload_bessel_tables());
-    CK(chomp_upload_sigma_tables(glx[SIG_NQ], glw[SIG_NQ]));
+    CK(chomp_upload_sigma_tables(glx[SIG_NQ], glw[SIG_NQ], glx[SIG_NQ_S], glw[SIG_NQ_S]));
+    CK(chomp_upload_expf_table());
     Handle* h = new Handle();
     h->device = device;
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));

@@ -12,10 +12,13 @@
 
 namespace chomp {
 
-#define SIG_NQ 16          // Gauss-Legendre order per sigma(R) panel
+#define SIG_NQ 16          // Gauss-Legendre order per linear sigma(R) panel (W^2 oscillates: 2.5 periods per panel)
+#define SIG_NQ_S 8         // order on the x < 1 and tail panels (smooth integrands; error < 1e-10 of sigma^2)
+#define SIG_LOW_DL 2.0     // width in ln x of the fixed x < 1 panels [-2 (j + 1), -2 j]
+#define SIG_LOW_MAX 6
 #define SIG_XSPLIT 48.0    // beyond x = kR = 48 (96 for R >= 8 Mpc/h) only the non-oscillatory part of W^2 is integrated
 #define SIG_DX 8.0         // panel width in x between 1 and SIG_XSPLIT
-#define SIG_NLOW 4         // geometric panels below x = 1 (4 + 6 + 2 panels x 16 nodes = 6 full warp passes)
+#define SIG_NLOW 4         // geometric panels below x_one when the fixed lattice does not apply
 #define SIG_NTAIL 2        // geometric panels beyond SIG_XSPLIT
 
 // squared top-hat window W^2(x), W = 3 (sin x / x^3 - cos x / x^2)   (cosmology.py:651-652)
@@ -38,8 +41,27 @@ __device__ __forceinline__ double tophat2(double x) {
 #define SIG_LIN_MAX 12     // panels up to x = 97 (2 SIG_XSPLIT)
 __device__ double g_sig_lnx[SIG_LIN_MAX * SIG_NQ];
 __device__ double g_sig_w2w[SIG_LIN_MAX * SIG_NQ];
-static inline cudaError_t chomp_upload_sigma_tables(const double* glx16, const double* glw16) {
+// same for the fixed panels below x = 1 (Gauss-Legendre in ln x): ln x and W^2(x) dln x
+__device__ double g_sig_low_lnx[SIG_LOW_MAX * SIG_NQ_S];
+__device__ double g_sig_low_w2w[SIG_LOW_MAX * SIG_NQ_S];
+static inline cudaError_t chomp_upload_sigma_tables(const double* glx16, const double* glw16, const double* glx8,
+                                                    const double* glw8) {
     static double lnx[SIG_LIN_MAX * SIG_NQ], w2w[SIG_LIN_MAX * SIG_NQ];
+    static double llnx[SIG_LOW_MAX * SIG_NQ_S], lw2w[SIG_LOW_MAX * SIG_NQ_S];
+    for (int j = 0; j < SIG_LOW_MAX; ++j)
+        for (int q = 0; q < SIG_NQ_S; ++q) {
+            const double half = 0.5 * SIG_LOW_DL;
+            const double lx = -SIG_LOW_DL * j - half + half * glx8[q];
+            const double x = exp(lx), x2 = x * x;
+            const double W = x < 0.1 ? 1.0 + x2 * (-0.1 + x2 * (1.0 / 280.0 + x2 * (-1.0 / 15120.0 + x2 / 1330560.0)))
+                                     : 3.0 * (sin(x) - x * cos(x)) / (x * x * x);
+            llnx[j * SIG_NQ_S + q] = lx;
+            lw2w[j * SIG_NQ_S + q] = W * W * half * glw8[q];
+        }
+    cudaError_t e0 = cudaMemcpyToSymbol(g_sig_low_lnx, llnx, sizeof llnx);
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaMemcpyToSymbol(g_sig_low_w2w, lw2w, sizeof lw2w);
+    if (e0 != cudaSuccess) return e0;
     for (int j = 0; j < SIG_LIN_MAX; ++j)
         for (int q = 0; q < SIG_NQ; ++q) {
             const double a = 1.0 + SIG_DX * j, half = 0.5 * SIG_DX;
@@ -74,7 +96,7 @@ struct D2Table {
         const double um = u + 1.0, u1 = u - 1.0, u2 = u - 2.0;
         const double f = tab[j - 1] * (-(1.0 / 6.0) * u * u1 * u2) + tab[j] * (0.5 * um * u1 * u2) +
                          tab[j + 1] * (-0.5 * um * u * u2) + tab[j + 2] * ((1.0 / 6.0) * um * u * u1);
-        return exp(f);
+        return exp_fast(f);
     }
     __device__ __forceinline__ double at_lnk(double lnk) const { return (*this)(0.0, lnk); }
 };
@@ -114,7 +136,6 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
     if (xs > x_one) n_lin = (int)ceil((xs - x_one) / SIG_DX - 1e-9);
     if (n_lin < 0) n_lin = 0;
     const int n_tail = (x_hi > xs) ? SIG_NTAIL : 0;
-    const int n_pan = SIG_NLOW + n_lin + n_tail;
     // five logarithms, one per lane, handed round by shuffles (callers are whole warps)
     double lnR, l_lo, l_one, l_s, l_hi;
     {
@@ -128,7 +149,18 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
         l_hi = __shfl_sync(0xffffffffu, lg, base + 4);
     }
     const bool lattice = x_one == 1.0;     // the linear panels sit on the tabulated lattice
-    const int n_nodes = n_pan * SIG_NQ;
+    // x < 1: fixed panels of the tabulated lattice down to the one that holds x_lo, which is cut
+    // at x_lo and integrated on the spot
+    int j_lo = 0;
+    bool lat_low = lattice && x_lo < 1.0;
+    if (lat_low) {
+        j_lo = (int)floor(-l_lo * (1.0 / SIG_LOW_DL));
+        if (j_lo >= SIG_LOW_MAX) lat_low = false;
+    }
+    const int n_low = lat_low ? j_lo + 1 : SIG_NLOW;
+    // nodes are dealt out in slots of 8: one per low / tail panel, two per linear panel
+    const int n_slots = n_low + 2 * n_lin + n_tail;
+    const int n_nodes = n_slots * SIG_NQ_S;
     double acc = 0.0;
     // the two end-point terms of the oscillatory tail ride along as virtual nodes
     for (int idx = rank; idx < n_nodes + (n_tail ? 2 : 0); idx += size) {
@@ -136,12 +168,11 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
             acc += (idx == n_nodes) ? sigma_tail_edge(pk, x_hi, R) : -sigma_tail_edge(pk, xs, R);
             continue;
         }
-        const int p = idx / SIG_NQ, q = idx - p * SIG_NQ;
-        const double t = c_glx[SIG_NQ][q], wq = c_glw[SIG_NQ][q];
+        const int slot = idx >> 3, q8 = idx & 7;
         double x, lnk, wgt, w2;
-        if (p >= SIG_NLOW && p < SIG_NLOW + n_lin) {
+        if (slot >= n_low && slot < n_low + 2 * n_lin) {
             // Gauss-Legendre in x on [x_one + 8 j, x_one + 8 (j + 1)]: dlnk = dx / x
-            const int jp = p - SIG_NLOW;
+            const int jp = (slot - n_low) >> 1, q = ((slot - n_low) & 1) * SIG_NQ_S + q8;
             if (lattice && jp < n_lin - 1 && jp < SIG_LIN_MAX) {
                 const double lk = g_sig_lnx[jp * SIG_NQ + q] - lnR;
                 acc += g_sig_w2w[jp * SIG_NQ + q] * pk.at_lnk(lk);
@@ -150,26 +181,36 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
             const double a = x_one + SIG_DX * jp;
             const double b = (jp == n_lin - 1) ? xs : a + SIG_DX;
             const double half = 0.5 * (b - a);
-            x = 0.5 * (a + b) + half * t;
+            x = 0.5 * (a + b) + half * c_glx[SIG_NQ][q];
             lnk = log(x) - lnR;
-            wgt = half * wq / x;
+            wgt = half * c_glw[SIG_NQ][q] / x;
             w2 = tophat2(x);
         } else {
             double a, b;
-            const bool tail = p >= SIG_NLOW;
+            const bool tail = slot >= n_low;
             if (!tail) {
-                a = l_lo + (l_one - l_lo) * p / SIG_NLOW;
-                b = l_lo + (l_one - l_lo) * (p + 1) / SIG_NLOW;
+                if (lat_low) {
+                    if (slot < j_lo) {
+                        const double lk = g_sig_low_lnx[slot * SIG_NQ_S + q8] - lnR;
+                        acc += g_sig_low_w2w[slot * SIG_NQ_S + q8] * pk.at_lnk(lk);
+                        continue;
+                    }
+                    a = l_lo;
+                    b = -SIG_LOW_DL * j_lo;
+                } else {
+                    a = l_lo + (l_one - l_lo) * slot / SIG_NLOW;
+                    b = l_lo + (l_one - l_lo) * (slot + 1) / SIG_NLOW;
+                }
             } else {
-                const int jp = p - SIG_NLOW - n_lin;
+                const int jp = slot - n_low - 2 * n_lin;
                 a = l_s + (l_hi - l_s) * jp / SIG_NTAIL;
                 b = l_s + (l_hi - l_s) * (jp + 1) / SIG_NTAIL;
             }
             const double half = 0.5 * (b - a);
-            const double lx = 0.5 * (a + b) + half * t;
-            x = exp(lx);
+            const double lx = 0.5 * (a + b) + half * c_glx[SIG_NQ_S][q8];
+            x = exp_fast(lx);
             lnk = lx - lnR;
-            wgt = half * wq;
+            wgt = half * c_glw[SIG_NQ_S][q8];
             if (tail) {
                 const double x2 = x * x;
                 w2 = 9.0 * (1.0 + x2) / (2.0 * x2 * x2 * x2);
