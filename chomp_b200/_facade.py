@@ -61,6 +61,8 @@ def set_window(cfg, slot, window):
     cfg.dndz_zmin[slot], cfg.dndz_zmax[slot] = float(d.z_min), float(d.z_max)
     for j, v in enumerate(d._params()):
         cfg.dndz_p[slot][j] = float(v)
+    if d._kind == _lib.DNDZ_TABLE:      # the table itself travels when an engine takes the config
+        cfg.__dict__.setdefault("_dndz_uploads", {})[slot] = d
 
 
 def like_input(x, values):
@@ -82,6 +84,12 @@ class OnePoint(object):
         self.eng = engine.Engine()
 
     def configure(self, cfg):
+        up = getattr(cfg, "_dndz_uploads", {})
+        if len(up) == 2 and up[0] is up[1]:
+            up[0]._upload(self.eng, 2)
+        else:
+            for slot, d in up.items():
+                d._upload(self.eng, slot)
         self.eng.configure(cfg)
 
     def ev(self, what, x, aux=0.0):

@@ -21,7 +21,7 @@ P_LINEAR, P_MM, P_GM, P_GG = 0, 1, 2, 3
 TRISPECTRUM_MOMENT = {"power_mmmm": 0, "power_gmmm": 1, "power_ggmm": 2, "power_gggm": 3, "power_gggg": 4}
 POWER_SPEC = {"linear_power": P_LINEAR, "power_mm": P_MM, "power_gm": P_GM,
               "power_mg": P_GM, "power_gg": P_GG}
-DNDZ_GAUSSIAN, DNDZ_MAGLIM = 0, 1
+DNDZ_GAUSSIAN, DNDZ_MAGLIM, DNDZ_TABLE = 0, 1, 2
 WINDOW_GALAXY, WINDOW_CONVERGENCE = 0, 1
 ST_NONFINITE, ST_MASS_WALK, ST_NODE_OVERFLOW, ST_DOMAIN = 1, 2, 4, 8
 (EVAL_LINEAR_POWER, EVAL_SIGMA_R, EVAL_NU_OF_MASS, EVAL_MASS_OF_NU, EVAL_F_NU,
@@ -64,7 +64,8 @@ class Config(ctypes.Structure):
         ("ktheta_min", ctypes.c_double), ("ktheta_max", ctypes.c_double),
         ("bessel_limit", ctypes.c_double),
         ("corr_k_min", ctypes.c_double), ("corr_k_max", ctypes.c_double),
-        ("reserved_d", ctypes.c_double*4),
+        ("dndz_table", ctypes.c_void_p*2), ("dndz_table_n", ctypes.c_int32*2),
+        ("reserved_d", ctypes.c_double*1),
     ]
 
 
@@ -92,6 +93,8 @@ _SIGNATURES = {
     "chomp_b200_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
     "chomp_b200_destroy": (None, [ctypes.c_void_p]),
     "chomp_b200_configure": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Config)]),
+    "chomp_b200_set_dndz_table": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_void_p]),
     "chomp_b200_reserve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "chomp_b200_limber_tables": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_void_p]),

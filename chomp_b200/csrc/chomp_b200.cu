@@ -54,6 +54,9 @@ struct Handle {
     int cap_points = 0;
     int node_cap[N_NODE_LISTS] = {0, 0, 0, 0}, node_off[N_NODE_LISTS] = {0, 0, 0, 0}, node_cap_total = 0;
     long long launches = 0;
+    double* dndz_tab[2] = {nullptr, nullptr};     // CHOMP_DNDZ_TABLE: breaks[n + 1], coef[n][4]
+    int dndz_tab_n[2] = {0, 0};
+    unsigned long long dndz_tab_id[2] = {0, 0};   // bumped at every upload (same_window test)
     // device scratch (all FP64 unless noted)
     double *zbar = nullptr, *dbar = nullptr, *knodes = nullptr, *kcoef = nullptr, *chi_nodes = nullptr,
            *win_nodes = nullptr, *win_chi = nullptr, *win_coef = nullptr, *kchi = nullptr, *grid0 = nullptr,
@@ -142,7 +145,9 @@ int check_cfg(const Cfg& c) {
     if (c.corr_k_max > 0 && c.corr_k_max != c.k_max) FAIL("Correlation(k_max != halo k_max) is not supported yet");
     for (int i = 0; i < 2; ++i) {
         if (c.window_kind[i] != CHOMP_WINDOW_GALAXY && c.window_kind[i] != CHOMP_WINDOW_CONVERGENCE) FAIL("unknown window_kind");
-        if (c.dndz_kind[i] != CHOMP_DNDZ_GAUSSIAN && c.dndz_kind[i] != CHOMP_DNDZ_MAGLIM) FAIL("unknown dndz_kind");
+        if (c.dndz_kind[i] != CHOMP_DNDZ_GAUSSIAN && c.dndz_kind[i] != CHOMP_DNDZ_MAGLIM &&
+            c.dndz_kind[i] != CHOMP_DNDZ_TABLE)
+            FAIL("unknown dndz_kind");
         if (!(c.dndz_zmax[i] > c.dndz_zmin[i])) FAIL("dndz z range empty");
     }
     return 0;
@@ -216,9 +221,37 @@ void chomp_b200_destroy(void* handle) {
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_theta) cudaFree(h->d_theta);
     if (h->d_status) cudaFree(h->d_status);
+    for (int i = 0; i < 2; ++i) if (h->dndz_tab[i]) cudaFree(h->dndz_tab[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->ev[0]) for (int i = 0; i <= CHOMP_N_KERNELS; ++i) cudaEventDestroy(h->ev[i]);
     delete h;
+}
+
+int chomp_b200_set_dndz_table(void* handle, int which, int n_intervals, const double* breaks_host,
+                              const double* coef_host) {
+    Handle* h = (Handle*)handle;
+    if (!h || !breaks_host || !coef_host) FAIL("null argument");
+    if (which < 0 || which > 2) FAIL("which must be 0 (window a), 1 (window b) or 2 (both)");
+    if (n_intervals < 1 || n_intervals > (1 << 20)) FAIL("n_intervals out of range");
+    for (int i = 0; i < n_intervals; ++i)
+        if (!(breaks_host[i + 1] > breaks_host[i])) FAIL("breaks must increase strictly");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    static unsigned long long next_id = 0;
+    const unsigned long long id = ++next_id;
+    for (int i = 0; i < 2; ++i) {
+        if (which != 2 && which != i) continue;
+        if (h->dndz_tab[i]) cudaFree(h->dndz_tab[i]);
+        h->dndz_tab[i] = nullptr;
+        const size_t nd = (size_t)n_intervals + 1 + 4 * (size_t)n_intervals;
+        CK(cudaMalloc(&h->dndz_tab[i], nd * sizeof(double)));
+        CK(cudaMemcpy(h->dndz_tab[i], breaks_host, ((size_t)n_intervals + 1) * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->dndz_tab[i] + n_intervals + 1, coef_host, 4 * (size_t)n_intervals * sizeof(double),
+                      cudaMemcpyHostToDevice));
+        h->dndz_tab_n[i] = n_intervals;
+        h->dndz_tab_id[i] = id;
+    }
+    return 0;
 }
 
 int chomp_b200_configure(void* handle, const chomp_b200_config* cfg) {
@@ -231,10 +264,17 @@ int chomp_b200_configure(void* handle, const chomp_b200_config* cfg) {
                         h->cfg.n_kernel != cfg->n_kernel || h->cfg.nq_nu != cfg->nq_nu ||
                         (h->cfg.tri_moment >= 0) != (cfg->tri_moment >= 0);
     h->cfg = *cfg;
+    for (int i = 0; i < 2; ++i) {
+        const bool tab = cfg->dndz_kind[i] == CHOMP_DNDZ_TABLE;
+        if (tab && !h->dndz_tab[i]) FAIL("dndz_kind = CHOMP_DNDZ_TABLE but chomp_b200_set_dndz_table was not called");
+        h->cfg.dndz_table[i] = tab ? h->dndz_tab[i] : nullptr;
+        h->cfg.dndz_table_n[i] = tab ? h->dndz_tab_n[i] : 0;
+    }
     h->same_window = (cfg->window_kind[0] == cfg->window_kind[1] && cfg->dndz_kind[0] == cfg->dndz_kind[1] &&
                       cfg->dndz_zmin[0] == cfg->dndz_zmin[1] && cfg->dndz_zmax[0] == cfg->dndz_zmax[1] &&
                       cfg->dndz_p[0][0] == cfg->dndz_p[1][0] && cfg->dndz_p[0][1] == cfg->dndz_p[1][1] &&
-                      cfg->dndz_p[0][2] == cfg->dndz_p[1][2]);
+                      cfg->dndz_p[0][2] == cfg->dndz_p[1][2] &&
+                      (cfg->dndz_kind[0] != CHOMP_DNDZ_TABLE || h->dndz_tab_id[0] == h->dndz_tab_id[1]));
     h->configured = true;
     // opt in to > 48 KB dynamic shared memory where a stage needs it
     CK(cudaFuncSetAttribute(limber_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -585,8 +625,7 @@ eval_kernel(const Cfg cfg, int what, int n, const double* __restrict__ x, double
             case CHOMP_EVAL_GROWTH_APPROX: r = growth_approx(c, 1.0 / (1.0 + v)) / growth_approx(c, 1.0); break;
             case CHOMP_EVAL_DNDZ_A: case CHOMP_EVAL_DNDZ_B: {                    // kernel.py:67-86
                 const int wi = (what == CHOMP_EVAL_DNDZ_B) ? 1 : 0;
-                Dndz d{cfg.dndz_kind[wi], cfg.dndz_zmin[wi], cfg.dndz_zmax[wi], cfg.dndz_p[wi][0], cfg.dndz_p[wi][1],
-                       cfg.dndz_p[wi][2], cx.dndz_norm[wi]};
+                const Dndz d = make_dndz(cfg, wi, cx.dndz_norm[wi]);
                 r = aux != 0.0 ? dndz_raw(d, v) : dndz_eval(d, v);
             } break;
             default: r = nan("");

@@ -49,8 +49,34 @@ __device__ __forceinline__ double grid_growth(const EpochGrid& g, double z) {
 struct Dndz {
     int kind;
     double z_min, z_max, p0, p1, p2, norm;
+    const double* tab;      // CHOMP_DNDZ_TABLE: breaks[n + 1] then coef[n][4] (global memory)
+    int n;
 };
+__device__ __forceinline__ Dndz make_dndz(const Cfg& cfg, int i, double norm) {
+    return Dndz{cfg.dndz_kind[i], cfg.dndz_zmin[i], cfg.dndz_zmax[i], cfg.dndz_p[i][0], cfg.dndz_p[i][1],
+                cfg.dndz_p[i][2], norm, cfg.dndz_table[i], cfg.dndz_table_n[i]};
+}
+// dNdzInterpolation.raw_dndz (kernel.py:207-208): the piece that holds z, end pieces extrapolating
+__device__ __noinline__ double dndz_table_eval(const double* __restrict__ tab, int n, double z) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(tab + mid) <= z) lo = mid; else hi = mid;
+    }
+    const double t = z - __ldg(tab + lo);
+    const double* c = tab + (n + 1) + 4 * lo;
+    return fma(t, fma(t, fma(t, __ldg(c + 3), __ldg(c + 2)), __ldg(c + 1)), __ldg(c));
+}
+// integral of piece i over its intersection with [a, b]
+__device__ __forceinline__ double dndz_table_piece(const double* __restrict__ tab, int n, int i, double a, double b) {
+    const double x0 = tab[i], lo = fmax(a, x0) - x0, hi = fmin(b, tab[i + 1]) - x0;
+    if (!(hi > lo)) return 0.0;
+    const double* c = tab + (n + 1) + 4 * i;
+    auto F = [&](double t) { return t * (c[0] + t * (c[1] * 0.5 + t * (c[2] * (1.0 / 3.0) + t * (c[3] * 0.25)))); };
+    return F(hi) - F(lo);
+}
 __device__ __forceinline__ double dndz_raw(const Dndz& d, double z) {
+    if (d.kind == CHOMP_DNDZ_TABLE) return dndz_table_eval(d.tab, d.n, z);
     if (d.kind == CHOMP_DNDZ_GAUSSIAN)                          // kernel.py:110-112
         return exp(-1.0 * (z - d.p0) * (z - d.p0) / (2.0 * d.p1 * d.p1));
     return pow(z, d.p0) * exp(-1.0 * pow(z / d.p1, d.p2));      // kernel.py:177-179
@@ -155,10 +181,7 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     g[0].z_min = cfg.zk_min < 0.0 ? 0.0 : cfg.zk_min; g[0].z_max = cfg.zk_max;
     Dndz dist[2];
     for (int i = 0; i < 2; ++i) {
-        dist[i].kind = cfg.dndz_kind[i];
-        dist[i].z_min = cfg.dndz_zmin[i]; dist[i].z_max = cfg.dndz_zmax[i];
-        dist[i].p0 = cfg.dndz_p[i][0]; dist[i].p1 = cfg.dndz_p[i][1]; dist[i].p2 = cfg.dndz_p[i][2];
-        dist[i].norm = 1.0;
+        dist[i] = make_dndz(cfg, i, 1.0);
         double zlo = (cfg.window_kind[i] == CHOMP_WINDOW_GALAXY) ? dist[i].z_min : 0.0;
         if (zlo < eps) zlo = eps;
         g[1 + i].z_min = zlo; g[1 + i].z_max = dist[i].z_max;
@@ -201,7 +224,11 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     // ---- dN/dz normalisations (kernel.py:43-54): 16 panels x GL-8 --------------------------------
     for (int i = 0; i < (same_window ? 1 : 2); ++i) {
         double v = 0.0;
-        if (tid < DNDZ_PANELS * 8) {
+        if (dist[i].kind == CHOMP_DNDZ_TABLE) {
+            // piecewise polynomial: every piece integrated in closed form
+            for (int j = tid; j < dist[i].n; j += blockDim.x)
+                v += dndz_table_piece(dist[i].tab, dist[i].n, j, dist[i].z_min, dist[i].z_max);
+        } else if (tid < DNDZ_PANELS * 8) {
             const int pnl = tid >> 3, q = tid & 7;
             const double a = dist[i].z_min + (dist[i].z_max - dist[i].z_min) * pnl / DNDZ_PANELS;
             const double bb = dist[i].z_min + (dist[i].z_max - dist[i].z_min) * (pnl + 1) / DNDZ_PANELS;

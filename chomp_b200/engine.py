@@ -64,12 +64,47 @@ def theta_bins(theta_min_deg, theta_max_deg, bins_per_decade=5.0):
     return np.array(centres)
 
 
+def fitpack_piecewise(z_array, p_array, weights=None, interpolation_order=2, smoothing=None):
+    """dNdzInterpolation's spline (kernel.py:191-204) in piecewise-polynomial form.
+
+    The reference builds it with FITPACK through scipy (InterpolatedUnivariateSpline, or
+    UnivariateSpline when ``smoothing`` is given); so does this -- it is input preparation on a
+    handful of numbers, done once per survey -- and hands the device one cubic per knot interval:
+    returns (breaks[n + 1], coef[n, 4]) with p(z) = sum_j coef[i, j] (z - breaks[i])**j."""
+    try:
+        from scipy.interpolate import InterpolatedUnivariateSpline, PPoly, UnivariateSpline
+    except ImportError as exc:   # pragma: no cover
+        raise _lib.ChompError("dNdzInterpolation needs scipy (FITPACK), as the reference does") from exc
+    z_array = np.ascontiguousarray(z_array, dtype=np.float64)
+    p_array = np.ascontiguousarray(p_array, dtype=np.float64)
+    if not 1 <= int(interpolation_order) <= 3:
+        raise ValueError("interpolation_order must be 1, 2 or 3 (the device evaluates cubics)")
+    if smoothing is None:
+        spl = InterpolatedUnivariateSpline(z_array, p_array, w=weights, k=interpolation_order)
+    else:
+        spl = UnivariateSpline(z_array, p_array, w=weights, k=interpolation_order, s=smoothing)
+    pp = PPoly.from_spline(spl._eval_args)
+    keep = np.diff(pp.x) > 0                      # drop the repeated end knots
+    c = pp.c[::-1][:, keep]                       # ascending powers, [order + 1, n]
+    coef = np.zeros((c.shape[1], 4))
+    coef[:, :c.shape[0]] = c.T
+    breaks = np.concatenate([pp.x[:-1][keep], pp.x[-1:]])
+    return np.ascontiguousarray(breaks), np.ascontiguousarray(coef)
+
+
 class RedshiftDistribution(object):
     """Parameters of a dNdzGaussian / dNdzMagLim after the constructors' range
-    clipping (kernel.py:100-106, 160-175)."""
+    clipping (kernel.py:100-106, 160-175), or the table of a dNdzInterpolation."""
 
-    def __init__(self, kind, z_min, z_max, p):
+    def __init__(self, kind, z_min, z_max, p, breaks=None, coef=None):
         self.kind, self.z_min, self.z_max, self.p = kind, float(z_min), float(z_max), tuple(p)
+        self.breaks, self.coef = breaks, coef
+
+    @classmethod
+    def table(cls, z_array, p_array, weights=None, interpolation_order=2, smoothing=None):
+        """dNdzInterpolation(z_array, p_array, weights, interpolation_order, smoothing), kernel.py:191-205."""
+        breaks, coef = fitpack_piecewise(z_array, p_array, weights, interpolation_order, smoothing)
+        return cls(_lib.DNDZ_TABLE, z_array[0], z_array[-1], (0.0, 0.0, 0.0), breaks, coef)
 
     @classmethod
     def gaussian(cls, z_min, z_max, z0, sigma_z):
@@ -236,8 +271,25 @@ class Engine(object):
             pass
 
     # -- plumbing -----------------------------------------------------------
+    def set_dndz_table(self, which, breaks, coef):
+        """Upload a tabulated dN/dz (which = 0 / 1: window a / b, 2: both); configure() afterwards."""
+        breaks = np.ascontiguousarray(breaks, dtype=np.float64)
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        if coef.shape != (breaks.size - 1, 4):
+            raise ValueError("coef must be [len(breaks) - 1, 4]")
+        _lib.check(self.lib.chomp_b200_set_dndz_table(self._h, int(which), int(breaks.size - 1),
+                                                     breaks.ctypes.data_as(ctypes.c_void_p),
+                                                     coef.ctypes.data_as(ctypes.c_void_p)))
+
     def configure(self, config):
         if isinstance(config, Survey):
+            da, db = config.dist
+            if da.kind == _lib.DNDZ_TABLE and db is da:
+                self.set_dndz_table(2, da.breaks, da.coef)
+            else:
+                for i, d in enumerate((da, db)):
+                    if d.kind == _lib.DNDZ_TABLE:
+                        self.set_dndz_table(i, d.breaks, d.coef)
             config = config.config()
         _lib.check(self.lib.chomp_b200_configure(self._h, ctypes.byref(config)))
         self.cfg = config

@@ -3,8 +3,8 @@ dNdzMagLim (kernel.py:26-179), WindowFunctionGalaxy / WindowFunctionConvergence
 (:211-484), Kernel / GalaxyGalaxyLensingKernel (:559-839), numerics on the GPU.
 
 Not provided (outside BASELINE.json's configs):
-dNdChiGaussian, dNdzInterpolation, the delta-function and flat windows,
-KernelGalaxyDelta, KernelCovariance.  ``force_quad`` is accepted and ignored:
+dNdChiGaussian, the delta-function and flat windows, KernelGalaxyDelta,
+KernelCovariance.  ``force_quad`` is accepted and ignored:
 every integral is a converged fixed-order rule.  Kernel.__init__ does not write
 the reference's debug files ``test_window_before/after`` (kernel.py:606, 608).
 """
@@ -35,9 +35,13 @@ class dNdz(object):
             cfg.dndz_zmin[i], cfg.dndz_zmax[i] = float(self.z_min), float(self.z_max)
             for j, v in enumerate(self._params()):
                 cfg.dndz_p[i][j] = float(v)
+        self._upload(gpu.eng, 2)
         gpu.configure(cfg)
         gpu.eng.limber_tables(_facade.cosmo_row(defaults.default_cosmo_dict))
         return gpu
+
+    def _upload(self, eng, which):
+        """Hook for distributions that carry a table (dNdzInterpolation)."""
 
     def normalize(self):
         self.norm = float(self._device().table(_lib.T_DNDZ_NORM)[0])
@@ -93,6 +97,24 @@ class dNdzMagLim(dNdz):
 
     def _params(self):
         return (self.a, self.z0, self.b)
+
+
+class dNdzInterpolation(dNdz):
+    """p(z) from an array of redshifts and probabilities (kernel.py:181-208): the reference's FITPACK
+    spline (order 2 by default), evaluated on the device from its piecewise-polynomial form."""
+    _kind = _lib.DNDZ_TABLE
+
+    def __init__(self, z_array, p_array, weights=None, interpolation_order=2, smoothing=None):
+        from . import engine
+        self._breaks, self._coef = engine.fitpack_piecewise(z_array, p_array, weights, interpolation_order,
+                                                            smoothing)
+        dNdz.__init__(self, z_array[0], z_array[-1])
+
+    def _params(self):
+        return (0.0, 0.0, 0.0)
+
+    def _upload(self, eng, which):
+        eng.set_dndz_table(which, self._breaks, self._coef)
 
 
 class WindowFunction(object):

@@ -42,7 +42,8 @@ enum { CHOMP_HOD_ZHENG = 0, CHOMP_HOD_MANDELBAUM = 1 };
 /* power spectra (halo.py:266, 277, 322, 391) */
 enum { CHOMP_P_LINEAR = 0, CHOMP_P_MM = 1, CHOMP_P_GM = 2, CHOMP_P_GG = 3 };
 /* redshift distributions (kernel.py:89-112, 148-179) and windows (kernel.py:360-387, 409-484) */
-enum { CHOMP_DNDZ_GAUSSIAN = 0, CHOMP_DNDZ_MAGLIM = 1 };
+enum { CHOMP_DNDZ_GAUSSIAN = 0, CHOMP_DNDZ_MAGLIM = 1,
+       CHOMP_DNDZ_TABLE = 2 /* dNdzInterpolation (kernel.py:181-208): piecewise cubic set with chomp_b200_set_dndz_table */ };
 enum { CHOMP_WINDOW_GALAXY = 0, CHOMP_WINDOW_CONVERGENCE = 1 };
 /* per-point status bits */
 enum {
@@ -81,7 +82,11 @@ typedef struct chomp_b200_config {
     double ktheta_min, ktheta_max;     /* Kernel(ktheta_min, ktheta_max, ...)            */
     double bessel_limit;      /* special.jn_zeros(order, kernel_bessel_limit)[-1]        */
     double corr_k_min, corr_k_max;     /* Correlation(k_min=, k_max=); <= 0: halo limits */
-    double reserved_d[4];
+    /* CHOMP_DNDZ_TABLE: filled in by chomp_b200_configure from the tables given to
+     * chomp_b200_set_dndz_table (whatever the caller puts here is ignored) */
+    const double* dndz_table[2];
+    int32_t dndz_table_n[2];
+    double reserved_d[1];
 } chomp_b200_config;
 
 int chomp_b200_version(void);
@@ -91,6 +96,14 @@ const char* chomp_b200_last_error(void);
 int chomp_b200_create(void** handle, int device);
 void chomp_b200_destroy(void* handle);
 int chomp_b200_configure(void* handle, const chomp_b200_config* cfg);
+/* Tabulated redshift distribution -- replaces dNdzInterpolation.__init__ / raw_dndz
+ * (kernel.py:191-208): the reference's FITPACK spline handed over in piecewise-polynomial form,
+ * p(z) = c[i][0] + c[i][1] t + c[i][2] t^2 + c[i][3] t^3 with t = z - breaks[i] on
+ * [breaks[i], breaks[i+1]] (end pieces extrapolate).  HOST pointers: breaks[n_intervals + 1],
+ * coef[n_intervals][4]; copied.  which = 0 / 1: window a / b, 2: both.  Call before chomp_b200_configure
+ * with dndz_kind[which] = CHOMP_DNDZ_TABLE. */
+int chomp_b200_set_dndz_table(void* handle, int which, int n_intervals, const double* breaks_host,
+                              const double* coef_host);
 /* (re)allocate device scratch for batches of up to max_points parameter points */
 int chomp_b200_reserve(void* handle, int max_points);
 

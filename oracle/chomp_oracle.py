@@ -771,6 +771,42 @@ class dNdzMagLim(dNdz):                                   # kernel.py:148-179
         return [float(self.a), self.z0, float(self.b)]
 
 
+class dNdzInterpolation(dNdz):                            # kernel.py:181-208
+    """p(z) tabulated at z_array, interpolated by FITPACK (scipy, the reference's own
+    provider: third-party arithmetic)."""
+    kind = 2
+
+    def __init__(self, z_array, p_array, weights=None, interpolation_order=2,
+                 smoothing=None, prec=None, integ=None):
+        from scipy.interpolate import UnivariateSpline
+        z_array = np.asarray(z_array, dtype=float)
+        p_array = np.asarray(p_array, dtype=float)
+        if smoothing is None:                             # kernel.py:197-200
+            self._p_of_z = _IUS(z_array, p_array, w=weights,
+                                                        k=interpolation_order)
+        else:                                             # kernel.py:201-204
+            self._p_of_z = UnivariateSpline(z_array, p_array, w=weights,
+                                            k=interpolation_order, s=smoothing)
+        self._init(z_array[0], z_array[-1], prec, integ)
+
+    def raw(self, z):                                     # kernel.py:207-208
+        return self._p_of_z(z)
+
+    def smooth_marks(self):
+        return self._p_of_z.get_knots()
+
+    def piecewise(self):
+        """(breaks[n+1], coef[n,4]): the spline as one cubic per knot interval,
+        p(z) = c0 + c1 t + c2 t^2 + c3 t^3, t = z - breaks[i]."""
+        from scipy.interpolate import PPoly
+        pp = PPoly.from_spline(self._p_of_z._eval_args)
+        keep = np.diff(pp.x) > 0
+        c = pp.c[::-1, keep]                              # ascending powers
+        coef = np.zeros((c.shape[1], 4))
+        coef[:, :c.shape[0]] = c.T
+        return np.concatenate([pp.x[:-1][keep], pp.x[-1:]]), coef
+
+
 # ----------------------------------------------------------------------------
 # kernel.WindowFunction*  (kernel.py:211-484)
 # ----------------------------------------------------------------------------

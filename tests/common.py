@@ -45,7 +45,7 @@ def oracle_wtheta(cosmo, halo, hod, dist_a, dist_b=None, window_a="galaxy", wind
 
     def make_dist(spec):
         kind, args = spec
-        cls = O.dNdzGaussian if kind == "gaussian" else O.dNdzMagLim
+        cls = {"gaussian": O.dNdzGaussian, "table": O.dNdzInterpolation}.get(kind, O.dNdzMagLim)
         return cls(*args, prec=prec, integ=integ)
 
     def make_window(kind, dist, cm):
@@ -114,3 +114,10 @@ def cov_err(got, ref):
     got, ref = np.asarray(got, dtype=float), np.asarray(ref, dtype=float)
     d = np.sqrt(np.abs(np.outer(np.diag(ref), np.diag(ref))))
     return float(np.max(np.abs(got - ref)/np.where(d > 0, d, 1.0)))
+
+
+def interp_table():
+    """A tabulated p(z) for the dNdzInterpolation cases: 25 samples of z^2 exp(-(z/0.45)^1.5)
+    on [0.02, 1.7] (unnormalised, as a photometric-redshift histogram would be)."""
+    z = np.linspace(0.02, 1.7, 25)
+    return z, z*z*np.exp(-(z/0.45)**1.5)
