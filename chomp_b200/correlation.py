@@ -86,6 +86,44 @@ class Correlation(object):
         w = gpu.eng.wtheta_stage(1, _lib.POWER_SPEC[self._power_name], _facade.flat(theta_rad))
         return _facade.like_input(theta_rad, w.cpu().numpy()[0])
 
+    def correlation_batch(self, cosmo_dicts, halo_dicts=None, hod_dicts=None, theta_rad=None):
+        """w(theta) for a whole batch of parameter points in one pass of the four GPU stages:
+        what ``for d in dicts: corr.set_cosmology(d); corr.set_halo(..); corr.set_hod(..);
+        corr.compute_correlation()`` (examples/example_script.py:141-143,
+        simulation_design.py:116-138) computes point by point -- each point's z_bar comes from its
+        own cosmology, as Correlation.set_cosmology does.  Entries of halo_dicts / hod_dicts may
+        be None (or the lists omitted) to keep this object's current values.
+        Returns (w [B, n_theta], status [B])."""
+        h = self.halo
+        B = len(cosmo_dicts)
+        halo_dicts = halo_dicts or [None]*B
+        hod_dicts = hod_dicts or [None]*B
+        cur_halo, cur_hod = h.get_halo(), h.get_hod()
+        kind = h.local_hod._kind
+        cosmo = engine.pack_params(cosmo_dicts, _lib.COSMO_KEYS)
+        halo = engine.pack_params([d if d is not None else cur_halo for d in halo_dicts], _lib.HALO_KEYS)
+        keys = _lib.HOD_ZHENG_KEYS if kind == _lib.HOD_ZHENG else _lib.HOD_MANDELBAUM_KEYS
+        hod = np.zeros((B, _lib.N_HOD))
+        for i, d in enumerate(hod_dicts):
+            d = d if d is not None else cur_hod
+            hod[i, :len(keys)] = [d[k] for k in keys]
+        h._ensure()
+        cfg = self.kernel._config()
+        hc = h._gpu.eng.cfg
+        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "tri_moment"):
+            setattr(cfg, name, getattr(hc, name))
+        if cfg.use_halofit:
+            raise NotImplementedError("correlation_batch with HaloFit spectra")
+        gpu = getattr(self, "_batch_gpu", None)
+        if gpu is None:
+            gpu = self._batch_gpu = _facade.OnePoint()
+        gpu.configure(cfg)
+        theta = self.theta_array if theta_rad is None else _facade.flat(theta_rad)
+        import torch
+        status = torch.zeros(B, dtype=torch.int32, device="cuda:%d" % gpu.eng.device)
+        w = gpu.eng.wtheta(cosmo, halo, hod, theta, _lib.POWER_SPEC[self._power_name], status=status)
+        return w.cpu().numpy(), status.cpu().numpy()
+
     def _stage_on_halo_handle(self):
         """Replay the Limber stage on the handle that holds the halo's tables and pin z_bar."""
         h = self.halo
