@@ -660,14 +660,16 @@ cov_ng_kernel(const Cfg cfg, const CovP cp, int b0, int nb_chunk, const double* 
             const double* Ui = U + i * nk;
             const double* Mi = Mu + i * nk;
             const double* Ti = TW + (size_t)i * ntot;
+            const double ihx = 1.0 / hx;
             for (int qq = lane; qq < ntot; qq += 32) {
                 double y = xq[qq] + ltb;
                 if (y <= x1) {                                    // kernel.py:1004-1008
                     if (y < x0) y = x0;
-                    int j = (int)floor((y - x0) / hx);
+                    int j = (int)((y - x0) * ihx);
                     j = j < 0 ? 0 : (j > nk - 2 ? nk - 2 : j);
-                    const double t = (y - (x0 + hx * j)) / hx;
-                    const double v = exp(nak_eval(Ui[j], Ui[j + 1], Mi[j], Mi[j + 1], hx, t)) + kmin10;
+                    const double t = (y - (x0 + hx * j)) * ihx;
+                    // ln(K - 10 K_min) is a table value of moderate size: the constant-bank exp applies
+                    const double v = exp_fast(nak_eval(Ui[j], Ui[j + 1], Mi[j], Mi[j + 1], hx, t)) + kmin10;
                     acc = fma(Ti[qq], v, acc);
                 }
             }
