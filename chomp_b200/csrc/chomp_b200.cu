@@ -583,13 +583,13 @@ eval_kernel(const Cfg cfg, int what, int n, const double* __restrict__ x, double
             case CHOMP_EVAL_FIRST_MOMENT: case CHOMP_EVAL_SECOND_MOMENT: {
                 const HodP h = load_hod(cfg.hod_kind, cx.hod, cfg.halo_precision);
                 double n1, n2;
-                hod_moments(h, v, n1, n2);
+                hod_moments(h, v, log(v), n1, n2);
                 r = (what == CHOMP_EVAL_FIRST_MOMENT) ? n1 : n2;
             } break;
             case CHOMP_EVAL_NTH_MOMENT: {                       // HOD.nth_moment, hod.py:68-92
                 const HodP h = load_hod(cfg.hod_kind, cx.hod, cfg.halo_precision);
                 double n1, n2;
-                hod_moments(h, v, n1, n2);
+                hod_moments(h, v, log(v), n1, n2);
                 const int nmom = (int)aux;
                 if (nmom == 1) r = n1;
                 else if (nmom == 2) r = n2;

@@ -14,6 +14,27 @@ __constant__ double c_glw[CHOMP_MAX_GL + 1][CHOMP_MAX_GL];
 
 typedef chomp_b200_config Cfg;
 
+// exp(x) for |x| < 700 to a few 1e-16 relative, with the constants as constant-bank operands:
+// x = n ln 2 + r, |r| <= ln 2 / 2, degree-12 Taylor polynomial, 2^n added into the exponent field.
+// No special cases (overflow, NaN, denormal results): the callers' arguments are table values.
+#define EXPF_DEG 12
+static const double h_k_expf[EXPF_DEG + 4] = {
+    1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+    1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+    1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600};
+__constant__ double k_expf[EXPF_DEG + 4];
+static inline cudaError_t chomp_upload_expf_table() { return cudaMemcpyToSymbol(k_expf, h_k_expf, sizeof h_k_expf); }
+__device__ __forceinline__ double exp_fast(double x) {
+    const double n = rint(x * k_expf[0]);
+    double r = fma(n, k_expf[1], x);
+    r = fma(n, k_expf[2], r);
+    double p = k_expf[3 + EXPF_DEG];
+#pragma unroll
+    for (int i = EXPF_DEG - 1; i >= 0; --i) p = fma(p, r, k_expf[3 + i]);
+    return __hiloint2double(__double2hiint(p) + ((int)n * 1048576), __double2loint(p));
+}
+
+
 #define CHOMP_EPOCH_LEN 24
 enum { EP_Z = 0, EP_GROWTH, EP_SIGMA_NORM, EP_DELTA_C, EP_DELTA_V, EP_RHO_BAR, EP_LNM_MIN, EP_LNM_MAX, EP_NU_MIN,
        EP_NU_MAX, EP_F_NORM, EP_B_NORM, EP_LNM_STAR, EP_PK_AMP, EP_CHI, EP_WALK,
@@ -183,6 +204,18 @@ __device__ __forceinline__ void st_raw(double nu, double sta, double stq, double
     const double nup = nu * sta;
     const double pq = pow(nup, -stq);
     nu_f = (1.0 + pq) * sqrt(nup) * exp(-0.5 * nup);  // nu * f(nu) / f_norm
+    bias = 1.0 + (nup - 1.0) / delta_c + 2.0 * stq / (delta_c * (1.0 + 1.0 / pq));
+}
+
+// The same from ln(nu): every power is the exponential of a known logarithm (a handful of
+// constant-bank exp_fast calls instead of pow + sqrt + exp: the node loops stay small enough
+// for the instruction cache).  ln_sta = ln(st_little_a).
+__device__ __forceinline__ void st_raw_ln(double lnnu, double ln_sta, double stq, double delta_c, double& nu_f,
+                                          double& bias) {
+    const double lnup = lnnu + ln_sta;
+    const double nup = exp_fast(lnup);
+    const double pq = exp_fast(-stq * lnup);
+    nu_f = (1.0 + pq) * exp_fast(0.5 * lnup - 0.5 * nup);
     bias = 1.0 + (nup - 1.0) / delta_c + 2.0 * stq / (delta_c * (1.0 + 1.0 / pq));
 }
 

@@ -73,15 +73,16 @@ __device__ __noinline__ HodP load_hod(int kind, const double* __restrict__ p, do
     return h;
 }
 
-// <N>, <N(N-1)>  (hod.py:188-230 Zheng, 262-299 Mandelbaum)
-__device__ __noinline__ void hod_moments(const HodP& h, double M, double& n1, double& n2) {
-    const double lg = log10(M);
+// <N>, <N(N-1)>  (hod.py:188-230 Zheng, 262-299 Mandelbaum); lm = ln(M) is supplied by the
+// callers, who all have it
+__device__ __noinline__ void hod_moments(const HodP& h, double M, double lm, double& n1, double& n2) {
+    const double lg = lm * 0.43429448190325182765;
     double nc, ns;
     if (h.kind == CHOMP_HOD_ZHENG) {
         if (h.sigma <= 0.0) nc = (lg > h.log_M_min) ? 1.0 : 0.0;
         else nc = 0.5 * (1.0 + erf((lg - h.log_M_min) / h.sigma));
         const double d = M - h.M0;
-        ns = (d > 0.0) ? nc * pow(d / h.M1p, h.alpha) : 0.0;
+        ns = (d > 0.0) ? nc * exp_fast(h.alpha * log(d / h.M1p)) : 0.0;
     } else {
         nc = (lg >= h.log_M_0) ? 1.0 : 0.0;
         const double r = M / h.Mmin;
@@ -143,7 +144,10 @@ __device__ __noinline__ double lnnu_moment_crossing(const NuTab& t, const HodP& 
     const int lane = threadIdx.x & 31;
     double n1, n2;
     // the two ends, on lanes 0 and 1
-    hod_moments(h, exp(mass_of_nu_ln(t, exp(lane == 0 ? a : b))), n1, n2);
+    {
+        const double lm = mass_of_nu_ln(t, exp_fast(lane == 0 ? a : b));
+        hod_moments(h, exp_fast(lm), lm, n1, n2);
+    }
     const bool lt_end = (which == 1 ? n1 : n2) < 1.0;
     const unsigned ends = __ballot_sync(0xffffffffu, lt_end);
     if (!(ends & 1u) || (ends & 2u)) return nan("");
@@ -153,17 +157,18 @@ __device__ __noinline__ double lnnu_moment_crossing(const NuTab& t, const HodP& 
         const bool have = i < t.n - 1;
         const int ii = have ? i : 1;
         const double x = log(t.nu[ii]);
-        hod_moments(h, exp(t.lnm[ii]), n1, n2);
+        hod_moments(h, exp_fast(t.lnm[ii]), t.lnm[ii], n1, n2);
         const bool inside = have && x > a && x < b;
         const bool lt = (which == 1 ? n1 : n2) < 1.0;
         lo = fmax(lo, warp_max(inside && lt ? x : a));
         hi = fmin(hi, warp_min(inside && !lt ? x : b));
     }
-    const int kn = search_index(exp(0.5 * (lo + hi)), t.nu, t.n);
+    const int kn = search_index(exp_fast(0.5 * (lo + hi)), t.nu, t.n);
     for (int round = 0; round < 16 && hi - lo > 1e-15 * fabs(hi); ++round) {
         const double x = lo + (hi - lo) * ((lane + 1) * (1.0 / 33.0));
-        const double v = exp(x);
-        hod_moments(h, exp(spline_poly(t.c_lnm_nu, kn, v - t.nu[kn])), n1, n2);
+        const double v = exp_fast(x);
+        const double lm = spline_poly(t.c_lnm_nu, kn, v - t.nu[kn]);
+        hod_moments(h, exp_fast(lm), lm, n1, n2);
         const bool lt = (which == 1 ? n1 : n2) < 1.0;
         const double nlo = warp_max(lt ? x : lo), nhi = warp_min(lt ? hi : x);
         lo = nlo; hi = nhi;
@@ -319,6 +324,7 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     const double f_norm = e[EP_F_NORM], b_norm = e[EP_B_NORM], delta_c = e[EP_DELTA_C];
     const double rho_bar = e[EP_RHO_BAR], delta_v = e[EP_DELTA_V], lnm_star = e[EP_LNM_STAR];
     const double rv_coef = 3.0 / (4.0 * M_PI * delta_v * rho_bar);
+    const double ln_rv_coef = log(rv_coef), ln_sta = log(sta);
     double nbar = 0.0;
     int st = 0;
     const int n_lists = cfg.tri_moment >= 0 ? N_NODE_LISTS : N_KCLASS;
@@ -354,21 +360,21 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
                 x = 0.5 * (a + bb) + half * c_glx[nq][q];
                 wq = half * c_glw[nq][q];
             }
-            const double v = exp(x);
+            const double v = exp_fast(x);
             const int kn = pknot[p];
             const double lm = spline_poly(c1, kn, v - nu[kn]);      // MassFunction.ln_mass, mass_function.py:326
-            const double M = exp(lm);
+            const double M = exp_fast(lm);
             double nf, bias;
-            st_raw(v, sta, stq, delta_c, nf, bias);
+            st_raw_ln(x, ln_sta, stq, delta_c, nf, bias);
             const double wt = wq * nf * f_norm;          // d ln(nu) * nu f(nu)
             bias *= b_norm;
-            const double con = c0 * exp(beta * (lm - lnm_star));                           // halo.py:869-873
-            const double r_v = cbrt(rv_coef * M);                                          // halo.py:890-893
+            const double con = c0 * exp_fast(beta * (lm - lnm_star));                      // halo.py:869-873
+            const double r_v = exp_fast((ln_rv_coef + lm) * (1.0 / 3.0));                  // halo.py:890-893
             const double cp = 1.0 + con;
             const double lncp = log(cp);
             const double imk = 1.0 / (lncp - con / cp);                                    // halo.py:584
             double n1, n2;
-            hod_moments(h, M, n1, n2);
+            hod_moments(h, M, lm, n1, n2);
             const double in1 = (xmid > x_lo1) ? 1.0 : 0.0, in2 = (xmid > x_lo2) ? 1.0 : 0.0;
             rec[NF_CP * cap + idx] = cp;
             rec[NF_RS * cap + idx] = r_v / con;

@@ -165,26 +165,6 @@ __device__ __forceinline__ void sincos_reduced(double x, double& s, double& c) {
     c = ((q + 1) & 2) ? -b : b;
 }
 
-// exp(x) for |x| < 700 to a few 1e-16 relative, with the constants as constant-bank operands:
-// x = n ln 2 + r, |r| <= ln 2 / 2, degree-12 Taylor polynomial, 2^n added into the exponent field.
-// No special cases (overflow, NaN, denormal results): the callers' arguments are table values.
-#define EXPF_DEG 12
-static const double h_k_expf[EXPF_DEG + 4] = {
-    1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
-    1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
-    1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600};
-__constant__ double k_expf[EXPF_DEG + 4];
-static inline cudaError_t chomp_upload_expf_table() { return cudaMemcpyToSymbol(k_expf, h_k_expf, sizeof h_k_expf); }
-__device__ __forceinline__ double exp_fast(double x) {
-    const double n = rint(x * k_expf[0]);
-    double r = fma(n, k_expf[1], x);
-    r = fma(n, k_expf[2], r);
-    double p = k_expf[3 + EXPF_DEG];
-#pragma unroll
-    for (int i = EXPF_DEG - 1; i >= 0; --i) p = fma(p, r, k_expf[3 + i]);
-    return __hiloint2double(__double2hiint(p) + ((int)n * 1048576), __double2loint(p));
-}
-
 // x <= CHOMP_SICI_TINY_X: same series, degree CHOMP_SICI_DEG_T
 __device__ __forceinline__ void sici_series_tiny_c(double x, double& si, double& ci_nolog) {
     const double xx = x * x;
