@@ -137,6 +137,7 @@ __host__ __device__ inline size_t limber_smem_doubles(const Cfg& cfg, int same_w
            128 /*red + misc*/ + (LIMBER_THREADS / 32) * (nb / 2 + 2) /*per-warp int prefix sums*/;
 }
 
+#define LIMBER_SER_TERMS 12
 #ifndef LIMBER_MIN_BLOCKS
 #define LIMBER_MIN_BLOCKS 4
 #endif
@@ -169,7 +170,7 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     double* kn = p; p += nk;
     double* kc = p; p += 4 * nk;
     double* work = p; p += limber_work_doubles(cfg);
-    double* red = p; p += 64;
+    double* red = p; p += 128;
     int* pfx_all = (int*)p;           // (LIMBER_THREADS / 32) x (nb_max + 1) ints
     __shared__ int n_edge_s;
     __shared__ double s_misc[8];
@@ -377,10 +378,52 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     // widest base panel: below kt * width <= 2 no panel needs sub-division
     double wmax = 0.0;
     for (int pnl = 0; pnl < n_pan; ++pnl) wmax = fmax(wmax, edge[pnl + 1] - edge[pnl]);
+    // ---- small k theta: J_n(k theta chi) as a power series in (k theta chi / 2)^2 ------------------
+    // For k theta chi_max <= 2 every panel is whole, and
+    //   K = sum_m (-1)^m t^m / (m! (m + n)!) * sum_nodes fw (chi / chi_max)^(2 m + n),  t = (k theta chi_max / 2)^2
+    // (n = 0 or 2; 12 terms: truncation < 1e-17): the nodes are summed ONCE into 12 moments instead
+    // of once per K node.  That covers the lower ~60 % of the ln(k theta) table.
+    {
+        double mom[LIMBER_SER_TERMS];
+#pragma unroll
+        for (int m = 0; m < LIMBER_SER_TERMS; ++m) mom[m] = 0.0;
+        const double icm = 1.0 / chi_max_k;
+        for (int idx = tid; idx < n_pan * nq; idx += blockDim.x) {
+            const double r = chi_q[idx] * icm, r2 = r * r;
+            double pw = fw_q[idx] * (order == 0 ? 1.0 : r2);
+#pragma unroll
+            for (int m = 0; m < LIMBER_SER_TERMS; ++m) { mom[m] += pw; pw *= r2; }
+        }
+        // fixed-order reduction: lanes, then warps
+#pragma unroll
+        for (int m = 0; m < LIMBER_SER_TERMS; ++m) mom[m] = warp_sum(mom[m]);
+        __syncthreads();
+        if (lane == 0)
+            for (int m = 0; m < LIMBER_SER_TERMS; ++m) red[wid * LIMBER_SER_TERMS + m] = mom[m];
+        __syncthreads();
+    }
     int* pfx = pfx_all + wid * (nb_max + 1);     // per-warp prefix sums of node counts
     for (int j = wid; j < nk; j += nwarp) {
         const double lkt = (j == nk - 1) ? x1 : x0 + (x1 - x0) / (nk - 1) * j;
         const double kt = exp(lkt);
+        if (kt * chi_max_k <= 2.0 && cfg.bessel_limit >= 2.0) {
+            // series in t with the moments above (lane m holds term m)
+            const double t = 0.25 * kt * kt * chi_max_k * chi_max_k;
+            double term = 0.0;
+            if (lane < LIMBER_SER_TERMS) {
+                double mm = 0.0;
+                for (int ww = 0; ww < nwarp; ++ww) mm += red[ww * LIMBER_SER_TERMS + lane];
+                // (-1)^m t^m / (m! (m + n)!)
+                double cfac = (order == 0) ? 1.0 : 0.5 * t;          // n = 2: t^(m + 1) / (m! (m + 2)!)
+                for (int i = 1; i <= lane; ++i) cfac *= -t / ((double)i * (double)(i + order));
+                term = cfac * mm;
+            }
+            // sum the terms from the smallest up (ascending magnitude is descending m)
+            double accs = 0.0;
+            for (int m = LIMBER_SER_TERMS - 1; m >= 0; --m) accs += __shfl_sync(0xffffffffu, term, m);
+            if (lane == 0) kn[j] = accs;
+            continue;
+        }
         double top = cfg.bessel_limit / kt;
         if (top >= chi_max_k) top = chi_max_k;
         double acc = 0.0;

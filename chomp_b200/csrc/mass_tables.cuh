@@ -420,15 +420,18 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     //      [nu_min, nu_max], 8-point Gauss-Legendre on every knot interval of ln nu
     const double stq = hp[CHOMP_H_STQ], sta = hp[CHOMP_H_ST_LITTLE_A];
     double sf = 0.0, sfb = 0.0;
-    const double l_min = log(nu_min), l_max = log(nu_max);
+    // ln(nu) at the knots once (the spline scratch is free again), ends moved to nu_min / nu_max
+    double* lognu = work;
+    for (int i = tid; i < n; i += blockDim.x) lognu[i] = log(i == 0 ? nu_min : (i == n - 1 ? nu_max : nu[i]));
+    const double ln_sta = log(sta);
+    __syncthreads();
     for (int idx = tid; idx < (n - 1) * 8; idx += blockDim.x) {
         const int i = idx >> 3, q = idx & 7;
-        const double a = (i == 0) ? l_min : log(nu[i]);
-        const double bb = (i == n - 2) ? l_max : log(nu[i + 1]);
+        const double a = lognu[i], bb = lognu[i + 1];
         const double half = 0.5 * (bb - a);
         const double x = 0.5 * (a + bb) + half * c_glx[8][q];
         double nf, bi;
-        st_raw(exp(x), sta, stq, m.delta_c, nf, bi);
+        st_raw_ln(x, ln_sta, stq, m.delta_c, nf, bi);
         const double wgt = half * c_glw[8][q];
         sf += wgt * nf;
         sfb += wgt * nf * bi;
