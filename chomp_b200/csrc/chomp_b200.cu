@@ -336,7 +336,7 @@ int chomp_b200_reserve(void* handle, int max_points) {
     rc |= dev_alloc(h, &h->nodes, B * NODE_FIELDS * h->node_cap_total);
     rc |= dev_alloc(h, &h->n_nodes, B * N_NODE_LISTS);
     rc |= dev_alloc(h, &h->nbar, B);
-    rc |= dev_alloc(h, &h->rv_max, B);
+    rc |= dev_alloc(h, &h->rv_max, 3 * B);
     rc |= dev_alloc(h, &h->tri_w, B * h->node_cap[TRI_LIST]);
     h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0;
     rc |= dev_alloc(h, &h->raw, B * 5 * c.n_halo);

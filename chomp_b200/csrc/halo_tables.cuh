@@ -180,7 +180,7 @@ struct NodesOut {
     double* nodes;     // [B, cap_total * NODE_FIELDS]; class c occupies [off_c*NF, (off_c+cap_c)*NF), fields SoA
     int32_t* n_nodes;  // [B, N_NODE_LISTS]
     double* nbar;      // [B] n_bar / rho_bar
-    double* rv_max;    // [B] r_vir at the upper end of the mass table (sets the k classes)
+    double* rv_max;    // [B, 3] r_vir at the upper end of the mass table, and the first ln k index of k classes 1 and 2
     double* tri_w;     // [B, cap of the last class] weights of the 1-halo trispectrum integral (0-padded)
     int cap[N_NODE_LISTS];
     int off[N_NODE_LISTS];
@@ -195,6 +195,14 @@ __host__ __device__ inline int kclass_cap(int c, int n_mass, bool with_trispectr
     // at most six of the MAX_EXTRA_BREAKS slots are ever filled (two lower limits, M_0, the step /
     // slope change, two moment crossings)
     return (((n_mass - 1 + 6) * m + 31) / 32) * 32;
+}
+
+// first ln k node index whose phi = k * rv_max reaches `phi`
+__device__ __forceinline__ int kclass_first_index(double phi, double rv_max, double l0, double hk, int nk) {
+    const double x = (log(phi / rv_max) - l0) / hk;
+    if (!(x > 0.0)) return 0;
+    if (x >= (double)nk) return nk;
+    return (int)ceil(x);
 }
 
 #ifndef NODES_MIN_BLOCKS
@@ -408,7 +416,13 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     nbar = block_sum(nbar, red);
     if (tid == 0) {
         out.nbar[b] = nbar;
-        out.rv_max[b] = cbrt(rv_coef * exp(lnm[n - 1]));
+        const double rvm = cbrt(rv_coef * exp(lnm[n - 1]));
+        const int nkh = cfg.n_halo;
+        const double lk0 = log(cfg.k_min), hkh = (log(cfg.k_max) - lk0) / (nkh - 1);
+        const int i1 = kclass_first_index(KCLASS_PHI_1, rvm, lk0, hkh, nkh);
+        out.rv_max[3 * b] = rvm;
+        out.rv_max[3 * b + 1] = (double)i1;
+        out.rv_max[3 * b + 2] = (double)max(i1, kclass_first_index(KCLASS_PHI_2, rvm, lk0, hkh, nkh));
         if (!isfinite(nbar)) st |= CHOMP_ST_NONFINITE;
         if (status && st) atomicOr(status + b, st);
     }
@@ -420,14 +434,6 @@ __device__ __forceinline__ double exclusion_window(const SiciTables* t, double k
     sici(t, kR, si, ci);
     sincos(kR, &s, &c);
     return (kR * c + kR * kR * kR * ci + (2.0 - kR * kR) * s) / (3.0 * kR);
-}
-
-// first ln k node index whose phi = k * rv_max reaches `phi`
-__device__ __forceinline__ int kclass_first_index(double phi, double rv_max, double l0, double hk, int nk) {
-    const double x = (log(phi / rv_max) - l0) / hk;
-    if (!(x > 0.0)) return 0;
-    if (x >= (double)nk) return nk;
-    return (int)ceil(x);
 }
 
 // ---- small-argument series of the NFW profile numerator ---------------------------------------
@@ -485,9 +491,7 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
     const int nk = cfg.n_halo;
     const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hk = (l1 - l0) / (nk - 1);
     // which class / k range does this CTA own?
-    const double rv_max = nd.rv_max[b];
-    const int i1 = kclass_first_index(KCLASS_PHI_1, rv_max, l0, hk, nk);
-    const int i2 = max(i1, kclass_first_index(KCLASS_PHI_2, rv_max, l0, hk, nk));
+    const int i1 = (int)nd.rv_max[3 * b + 1], i2 = (int)nd.rv_max[3 * b + 2];     // set by nu_nodes_kernel
     const int first[N_KCLASS + 1] = {0, i1, i2, nk};
     int chunk = blockIdx.x, cls = -1, k_begin = 0, k_end = 0;
     for (int c = 0; c < N_KCLASS; ++c) {
@@ -623,7 +627,7 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
     const double ik_hi = 1.0 / k_hi;
     for (int ik = k_begin + w; ik < k_end; ik += nwarp) {
         const double lnk = (ik == nk - 1) ? l1 : l0 + hk * ik;                      // halo.py:49-51
-        const double k = exp(lnk);
+        const double k = exp_fast(lnk);
         double a_hm = 0.0, a_pmm = 0.0, a_hg = 0.0, a_gm = 0.0, a_gg = 0.0;
         for (int base = i_lo; base < nn_pad; base += 32) {      // warp-uniform trip count (collectives inside)
             const bool valid = base + lane < nn_pad;
