@@ -35,6 +35,9 @@ enum { NF_CP = 0, NF_RS, NF_LNCP, NF_W_HM, NF_W_PMM, NF_W_HG, NF_W_GM, NF_W_GG }
 #define N_KCLASS 3
 #define KCLASS_PHI_1 45.0
 #define KCLASS_PHI_2 180.0
+// per-panel order inside a class: local phase k_top(class) * r_vir(panel top)
+#define KPANEL_PHI_1 20.0
+#define KPANEL_PHI_2 90.0
 // A fourth node list serves the 1-halo trispectrum only (built when cfg.tri_moment >= 0): its
 // M^3 weighting moves the integrand to high masses, where y(k, M) oscillates fastest, so every
 // panel is cut in two halves of order 16 ("32").
@@ -296,11 +299,23 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
         x_singular = x_sing;
     }
     __syncthreads();
-    // per panel (in parallel): spline interval and the Gauss-Legendre order in each k class;
-    // panels inside the erf edge of the central occupation get the "sharp" order
+    // per panel (in parallel): spline interval and the Gauss-Legendre order in each k class.  The
+    // class order (set by the phase phi = k r_vir at the TOP of the mass table) is only needed where
+    // the profile really oscillates that fast: a panel whose own phase k_top(class) r_vir(panel top)
+    // stays below KPANEL_PHI_1 / _2 gets order 4 / 8 (scratch/adaptive_orders.py: same accuracy,
+    // less than half the nodes in the two fine lists).  Panels inside the erf edge of the central
+    // occupation get at least the "sharp" order.
+    const double rv_coef = 3.0 / (4.0 * M_PI * e[EP_DELTA_V] * e[EP_RHO_BAR]);
+    const double rvm = cbrt(rv_coef * exp(lnm[n - 1]));
+    const int nkh = cfg.n_halo;
+    const double lk0 = log(cfg.k_min), hkh = (log(cfg.k_max) - lk0) / (nkh - 1);
+    const int ic1 = kclass_first_index(KCLASS_PHI_1, rvm, lk0, hkh, nkh);
+    const int ic2 = max(ic1, kclass_first_index(KCLASS_PHI_2, rvm, lk0, hkh, nkh));
     {
         const double ln10 = 2.302585092994046;
         const double sharp_lo = (h.log_M_min - 3.5 * h.sigma) * ln10, sharp_hi = (h.log_M_min + 3.5 * h.sigma) * ln10;
+        // largest k of each class's ln k nodes (the trispectrum list serves every k)
+        const double k_top[N_NODE_LISTS] = {exp(lk0 + hkh * max(ic1 - 1, 0)), exp(lk0 + hkh * max(ic2 - 1, 0)), cfg.k_max, cfg.k_max};
         for (int p = tid; p < n_edge - 1; p += blockDim.x) {
             const double xm = 0.5 * (edge[p] + edge[p + 1]);
             const int kn = search_index(exp(xm), nu, n);
@@ -309,8 +324,15 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
             const double lm_hi = spline_poly(c1, kn, exp(edge[p + 1]) - nu[kn]);
             const bool sharp = (h.kind == CHOMP_HOD_ZHENG) && h.sigma > 0.0 && lm_hi > sharp_lo && lm_lo < sharp_hi;
             const bool sing = edge[p] >= x_singular - 1e-12 && edge[p] <= x_singular + 0.02;
+            const double rv_p = cbrt(rv_coef * exp(lm_hi));
             for (int c = 0; c < N_NODE_LISTS; ++c) {
-                int o = sharp ? k_class_sharp[c] : k_class_base[c];
+                int o = k_class_base[c];
+                if (c < N_KCLASS) {
+                    const double phi_p = k_top[c] * rv_p;
+                    const int o_local = phi_p < KPANEL_PHI_1 ? 4 : (phi_p < KPANEL_PHI_2 ? 8 : 16);
+                    if (o_local < o) o = o_local;
+                }
+                if (sharp && o < k_class_sharp[c]) o = (c < N_KCLASS) ? max(o, 10) : k_class_sharp[c];
                 if (sing && o < SING_MIN_ORDER) o = SING_MIN_ORDER;
                 pstart[c * max_edge + p] = o;
             }
@@ -331,7 +353,6 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     const double c0 = hp[CHOMP_H_C0] / (1.0 + e[EP_Z]);                   // halo.py:65
     const double f_norm = e[EP_F_NORM], b_norm = e[EP_B_NORM], delta_c = e[EP_DELTA_C];
     const double rho_bar = e[EP_RHO_BAR], delta_v = e[EP_DELTA_V], lnm_star = e[EP_LNM_STAR];
-    const double rv_coef = 3.0 / (4.0 * M_PI * delta_v * rho_bar);
     const double ln_rv_coef = log(rv_coef), ln_sta = log(sta);
     double nbar = 0.0;
     int st = 0;
@@ -416,13 +437,9 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     nbar = block_sum(nbar, red);
     if (tid == 0) {
         out.nbar[b] = nbar;
-        const double rvm = cbrt(rv_coef * exp(lnm[n - 1]));
-        const int nkh = cfg.n_halo;
-        const double lk0 = log(cfg.k_min), hkh = (log(cfg.k_max) - lk0) / (nkh - 1);
-        const int i1 = kclass_first_index(KCLASS_PHI_1, rvm, lk0, hkh, nkh);
         out.rv_max[3 * b] = rvm;
-        out.rv_max[3 * b + 1] = (double)i1;
-        out.rv_max[3 * b + 2] = (double)max(i1, kclass_first_index(KCLASS_PHI_2, rvm, lk0, hkh, nkh));
+        out.rv_max[3 * b + 1] = (double)ic1;
+        out.rv_max[3 * b + 2] = (double)ic2;
         if (!isfinite(nbar)) st |= CHOMP_ST_NONFINITE;
         if (status && st) atomicOr(status + b, st);
     }
