@@ -36,8 +36,10 @@ enum { NF_CP = 0, NF_RS, NF_LNCP, NF_W_HM, NF_W_PMM, NF_W_HG, NF_W_GM, NF_W_GG }
 #define KCLASS_PHI_1 45.0
 #define KCLASS_PHI_2 180.0
 // per-panel order inside a class: local phase k_top(class) * r_vir(panel top)
-#define KPANEL_PHI_1 20.0
-#define KPANEL_PHI_2 90.0
+#ifndef KPANEL_PHI_1
+#define KPANEL_PHI_1 12.0
+#define KPANEL_PHI_2 60.0
+#endif
 // A fourth node list serves the 1-halo trispectrum only (built when cfg.tri_moment >= 0): its
 // M^3 weighting moves the integrand to high masses, where y(k, M) oscillates fastest, so every
 // panel is cut in two halves of order 16 ("32").
