@@ -294,27 +294,45 @@ __device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scal
     double t1 = -g0 / 0.35;                       // d ln nu / d ln M is 0.15 ... 0.7
     double g1 = 0.0;
     const double t_max = J * ln_step;
-    // sigma(R) carries quadrature noise of ~1e-9, and only the step index is needed: stop early
+    // sigma(R) carries quadrature noise of ~1e-9, and only the step index is needed: the search
+    // stops as soon as the root t* is pinned between two steps of the walk.  ln nu is nearly linear
+    // in ln M, so the secant-corrected estimate t_c = t1 - g1 / slope is off by far less than the
+    // correction itself; a quarter of it (plus the noise floor) is taken as the bound.
+    double slope = 0.35;
+    int j = 0;
+    bool certain = false;
     for (int it = 0; it < 10; ++it) {
         t1 = fmax(-t_max, fmin(t_max, t1));
         g1 = log(team_nu_m(tm, m, M0 * exp(t1)) * nu_scale) - target;
+        if (it > 0 && t1 != t0) slope = (g1 - g0) / (t1 - t0);
+        const double corr = (fabs(slope) > 0.05) ? g1 / slope : g1 / 0.05;
+        const double tc = t1 - corr;
+        const double s = fabs(tc) / ln_step, fl = floor(s);
+        const double d = fmin(s - fl, fl + 1.0 - s) * ln_step;
+        if (it > 0 && tc * dir > 0.0 && fabs(tc) < t_max && d > 4.0 * (0.25 * fabs(corr) + 2e-7)) {
+            j = (int)fl + 1;                 // first step beyond the root
+            certain = true;
+            break;
+        }
         if (fabs(g1) < 2e-8 || fabs(t1 - t0) < 1e-7) break;
         const double t2 = t1 - g1 * (t1 - t0) / (g1 - g0);
         t0 = t1; g0 = g1; t1 = t2;
     }
-    int j = (int)ceil(fabs(t1) / ln_step - 1e-7);
-    if (j < 1) j = 1;
-    // settle on the first step that passes, exactly as the sequential walk would
-    for (int guard = 0; guard < 8; ++guard) {
-        if (j > J) return -1;
-        const double nu_j = team_nu_m(tm, m, M0 * pow(1.05, (double)(dir * j))) * nu_scale;
-        const bool ok_j = want_le ? (nu_j <= thr) : (nu_j >= thr);
-        if (!ok_j) { ++j; continue; }
-        if (j == 1) break;
-        const double nu_p = team_nu_m(tm, m, M0 * pow(1.05, (double)(dir * (j - 1)))) * nu_scale;
-        const bool ok_p = want_le ? (nu_p <= thr) : (nu_p >= thr);
-        if (ok_p) { --j; continue; }
-        break;
+    if (!certain) {
+        j = (int)ceil(fabs(t1) / ln_step - 1e-7);
+        if (j < 1) j = 1;
+        // settle on the first step that passes, exactly as the sequential walk would
+        for (int guard = 0; guard < 8; ++guard) {
+            if (j > J) return -1;
+            const double nu_j = team_nu_m(tm, m, M0 * pow(1.05, (double)(dir * j))) * nu_scale;
+            const bool ok_j = want_le ? (nu_j <= thr) : (nu_j >= thr);
+            if (!ok_j) { ++j; continue; }
+            if (j == 1) break;
+            const double nu_p = team_nu_m(tm, m, M0 * pow(1.05, (double)(dir * (j - 1)))) * nu_scale;
+            const bool ok_p = want_le ? (nu_p <= thr) : (nu_p >= thr);
+            if (ok_p) { --j; continue; }
+            break;
+        }
     }
     *mass_out = M0 * pow(1.05, (double)(dir * j));
     return j;
