@@ -392,9 +392,28 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     double m_lo = 1.0e9, m_hi = 1.0e16;
     const bool fixed_limits = cfg.mass_min > 0.0 && cfg.mass_max > 0.0;
     if (fixed_limits) { m_lo = cfg.mass_min; m_hi = cfg.mass_max; }
-    if (w == 0) { const double v = warp_sigma2(m.pk, 8.0, m.k_min, m.k_max); if (lane == 0) red[0] = v; }
-    if (w == 1 && !fixed_limits) { const double v = warp_nu_m(m, m_lo); if (lane == 0) red[1] = v; }
-    if (w == 2 && !fixed_limits) { const double v = warp_nu_m(m, m_hi); if (lane == 0) red[2] = v; }
+    // sigma_8, nu(1e9), nu(1e16) side by side on groups of 2 / 3 / 3 warps (warp partials in
+    // red[8 ..], summed in warp order)
+    {
+        const int grp = (w < 2 || fixed_limits) ? 0 : (w < 5 ? 1 : 2);
+        const int g_first = grp == 0 ? 0 : (grp == 1 ? 2 : 5);
+        const int g_warps = fixed_limits ? nw : (grp == 0 ? 2 : 3);
+        const double R = grp == 0 ? 8.0 : cbrt(3.0 * (grp == 1 ? m_lo : m_hi) / (4.0 * M_PI * m.rho_bar));
+        const double part = warp_sum(sigma2_partial(m.pk, R, m.k_min, m.k_max, tid - 32 * g_first, 32 * g_warps));
+        if (lane == 0) red[8 + w] = part;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (fixed_limits) {
+            double v = 0.0;
+            for (int i = 0; i < nw; ++i) v += red[8 + i];
+            red[0] = v;
+        } else {
+            red[0] = red[8] + red[9];
+            red[1] = m.delta_c * m.delta_c / ((red[10] + red[11]) + red[12]);
+            red[2] = m.delta_c * m.delta_c / ((red[13] + red[14]) + red[15]);
+        }
+    }
     __syncthreads();
     const double s8_raw = sqrt(red[0]);
     const double sigma_norm = c.s8 * growth / s8_raw;
@@ -422,8 +441,16 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     const double lnm_min = log(m_lo), lnm_max = log(m_hi);
     const double hM = (lnm_max - lnm_min) / (n - 1);
     // ---- nu at the mass nodes (mass_function.py:205-209) -----------------------------
+    // the warps draw the nodes from a shared counter, heaviest (largest R: most panels) first
+    __shared__ int next_node;
+    if (tid == 0) next_node = 0;
     __syncthreads();
-    for (int i = w; i < n; i += nw) {
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&next_node, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n) break;
+        const int i = n - 1 - t;
         const double lm = (i == n - 1) ? lnm_max : lnm_min + hM * i;
         const double v = warp_nu_m(m, exp(lm)) * nu_scale;
         if (lane == 0) { lnm[i] = lm; nu[i] = v; }
