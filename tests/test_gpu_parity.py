@@ -36,8 +36,14 @@ def _run_point(eng, survey, cosmo, halo, hod, which):
     return w.cpu().numpy()[0], int(status.cpu()[0])
 
 
+# concentrations below 1 at the high-mass end (c = 2.2 (M / M*)^-0.25): nodes that cannot use the
+# small-argument series of the profile (its recurrence runs forward, c >= 1) and the both-arguments-
+# small branch of the table-driven profile
+H_DICT_LOW_C = dict(H_DICT, c0=2.2, beta=-0.25)
+
 CASES = [
     ("base", C_DICT, H_DICT, HOD_DICT),
+    ("low_concentration", C_DICT, H_DICT_LOW_C, HOD_DICT),
     ("cosmo2", C_DICT_2, H_DICT, HOD_DICT),
     ("halo2", C_DICT, H_DICT_2, HOD_DICT),
     ("hod2", C_DICT, H_DICT, HOD_DICT_2),
