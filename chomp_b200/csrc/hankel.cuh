@@ -136,7 +136,10 @@ __host__ __device__ inline int hankel_nodes(const Cfg& cfg) { return (cfg.n_halo
 // grid (B), 256 threads.  Phase 1: G_q = w_q k^2 P(k_q) / (2 pi D^2) at the theta-independent
 // Gauss-Legendre nodes (each halo-table interval cut into `sub` equal pieces).  Phase 2: one
 // warp per theta sums G_q K(x_q + ln theta).
-__global__ void __launch_bounds__(256)
+#ifndef WTHETA_MIN_BLOCKS
+#define WTHETA_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, WTHETA_MIN_BLOCKS)
 wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __restrict__ theta,
               const double* __restrict__ cosmo, const double* __restrict__ epoch, const double* __restrict__ dbar,
               const double* __restrict__ htab, const double* __restrict__ hcoef,
@@ -174,7 +177,7 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
         const double pa = a + (bb - a) * s / sub, pb = (s == sub - 1) ? bb : a + (bb - a) * (s + 1) / sub;
         const double half = 0.5 * (pb - pa);
         const double x = 0.5 * (pa + pb) + half * c_glx[nq][q];
-        const double k = exp(x);
+        const double k = exp_fast(x);
         const double dx = x - a;
         double P = 2.0 * M_PI * M_PI * delta2(pk, k, x) / (k * k * k);
         if (which != CHOMP_P_LINEAR) {

@@ -382,9 +382,11 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         // ln Delta^2 table over every k the sigma(R) range rules can reach: [k_min / 100, 100 k_max]
         const double t0 = log(cfg.k_min / 100.0) - 0.05, t1 = log(cfg.k_max * 100.0) + 0.05;
         const double th = (t1 - t0) / (D2_TABLE_N - 1);
+        const double ln_amp = log(pk1.amp);
         for (int j = tid; j < D2_TABLE_N; j += blockDim.x) {
             const double lk = t0 + th * j;
-            d2tab[j] = log(delta2(pk1, exp(lk), lk));
+            // ln Delta^2 = ln amp + (3 + n)(ln k - ln H0) + 2 ln T(k): no exp / log round trip
+            d2tab[j] = ln_amp + pk1.expo * (lk - pk1.ln_H0) + 2.0 * log(transfer_eh(pk1, exp_fast(lk)));
         }
         m.pk.tab = d2tab; m.pk.l0 = t0; m.pk.inv_h = 1.0 / th;
     }
