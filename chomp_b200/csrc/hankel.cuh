@@ -137,7 +137,7 @@ __host__ __device__ inline int hankel_nodes(const Cfg& cfg) { return (cfg.n_halo
 // Gauss-Legendre nodes (each halo-table interval cut into `sub` equal pieces).  Phase 2: one
 // warp per theta sums G_q K(x_q + ln theta).
 #ifndef WTHETA_MIN_BLOCKS
-#define WTHETA_MIN_BLOCKS 3
+#define WTHETA_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(256, WTHETA_MIN_BLOCKS)
 wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __restrict__ theta,
