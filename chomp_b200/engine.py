@@ -64,25 +64,82 @@ def theta_bins(theta_min_deg, theta_max_deg, bins_per_decade=5.0):
     return np.array(centres)
 
 
-def fitpack_piecewise(z_array, p_array, weights=None, interpolation_order=2, smoothing=None):
-    """dNdzInterpolation's spline (kernel.py:191-204) in piecewise-polynomial form.
+def _bspline_basis(t, k, x):
+    """All B-splines of degree k on the knot vector t at the points x (Cox-de Boor): [len(x), len(t) - k - 1]."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(t) - k - 1
+    # degree 0: indicator of [t_j, t_j+1), the last non-empty interval closed on the right
+    B = np.zeros((len(x), len(t) - 1))
+    last = np.max(np.nonzero(np.diff(t) > 0)[0])
+    for j in range(len(t) - 1):
+        if t[j + 1] > t[j]:
+            hi = (x <= t[j + 1]) if j == last else (x < t[j + 1])
+            B[:, j] = (x >= t[j]) & hi
+    for d in range(1, k + 1):
+        Bn = np.zeros((len(x), len(t) - 1 - d))
+        for j in range(len(t) - 1 - d):
+            left = t[j + d] - t[j]
+            right = t[j + d + 1] - t[j + 1]
+            if left > 0:
+                Bn[:, j] += (x - t[j])/left*B[:, j]
+            if right > 0:
+                Bn[:, j] += (t[j + d + 1] - x)/right*B[:, j + 1]
+        B = Bn
+    return B[:, :n]
 
-    The reference builds it with FITPACK through scipy (InterpolatedUnivariateSpline, or
-    UnivariateSpline when ``smoothing`` is given); so does this -- it is input preparation on a
-    handful of numbers, done once per survey -- and hands the device one cubic per knot interval:
-    returns (breaks[n + 1], coef[n, 4]) with p(z) = sum_j coef[i, j] (z - breaks[i])**j."""
+
+def interpolating_spline_piecewise(z_array, p_array, k=2):
+    """The interpolating spline FITPACK builds for s = 0 (what InterpolatedUnivariateSpline is;
+    reference kernel.py:197-200), restated: knots as in FITPACK's fpcurf -- for odd k the data
+    abscissae without the (k + 1) / 2 outermost interior ones on each side ("not-a-knot"), for even
+    k the mid-points of the interior data intervals -- and the B-spline coefficients from the
+    collocation system.  Returned in piecewise-polynomial form: (breaks[n + 1], coef[n, 4])."""
+    x = np.ascontiguousarray(z_array, dtype=np.float64)
+    y = np.ascontiguousarray(p_array, dtype=np.float64)
+    m = x.size
+    if not 1 <= k <= 3:
+        raise ValueError("interpolation_order must be 1, 2 or 3 (the device evaluates cubics)")
+    if m <= k or np.any(np.diff(x) <= 0):
+        raise ValueError("need more than k strictly increasing abscissae")
+    if k % 2:
+        interior = x[(k + 1)//2:m - (k + 1)//2]
+    else:
+        interior = 0.5*(x[k//2:m - k//2 - 1] + x[k//2 + 1:m - k//2])
+    t = np.concatenate([[x[0]]*(k + 1), interior, [x[-1]]*(k + 1)])
+    c = np.linalg.solve(_bspline_basis(t, k, x), y)
+    breaks = np.unique(t)
+    coef = np.zeros((breaks.size - 1, 4))
+    # one polynomial of degree k per knot interval: exact fit through k + 1 of its own values
+    u = 0.5*(1.0 - np.cos(np.pi*(np.arange(k + 1) + 0.5)/(k + 1)))           # Chebyshev points in (0, 1)
+    V = np.vander(u, k + 1, increasing=True)
+    for i in range(breaks.size - 1):
+        h = breaks[i + 1] - breaks[i]
+        vals = _bspline_basis(t, k, breaks[i] + h*u) @ c
+        coef[i, :k + 1] = np.linalg.solve(V, vals)/h**np.arange(k + 1)
+    return np.ascontiguousarray(breaks), np.ascontiguousarray(coef)
+
+
+def fitpack_piecewise(z_array, p_array, weights=None, interpolation_order=2, smoothing=None):
+    """dNdzInterpolation's spline (kernel.py:191-204) in piecewise-polynomial form: returns
+    (breaks[n + 1], coef[n, 4]) with p(z) = sum_j coef[i, j] (z - breaks[i])**j.
+
+    ``smoothing is None`` (the reference's default): the interpolating spline, built here
+    (`interpolating_spline_piecewise`; positive weights do not change an interpolating spline).
+    A smoothing spline (kernel.py:201-204) needs FITPACK's adaptive knot placement and is taken
+    from scipy, as the reference does -- input preparation on a handful of numbers, once per survey."""
+    if smoothing is None:
+        if weights is not None and np.any(np.asarray(weights) <= 0):
+            raise ValueError("weights must be positive")
+        return interpolating_spline_piecewise(z_array, p_array, int(interpolation_order))
     try:
-        from scipy.interpolate import InterpolatedUnivariateSpline, PPoly, UnivariateSpline
+        from scipy.interpolate import PPoly, UnivariateSpline
     except ImportError as exc:   # pragma: no cover
-        raise _lib.ChompError("dNdzInterpolation needs scipy (FITPACK), as the reference does") from exc
+        raise _lib.ChompError("a smoothing dNdzInterpolation needs scipy (FITPACK), as the reference does") from exc
     z_array = np.ascontiguousarray(z_array, dtype=np.float64)
     p_array = np.ascontiguousarray(p_array, dtype=np.float64)
     if not 1 <= int(interpolation_order) <= 3:
         raise ValueError("interpolation_order must be 1, 2 or 3 (the device evaluates cubics)")
-    if smoothing is None:
-        spl = InterpolatedUnivariateSpline(z_array, p_array, w=weights, k=interpolation_order)
-    else:
-        spl = UnivariateSpline(z_array, p_array, w=weights, k=interpolation_order, s=smoothing)
+    spl = UnivariateSpline(z_array, p_array, w=weights, k=interpolation_order, s=smoothing)
     pp = PPoly.from_spline(spl._eval_args)
     keep = np.diff(pp.x) > 0                      # drop the repeated end knots
     c = pp.c[::-1][:, keep]                       # ascending powers, [order + 1, n]
