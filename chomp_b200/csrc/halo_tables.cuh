@@ -2,8 +2,10 @@
 //
 //   nu_nodes_kernel    per point: kink-aware Gauss-Legendre node list in ln(nu) with every
 //                      k-independent factor folded into per-node weights, plus n_bar
-//   halo_sums_kernel   one warp per (point, k): NFW Fourier profile at every node and the
-//                      five sums h_m, pp_mm, h_g, pp_gm, pp_gg               (the hot kernel)
+//   halo_sums_kernel   one CTA per (point, chunk of ln k nodes): small-argument series of the NFW
+//                      Fourier profile summed into moments once per chunk, table-driven profile
+//                      at the remaining nodes, one warp per ln k node; the five sums h_m, pp_mm,
+//                      h_g, pp_gm, pp_gg                                       (the hot kernel)
 //   halo_splines_kernel per point: normalisations and the five not-a-knot splines in ln k
 //
 // Replaces (reference): Halo._calculate_n_bar halo.py:674-707; _initialize_h_m :904-927,
@@ -14,7 +16,8 @@
 // The reference integrates each of these with Romberg over ln(nu) and ignores the kinks of
 // the integrands; here the range is cut at every point where an integrand is not smooth
 // (knots of the ln M(nu) spline, HOD lower limits, the satellite turn-on M_0, the
-// <N> = 1 and <N(N-1)> = 1 exponent switches) and each panel gets an nq_nu-point rule.
+// <N> = 1 and <N(N-1)> = 1 exponent switches) and each panel gets a Gauss-Legendre rule whose
+// order follows the local phase k r_vir of the profile (three node lists for three k classes).
 #pragma once
 #include "common.cuh"
 #include "special.cuh"

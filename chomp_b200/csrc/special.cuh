@@ -1,13 +1,15 @@
 // Device special functions for the halo-model hot path (FP64).
 //
-//   sici        sine / cosine integrals  -- replaces scipy.special.sici in the
-//               NFW Fourier profile (reference halo.py:578-579) and in the
-//               halo-exclusion window (halo.py:1232)
-//   bessel_j    J0 / J2                  -- replaces scipy.special.j0 / jn(2, .)
-//               (reference kernel.py:712, 839)
+//   sici          sine / cosine integrals  -- replaces scipy.special.sici in the halo-exclusion
+//                 window (halo.py:1232) and in the element-wise Halo.y accessor
+//   nfw_rho_tab   NFW Fourier-profile numerator (reference halo.py:574-583) for the hot loops:
+//                 branch-free, range tables of the Si/Ci auxiliary functions in shared memory
+//   sincos_reduced, sici_series_c          building blocks with constant-bank coefficients
+//   bessel_j      J0 / J2                  -- replaces scipy.special.j0 / jn(2, .)
+//                 (reference kernel.py:712, 839): piecewise polynomials below the 8th zero
 //
-// Coefficients come from tools/gen_special.py (Chebyshev interpolants built with
-// mpmath, max relative error <= 4e-14 on f, g and <= 3e-16 on the series part).
+// Coefficients come from tools/gen_special.py, gen_nfw_tables.py, gen_bessel_tables.py
+// (Chebyshev interpolants built with mpmath; errors printed by the generators).
 #pragma once
 #include <math.h>
 #include "special_coeffs.cuh"
@@ -165,26 +167,8 @@ __device__ __forceinline__ void sincos_reduced(double x, double& s, double& c) {
     c = ((q + 1) & 2) ? -b : b;
 }
 
-// x <= CHOMP_SICI_TINY_X: same series, degree CHOMP_SICI_DEG_T
-__device__ __forceinline__ void sici_series_tiny_c(double x, double& si, double& ci_nolog) {
-    const double xx = x * x;
-    const double s = (xx - CHOMP_SI_TINY_MID) * CHOMP_SI_TINY_IHALF;
-    double p = k_si_tiny[CHOMP_SICI_DEG_T];
-    double q = k_ci_tiny[CHOMP_SICI_DEG_T];
-#pragma unroll
-    for (int i = CHOMP_SICI_DEG_T - 1; i >= 0; --i) {
-        p = fma(p, s, k_si_tiny[i]);
-        q = fma(q, s, k_ci_tiny[i]);
-    }
-    si = x * p;
-    ci_nolog = fma(xx, q, CHOMP_EULER);
-}
-
-// ---------------------------------------------------------------------------------------
-// Warp-uniform fast path.  The nu nodes are ordered by mass, so the 32 lanes of a warp
-// almost always fall into the same Si/Ci ranges; the polynomials are then evaluated with
-// the coefficients as constant-bank operands of the DFMA instructions (no loads at all).
-// ---------------------------------------------------------------------------------------
+// Same series with the coefficients as constant-bank operands (used by the both-arguments-small
+// branch of the table-driven profile below).
 __device__ __forceinline__ void sici_series_c(double x, double& si, double& ci_nolog) {
     const double xx = x * x;
     const double s = (xx - CHOMP_SI_SMALL_MID) * CHOMP_SI_SMALL_IHALF;
@@ -197,102 +181,6 @@ __device__ __forceinline__ void sici_series_c(double x, double& si, double& ci_n
     }
     si = x * p;
     ci_nolog = fma(xx, q, CHOMP_EULER);
-}
-
-template <int R>
-__device__ __forceinline__ void sici_aux_c(double x, double sx, double cx, double& si, double& ci) {
-    const double ix = 1.0 / x;
-    const double u = ix * ix;
-    const double s = (u - k_sici_urange[R][0]) * k_sici_urange[R][1];
-    double f = k_sici_F[R][CHOMP_SICI_DEG_L];
-    double g = k_sici_G[R][CHOMP_SICI_DEG_L];
-#pragma unroll
-    for (int i = CHOMP_SICI_DEG_L - 1; i >= 0; --i) {
-        f = fma(f, s, k_sici_F[R][i]);
-        g = fma(g, s, k_sici_G[R][i]);
-    }
-    f *= ix;
-    g *= u;
-    si = CHOMP_PI_2 - f * cx - g * sx;
-    ci = f * sx - g * cx;
-}
-
-__device__ __forceinline__ int sici_range(double x) {
-    return (x >= CHOMP_SICI_X2) ? 2 : ((x >= CHOMP_SICI_X1) ? 1 : 0);
-}
-
-template <int R1, int R2>
-__device__ __forceinline__ void nfw_large_large(double z, double z2, double s1, double c1, double s2, double c2,
-                                                double& dsi, double& dci) {
-    double si1, ci1, si2, ci2;
-    sici_aux_c<R1>(z, s1, c1, si1, ci1);
-    sici_aux_c<R2>(z2, s2, c2, si2, ci2);
-    dsi = si2 - si1;
-    dci = ci2 - ci1;
-}
-template <int R2>
-__device__ __forceinline__ void nfw_small_large(double z, double z2, double s2, double c2, double& dsi, double& dci) {
-    double si1, ci1, si2, ci2;
-    sici_series_c(z, si1, ci1);
-    sici_aux_c<R2>(z2, s2, c2, si2, ci2);
-    dsi = si2 - si1;
-    dci = ci2 - (ci1 + log(z));
-}
-
-// Same value as nfw_rho_k; all 32 lanes of the warp must call it together.  Lanes with
-// `skip` set get 0 back and cost nothing.  The lanes of a warp hold neighbouring masses, so they
-// fall into one or two Si/Ci range combinations ("keys"); the warp walks the distinct keys that
-// are present and evaluates each with the coefficients as constant-bank operands, the lanes of
-// the other keys masked off.
-__device__ __forceinline__ double nfw_rho_k_warp(double z, double cp, double lncp, bool skip = false) {
-    double z2 = cp * z;
-    double s1, c1, s2, c2;
-    sincos_reduced(z, s1, c1);
-    sincos_reduced(z2, s2, c2);
-    const double sin_cz = s2 * c1 - c2 * s1;
-    const bool small1 = z <= CHOMP_SICI_SMALL_X, small2 = z2 <= CHOMP_SICI_SMALL_X;
-    const int key = skip ? -1
-                         : ((z2 <= CHOMP_SICI_TINY_X)
-                                ? 13
-                                : (small2 ? 0 : (small1 ? 1 + sici_range(z2) : 4 + 3 * sici_range(z) + sici_range(z2))));
-    double dsi = 0.0, dci = 0.0;
-    unsigned rem = __ballot_sync(0xffffffffu, !skip);
-    while (rem) {
-        const int key0 = __shfl_sync(0xffffffffu, key, __ffs(rem) - 1);
-        const bool mine = key == key0;
-        if (mine) {
-            // the arguments are made opaque here: everything below is loop-invariant and free of
-            // side effects, and the compiler would otherwise hoist ALL cases out of the loop
-            asm volatile("" : "+d"(z), "+d"(z2));
-            switch (key0) {
-                case 0: {
-                    double si1, ci1, si2, ci2;
-                    sici_series_c(z, si1, ci1);
-                    sici_series_c(z2, si2, ci2);
-                    dsi = si2 - si1;
-                    dci = lncp + (ci2 - ci1);
-                } break;
-                case 13: {
-                    double si1, ci1, si2, ci2;
-                    sici_series_tiny_c(z, si1, ci1);
-                    sici_series_tiny_c(z2, si2, ci2);
-                    dsi = si2 - si1;
-                    dci = lncp + (ci2 - ci1);
-                } break;
-                case 1: nfw_small_large<0>(z, z2, s2, c2, dsi, dci); break;
-                case 2: nfw_small_large<1>(z, z2, s2, c2, dsi, dci); break;
-                case 3: nfw_small_large<2>(z, z2, s2, c2, dsi, dci); break;
-                case 4: nfw_large_large<0, 0>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-                case 5: nfw_large_large<0, 1>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-                case 6: nfw_large_large<0, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-                case 8: nfw_large_large<1, 1>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-                case 9: nfw_large_large<1, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;
-                default: nfw_large_large<2, 2>(z, z2, s1, c1, s2, c2, dsi, dci); break;   // 12
-            }
-        }
-        rem &= ~__ballot_sync(0xffffffffu, mine);
-    }
-    return skip ? 0.0 : c1 * dci + s1 * dsi - sin_cz / z2;
 }
 
 // ---------------------------------------------------------------------------------------
