@@ -39,14 +39,15 @@ __device__ __forceinline__ double tophat2(double x) {
 // R (nor on the parameter point): ln x and  W^2(x) dx/x  at those nodes are tabulated once, at
 // create().  Only Delta^2(x / R) is left to evaluate per node.
 #define SIG_LIN_MAX 12     // panels up to x = 97 (2 SIG_XSPLIT)
-__device__ double g_sig_lnx[SIG_LIN_MAX * SIG_NQ];
-__device__ double g_sig_w2w[SIG_LIN_MAX * SIG_NQ];
+// two more rows: the truncated last panels [41, 48] and [89, 96] of the two split points
+__device__ double g_sig_lnx[(SIG_LIN_MAX + 2) * SIG_NQ];
+__device__ double g_sig_w2w[(SIG_LIN_MAX + 2) * SIG_NQ];
 // same for the fixed panels below x = 1 (Gauss-Legendre in ln x): ln x and W^2(x) dln x
 __device__ double g_sig_low_lnx[SIG_LOW_MAX * SIG_NQ_S];
 __device__ double g_sig_low_w2w[SIG_LOW_MAX * SIG_NQ_S];
 static inline cudaError_t chomp_upload_sigma_tables(const double* glx16, const double* glw16, const double* glx8,
                                                     const double* glw8) {
-    static double lnx[SIG_LIN_MAX * SIG_NQ], w2w[SIG_LIN_MAX * SIG_NQ];
+    static double lnx[(SIG_LIN_MAX + 2) * SIG_NQ], w2w[(SIG_LIN_MAX + 2) * SIG_NQ];
     static double llnx[SIG_LOW_MAX * SIG_NQ_S], lw2w[SIG_LOW_MAX * SIG_NQ_S];
     for (int j = 0; j < SIG_LOW_MAX; ++j)
         for (int q = 0; q < SIG_NQ_S; ++q) {
@@ -62,9 +63,12 @@ static inline cudaError_t chomp_upload_sigma_tables(const double* glx16, const d
     if (e0 != cudaSuccess) return e0;
     e0 = cudaMemcpyToSymbol(g_sig_low_w2w, lw2w, sizeof lw2w);
     if (e0 != cudaSuccess) return e0;
-    for (int j = 0; j < SIG_LIN_MAX; ++j)
+    for (int j = 0; j < SIG_LIN_MAX + 2; ++j)
         for (int q = 0; q < SIG_NQ; ++q) {
-            const double a = 1.0 + SIG_DX * j, half = 0.5 * SIG_DX;
+            double a = 1.0 + SIG_DX * j, b = a + SIG_DX;
+            if (j == SIG_LIN_MAX) { b = SIG_XSPLIT; a = b - fmod(b - 1.0, SIG_DX); }                 // [41, 48]
+            if (j == SIG_LIN_MAX + 1) { b = 2.0 * SIG_XSPLIT; a = b - fmod(b - 1.0, SIG_DX); }       // [89, 96]
+            const double half = 0.5 * (b - a);
             const double x = a + half + half * glx16[q];
             const double W = 3.0 * (sin(x) - x * cos(x)) / (x * x * x);
             lnx[j * SIG_NQ + q] = log(x);
@@ -100,19 +104,6 @@ struct D2Table {
     }
     __device__ __forceinline__ double at_lnk(double lnk) const { return (*this)(0.0, lnk); }
 };
-
-// first-order end-point term of the oscillatory tail
-//   int F(x)/x [B cos 2x + C sin 2x] dx,  B = 9 (x^2-1) / (2 x^6),  C = -9 / x^5
-template <class D2>
-__device__ __forceinline__ double sigma_tail_edge(const D2& d2, double x, double R) {
-    const double k = x / R;
-    const double F = d2(k, log(k)) / x;
-    const double x2 = x * x;
-    const double B = 9.0 * (x2 - 1.0) / (2.0 * x2 * x2 * x2), C = -9.0 / (x2 * x2 * x);
-    double s, c;
-    sincos_reduced(2.0 * x, s, c);
-    return F * (B * s - C * c) * 0.5;
-}
 
 // sigma^2(R) = int dlnk Delta^2(k) W^2(kR) over the reference's k range
 // (cosmology.py:611-638); executed by one full warp, result in every lane.
@@ -161,23 +152,43 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
     // nodes are dealt out in slots of 8: one per low / tail panel, two per linear panel
     const int n_slots = n_low + 2 * n_lin + n_tail;
     const int n_nodes = n_slots * SIG_NQ_S;
+    // the truncated last linear panel is on the lattice too when it ends at one of the two split points
+    const int last_tab = !lattice ? -1
+                         : ((xs == SIG_XSPLIT && n_lin == 6) ? SIG_LIN_MAX
+                            : ((xs == 2.0 * SIG_XSPLIT && n_lin == 12) ? SIG_LIN_MAX + 1 : -1));
     double acc = 0.0;
-    // the two end-point terms of the oscillatory tail ride along as virtual nodes
+    // the two end-point terms of the oscillatory tail ride along as two more tail nodes
     for (int idx = rank; idx < n_nodes + (n_tail ? 2 : 0); idx += size) {
-        if (idx >= n_nodes) {
-            acc += (idx == n_nodes) ? sigma_tail_edge(pk, x_hi, R) : -sigma_tail_edge(pk, xs, R);
-            continue;
-        }
         const int slot = idx >> 3, q8 = idx & 7;
-        double x, lnk, wgt, w2;
-        if (slot >= n_low && slot < n_low + 2 * n_lin) {
-            // Gauss-Legendre in x on [x_one + 8 j, x_one + 8 (j + 1)]: dlnk = dx / x
-            const int jp = (slot - n_low) >> 1, q = ((slot - n_low) & 1) * SIG_NQ_S + q8;
-            if (lattice && jp < n_lin - 1 && jp < SIG_LIN_MAX) {
-                const double lk = g_sig_lnx[jp * SIG_NQ + q] - lnR;
-                acc += g_sig_w2w[jp * SIG_NQ + q] * pk.at_lnk(lk);
+        const bool edge = idx >= n_nodes;
+        const bool lin = !edge && slot >= n_low && slot < n_low + 2 * n_lin;
+        // ---- nodes on the tabulated lattices: only Delta^2 is left to evaluate ----------------
+        {
+            int ti = -1;            // row of the linear tables, or 64 + row of the x < 1 tables
+            if (lin) {
+                const int jp = (slot - n_low) >> 1;
+                if (lattice && jp < n_lin - 1 && jp < SIG_LIN_MAX) ti = jp;
+                else if (jp == n_lin - 1) ti = last_tab;
+            } else if (!edge && slot < n_low && lat_low && slot < j_lo) {
+                ti = 64 + slot;
+            }
+            if (ti >= 0) {
+                double lx, ww;
+                if (ti < 64) {
+                    const int q = ((slot - n_low) & 1) * SIG_NQ_S + q8;
+                    lx = g_sig_lnx[ti * SIG_NQ + q]; ww = g_sig_w2w[ti * SIG_NQ + q];
+                } else {
+                    lx = g_sig_low_lnx[(ti - 64) * SIG_NQ_S + q8]; ww = g_sig_low_w2w[(ti - 64) * SIG_NQ_S + q8];
+                }
+                acc += ww * pk.at_lnk(lx - lnR);
                 continue;
             }
+        }
+        // ---- nodes evaluated on the spot -------------------------------------------------------
+        double x, lnk, wgt, w2;
+        if (lin) {
+            // Gauss-Legendre in x on [x_one + 8 j, x_one + 8 (j + 1)]: dlnk = dx / x
+            const int jp = (slot - n_low) >> 1, q = ((slot - n_low) & 1) * SIG_NQ_S + q8;
             const double a = x_one + SIG_DX * jp;
             const double b = (jp == n_lin - 1) ? xs : a + SIG_DX;
             const double half = 0.5 * (b - a);
@@ -185,16 +196,22 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
             lnk = log(x) - lnR;
             wgt = half * c_glw[SIG_NQ][q] / x;
             w2 = tophat2(x);
+        } else if (edge) {
+            // first-order end-point term of the oscillatory tail:  +- F(x)/x [B sin 2x - C cos 2x] / 2,
+            // B = 9 (x^2 - 1) / (2 x^6),  C = -9 / x^5, at x_hi (+) and at the split point (-)
+            const bool top = idx == n_nodes;
+            x = top ? x_hi : xs;
+            lnk = (top ? l_hi : l_s) - lnR;
+            const double x2 = x * x;
+            double s2, c2;
+            sincos_reduced(2.0 * x, s2, c2);
+            w2 = 9.0 * (x2 - 1.0) / (2.0 * x2 * x2 * x2) * s2 + 9.0 / (x2 * x2 * x) * c2;
+            wgt = (top ? 0.5 : -0.5) / x;
         } else {
             double a, b;
             const bool tail = slot >= n_low;
             if (!tail) {
                 if (lat_low) {
-                    if (slot < j_lo) {
-                        const double lk = g_sig_low_lnx[slot * SIG_NQ_S + q8] - lnR;
-                        acc += g_sig_low_w2w[slot * SIG_NQ_S + q8] * pk.at_lnk(lk);
-                        continue;
-                    }
                     a = l_lo;
                     b = -SIG_LOW_DL * j_lo;
                 } else {
