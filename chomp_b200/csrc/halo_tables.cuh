@@ -213,6 +213,21 @@ __device__ __forceinline__ int kclass_first_index(double phi, double rv_max, dou
     return (int)ceil(x);
 }
 
+// weight of a node of the 1-halo trispectrum integral: d ln(nu) nu f(nu) M^3 <moment> / rho_bar^3
+// (halo_trispectrum.py:131-151; full nu range).  Out of line: the trispectrum list is built only on
+// request and its pow() should not sit in the node loop's instruction stream.
+__device__ __noinline__ double tri_node_weight(int tri_moment, double wt, double mr, double n1, double n2) {
+    double mom = 1.0;
+    if (tri_moment == 1) mom = n1;
+    else if (tri_moment == 2) mom = n2;
+    else if (tri_moment >= 3) {
+        const double a2 = (n1 != 0.0) ? n2 / (n1 * n1) : 0.0;       // HOD.nth_moment, hod.py:68-92
+        mom = pow(n1, (double)tri_moment);
+        for (int jm = 0; jm < tri_moment; ++jm) mom *= (jm * a2 - jm + 1);
+    }
+    return wt * mr * mr * mr * mom;
+}
+
 #ifndef NODES_MIN_BLOCKS
 #define NODES_MIN_BLOCKS 8
 #endif
@@ -362,13 +377,16 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     double nbar = 0.0;
     int st = 0;
     const int n_lists = cfg.tri_moment >= 0 ? N_NODE_LISTS : N_KCLASS;
+#pragma unroll 1
     for (int c = 0; c < n_lists; ++c) {
         const int* ps = pstart + c * max_edge;
         const int total = ps[n_pan];
         const int cap = out.cap[c];
         if (total > cap) st |= CHOMP_ST_NODE_OVERFLOW;
         double* rec = out.nodes + ((size_t)b * out.cap_total + out.off[c]) * NODE_FIELDS;
-        // one thread per (panel, node): walk the panels with a running index
+        // one thread per (panel, node): walk the panels with a running index (not unrolled: four
+        // copies of this body overflow the instruction cache)
+#pragma unroll 1
         for (int idx = tid; idx < total && idx < cap; idx += blockDim.x) {
             int p = 0, hi = n_pan;          // panel with ps[p] <= idx < ps[p+1]
             while (hi - p > 1) { const int mid = (p + hi) >> 1; if (ps[mid] <= idx) p = mid; else hi = mid; }
@@ -421,19 +439,7 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
             const double wgg = in2 * wt * n2 / M;                                           // halo.py:1032-1041
             rec[NF_W_GG * cap + idx] = (n2 < 1.0) ? -wgg * imk : wgg * imk * imk;
             if (c == N_KCLASS - 1) nbar += in1 * wt * n1 / M;                               // halo.py:704-707
-            if (c == TRI_LIST) {
-                // d ln(nu) nu f(nu) M^3 <moment> / rho_bar^3 (halo_trispectrum.py:131-151); full nu range
-                double mom = 1.0;
-                if (cfg.tri_moment == 1) mom = n1;
-                else if (cfg.tri_moment == 2) mom = n2;
-                else if (cfg.tri_moment >= 3) {
-                    const double a2 = (n1 != 0.0) ? n2 / (n1 * n1) : 0.0;       // HOD.nth_moment, hod.py:68-92
-                    mom = pow(n1, (double)cfg.tri_moment);
-                    for (int jm = 0; jm < cfg.tri_moment; ++jm) mom *= (jm * a2 - jm + 1);
-                }
-                const double mr = M / rho_bar;
-                out.tri_w[(size_t)b * cap + idx] = wt * mr * mr * mr * mom;
-            }
+            if (c == TRI_LIST) out.tri_w[(size_t)b * cap + idx] = tri_node_weight(cfg.tri_moment, wt, M / rho_bar, n1, n2);
         }
         if (c == TRI_LIST)
             for (int idx = total + tid; idx < cap; idx += blockDim.x) out.tri_w[(size_t)b * cap + idx] = 0.0;

@@ -75,7 +75,8 @@ __device__ __forceinline__ double dndz_table_piece(const double* __restrict__ ta
     auto F = [&](double t) { return t * (c[0] + t * (c[1] * 0.5 + t * (c[2] * (1.0 / 3.0) + t * (c[3] * 0.25)))); };
     return F(hi) - F(lo);
 }
-__device__ __forceinline__ double dndz_raw(const Dndz& d, double z) {
+// out of line: the pow / exp of the analytic forms are inlined once, not at every call site
+__device__ __noinline__ double dndz_raw(const Dndz& d, double z) {
     if (d.kind == CHOMP_DNDZ_TABLE) return dndz_table_eval(d.tab, d.n, z);
     if (d.kind == CHOMP_DNDZ_GAUSSIAN)                          // kernel.py:110-112
         return exp(-1.0 * (z - d.p0) * (z - d.p0) / (2.0 * d.p1 * d.p1));

@@ -111,13 +111,29 @@ struct D2Table {
 //   sigma^2(R) = int dlnk Delta^2(k) W^2(kR) over the reference's k range (cosmology.py:611-638).
 // `rank` / `size`: position of the thread in the group (a warp or a slice of the CTA) that
 // evaluates this sigma together; the caller reduces over the group.
+// k range of the sigma(R) integrals with its logarithms (taken once per kernel)
+struct SigLim {
+    double k_min, k_max, ln_k_min, ln_k_max;
+};
+__device__ __forceinline__ SigLim make_siglim(double k_min, double k_max) { return SigLim{k_min, k_max, log(k_min), log(k_max)}; }
+
+// lnR = ln(R) comes from the caller (who has ln M); every other logarithm the panels need follows
+// from it and from constants.
 template <class D2>
-__device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_min, double k_max, int rank, int size) {
+__device__ __noinline__ double sigma2_partial(const D2& pk, double R, double lnR, const SigLim& lim, int rank, int size) {
     // integration range rules, cosmology.py:611-629
-    double k_lo = k_min, k_hi = k_max;
-    const double need_lo = 1.0 / R / 10.0, need_hi = 1.0 / R * 14.0662;
-    if (need_lo <= k_lo) k_lo = (need_lo > k_min / 100.0) ? need_lo : k_min / 100.0;
-    if (need_hi >= k_hi) k_hi = (need_hi < k_max * 100.0) ? need_hi : k_max * 100.0;
+    const double k_min = lim.k_min, k_max = lim.k_max;
+    double k_lo = k_min, k_hi = k_max, ln_k_lo = lim.ln_k_min, ln_k_hi = lim.ln_k_max;
+    const double iR = 1.0 / R;
+    const double need_lo = iR / 10.0, need_hi = iR * 14.0662;
+    if (need_lo <= k_lo) {
+        if (need_lo > k_min / 100.0) { k_lo = need_lo; ln_k_lo = -2.3025850929940455 - lnR; }
+        else { k_lo = k_min / 100.0; ln_k_lo = lim.ln_k_min - 4.605170185988092; }
+    }
+    if (need_hi >= k_hi) {
+        if (need_hi < k_max * 100.0) { k_hi = need_hi; ln_k_hi = 2.643774756468092 - lnR; }     // ln 14.0662
+        else { k_hi = k_max * 100.0; ln_k_hi = lim.ln_k_max + 4.605170185988092; }
+    }
     const double x_lo = k_lo * R, x_hi = k_hi * R;
     // large spheres: nu ~ 40 there and ln f(nu) amplifies an error in sigma 14-fold, so the
     // oscillatory part is carried twice as far
@@ -127,18 +143,10 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
     if (xs > x_one) n_lin = (int)ceil((xs - x_one) / SIG_DX - 1e-9);
     if (n_lin < 0) n_lin = 0;
     const int n_tail = (x_hi > xs) ? SIG_NTAIL : 0;
-    // five logarithms, one per lane, handed round by shuffles (callers are whole warps)
-    double lnR, l_lo, l_one, l_s, l_hi;
-    {
-        const int sub = threadIdx.x & 7;
-        const double lg = log(sub == 0 ? R : (sub == 1 ? x_lo : (sub == 2 ? x_one : (sub == 3 ? xs : x_hi))));
-        const int base = threadIdx.x & 24;
-        lnR = __shfl_sync(0xffffffffu, lg, base);
-        l_lo = __shfl_sync(0xffffffffu, lg, base + 1);
-        l_one = __shfl_sync(0xffffffffu, lg, base + 2);
-        l_s = __shfl_sync(0xffffffffu, lg, base + 3);
-        l_hi = __shfl_sync(0xffffffffu, lg, base + 4);
-    }
+    // logarithms of the panel ends
+    const double l_lo = ln_k_lo + lnR, l_hi = ln_k_hi + lnR;
+    const double l_s = (xs < x_hi) ? (R >= 8.0 ? 4.564348191467836 : 3.871201010907891) : l_hi;   // ln 96, ln 48
+    const double l_one = (x_one == 1.0) ? 0.0 : (x_one == xs ? l_s : l_lo);
     const bool lattice = x_one == 1.0;     // the linear panels sit on the tabulated lattice
     // x < 1: fixed panels of the tabulated lattice down to the one that holds x_lo, which is cut
     // at x_lo and integrated on the spot
@@ -242,11 +250,11 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double k_m
 
 // one full warp; result in every lane
 template <class D2>
-__device__ inline double warp_sigma2(const D2& pk, double R, double k_min, double k_max) {
-    return warp_sum(sigma2_partial(pk, R, k_min, k_max, threadIdx.x & 31, 32));
+__device__ inline double warp_sigma2(const D2& pk, double R, double lnR, const SigLim& lim) {
+    return warp_sum(sigma2_partial(pk, R, lnR, lim, threadIdx.x & 31, 32));
 }
 __device__ inline double warp_sigma2(const PkParams& pk, double R, double k_min, double k_max) {
-    return warp_sigma2(D2Direct{pk}, R, k_min, k_max);
+    return warp_sigma2(D2Direct{pk}, R, log(R), make_siglim(k_min, k_max));
 }
 
 // A "team" is one half of the 256-thread CTA (4 warps) with its own named barrier, so that
@@ -267,25 +275,27 @@ __device__ inline double team_sum(const Team& t, double v) {
     return (t.red[0] + t.red[1]) + (t.red[2] + t.red[3]);
 }
 template <class D2>
-__device__ inline double team_sigma2(const Team& t, const D2& pk, double R, double k_min, double k_max) {
-    return team_sum(t, sigma2_partial(pk, R, k_min, k_max, t.rank, TEAM_SIZE));
+__device__ inline double team_sigma2(const Team& t, const D2& pk, double R, double lnR, const SigLim& lim) {
+    return team_sum(t, sigma2_partial(pk, R, lnR, lim, t.rank, TEAM_SIZE));
 }
 
 struct MassCtx {
     D2Table pk;
-    double delta_c, rho_bar, k_min, k_max;
+    SigLim lim;
+    double delta_c, rho_bar;
+    double ln_r_coef;      // ln(3 / (4 pi rho_bar)): ln R = (ln M + ln_r_coef) / 3  (cosmology.py:662-672)
 };
 
-// nu(M) = (delta_c / sigma(M))^2, warp-collective (cosmology.py:662-699)
-__device__ inline double warp_nu_m(const MassCtx& m, double mass) {
-    const double R = cbrt(3.0 * mass / (4.0 * M_PI * m.rho_bar));
-    const double s2 = warp_sigma2(m.pk, R, m.k_min, m.k_max);
+// nu(M) = (delta_c / sigma(M))^2 from ln M, warp-collective (cosmology.py:662-699)
+__device__ inline double warp_nu_lm(const MassCtx& m, double lm) {
+    const double lnR = (lm + m.ln_r_coef) * (1.0 / 3.0);
+    const double s2 = warp_sigma2(m.pk, exp_fast(lnR), lnR, m.lim);
     return m.delta_c * m.delta_c / s2;
 }
 // same, team-collective
-__device__ inline double team_nu_m(const Team& t, const MassCtx& m, double mass) {
-    const double R = cbrt(3.0 * mass / (4.0 * M_PI * m.rho_bar));
-    const double s2 = team_sigma2(t, m.pk, R, m.k_min, m.k_max);
+__device__ inline double team_nu_lm(const Team& t, const MassCtx& m, double lm) {
+    const double lnR = (lm + m.ln_r_coef) * (1.0 / 3.0);
+    const double s2 = team_sigma2(t, m.pk, exp_fast(lnR), lnR, m.lim);
     return m.delta_c * m.delta_c / s2;
 }
 
@@ -305,7 +315,7 @@ __device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scal
     if (hi_edge < nu0) { dir = -1; thr = hi_edge; want_le = true; }        // "too high": M /= 1.05 until nu <= hi_edge
     else if (lo_edge > nu0) { dir = +1; thr = lo_edge; want_le = false; }  // "too low":  M *= 1.05 until nu >= lo_edge
     else return 0;
-    const double ln_step = log(1.05), target = log(thr);
+    const double ln_step = log(1.05), target = log(thr), ln_M0 = log(M0);
     // secant on g(t) = ln nu(M0 e^t) - target
     double t0 = 0.0, g0 = log(nu0) - target;
     double t1 = -g0 / 0.35;                       // d ln nu / d ln M is 0.15 ... 0.7
@@ -320,7 +330,7 @@ __device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scal
     bool certain = false;
     for (int it = 0; it < 10; ++it) {
         t1 = fmax(-t_max, fmin(t_max, t1));
-        g1 = log(team_nu_m(tm, m, M0 * exp(t1)) * nu_scale) - target;
+        g1 = log(team_nu_lm(tm, m, ln_M0 + t1) * nu_scale) - target;
         if (it > 0 && t1 != t0) slope = (g1 - g0) / (t1 - t0);
         const double corr = (fabs(slope) > 0.05) ? g1 / slope : g1 / 0.05;
         const double tc = t1 - corr;
@@ -341,11 +351,11 @@ __device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scal
         // settle on the first step that passes, exactly as the sequential walk would
         for (int guard = 0; guard < 8; ++guard) {
             if (j > J) return -1;
-            const double nu_j = team_nu_m(tm, m, M0 * pow(1.05, (double)(dir * j))) * nu_scale;
+            const double nu_j = team_nu_lm(tm, m, ln_M0 + dir * j * ln_step) * nu_scale;
             const bool ok_j = want_le ? (nu_j <= thr) : (nu_j >= thr);
             if (!ok_j) { ++j; continue; }
             if (j == 1) break;
-            const double nu_p = team_nu_m(tm, m, M0 * pow(1.05, (double)(dir * (j - 1)))) * nu_scale;
+            const double nu_p = team_nu_lm(tm, m, ln_M0 + dir * (j - 1) * ln_step) * nu_scale;
             const bool ok_p = want_le ? (nu_p <= thr) : (nu_p >= thr);
             if (ok_p) { --j; continue; }
             break;
@@ -391,7 +401,8 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     MassCtx m;
     m.delta_c = delta_c_z(c, z);
     m.rho_bar = rho_bar_z(c, z);
-    m.k_min = cfg.k_min; m.k_max = cfg.k_max;
+    m.lim = make_siglim(cfg.k_min, cfg.k_max);
+    m.ln_r_coef = log(3.0 / (4.0 * M_PI * m.rho_bar));
     // Every sigma(R) is evaluated with sigma_norm = 1; nu scales as 1 / sigma_norm^2
     // (cosmology.py:118-119, 574-587).  Round 0: sigma_8, nu(1e9) and nu(1e16) on three warps.
     const PkParams pk1 = make_pk(c, growth, 1.0);
@@ -417,8 +428,9 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         const int grp = (w < 2 || fixed_limits) ? 0 : (w < 5 ? 1 : 2);
         const int g_first = grp == 0 ? 0 : (grp == 1 ? 2 : 5);
         const int g_warps = fixed_limits ? nw : (grp == 0 ? 2 : 3);
-        const double R = grp == 0 ? 8.0 : cbrt(3.0 * (grp == 1 ? m_lo : m_hi) / (4.0 * M_PI * m.rho_bar));
-        const double part = warp_sum(sigma2_partial(m.pk, R, m.k_min, m.k_max, tid - 32 * g_first, 32 * g_warps));
+        const double lnR = grp == 0 ? 2.0794415416798357 : (log(grp == 1 ? m_lo : m_hi) + m.ln_r_coef) * (1.0 / 3.0);
+        const double R = grp == 0 ? 8.0 : exp_fast(lnR);
+        const double part = warp_sum(sigma2_partial(m.pk, R, lnR, m.lim, tid - 32 * g_first, 32 * g_warps));
         if (lane == 0) red[8 + w] = part;
     }
     __syncthreads();
@@ -471,7 +483,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         if (t >= n) break;
         const int i = n - 1 - t;
         const double lm = (i == n - 1) ? lnm_max : lnm_min + hM * i;
-        const double v = warp_nu_m(m, exp(lm)) * nu_scale;
+        const double v = warp_nu_lm(m, lm) * nu_scale;
         if (lane == 0) { lnm[i] = lm; nu[i] = v; }
     }
     __syncthreads();

@@ -256,6 +256,7 @@ __device__ __forceinline__ double nfw_rho_tab(const NfwTables* t, double z, doub
 // J0 / J2 for x >= 0: piecewise degree-12 polynomials below x = 28 (tools/gen_bessel_tables.py;
 // the Limber integrals stop at the 8th zero, j_{0,8} = 24.35 / j_{2,8} = 27.42), the library
 // routines beyond.
+__device__ __noinline__ double bessel_j_library(int order, double x) { return order == 0 ? j0(x) : jn(2, x); }
 __device__ __forceinline__ double bessel_j(int order, double x) {
     if (x < BESSEL_NR * BESSEL_WIDTH) {
         const int r = (int)(x * (1.0 / BESSEL_WIDTH));
@@ -266,7 +267,7 @@ __device__ __forceinline__ double bessel_j(int order, double x) {
         for (int j = BESSEL_DEG - 1; j >= 0; --j) p = fma(p, s, __ldg(c + j * BESSEL_NR));
         return p;
     }
-    return order == 0 ? j0(x) : jn(2, x);
+    return bessel_j_library(order, x);     // out of line: one copy, away from the hot loops
 }
 
 }  // namespace chomp
