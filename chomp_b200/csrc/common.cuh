@@ -116,7 +116,7 @@ __device__ __forceinline__ double E0(const Cosmo& c, double z) {
     return c.ol + c.om / (a * a * a) + c.orad / (a * a * a * a);
 }
 // 1/H(z) in Mpc/h (cosmology.py:153-162)
-__device__ __noinline__ double inv_hubble(const Cosmo& c, double z) { return 1.0 / (c.H0 * sqrt(E0(c, z))); }
+__device__ __forceinline__ double inv_hubble(const Cosmo& c, double z) { return 1.0 / (c.H0 * sqrt(E0(c, z))); }
 
 // Carroll et al. closed form, which is what growth_factor_eval returns (cosmology.py:215-231, 326)
 __device__ __forceinline__ double growth_approx(const Cosmo& c, double a) {
