@@ -477,10 +477,10 @@ __device__ __forceinline__ double exclusion_window(const SiciTables* t, double k
 // (coef = a for the sums linear in rho, a*a for the quadratic ones), evaluated per k as a
 // polynomial in (k / k_hi)^2: those (k, node) pairs are never visited.
 #ifndef SER_DEG
-#define SER_DEG 9
+#define SER_DEG 11
 #endif
 #ifndef SER_X
-#define SER_X 2.0
+#define SER_X 3.0
 #endif
 #define SER_NC (SER_DEG + 1)
 #define SER_MIN_C 1.0          // the recurrence is run forward: nodes with c < 1 take the general path

@@ -374,7 +374,7 @@ struct MassOut {
 };
 
 #ifndef MASS_MIN_BLOCKS
-#define MASS_MIN_BLOCKS 3
+#define MASS_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(256, MASS_MIN_BLOCKS)
 mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const double* __restrict__ halo,
