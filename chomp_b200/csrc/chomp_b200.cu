@@ -198,6 +198,7 @@ int chomp_b200_create(void** handle, int device) {
     CK(chomp_upload_special_tables());
     CK(chomp_upload_sincos_table());
     CK(chomp_upload_nfw_tables());
+    CK(chomp_upload_spline_tables());
     CK(chomp_upload_bessel_tables());
     CK(chomp_upload_sigma_tables(glx[SIG_NQ], glw[SIG_NQ], glx[SIG_NQ_S], glw[SIG_NQ_S]));
     CK(chomp_upload_expf_table());

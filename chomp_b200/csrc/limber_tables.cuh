@@ -210,15 +210,31 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
         G.chi[i] = acc;
     }
     __syncthreads();
-    if (tid < n_grid) { EpochGrid& G = g[tid]; for (int i = 1; i < nz; ++i) G.chi[i] += G.chi[i - 1]; }
+    if (wid < n_grid) {      // running sums chi_i = sum_{j <= i} (panel integrals): one warp scan per grid
+        EpochGrid& G = g[wid];
+        double carry = 0.0;
+        for (int base = 0; base < nz; base += 32) {
+            const int i = base + lane;
+            double v = i < nz ? G.chi[i] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += up;
+            }
+            v += carry;
+            if (i < nz) G.chi[i] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
     __syncthreads();
     for (int sp = wid; sp < 3 * n_grid; sp += nwarp) {      // one spline per warp at a time
         EpochGrid& G = g[sp / 3];
         double* wk = work + (size_t)wid * 5 * nz;
         switch (sp % 3) {
-            case 0: spline_build_warp(nz, G.z, G.chi, G.c_chi_z, wk); break;     // cosmology.py:795-796
-            case 1: spline_build_warp(nz, G.chi, G.z, G.c_z_chi, wk); break;     // :797-798
-            default: spline_build_warp(nz, G.z, G.growth, G.c_g_z, wk); break;   // :814-815
+            // the z grid is uniform: chi(z) and D(z) take the division-free uniform builder
+            case 0: spline_build_uniform_warp(nz, (G.z_max - G.z_min) / (nz - 1), G.chi, G.c_chi_z, wk); break;   // cosmology.py:795-796
+            case 1: spline_build_warp(nz, G.chi, G.z, G.c_z_chi, wk); break;                                      // :797-798
+            default: spline_build_uniform_warp(nz, (G.z_max - G.z_min) / (nz - 1), G.growth, G.c_g_z, wk); break; // :814-815
         }
     }
     __syncthreads();
@@ -302,12 +318,8 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     if (wid < (same_window ? 1 : 2)) {
         Window& W = win[wid];
         double* wk = work + (size_t)wid * 6 * nw;
-        // uniform chi nodes: build with explicit abscissae
-        double* xs = wk + 5 * nw;
-        const double hw = (W.chi_max - W.chi_min) / (nw - 1);
-        for (int j = lane; j < nw; j += 32) xs[j] = (j == nw - 1) ? W.chi_max : W.chi_min + hw * j;
-        __syncwarp();
-        spline_build_warp(nw, xs, W.wf, W.coef, wk);
+        // uniform chi nodes
+        spline_build_uniform_warp(nw, (W.chi_max - W.chi_min) / (nw - 1), W.wf, W.coef, wk);
     }
     __syncthreads();
     if (same_window) win[1] = win[0];
@@ -378,7 +390,14 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     const int order = cfg.bessel_order;
     // widest base panel: below kt * width <= 2 no panel needs sub-division
     double wmax = 0.0;
-    for (int pnl = 0; pnl < n_pan; ++pnl) wmax = fmax(wmax, edge[pnl + 1] - edge[pnl]);
+    for (int pnl = tid; pnl < n_pan; pnl += blockDim.x) wmax = fmax(wmax, edge[pnl + 1] - edge[pnl]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    __syncthreads();
+    if (lane == 0) red[96 + wid] = wmax;
+    __syncthreads();
+    wmax = 0.0;
+    for (int ww = 0; ww < nwarp; ++ww) wmax = fmax(wmax, red[96 + ww]);
     // ---- small k theta: J_n(k theta chi) as a power series in (k theta chi / 2)^2 ------------------
     // For k theta chi_max <= 2 every panel is whole, and
     //   K = sum_m (-1)^m t^m / (m! (m + n)!) * sum_nodes fw (chi / chi_max)^(2 m + n),  t = (k theta chi_max / 2)^2
@@ -476,12 +495,7 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
         if (lane == 0) kn[j] = acc;
     }
     __syncthreads();
-    if (wid == 0) {
-        double* xs = work + 5 * nk;
-        for (int j = lane; j < nk; j += 32) xs[j] = (j == nk - 1) ? x1 : x0 + (x1 - x0) / (nk - 1) * j;
-        __syncwarp();
-        spline_build_warp(nk, xs, kn, kc, work);          // kernel.py:645-646
-    }
+    if (wid == 0) spline_build_uniform_warp(nk, (x1 - x0) / (nk - 1), kn, kc, work);   // kernel.py:645-646
     __syncthreads();
     // ---- write out ------------------------------------------------------------------------------------
     if (tid == 0) {

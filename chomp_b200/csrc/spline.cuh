@@ -8,6 +8,7 @@
 // x[n-2], stored as per-interval polynomial coefficients
 //     y(x) = c0 + t (c1 + t (c2 + t c3)),   t = x - x[i].
 #pragma once
+#include <cuda_runtime.h>
 
 namespace chomp {
 
@@ -120,6 +121,55 @@ __device__ __noinline__ void spline_build_warp(int n, const double* __restrict__
         coef[4 * i + 1] = coef[4 * i + 1] - h * (2.0 * m[i] + m[i + 1]) * (1.0 / 6.0);
         coef[4 * i + 2] = 0.5 * m[i];
         coef[4 * i + 3] = (m[i + 1] - m[i]) / (6.0 * h);
+    }
+    __syncwarp();
+}
+
+// Uniform abscissae x_i = x0 + i h: the not-a-knot system reduces to  m_1 = r_1 / 6,
+// m_{n-2} = r_{n-2} / 6,  m_{i-1} + 4 m_i + m_{i+1} = r_i  in between (r_i = 6 (y_{i+1} - 2 y_i +
+// y_{i-1}) / h^2), whose Thomas factors c_i = 1 / (4 - c_{i-1}) depend on nothing: they come from a
+// constant table (c_i is 2 - sqrt(3) to rounding from i = 24 on), so the serial sweeps are two
+// dependent operations per row and free of divisions.  Warp-collective; work[n] scratch.
+#define NAK_CP_TABLE 24
+__constant__ double k_nak_cp[NAK_CP_TABLE];
+static inline cudaError_t chomp_upload_spline_tables() {
+    double cp[NAK_CP_TABLE];
+    cp[0] = 0.0; cp[1] = 0.0;
+    for (int i = 2; i < NAK_CP_TABLE; ++i) cp[i] = 1.0 / (4.0 - cp[i - 1]);
+    return cudaMemcpyToSymbol(k_nak_cp, cp, sizeof cp);
+}
+__device__ __noinline__ void spline_build_uniform_warp(int n, double h, const double* __restrict__ y,
+                                                       double* __restrict__ coef, double* __restrict__ work) {
+    const int lane = threadIdx.x & 31;
+    double* m = work;
+    const double s = 6.0 / (h * h);
+    for (int i = 1 + lane; i <= n - 2; i += 32) m[i] = s * ((y[i + 1] - y[i]) - (y[i] - y[i - 1]));
+    __syncwarp();
+    if (lane == 0) {
+        double mprev = m[1] * (1.0 / 6.0);
+        m[1] = mprev;
+        for (int i = 2; i <= n - 3; ++i) {
+            const double c = i < NAK_CP_TABLE ? k_nak_cp[i] : 0.26794919243112270647;
+            mprev = (m[i] - mprev) * c;
+            m[i] = mprev;
+        }
+        double mnext = m[n - 2] * (1.0 / 6.0);
+        m[n - 2] = mnext;
+        for (int i = n - 3; i >= 2; --i) {
+            const double c = i < NAK_CP_TABLE ? k_nak_cp[i] : 0.26794919243112270647;
+            mnext = m[i] - c * mnext;
+            m[i] = mnext;
+        }
+        m[0] = 2.0 * m[1] - m[2];
+        m[n - 1] = 2.0 * m[n - 2] - m[n - 3];
+    }
+    __syncwarp();
+    const double ih = 1.0 / h;
+    for (int i = lane; i < n - 1; i += 32) {
+        coef[4 * i + 0] = y[i];
+        coef[4 * i + 1] = (y[i + 1] - y[i]) * ih - h * (2.0 * m[i] + m[i + 1]) * (1.0 / 6.0);
+        coef[4 * i + 2] = 0.5 * m[i];
+        coef[4 * i + 3] = (m[i + 1] - m[i]) * (ih * (1.0 / 6.0));
     }
     __syncwarp();
 }
