@@ -372,7 +372,7 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     const double stq = hp[CHOMP_H_STQ], sta = hp[CHOMP_H_ST_LITTLE_A], beta = hp[CHOMP_H_BETA];
     const double c0 = hp[CHOMP_H_C0] / (1.0 + e[EP_Z]);                   // halo.py:65
     const double f_norm = e[EP_F_NORM], b_norm = e[EP_B_NORM], delta_c = e[EP_DELTA_C];
-    const double rho_bar = e[EP_RHO_BAR], delta_v = e[EP_DELTA_V], lnm_star = e[EP_LNM_STAR];
+    const double rho_bar = e[EP_RHO_BAR], lnm_star = e[EP_LNM_STAR];
     const double ln_rv_coef = log(rv_coef), ln_sta = log(sta);
     double nbar = 0.0;
     int st = 0;
@@ -714,9 +714,8 @@ halo_splines_kernel(const Cfg cfg, int B, const double* __restrict__ raw, const 
     const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = cfg.n_halo;
     double* sy = sm + (size_t)t * 3 * n;   // node values
-    double* sm2 = sy + n;                  // rhs -> second derivatives m
-    double* scp = sm2 + n;                 // modified upper diagonal
-    const double h = (log(cfg.k_max) - log(cfg.k_min)) / (n - 1), ih = 1.0 / h;
+    double* sm2 = sy + n;                  // second derivatives
+    const double h = (log(cfg.k_max) - log(cfg.k_min)) / (n - 1);
     const double nb = nbar[b], rho_bar = epoch[(size_t)b * CHOMP_EPOCH_LEN + EP_RHO_BAR];
     const double scale = t < 2 ? 1.0 : (t == 2 ? 1.0 / nb : (t == 3 ? 1.0 / (nb * rho_bar) : 1.0 / (nb * nb * rho_bar)));
     const double* __restrict__ y_in = raw + ((size_t)b * 5 + t) * n;
@@ -731,41 +730,8 @@ halo_splines_kernel(const Cfg cfg, int B, const double* __restrict__ raw, const 
     }
     if (bad && status) atomicOr(status + b, CHOMP_ST_NONFINITE);
     __syncwarp();
-    for (int i = 1 + lane; i <= n - 2; i += 32) sm2[i] = 6.0 * ((sy[i + 1] - sy[i]) - (sy[i] - sy[i - 1])) * ih;
-    __syncwarp();
-    if (lane == 0) {
-        // not-a-knot with equal spacing: rows 1 and n-2 reduce to 6 h m_i = rhs_i (see spline.cuh)
-        const double i6h = 1.0 / (6.0 * h);
-        double cp_prev = 0.0, m_prev = sm2[1] * i6h;
-        sm2[1] = m_prev;
-        scp[1] = 0.0;
-        for (int i = 2; i <= n - 3; ++i) {
-            const double inv = 1.0 / (4.0 * h - h * cp_prev);
-            cp_prev = h * inv;
-            m_prev = (sm2[i] - h * m_prev) * inv;
-            scp[i] = cp_prev;
-            sm2[i] = m_prev;
-        }
-        double m_next = sm2[n - 2] * i6h;
-        sm2[n - 2] = m_next;
-        for (int i = n - 3; i >= 2; --i) {
-            m_next = sm2[i] - scp[i] * m_next;
-            sm2[i] = m_next;
-        }
-        sm2[0] = 2.0 * sm2[1] - sm2[2];
-        sm2[n - 1] = 2.0 * sm2[n - 2] - sm2[n - 3];
-    }
-    __syncwarp();
-    for (int idx = lane; idx < 4 * (n - 1); idx += 32) {
-        const int i = idx >> 2, k = idx & 3;
-        const double mi = sm2[i], mn = sm2[i + 1];
-        double v;
-        if (k == 0) v = sy[i];
-        else if (k == 1) v = (sy[i + 1] - sy[i]) * ih - h * (2.0 * mi + mn) / 6.0;
-        else if (k == 2) v = 0.5 * mi;
-        else v = (mn - mi) / (6.0 * h);
-        c[idx] = v;
-    }
+    // not-a-knot spline on the uniform ln k grid: division-free sweeps (spline.cuh)
+    spline_build_uniform_warp(n, h, sy, c, sm2);
 }
 
 }  // namespace chomp
