@@ -468,7 +468,7 @@ __device__ __forceinline__ double exclusion_window(const SiciTables* t, double k
 // rho(k, M) = int_0^c dx x/(1+x)^2 j0(k r_s x)  (the integral halo.py:574-583 is the closed form of)
 //           = sum_n a_n(c) t^n,   t = (k r_s c)^2 = (k r_vir)^2,
 //   a_n(c) = (-1)^n J_{2n+1}(c) / ((2n+1)! c^{2n}),   J_m(c) = int_0^c x^m / (1+x)^2 dx.
-// J_m / c^m follows the stable (for c >= 1) forward recurrence  j_m = (l_{m-1} - j_{m-1}) / c,
+// J_m / c^m follows the forward recurrence (stable for c >= 1, accurate enough down to c = 0.3)  j_m = (l_{m-1} - j_{m-1}) / c,
 // l_m = 1/m - l_{m-1} / c  with  l_0 = ln(1+c), j_0 = c / (1+c).  With t <= SER_X^2 and degree
 // SER_DEG the truncation error is below 4e-15 (scratch/series_check.py).
 // Because every k-independent factor of the five integrands is already folded into the node
@@ -483,7 +483,8 @@ __device__ __forceinline__ double exclusion_window(const SiciTables* t, double k
 #define SER_X 3.0
 #endif
 #define SER_NC (SER_DEG + 1)
-#define SER_MIN_C 1.0          // the recurrence is run forward: nodes with c < 1 take the general path
+#define SER_MIN_C 0.3          // the forward recurrence loses c^-(2n+1) in a_n: still 7e-15 overall at c = 0.3
+                               // (scratch/series_check.py); nodes below take the general path
 
 __device__ __forceinline__ void nfw_series_coeffs(double c, double cp, double lncp, double (&a)[SER_NC]) {
     const double ic = 1.0 / c;

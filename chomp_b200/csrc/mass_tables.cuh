@@ -487,7 +487,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         if (lane == 0) { lnm[i] = lm; nu[i] = v; }
     }
     __syncthreads();
-    if (w == 0) spline_build_warp(n, lnm, nu, c2, work);          // nu(ln M)
+    if (w == 0) spline_build_uniform_warp(n, hM, nu, c2, work);   // nu(ln M): uniform ln M grid
     if (w == 1) spline_build_warp(n, nu, lnm, c1, work + 5 * n);  // ln M(nu)
     __syncthreads();
     const double nu_min = 1.001 * nu[0], nu_max = 0.999 * nu[n - 1];  // mass_function.py:212-213

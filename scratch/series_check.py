@@ -43,3 +43,16 @@ for X, DD in ((1.5, 8), (2.0, 9), (2.0, 10), (3.0, 12), (4.0, 14)):
             s = np.polyval(a[::-1], zc*zc); e = exact(zc/c, c)
             w = max(w, abs(s/e-1))
     print(X, DD, "max rel err %.2e" % w)
+import mpmath as mp
+mp.mp.dps = 30
+def exact_mp(z, c):
+    z = mp.mpf(z); c = mp.mpf(c); cp = 1+c
+    return float(mp.cos(z)*(mp.ci(cp*z)-mp.ci(z)) + mp.sin(z)*(mp.si(cp*z)-mp.si(z)) - mp.sin(c*z)/(cp*z))
+print("---- small concentrations, X = 3, D = 11 (forward recurrence below c = 1)")
+for c in (0.2, 0.3, 0.4, 0.5, 0.7, 0.9):
+    a = coeffs(c, 11)
+    w = 0
+    for zc in np.linspace(0.05, 3.0, 60):
+        s = np.polyval(a[::-1], zc*zc); e = exact_mp(zc/c, c) if 'exact_mp' in globals() else exact(zc/c, c)
+        w = max(w, abs(s/e-1))
+    print("c=%.1f max rel err %.2e" % (c, w))
