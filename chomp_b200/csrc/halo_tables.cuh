@@ -64,20 +64,21 @@ struct HodP {
 };
 
 __device__ __noinline__ HodP load_hod(int kind, const double* __restrict__ p, double halo_precision) {
+    const double ln10 = 2.302585092994046;
     HodP h;
     h.kind = kind;
     if (kind == CHOMP_HOD_ZHENG) {
         h.log_M_min = p[0]; h.sigma = p[1]; h.log_M_0 = p[2]; h.log_M_1p = p[3]; h.alpha = p[4]; h.w = 0.0;
-        h.first_zero = pow(10.0, h.log_M_min + h.sigma * erfinv(2.0 * halo_precision - 1.0));
-        h.second_zero = pow(10.0, h.log_M_0);   // the reference's clamp is a typo'd no-op (hod.py:183-184)
+        h.first_zero = exp_fast(ln10 * (h.log_M_min + h.sigma * erfinv(2.0 * halo_precision - 1.0)));
+        h.second_zero = exp_fast(ln10 * h.log_M_0);   // the reference's clamp is a typo'd no-op (hod.py:183-184)
     } else {
         h.log_M_0 = p[0]; h.w = p[1]; h.log_M_min = log10(3.0) + p[0];
         h.sigma = 0.0; h.log_M_1p = 0.0; h.alpha = 0.0;
         h.first_zero = -1.0; h.second_zero = -1.0;
     }
-    h.M0 = pow(10.0, h.log_M_0);
-    h.M1p = pow(10.0, h.log_M_1p);
-    h.Mmin = pow(10.0, h.log_M_min);
+    h.M0 = exp_fast(ln10 * h.log_M_0);
+    h.M1p = exp_fast(ln10 * h.log_M_1p);
+    h.Mmin = exp_fast(ln10 * h.log_M_min);
     return h;
 }
 
@@ -257,12 +258,15 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
         c1[i] = g_c1[(size_t)b * 4 * n + i];
         c2[i] = g_c2[(size_t)b * 4 * n + i];
     }
+    // the HOD constants (an erfinv and a few exponentials) once per CTA
+    __shared__ HodP s_hod;
+    if (tid == blockDim.x - 1) s_hod = load_hod(cfg.hod_kind, hod + (size_t)b * CHOMP_N_HOD, cfg.halo_precision);
     __syncthreads();
     NuTab t{n, lnm, nu, c1, c2};
     const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
     const double nu_min = e[EP_NU_MIN], nu_max = e[EP_NU_MAX];
     const double l_min = log(nu_min), l_max = log(nu_max);
-    const HodP h = load_hod(cfg.hod_kind, hod + (size_t)b * CHOMP_N_HOD, cfg.halo_precision);
+    const HodP h = s_hod;
     // lower limits of the galaxy integrals (halo.py:675-679, 935-939, 1002-1006, 1049-1053)
     double x_lo1 = l_min, x_lo2 = l_min;
     if (h.first_zero > -1.0 && h.first_zero > exp(e[EP_LNM_MIN])) x_lo1 = log(nu_of_lnm(t, log(h.first_zero)));
