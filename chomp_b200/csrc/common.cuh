@@ -68,6 +68,14 @@ __device__ __forceinline__ double warp_fold8(double (&v)[8]) {
     double t = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
     return t + __shfl_xor_sync(0xffffffffu, t, 1);
 }
+// eight values over each aligned group of eight lanes: lane j of a group returns the group total of
+// input index j (a complete transpose-reduce in 7 shuffles)
+__device__ __forceinline__ double group8_fold8(double (&v)[8]) {
+    warp_fold_step<4>(v, 4);
+    warp_fold_step<2>(v, 2);
+    warp_fold_step<1>(v, 1);
+    return v[0];
+}
 __device__ __forceinline__ double warp_fold16(double (&v)[16]) {
     warp_fold_step<8>(v, 16);
     warp_fold_step<4>(v, 8);

@@ -658,13 +658,22 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
     }
     __syncthreads();
     const double ik_hi = 1.0 / k_hi;
-    for (int ik = k_begin + w; ik < k_end; ik += nwarp) {
-        const double lnk = (ik == nk - 1) ? l1 : l0 + hk * ik;                      // halo.py:49-51
+    // Large chunks: four ln k nodes per warp pass, eight lanes each striding the nodes -- everything
+    // below is per-lane (no warp-uniform dispatch), the per-k epilogue is shared by four k and few
+    // lanes idle when only a handful of nodes lie beyond the moment prefix.  Small chunks (the two
+    // fine k classes): one k per warp, so that every warp of the CTA has work.
+    const int kl = (k_end - k_begin >= 64) ? 8 : 32;             // lanes per ln k node
+    const int kpw = 32 / kl, grp = lane / kl, gl = lane & (kl - 1);
+    for (int ik0 = k_begin + kpw * w; ik0 < k_end; ik0 += kpw * nwarp) {
+        const int ik = ik0 + grp;
+        const bool live = ik < k_end;
+        const int ikc = live ? ik : k_end - 1;
+        const double lnk = (ikc == nk - 1) ? l1 : l0 + hk * ikc;                    // halo.py:49-51
         const double k = exp_fast(lnk);
         double a_hm = 0.0, a_pmm = 0.0, a_hg = 0.0, a_gm = 0.0, a_gg = 0.0;
-        for (int base = i_lo; base < nn_pad; base += 32) {      // warp-uniform trip count (collectives inside)
-            const bool valid = base + lane < nn_pad;
-            const int i = valid ? base + lane : nn_pad - 1;
+        for (int base = i_lo; base < nn_pad; base += kl) {
+            const bool valid = base + gl < nn_pad;
+            const int i = valid ? base + gl : nn_pad - 1;
             const double cp = s_cp[i], rs = s_rs[i];
             const double z = k * rs;
             const double zc = z * (cp - 1.0);
@@ -690,9 +699,11 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
             a_gg = fma(fabs(wgg), (wgg < 0.0) ? rho : rho2, a_gg);
         }
         double v8[8] = {a_hm, a_pmm, a_hg, a_gm, a_gg, 0.0, 0.0, 0.0};
-        double v = warp_fold8(v8);                               // lane 4 s holds sum s
-        if ((lane & 3) == 0 && lane < 20) {
-            const int s5 = lane >> 2;
+        double v;
+        int s5;                                                   // which of the five sums this lane holds
+        if (kl == 8) { v = group8_fold8(v8); s5 = gl; }           // lane s of the group holds sum s
+        else { v = warp_fold8(v8); s5 = (lane & 3) ? 8 : (lane >> 2); }   // lane 4 s holds sum s
+        if (s5 < 5 && live) {
             if (i_lo > 0) {
                 const double r = k * ik_hi, sc = r * r;
                 double p = s_mom[16 * (SER_DEG / 3) + 5 * (SER_DEG % 3) + s5];
