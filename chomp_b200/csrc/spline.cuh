@@ -66,6 +66,7 @@ __device__ __noinline__ void spline_build(int n, const double* __restrict__ x, c
     }
 }
 
+#define SPLINE_PCR_ROWS 2      // rows per lane in the parallel cyclic reduction (n - 2 <= 64)
 // Same spline, built by one WARP (all 32 lanes must call it; work[5*n] scratch in shared memory).
 // Spacings, chord slopes, the tridiagonal rows and the coefficient pass are lane-parallel; only
 // the two sweeps of the Thomas algorithm -- a serial chain of one reciprocal per row -- run on
@@ -98,7 +99,41 @@ __device__ __noinline__ void spline_build_warp(int n, const double* __restrict__
         m[i] = 6.0 * (coef[4 * i + 1] - coef[4 * (i - 1) + 1]);
     }
     __syncwarp();
-    if (lane == 0) {
+    if (last <= 32 * SPLINE_PCR_ROWS) {
+        // parallel cyclic reduction over the rows 1 .. last (diagonally dominant: stable): log2(n)
+        // steps, every lane eliminating the neighbours at distance s of its own rows -- instead of
+        // a serial chain of one division per row
+        for (int s = 1; s < last; s <<= 1) {
+            double na[SPLINE_PCR_ROWS], nb[SPLINE_PCR_ROWS], nc[SPLINE_PCR_ROWS], nd[SPLINE_PCR_ROWS];
+#pragma unroll
+            for (int t = 0; t < SPLINE_PCR_ROWS; ++t) {
+                const int i = 1 + lane + 32 * t;
+                na[t] = nb[t] = nc[t] = nd[t] = 0.0;
+                if (i <= last) {
+                    double bb = dg[i], d = m[i], aa = 0.0, cc = 0.0;
+                    const int im = i - s, ip = i + s;
+                    if (im >= 1) { const double al = -lo[i] / dg[im]; aa = al * lo[im]; bb += al * up[im]; d += al * m[im]; }
+                    if (ip <= last) { const double ga = -up[i] / dg[ip]; cc = ga * up[ip]; bb += ga * lo[ip]; d += ga * m[ip]; }
+                    na[t] = aa; nb[t] = bb; nc[t] = cc; nd[t] = d;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < SPLINE_PCR_ROWS; ++t) {
+                const int i = 1 + lane + 32 * t;
+                if (i <= last) { lo[i] = na[t]; dg[i] = nb[t]; up[i] = nc[t]; m[i] = nd[t]; }
+            }
+            __syncwarp();
+        }
+        for (int i = 1 + lane; i <= last; i += 32) m[i] = m[i] / dg[i];
+        __syncwarp();
+        if (lane == 0) {
+            const double h0 = x[1] - x[0], h1 = x[2] - x[1];
+            m[0] = (1.0 + h0 / h1) * m[1] - (h0 / h1) * m[2];
+            const double hl2 = x[n - 2] - x[n - 3], hr2 = x[n - 1] - x[n - 2];
+            m[n - 1] = (1.0 + hr2 / hl2) * m[n - 2] - (hr2 / hl2) * m[n - 3];
+        }
+    } else if (lane == 0) {
         double cprev = 0.0, mprev = 0.0;
         for (int i = 1; i <= last; ++i) {
             const double l = lo[i];
