@@ -326,7 +326,7 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     // per panel (in parallel): spline interval and the Gauss-Legendre order in each k class.  The
     // class order (set by the phase phi = k r_vir at the TOP of the mass table) is only needed where
     // the profile really oscillates that fast: a panel whose own phase k_top(class) r_vir(panel top)
-    // stays below KPANEL_PHI_1 / _2 gets order 4 / 8 (scratch/adaptive_orders.py: same accuracy,
+    // stays below KPANEL_PHI_1 / _2 gets order 4 / 8 (tools/adaptive_orders.py: same accuracy,
     // less than half the nodes in the two fine lists).  Panels inside the erf edge of the central
     // occupation get at least the "sharp" order.
     const double rv_coef = 3.0 / (4.0 * M_PI * e[EP_DELTA_V] * e[EP_RHO_BAR]);
@@ -474,7 +474,7 @@ __device__ __forceinline__ double exclusion_window(const SiciTables* t, double k
 //   a_n(c) = (-1)^n J_{2n+1}(c) / ((2n+1)! c^{2n}),   J_m(c) = int_0^c x^m / (1+x)^2 dx.
 // J_m / c^m follows the forward recurrence (stable for c >= 1, accurate enough down to c = 0.3)  j_m = (l_{m-1} - j_{m-1}) / c,
 // l_m = 1/m - l_{m-1} / c  with  l_0 = ln(1+c), j_0 = c / (1+c).  With t <= SER_X^2 and degree
-// SER_DEG the truncation error is below 4e-15 (scratch/series_check.py).
+// SER_DEG the truncation error is below 4e-15 (tools/series_check.py).
 // Because every k-independent factor of the five integrands is already folded into the node
 // weights, the part of each sum that comes from nodes with k r_vir <= SER_X for EVERY k of a CTA's
 // chunk collapses into 5 (SER_DEG + 1) moments  S[s][n] = sum_i w_s(i) coef_n(i) (k_hi r_vir,i)^2n
@@ -488,7 +488,7 @@ __device__ __forceinline__ double exclusion_window(const SiciTables* t, double k
 #endif
 #define SER_NC (SER_DEG + 1)
 #define SER_MIN_C 0.3          // the forward recurrence loses c^-(2n+1) in a_n: still 7e-15 overall at c = 0.3
-                               // (scratch/series_check.py); nodes below take the general path
+                               // (tools/series_check.py); nodes below take the general path
 
 __device__ __forceinline__ void nfw_series_coeffs(double c, double cp, double lncp, double (&a)[SER_NC]) {
     const double ic = 1.0 / c;

@@ -1,6 +1,6 @@
 import json, numpy as np
 g = json.load(open('/root/repo/tests/golden/reference_covariance.json'))
-t = np.load('/root/repo/scratch/cov_tight16.npz')
+t = np.load('/root/repo/tools/cov_tight16.npz')
 c = g['cases']['power_gggg']
 n = len(c['bins_center'])
 K = np.array(c['kernel_NG_table']).reshape(50,50)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # time each variant library with the bench (no CPU arm); parity tests on the default build only
 for v in "$@"; do
-  export CHOMP_B200_LIB=/root/repo/scratch/variants/$v.so
+  export CHOMP_B200_LIB=/root/repo/tools/variants/$v.so
   timeout 200 python bench.py --no-cpu-baseline 2>gpurun_out/bench_$v.err | tail -1 > gpurun_out/bench_$v.json
   python - "$v" <<'PY'
 import json, sys

@@ -30,4 +30,4 @@ if __name__ == "__main__":
     total,P,G,NG = cov.get_covariance(parts=True); print("cov %.1fs"%(time.time()-t0))
     np.set_printoptions(linewidth=200, precision=4)
     print(np.diag(P)); print(np.diag(G)); print(np.diag(NG)); print(G[0], NG[0])
-    np.savez('/root/repo/scratch/cov_tight16.npz', K=T, P=P, G=G, NG=NG, proj=cov.proj_nodes, tri=cov.tri._i04)
+    np.savez('/root/repo/tools/cov_tight16.npz', K=T, P=P, G=G, NG=NG, proj=cov.proj_nodes, tri=cov.tri._i04)

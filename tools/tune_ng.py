@@ -7,12 +7,12 @@ from common import C_DICT, H_DICT, HOD_DICT, oracle_covariance
 for n_halo in (50, 200):
     cov = oracle_covariance(C_DICT, H_DICT, HOD_DICT, theta_deg=(0.01, 1.0), tri_z=0.5, integ=Tight(16),
                             prec=O.precision(halo_npoints=n_halo))
-    K = np.load('/root/repo/scratch/cov_tight16.npz')['K']; cov.kernel.set_table(K)
-    if n_halo == 50: cov.tri._i04 = np.load('/root/repo/scratch/cov_tight16.npz')['tri']
+    K = np.load('/root/repo/tools/cov_tight16.npz')['K']; cov.kernel.set_table(K)
+    if n_halo == 50: cov.tri._i04 = np.load('/root/repo/tools/cov_tight16.npz')['tri']
     else:
         # smooth stand-in: interpolate the 50-node table (log-space bicubic) to 200 nodes
         from scipy.interpolate import RectBivariateSpline
-        t50 = np.load('/root/repo/scratch/cov_tight16.npz')['tri']; x50 = np.linspace(np.log(1e-3), np.log(100.), 50)
+        t50 = np.load('/root/repo/tools/cov_tight16.npz')['tri']; x50 = np.linspace(np.log(1e-3), np.log(100.), 50)
         sp = RectBivariateSpline(x50, x50, np.log(t50)); x200 = cov.tri.ln_k_nodes
         cov.tri._i04 = np.exp(sp(x200, x200))
     bins = cov.bins[:, 2]

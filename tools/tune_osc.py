@@ -5,7 +5,7 @@ from scipy import special
 from oracle.quadrature import Tight, gl_nodes
 from try_cov import build
 cov = build(Tight(16)); kc = cov.kernel
-ref = np.load('/root/repo/scratch/cov_tight16.npz')['K']
+ref = np.load('/root/repo/tools/cov_tight16.npz')['K']
 x = kc.ln_ktheta_nodes
 edges = np.unique(np.concatenate([kc.windows[0].chi_nodes, kc.cosmo.chi_nodes, [kc.chi_min, kc.chi_max]]))
 edges = edges[(edges >= kc.chi_min) & (edges <= kc.chi_max)]
