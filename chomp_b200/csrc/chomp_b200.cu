@@ -7,7 +7,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/chomp_b200.h"
@@ -46,12 +49,44 @@ static thread_local std::string g_err;
 
 namespace {
 
+// Opt-in to > 48 KB of dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is state of
+// the FUNCTION (per device), shared by every handle: it is only ever raised, to the largest size any
+// handle has asked for, and it is checked at every launch site -- never lowered from configure().
+int smem_opt_in_impl(const void* func, int device, size_t bytes, const char* name) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> granted;
+    if (bytes <= 48 * 1024) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = granted[std::make_pair(func, device)];
+    if (bytes <= have) return 0;
+    if (bytes > 227 * 1024) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s needs %zu bytes of shared memory per CTA (limit 232448): table sizes too large", name, bytes);
+        g_err = buf;
+        return 2;
+    }
+    CK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+    return 0;
+}
+#define SMEM_OPT_IN(kernel, h, bytes)                                                          \
+    do {                                                                                       \
+        if (int rc_ = smem_opt_in_impl((const void*)(kernel), (h)->device, (bytes), #kernel)) return rc_; \
+    } while (0)
+
 struct Handle {
     int device = 0;
     bool configured = false;
     Cfg cfg;
     int same_window = 0;
     int cap_points = 0;
+    // batch sizes the stages last ran with (0 after the scratch was re-allocated): later stages and the
+    // evaluators refuse rows nobody computed
+    int done_limber = 0, done_mass = 0, done_halo = 0, done_params = 0;
+    // ordering between the caller's streams and the private stream of the *_host call: every stage
+    // call on a foreign stream leaves an event behind that the private stream waits on
+    cudaEvent_t order_ev = nullptr;
+    bool order_pending = false, capturing = false;
     int node_cap[N_NODE_LISTS] = {0, 0, 0, 0}, node_off[N_NODE_LISTS] = {0, 0, 0, 0}, node_cap_total = 0;
     long long launches = 0;
     double* dndz_tab[2] = {nullptr, nullptr};     // CHOMP_DNDZ_TABLE: breaks[n + 1], coef[n][4]
@@ -110,6 +145,15 @@ void gauss_legendre(int n, double* x, double* w) {
     }
 }
 
+inline void note_stream(Handle* h, cudaStream_t s) {
+    if (s == h->own_stream || h->capturing || !h->order_ev) return;
+    if (cudaEventRecord(h->order_ev, s) == cudaSuccess) h->order_pending = true;
+}
+#define NEED_STAGE(done, B, what)                                                                       \
+    do {                                                                                                \
+        if ((done) < (B)) FAIL("stage order: " what " has not been computed for this batch on this handle"); \
+    } while (0)
+
 // event slot `i` is recorded before kernel i; slot i+1 after it
 inline void mark(Handle* h, int i, cudaStream_t s) {
     if (h->timing) cudaEventRecord(h->ev[i], s);
@@ -123,10 +167,23 @@ int dev_alloc(Handle* h, T** p, size_t count) {
     return 0;
 }
 
+// replace a buffer by a larger one: the old generation is freed and leaves the allocation list
+template <typename T>
+int dev_regrow(Handle* h, T** p, size_t count) {
+    if (*p) {
+        for (size_t i = 0; i < h->allocs.size(); ++i)
+            if (h->allocs[i] == (void*)*p) { h->allocs.erase(h->allocs.begin() + i); break; }
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    return dev_alloc(h, p, count);
+}
+
 void free_scratch(Handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     h->allocs.clear();
     h->cap_points = 0;
+    h->done_limber = h->done_mass = h->done_halo = h->done_params = 0;
     h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0;
     h->cov = CovOut{}; h->cov_tri = TriScratch{}; h->cov_points = 0; h->cov_bins = 0; h->cov_chunk = 0; h->kng_ready = false;
 }
@@ -202,9 +259,11 @@ int chomp_b200_create(void** handle, int device) {
     CK(chomp_upload_bessel_tables());
     CK(chomp_upload_sigma_tables(glx[SIG_NQ], glw[SIG_NQ], glx[SIG_NQ_S], glw[SIG_NQ_S]));
     CK(chomp_upload_expf_table());
+    CK(chomp_upload_limber_tables());
     Handle* h = new Handle();
     h->device = device;
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
     *handle = h;
     return 0;
 }
@@ -224,6 +283,7 @@ void chomp_b200_destroy(void* handle) {
     if (h->d_status) cudaFree(h->d_status);
     for (int i = 0; i < 2; ++i) if (h->dndz_tab[i]) cudaFree(h->dndz_tab[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->order_ev) cudaEventDestroy(h->order_ev);
     if (h->ev[0]) for (int i = 0; i <= CHOMP_N_KERNELS; ++i) cudaEventDestroy(h->ev[i]);
     delete h;
 }
@@ -277,12 +337,7 @@ int chomp_b200_configure(void* handle, const chomp_b200_config* cfg) {
                       cfg->dndz_p[0][2] == cfg->dndz_p[1][2] &&
                       (cfg->dndz_kind[0] != CHOMP_DNDZ_TABLE || h->dndz_tab_id[0] == h->dndz_tab_id[1]));
     h->configured = true;
-    // opt in to > 48 KB dynamic shared memory where a stage needs it
-    CK(cudaFuncSetAttribute(limber_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(limber_smem_doubles(h->cfg, h->same_window) * sizeof(double))));
-    CK(cudaFuncSetAttribute(halo_splines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(15 * (size_t)h->cfg.n_halo * sizeof(double))));
-    CK(cudaFuncSetAttribute(wtheta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wtheta_smem(h->cfg)));
+    // > 48 KB of dynamic shared memory: asked for (and only ever raised) at the launch sites
     if (resize && h->cap_points > 0) {
         const int n = h->cap_points;
         CK(cudaDeviceSynchronize());
@@ -308,8 +363,6 @@ int chomp_b200_reserve(void* handle, int max_points) {
         h->node_off[k] = h->node_cap_total;
         h->node_cap_total += h->node_cap[k];
     }
-    CK(cudaFuncSetAttribute(halo_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(sums_doubles(h) * sizeof(double) + sizeof(SiciTables))));
     int rc = 0;
     rc |= dev_alloc(h, &h->zbar, B);
     rc |= dev_alloc(h, &h->dbar, B);
@@ -369,11 +422,15 @@ int chomp_b200_limber_tables(void* handle, int B, const double* cosmo_dev, int32
     LimberOut out{h->zbar, h->dbar, h->knodes, h->kcoef, h->chi_nodes, h->win_nodes, h->win_chi, h->win_coef, h->kchi,
                   h->grid0, h->dndz_norm, h->edges, h->n_edges};
     const size_t smem = limber_smem_doubles(h->cfg, h->same_window) * sizeof(double);
+    SMEM_OPT_IN(limber_tables_kernel, h, smem);
     mark(h, CHOMP_K_LIMBER, s);
     limber_tables_kernel<<<B, LIMBER_THREADS, smem, s>>>(h->cfg, B, h->same_window, h->cosmo, out, status_dev);
     mark(h, CHOMP_K_LIMBER + 1, s);
     h->launches += 1;
     CK(cudaGetLastError());
+    h->done_limber = B;
+    if (h->done_params < B) h->done_params = B;
+    note_stream(h, s);
     return 0;
 }
 
@@ -381,17 +438,23 @@ int chomp_b200_mass_tables(void* handle, int B, const double* cosmo_dev, const d
                            const double* z_dev, int32_t* status_dev, void* stream) {
     Handle* h = (Handle*)handle;
     if (int rc = ensure(h, B)) return rc;
+    if (!z_dev) NEED_STAGE(h->done_limber, B, "z_bar (chomp_b200_limber_tables)");
     cudaStream_t s = (cudaStream_t)stream;
     if (cosmo_dev != h->cosmo)
         CK(cudaMemcpyAsync(h->cosmo, cosmo_dev, sizeof(double) * B * CHOMP_N_COSMO, cudaMemcpyDeviceToDevice, s));
     if (halo_dev != h->halo)
         CK(cudaMemcpyAsync(h->halo, halo_dev, sizeof(double) * B * CHOMP_N_HALO, cudaMemcpyDeviceToDevice, s));
     MassOut out{h->epoch, h->lnm_nodes, h->nu_nodes, h->c_lnm_nu, h->c_nu_lnm};
+    SMEM_OPT_IN(mass_tables_kernel, h, mass_smem(h->cfg));
     mark(h, CHOMP_K_MASS, s);
     mass_tables_kernel<<<B, 256, mass_smem(h->cfg), s>>>(h->cfg, B, h->cosmo, h->halo, z_dev, h->zbar, out, status_dev);
     mark(h, CHOMP_K_MASS + 1, s);
     h->launches += 1;
     CK(cudaGetLastError());
+    h->done_mass = B;
+    h->done_halo = 0;            // the halo tables of an earlier epoch no longer match
+    if (h->done_params < B) h->done_params = B;
+    note_stream(h, s);
     return 0;
 }
 
@@ -401,6 +464,7 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
                            int32_t* status_dev, void* stream) {
     Handle* h = (Handle*)handle;
     if (int rc = ensure(h, B)) return rc;
+    NEED_STAGE(h->done_mass, B, "the mass tables (chomp_b200_mass_tables)");
     cudaStream_t s = (cudaStream_t)stream;
     const Cfg& c = h->cfg;
     if (halo_dev != h->halo)
@@ -408,6 +472,9 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
     if (hod_dev != h->hod)
         CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
     NodesOut no = nodes_view(h);
+    SMEM_OPT_IN(nu_nodes_kernel, h, nodes_smem(c));
+    SMEM_OPT_IN(halo_sums_kernel, h, sums_smem(h));
+    SMEM_OPT_IN(halo_splines_kernel, h, 15 * (size_t)c.n_halo * sizeof(double));
     mark(h, CHOMP_K_NODES, s);
     nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
                                                   h->c_lnm_nu, h->c_nu_lnm, no, status_dev);
@@ -422,6 +489,8 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
     mark(h, CHOMP_K_SPLINES + 1, s);
     CK(cudaGetLastError());
     h->launches += 3;
+    h->done_halo = B;
+    note_stream(h, s);
     return 0;
 }
 
@@ -430,11 +499,15 @@ int chomp_b200_power(void* handle, int B, int which, int n_k, const double* k_de
     if (int rc = ensure(h, B)) return rc;
     if (which < CHOMP_P_LINEAR || which > CHOMP_P_GG) FAIL("unknown power spectrum");
     if (n_k <= 0) FAIL("n_k must be positive");
+    NEED_STAGE(h->done_mass, B, "the epoch scalars (chomp_b200_mass_tables)");
+    if (!(which == CHOMP_P_LINEAR || (h->cfg.use_halofit && which == CHOMP_P_MM)))
+        NEED_STAGE(h->done_halo, B, "the halo tables (chomp_b200_halo_tables)");
     dim3 grid((n_k + 255) / 256, B);
     power_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->cfg, B, which, n_k, k_dev, h->cosmo, h->epoch, h->htab,
                                                         h->hcoef, h->cfg.use_halofit ? h->hfit : nullptr, P_out_dev);
     h->launches += 1;
     CK(cudaGetLastError());
+    note_stream(h, (cudaStream_t)stream);
     return 0;
 }
 
@@ -444,6 +517,11 @@ int chomp_b200_wtheta(void* handle, int B, int which, int n_theta, const double*
     if (int rc = ensure(h, B)) return rc;
     if (which < CHOMP_P_LINEAR || which > CHOMP_P_GG) FAIL("unknown power spectrum");
     if (n_theta <= 0) FAIL("n_theta must be positive");
+    NEED_STAGE(h->done_limber, B, "the Limber kernel table (chomp_b200_limber_tables)");
+    NEED_STAGE(h->done_mass, B, "the epoch scalars (chomp_b200_mass_tables)");
+    if (!(which == CHOMP_P_LINEAR || (h->cfg.use_halofit && which == CHOMP_P_MM)))
+        NEED_STAGE(h->done_halo, B, "the halo tables (chomp_b200_halo_tables)");
+    SMEM_OPT_IN(wtheta_kernel, h, wtheta_smem(h->cfg));
     mark(h, CHOMP_K_WTHETA, (cudaStream_t)stream);
     wtheta_kernel<<<B, 256, wtheta_smem(h->cfg), (cudaStream_t)stream>>>(
         h->cfg, B, which, n_theta, theta_dev, h->cosmo, h->epoch, h->dbar, h->htab, h->hcoef, h->knodes, h->kcoef,
@@ -451,6 +529,7 @@ int chomp_b200_wtheta(void* handle, int B, int which, int n_theta, const double*
     mark(h, CHOMP_K_WTHETA + 1, (cudaStream_t)stream);
     h->launches += 1;
     CK(cudaGetLastError());
+    note_stream(h, (cudaStream_t)stream);
     return 0;
 }
 
@@ -478,6 +557,7 @@ int chomp_b200_wtheta_batch_host(void* handle, int B, const double* cosmo_host, 
         if (h->d_in) cudaFree(h->d_in);
         if (h->d_status) cudaFree(h->d_status);
         if (h->h_status) cudaFreeHost(h->h_status);
+        h->h_in = nullptr; h->d_in = nullptr; h->d_status = nullptr; h->h_status = nullptr; h->stage_in = 0;
         CK(cudaMallocHost((void**)&h->h_in, need_in * sizeof(double)));
         CK(cudaMalloc((void**)&h->d_in, need_in * sizeof(double)));
         CK(cudaMalloc((void**)&h->d_status, (size_t)B * sizeof(int32_t)));
@@ -487,16 +567,22 @@ int chomp_b200_wtheta_batch_host(void* handle, int B, const double* cosmo_host, 
     if (need_out > h->stage_out) {
         if (h->h_out) cudaFreeHost(h->h_out);
         if (h->d_out) cudaFree(h->d_out);
+        h->h_out = nullptr; h->d_out = nullptr; h->stage_out = 0;
         CK(cudaMallocHost((void**)&h->h_out, need_out * sizeof(double)));
         CK(cudaMalloc((void**)&h->d_out, need_out * sizeof(double)));
         h->stage_out = need_out;
     }
     if (n_theta > h->stage_theta) {
         if (h->d_theta) cudaFree(h->d_theta);
+        h->d_theta = nullptr; h->stage_theta = 0;
         CK(cudaMalloc((void**)&h->d_theta, (size_t)n_theta * sizeof(double)));
         h->stage_theta = n_theta;
     }
     cudaStream_t s = h->own_stream;
+    if (h->order_pending) {        // stage calls issued on the caller's streams share this handle's scratch
+        CK(cudaStreamWaitEvent(s, h->order_ev, 0));
+        h->order_pending = false;
+    }
     double* hc = h->h_in;
     double* hh = hc + (size_t)B * CHOMP_N_COSMO;
     double* ho = hh + (size_t)B * CHOMP_N_HALO;
@@ -652,7 +738,19 @@ int chomp_b200_eval(void* handle, int point, int what, int n, const double* x_de
                     void* stream) {
     Handle* h = (Handle*)handle;
     if (!h || !h->configured || h->cap_points <= 0) FAIL("no batch has been computed on this handle");
-    if (point < 0 || point >= h->cap_points) FAIL("point index out of range");
+    {
+        int done = h->done_params;
+        if (what == CHOMP_EVAL_KERNEL || what == CHOMP_EVAL_WINDOW_A || what == CHOMP_EVAL_WINDOW_B ||
+            what == CHOMP_EVAL_CHI_OF_Z || what == CHOMP_EVAL_Z_OF_CHI || what == CHOMP_EVAL_GROWTH_OF_Z ||
+            what == CHOMP_EVAL_DNDZ_A || what == CHOMP_EVAL_DNDZ_B)
+            done = h->done_limber;
+        else if (what == CHOMP_EVAL_LINEAR_POWER || what == CHOMP_EVAL_SIGMA_R || what == CHOMP_EVAL_NU_OF_MASS ||
+                 what == CHOMP_EVAL_MASS_OF_NU || what == CHOMP_EVAL_F_NU || what == CHOMP_EVAL_BIAS_NU ||
+                 what == CHOMP_EVAL_Y_NFW || what == CHOMP_EVAL_CONCENTRATION || what == CHOMP_EVAL_VIRIAL_RADIUS ||
+                 what == CHOMP_EVAL_SIGMA_OF_NU || what == CHOMP_EVAL_BIAS_2_NU)
+            done = h->done_mass;
+        if (point < 0 || point >= done) FAIL("point index beyond the last batch computed for this quantity");
+    }
     if (n <= 0) return 0;
     CK(cudaSetDevice(h->device));
     const Cfg& c = h->cfg;
@@ -674,6 +772,7 @@ int chomp_b200_mass_second_order(void* handle, int B, double* b2_norm_out_dev, i
     Handle* h = (Handle*)handle;
     if (int rc = ensure(h, B)) return rc;
     const Cfg& c = h->cfg;
+    SMEM_OPT_IN(mass_second_order_kernel, h, 8 * (size_t)c.n_mass * sizeof(double));
     mass_second_order_kernel<<<B, 64, 8 * (size_t)c.n_mass * sizeof(double), (cudaStream_t)stream>>>(
         c, B, h->halo, h->epoch, h->nu_nodes, h->sig_coef, h->b2_norm, status_dev);
     h->launches += 1;
@@ -688,7 +787,7 @@ int chomp_b200_halofit(void* handle, int B, double fit_z, double* params_out_dev
     if (int rc = ensure(h, B)) return rc;
     const Cfg& c = h->cfg;
     const size_t smem = (2 * HF_PANELS * HF_NQ + 8 * (size_t)c.n_halo + 11 * (size_t)c.n_halo + 16) * sizeof(double);
-    CK(cudaFuncSetAttribute(halofit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SMEM_OPT_IN(halofit_kernel, h, smem);
     halofit_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(c, B, fit_z, h->cosmo, h->epoch, h->hfit, h->hf_ls2, status_dev);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -704,10 +803,14 @@ int chomp_b200_cl(void* handle, int B, int which, int n_ell, const double* ell_d
     if (n_ell <= 0) FAIL("n_ell must be positive");
     const bool hf = h->cfg.use_halofit != 0;
     if (which < CHOMP_P_LINEAR || which > CHOMP_P_GG) FAIL("unknown power spectrum");
+    NEED_STAGE(h->done_limber, B, "the windows (chomp_b200_limber_tables)");
+    NEED_STAGE(h->done_mass, B, "the epoch scalars (chomp_b200_mass_tables)");
     if (!(which == CHOMP_P_LINEAR || (hf && which == CHOMP_P_MM))) {
+        NEED_STAGE(h->done_halo, B, "the halo tables (chomp_b200_halo_tables)");
         // table-based spectra: pieces no wider than 0.0625 in ln chi, split where the spectrum changes branch
         if ((size_t)h->edge_stride > COV_MAX_EDGES) FAIL("window / cosmology tables too fine for the C(l) kernel");
         const size_t smem = limber_stage_doubles(h->cfg) * sizeof(double);
+        SMEM_OPT_IN(cl_table_kernel, h, smem);
         cl_table_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(
             h->cfg, which, B, n_ell, ell_dev,
             LimberIn{h->grid0, h->win_chi, h->win_coef, h->kchi, h->edges, h->zbar, h->dbar, h->n_edges, h->edge_stride},
@@ -740,10 +843,9 @@ int chomp_b200_trispectrum_1h(void* handle, int B, double* T_out_dev, void* stre
     const int cap = h->node_cap[TRI_LIST];
     if (B > h->tri_points) {
         CK(cudaDeviceSynchronize());
-        CK(cudaMalloc((void**)&h->tri_A, sizeof(double) * (size_t)B * c.n_halo * cap));
-        CK(cudaMalloc((void**)&h->tri_T, sizeof(double) * (size_t)B * c.n_halo * c.n_halo));
-        h->allocs.push_back(h->tri_A);
-        h->allocs.push_back(h->tri_T);
+        h->tri_points = 0;
+        if (int rc = dev_regrow(h, &h->tri_A, (size_t)B * c.n_halo * cap)) return rc;
+        if (int rc = dev_regrow(h, &h->tri_T, (size_t)B * c.n_halo * c.n_halo)) return rc;
         h->tri_points = B;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -788,6 +890,8 @@ int chomp_b200_set_params(void* handle, int B, const double* cosmo_dev, const do
     if (cosmo_dev) CK(cudaMemcpyAsync(h->cosmo, cosmo_dev, sizeof(double) * B * CHOMP_N_COSMO, cudaMemcpyDeviceToDevice, s));
     if (halo_dev) CK(cudaMemcpyAsync(h->halo, halo_dev, sizeof(double) * B * CHOMP_N_HALO, cudaMemcpyDeviceToDevice, s));
     if (hod_dev) CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
+    if (h->done_params < B) h->done_params = B;
+    note_stream(h, s);
     return 0;
 }
 
@@ -950,27 +1054,28 @@ int cov_reserve(Handle* h, int B, int n_bins) {
         CK(cudaDeviceSynchronize());
         const size_t nk2 = (size_t)c.n_kernel * c.n_kernel;
         int rc = 0;
-        rc |= dev_alloc(h, &h->cov.kng, (size_t)B * nk2);
-        rc |= dev_alloc(h, &h->cov.lkng, (size_t)B * nk2);
-        rc |= dev_alloc(h, &h->cov.mkng, (size_t)B * nk2);
-        rc |= dev_alloc(h, &h->cov.kng_min, (size_t)B);
-        rc |= dev_alloc(h, &h->cov.zbar_ng, (size_t)B);
-        rc |= dev_alloc(h, &h->cov.d_ng, (size_t)B);
-        rc |= dev_alloc(h, &h->cov.proj, (size_t)B * 2 * c.n_kernel);
+        h->cov_points = 0;
+        rc |= dev_regrow(h, &h->cov.kng, (size_t)B * nk2);
+        rc |= dev_regrow(h, &h->cov.lkng, (size_t)B * nk2);
+        rc |= dev_regrow(h, &h->cov.mkng, (size_t)B * nk2);
+        rc |= dev_regrow(h, &h->cov.kng_min, (size_t)B);
+        rc |= dev_regrow(h, &h->cov.zbar_ng, (size_t)B);
+        rc |= dev_regrow(h, &h->cov.d_ng, (size_t)B);
+        rc |= dev_regrow(h, &h->cov.proj, (size_t)B * 2 * c.n_kernel);
         if (rc) return rc;
         h->cov_points = B;
         h->cov_bins = 0;
         const int chunk = B < 256 ? B : 256;
         const size_t nh = c.n_halo, nk = c.n_kernel, ntot = (size_t)hankel_nodes(c);
-        rc |= dev_alloc(h, &h->cov_tri.mcol, (size_t)chunk * nh * nh);
-        rc |= dev_alloc(h, &h->cov_tri.r, (size_t)chunk * nk * nh);
-        rc |= dev_alloc(h, &h->cov_tri.m2, (size_t)chunk * nk * nh);
-        rc |= dev_alloc(h, &h->cov_tri.tw, (size_t)chunk * nk * ntot);
+        rc |= dev_regrow(h, &h->cov_tri.mcol, (size_t)chunk * nh * nh);
+        rc |= dev_regrow(h, &h->cov_tri.r, (size_t)chunk * nk * nh);
+        rc |= dev_regrow(h, &h->cov_tri.m2, (size_t)chunk * nk * nh);
+        rc |= dev_regrow(h, &h->cov_tri.tw, (size_t)chunk * nk * ntot);
         if (rc) return rc;
         h->cov_chunk = chunk;
     }
     if (n_bins > h->cov_bins) {
-        if (int rc = dev_alloc(h, &h->cov.parts, (size_t)h->cov_points * 3 * n_bins * n_bins)) return rc;
+        if (int rc = dev_regrow(h, &h->cov.parts, (size_t)h->cov_points * 3 * n_bins * n_bins)) return rc;
         h->cov_bins = n_bins;
     }
     return 0;
@@ -990,7 +1095,7 @@ int chomp_b200_cov_kernel_ng(void* handle, int B, const chomp_b200_cov_params* p
     cudaStream_t s = (cudaStream_t)stream;
     const Cfg& c = h->cfg;
     const size_t smem = limber_stage_doubles(c) * sizeof(double);
-    CK(cudaFuncSetAttribute(cov_kng_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SMEM_OPT_IN(cov_kng_kernel, h, smem);
     dim3 grid(c.n_kernel, B);
     cov_kng_kernel<<<grid, COV_THREADS, smem, s>>>(c, *p, B, limber_view(h), h->cov);
     CK(cudaGetLastError());
@@ -1027,6 +1132,7 @@ int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, c
             if (hod_dev != h->hod)
                 CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
             NodesOut no = nodes_view(h);
+            SMEM_OPT_IN(nu_nodes_kernel, h, nodes_smem(c));
             nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
                                                           h->c_lnm_nu, h->c_nu_lnm, no, status_dev);
             CK(cudaGetLastError());
@@ -1036,6 +1142,7 @@ int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, c
         if (int rc = chomp_b200_mass_tables(handle, B, h->cosmo, halo_dev, nullptr, status_dev, stream)) return rc;
         if (int rc = chomp_b200_halo_tables(handle, B, h->halo, hod_dev, status_dev, stream)) return rc;
         const size_t smem = limber_stage_doubles(c) * sizeof(double);
+        SMEM_OPT_IN(cov_projected_kernel, h, smem);
         cov_projected_kernel<<<B, 128, smem, s>>>(c, *p, B, limber_view(h), h->cosmo, h->epoch, h->htab, h->hcoef,
                                                   c.use_halofit ? h->hfit : nullptr, h->cov, status_dev);
         CK(cudaGetLastError());
@@ -1047,7 +1154,7 @@ int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, c
             const int ntot = hankel_nodes(c);
             const size_t ng_smem = (2 * (size_t)c.n_kernel * c.n_kernel + ntot + 2 * (size_t)nb * c.n_kernel + c.n_kernel) * sizeof(double);
             if (ng_smem > 200 * 1024) FAIL("covariance: n_bins x kernel_npoints too large for the non-Gaussian kernel");
-            CK(cudaFuncSetAttribute(cov_ng_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ng_smem));
+            SMEM_OPT_IN(cov_ng_kernel, h, ng_smem);
             for (int b0 = 0; b0 < B; b0 += h->cov_chunk) {
                 const int n = (B - b0 < h->cov_chunk) ? B - b0 : h->cov_chunk;
                 cov_tri_nodes_kernel<<<n, COV_THREADS, 0, s>>>(c, *p, b0, n, h->tri_T, h->cov.d_ng, h->cov_tri);

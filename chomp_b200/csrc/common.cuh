@@ -118,13 +118,14 @@ __device__ inline Cosmo load_cosmo(const double* __restrict__ p, double cosmo_pr
     return c;
 }
 
-// (H(z)/H0)^2, no curvature term (cosmology.py:175-178)
+// (H(z)/H0)^2, no curvature term (cosmology.py:175-178): Omega_L + Omega_m / a^3 + Omega_r / a^4 with
+// 1 / a = 1 + z multiplied out (no division)
 __device__ __forceinline__ double E0(const Cosmo& c, double z) {
-    const double a = 1.0 / (1.0 + z);
-    return c.ol + c.om / (a * a * a) + c.orad / (a * a * a * a);
+    const double y = 1.0 + z, y2 = y * y;
+    return fma(c.orad * y2, y2, fma(c.om * y, y2, c.ol));
 }
-// 1/H(z) in Mpc/h (cosmology.py:153-162)
-__device__ __forceinline__ double inv_hubble(const Cosmo& c, double z) { return 1.0 / (c.H0 * sqrt(E0(c, z))); }
+// 1/H(z) in Mpc/h (cosmology.py:153-162): reciprocal square root, 1 / H0 = 2998 Mpc/h
+__device__ __forceinline__ double inv_hubble(const Cosmo& c, double z) { return rsqrt(E0(c, z)) * (2.998 * 100000.0 / 100.0); }
 
 // Carroll et al. closed form, which is what growth_factor_eval returns (cosmology.py:215-231, 326)
 __device__ __forceinline__ double growth_approx(const Cosmo& c, double a) {

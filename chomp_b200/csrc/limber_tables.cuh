@@ -133,12 +133,46 @@ __host__ __device__ inline size_t limber_edge_cap(const Cfg& cfg, int same_windo
 __host__ __device__ inline size_t limber_smem_doubles(const Cfg& cfg, int same_window) {
     const size_t nz = cfg.n_cosmo, nw = cfg.n_window, nk = cfg.n_kernel;
     const size_t nb = limber_edge_cap(cfg, same_window);
-    return 3 * (3 * nz + 12 * nz) + 2 * (nw + 4 * nw) + 2 * nz /*lens sums*/ + nb /*edges*/ +
+    const size_t n_grid = same_window ? 2 : 3, n_win = same_window ? 1 : 2;
+    return n_grid * (3 * nz + 12 * nz) + n_win * (nw + 4 * nw) + 2 * nz /*lens sums*/ + nb /*edges*/ +
            2 * nb * cfg.nq_limber /*chi_q, Fw_q*/ + nk + 4 * nk + limber_work_doubles(cfg) +
            128 /*red + misc*/ + (LIMBER_THREADS / 32) * (nb / 2 + 2) /*per-warp int prefix sums*/;
 }
 
 #define LIMBER_SER_TERMS 12
+// (-1)^m / (m! (m + n)!) for n = 0, 2: coefficients of (k theta chi / 2)^(2m + n) in J_n
+__constant__ double k_limber_ser[2][LIMBER_SER_TERMS];
+static inline cudaError_t chomp_upload_limber_tables() {
+    double t[2][LIMBER_SER_TERMS];
+    for (int o = 0; o < 2; ++o) {
+        const int n = 2 * o;
+        double fm = 1.0, fmn = (n == 0) ? 1.0 : 2.0;      // m!, (m + n)!
+        for (int m = 0; m < LIMBER_SER_TERMS; ++m) {
+            if (m > 0) { fm *= m; fmn *= (m + n); }
+            t[o][m] = ((m & 1) ? -1.0 : 1.0) / (fm * fmn);
+        }
+    }
+    return cudaMemcpyToSymbol(k_limber_ser, t, sizeof t);
+}
+
+// number of elements of the increasing sequence s[0..n) that are < x (strict) or <= x
+__device__ __forceinline__ int count_below(const double* __restrict__ s, int n, double x, bool or_equal) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const bool below = or_equal ? (s[mid] <= x) : (s[mid] < x);
+        if (below) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// the same for the uniform sequence a0 + h i (evaluated exactly as the callers evaluate it)
+__device__ __forceinline__ int count_below_uniform(double a0, double h, int n, double x, bool or_equal) {
+    int c = (int)ceil((x - a0) / h);
+    c = c < 0 ? 0 : (c > n ? n : c);
+    while (c > 0 && !(or_equal ? (a0 + h * (c - 1) <= x) : (a0 + h * (c - 1) < x))) --c;
+    while (c < n && (or_equal ? (a0 + h * c <= x) : (a0 + h * c < x))) ++c;
+    return c;
+}
 #ifndef LIMBER_MIN_BLOCKS
 #define LIMBER_MIN_BLOCKS 4
 #endif
@@ -153,14 +187,17 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
     const double eps = cfg.window_precision;
     // ---- carve shared memory ------------------------------------------------------------------
     double* p = sm;
+    const int n_grid = same_window ? 2 : 3;
     EpochGrid g[3];
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < n_grid; ++i) {
         g[i].n = nz;
         g[i].z = p; p += nz; g[i].chi = p; p += nz; g[i].growth = p; p += nz;
         g[i].c_chi_z = p; p += 4 * nz; g[i].c_z_chi = p; p += 4 * nz; g[i].c_g_z = p; p += 4 * nz;
     }
+    if (same_window) g[2] = g[1];          // one window: its grid and table serve as both
     Window win[2];
-    for (int i = 0; i < 2; ++i) { win[i].n = nw; win[i].wf = p; p += nw; win[i].coef = p; p += 4 * nw; }
+    for (int i = 0; i < (same_window ? 1 : 2); ++i) { win[i].n = nw; win[i].wf = p; p += nw; win[i].coef = p; p += 4 * nw; }
+    if (same_window) win[1] = win[0];
     double* lens0 = p; p += nz;       // suffix sums of  w f          over the window-cosmology panels
     double* lens1 = p; p += nz;       //                 w f / chi'
     const int nb_max = (int)limber_edge_cap(cfg, same_window);
@@ -188,26 +225,40 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
         if (zlo < eps) zlo = eps;
         g[1 + i].z_min = zlo; g[1 + i].z_max = dist[i].z_max;
     }
-    const int n_grid = same_window ? 2 : 3;
     // ---- chi(z), D(z) nodes: chi_i = chi_{i-1} + GL-8 over [z_{i-1}, z_i] ---------------------
+    // One (grid, node, Gauss-Legendre index) item per thread and round, the eight lanes of a node
+    // reduced by shuffles; the first node integrates [0, z_min] on four panels.
     const double g1 = growth_approx(c, 1.0);
-    for (int idx = tid; idx < n_grid * nz; idx += blockDim.x) {
-        const int gi = idx / nz, i = idx - gi * nz;
-        EpochGrid& G = g[gi];
-        const double zi = (i == nz - 1) ? G.z_max : G.z_min + (G.z_max - G.z_min) / (nz - 1) * i;
-        G.z[i] = zi;
-        G.growth[i] = growth_approx(c, 1.0 / (1.0 + zi)) / g1;
+    for (int base = 0; base < n_grid * nz * 8; base += blockDim.x) {
+        const int idx = base + tid;
+        const bool live = idx < n_grid * nz * 8;
+        const int node = live ? idx >> 3 : 0, q = idx & 7;
+        const int gi = node / nz, i = node - gi * nz;
+        // (no dynamic indexing of g[]: that would put the array in local memory)
+        const double gz_min = gi == 0 ? g[0].z_min : (gi == 1 ? g[1].z_min : g[2].z_min);
+        const double gz_max = gi == 0 ? g[0].z_max : (gi == 1 ? g[1].z_max : g[2].z_max);
+        double* gbase = sm + (size_t)gi * 15 * nz;          // z | chi | growth | coefficients
+        const double hz = (gz_max - gz_min) / (nz - 1);
+        const double zi = (i == nz - 1) ? gz_max : gz_min + hz * i;
         double acc = 0.0;
         if (i == 0) {
-            for (int pnl = 0; pnl < 4; ++pnl) {
-                const double a = zi * pnl / 4.0, bb = zi * (pnl + 1) / 4.0, half = 0.5 * (bb - a);
-                for (int q = 0; q < 8; ++q) acc += half * c_glw[8][q] * inv_hubble(c, 0.5 * (a + bb) + half * c_glx[8][q]);
-            }
+            if (zi > 0.0)
+                for (int pnl = 0; pnl < 4; ++pnl) {
+                    const double a = zi * pnl / 4.0, bb = zi * (pnl + 1) / 4.0, half = 0.5 * (bb - a);
+                    acc += half * c_glw[8][q] * inv_hubble(c, 0.5 * (a + bb) + half * c_glx[8][q]);
+                }
         } else {
-            const double a = G.z_min + (G.z_max - G.z_min) / (nz - 1) * (i - 1), half = 0.5 * (zi - a);
-            for (int q = 0; q < 8; ++q) acc += half * c_glw[8][q] * inv_hubble(c, 0.5 * (a + zi) + half * c_glx[8][q]);
+            const double a = gz_min + hz * (i - 1), half = 0.5 * (zi - a);
+            acc = half * c_glw[8][q] * inv_hubble(c, 0.5 * (a + zi) + half * c_glx[8][q]);
         }
-        G.chi[i] = acc;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (live && q == 0) {
+            gbase[i] = zi;
+            gbase[2 * nz + i] = growth_approx(c, 1.0 / (1.0 + zi)) / g1;
+            gbase[nz + i] = acc;
+        }
     }
     __syncthreads();
     if (wid < n_grid) {      // running sums chi_i = sum_{j <= i} (panel integrals): one warp scan per grid
@@ -238,7 +289,6 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
         }
     }
     __syncthreads();
-    if (same_window) g[2] = g[1];
     // ---- dN/dz normalisations (kernel.py:43-54): 16 panels x GL-8 --------------------------------
     for (int i = 0; i < (same_window ? 1 : 2); ++i) {
         double v = 0.0;
@@ -288,9 +338,21 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
                 lens0[pnl] = s0; lens1[pnl] = s1;
             }
             __syncthreads();
-            if (tid == 0) {
-                lens0[nz - 1] = 0.0; lens1[nz - 1] = 0.0;
-                for (int k = nz - 2; k >= 0; --k) { lens0[k] += lens0[k + 1]; lens1[k] += lens1[k + 1]; }
+            if (wid < 2) {       // suffix sums (entry nz - 1 = 0): warp scans over the reversed arrays
+                double* ls = wid == 0 ? lens0 : lens1;
+                double carry = 0.0;
+                for (int base = 0; base < nz; base += 32) {
+                    const int r = base + lane;               // reversed index: element nz - 1 - r
+                    double v = (r > 0 && r < nz) ? ls[nz - 1 - r] : 0.0;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double up = __shfl_up_sync(0xffffffffu, v, o);
+                        if (lane >= o) v += up;
+                    }
+                    v += carry;
+                    if (r < nz) ls[nz - 1 - r] = v;
+                    carry = __shfl_sync(0xffffffffu, v, 31);
+                }
             }
             __syncthreads();
             double g_chi_min = grid_chi(G, dist[i].z_min);            // kernel.py:437-441
@@ -315,18 +377,73 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
         }
         __syncthreads();
     }
-    if (wid < (same_window ? 1 : 2)) {
+    // ---- window splines (warps 0 [, 1]) side by side with the merge of the base-panel edges -----------
+    // Base panels of the chi integrals: union of the knots of both windows and of the kernel's chi(z)
+    // table.  The three sorted sequences are merged by rank: every candidate counts the members of the
+    // other two sequences below it (ties: window a, window b, table -- the order of a sequential merge).
+    const int n_spl = same_window ? 1 : 2;
+    const double zmin_k = fmax(g[1].z_min, g[2].z_min), zmax_k = fmin(g[1].z_max, g[2].z_max);
+    const double chi_min_k = fmax(eps, grid_chi(g[0], zmin_k)), chi_max_k = grid_chi(g[0], zmax_k);
+    const int nA = nw, nB = same_window ? 0 : nw, nC = nz, n_cand = nA + nB + nC;
+    double* cand = chi_q;                       // sorted candidates (chi_q / fw_q are filled later)
+    if (wid < n_spl) {
         Window& W = win[wid];
         double* wk = work + (size_t)wid * 6 * nw;
         // uniform chi nodes
         spline_build_uniform_warp(nw, (W.chi_max - W.chi_min) / (nw - 1), W.wf, W.coef, wk);
+    } else {
+        const double a0 = win[0].chi_min, ha = (win[0].chi_max - win[0].chi_min) / (nw - 1);
+        const double b0 = win[1].chi_min, hb = (win[1].chi_max - win[1].chi_min) / (nw - 1);
+        const double* cs = g[0].chi;
+        for (int id = tid - 32 * n_spl; id < n_cand; id += blockDim.x - 32 * n_spl) {
+            double x;
+            int rank;
+            if (id < nA) {
+                x = a0 + ha * id;
+                rank = id + (nB ? count_below_uniform(b0, hb, nB, x, false) : 0) + count_below(cs, nC, x, false);
+            } else if (id < nA + nB) {
+                x = b0 + hb * (id - nA);
+                rank = (id - nA) + count_below_uniform(a0, ha, nA, x, true) + count_below(cs, nC, x, false);
+            } else {
+                x = cs[id - nA - nB];
+                rank = (id - nA - nB) + count_below_uniform(a0, ha, nA, x, true) +
+                       (nB ? count_below_uniform(b0, hb, nB, x, true) : 0);
+            }
+            cand[rank] = x;
+        }
     }
     __syncthreads();
     if (same_window) win[1] = win[0];
+    {
+        // keep a candidate if it lies inside (chi_min, chi_max) and clear of its predecessor; positions
+        // by a block-wide exclusive scan of the flags (ballots inside the warps, warp totals in shared memory)
+        const double tol = 1e-9 * chi_max_k;
+        int* wtot = (int*)red;                  // nwarp + 1 ints
+        int run = 1;                            // edge[0] = chi_min_k
+        if (tid == 0) edge[0] = chi_min_k;
+        for (int base = 0; base < n_cand; base += blockDim.x) {
+            const int r = base + tid;
+            double x = 0.0;
+            bool keep = false;
+            if (r < n_cand) {
+                x = cand[r];
+                keep = x > chi_min_k + tol && x < chi_max_k - tol && (r == 0 || x > cand[r - 1] + tol);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const int before = __popc(bal & ((1u << lane) - 1u));
+            __syncthreads();
+            if (lane == 0) wtot[wid] = __popc(bal);
+            __syncthreads();
+            int off = run;
+            for (int ww = 0; ww < wid; ++ww) off += wtot[ww];
+            if (keep) edge[off + before] = x;
+            for (int ww = 0; ww < nwarp; ++ww) run += wtot[ww];
+        }
+        if (tid == 0) { edge[run] = chi_max_k; n_edge_s = run + 1; }
+    }
+    __syncthreads();
     // ---- kernel range, z_bar (kernel.py:594-639) -----------------------------------------------------
     LimberF F{win[0], win[1], g[0]};
-    const double zmin_k = fmax(g[1].z_min, g[2].z_min), zmax_k = fmin(g[1].z_max, g[2].z_max);
-    const double chi_min_k = fmax(eps, grid_chi(g[0], zmin_k)), chi_max_k = grid_chi(g[0], zmax_k);
     {
         double best = -1e300; int besti = 0;
         for (int j = tid; j < nk; j += blockDim.x) {
@@ -354,31 +471,10 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
             s_misc[1] = grid_growth(g[0], zb);           // Correlation.D_z, correlation.py:94
         }
     }
-    // ---- base panels: union of the knots of both windows and of the kernel's chi(z) table -------------
-    if (tid == 0) {
-        int cnt = 0;
-        edge[cnt++] = chi_min_k;
-        int ia = 0, ib = 0, ic = 0;
-        const double ha = (win[0].chi_max - win[0].chi_min) / (nw - 1), hb = (win[1].chi_max - win[1].chi_min) / (nw - 1);
-        const double tol = 1e-9 * chi_max_k;
-        while (true) {
-            const double xa = ia < nw ? win[0].chi_min + ha * ia : 1e300;
-            const double xb = (!same_window && ib < nw) ? win[1].chi_min + hb * ib : 1e300;
-            const double xc = ic < nz ? g[0].chi[ic] : 1e300;
-            double x = xa; int which = 0;
-            if (xb < x) { x = xb; which = 1; }
-            if (xc < x) { x = xc; which = 2; }
-            if (x >= 1e300) break;
-            if (which == 0) ++ia; else if (which == 1) ++ib; else ++ic;
-            if (x > edge[cnt - 1] + tol && x < chi_max_k - tol && cnt < nb_max - 1) edge[cnt++] = x;
-        }
-        edge[cnt++] = chi_max_k;
-        n_edge_s = cnt;
-    }
     __syncthreads();
     const int n_pan = n_edge_s - 1;
     for (int idx = tid; idx < n_pan * nq; idx += blockDim.x) {
-        const int pnl = idx / nq, q = idx - pnl * nq;
+        const int pnl = (nq == 4) ? idx >> 2 : idx / nq, q = idx - pnl * nq;
         const double a = edge[pnl], bb = edge[pnl + 1], half = 0.5 * (bb - a);
         const double x = 0.5 * (a + bb) + half * c_glx[nq][q];
         chi_q[idx] = x;
@@ -433,10 +529,10 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
             if (lane < LIMBER_SER_TERMS) {
                 double mm = 0.0;
                 for (int ww = 0; ww < nwarp; ++ww) mm += red[ww * LIMBER_SER_TERMS + lane];
-                // (-1)^m t^m / (m! (m + n)!)
-                double cfac = (order == 0) ? 1.0 : 0.5 * t;          // n = 2: t^(m + 1) / (m! (m + 2)!)
-                for (int i = 1; i <= lane; ++i) cfac *= -t / ((double)i * (double)(i + order));
-                term = cfac * mm;
+                // (-1)^m t^m / (m! (m + n)!)  (n = 2: one more power of t); the factorials are tabulated
+                double cfac = (order == 0) ? 1.0 : t;
+                for (int i = 1; i <= lane; ++i) cfac *= t;
+                term = cfac * k_limber_ser[order ? 1 : 0][lane] * mm;
             }
             // sum the terms from the smallest up (ascending magnitude is descending m)
             double accs = 0.0;
@@ -477,8 +573,9 @@ limber_tables_kernel(const Cfg cfg, int B, int same_window, const double* __rest
                 int lo = 0, hi = n_pan;            // panel with pfx[lo] <= idx < pfx[lo + 1]
                 while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= idx) lo = mid; else hi = mid; }
                 const int pnl = lo, local = idx - pfx[pnl];
-                const int nsub = (pfx[pnl + 1] - pfx[pnl]) / nq;
-                const int sidx = local / nq, q = local - sidx * nq;
+                int nsub, sidx, q;
+                if (nq == 4) { nsub = (pfx[pnl + 1] - pfx[pnl]) >> 2; sidx = local >> 2; q = local & 3; }
+                else { nsub = (pfx[pnl + 1] - pfx[pnl]) / nq; sidx = local / nq; q = local - sidx * nq; }
                 const double a = edge[pnl], bfull = edge[pnl + 1];
                 if (nsub == 1 && bfull <= top) {
                     acc += fw_q[pnl * nq + q] * bessel_j(order, kt * chi_q[pnl * nq + q]);

@@ -487,44 +487,47 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         if (lane == 0) { lnm[i] = lm; nu[i] = v; }
     }
     __syncthreads();
-    if (w == 0) spline_build_uniform_warp(n, hM, nu, c2, work);   // nu(ln M): uniform ln M grid
-    if (w == 1) spline_build_warp(n, nu, lnm, c1, work + 5 * n);  // ln M(nu)
-    __syncthreads();
+    // Two warps build the two splines; the other six meanwhile integrate the Sheth-Tormen
+    // normalisations and the comoving distance, which need the nu nodes only.
     const double nu_min = 1.001 * nu[0], nu_max = 0.999 * nu[n - 1];  // mass_function.py:212-213
-    const double lnm_star = spline_eval_search(c1, 1.0, nu, n);        // m_star = mass(1.0), :223
-    // ---- f_norm, bias_norm (mass_function.py:225-241): int f dnu = int nu f dln nu over
-    //      [nu_min, nu_max], 8-point Gauss-Legendre on every knot interval of ln nu
     const double stq = hp[CHOMP_H_STQ], sta = hp[CHOMP_H_ST_LITTLE_A];
-    double sf = 0.0, sfb = 0.0;
-    // ln(nu) at the knots once (the spline scratch is free again), ends moved to nu_min / nu_max
-    double* lognu = work;
-    for (int i = tid; i < n; i += blockDim.x) lognu[i] = log(i == 0 ? nu_min : (i == n - 1 ? nu_max : nu[i]));
-    const double ln_sta = log(sta);
-    __syncthreads();
-    for (int idx = tid; idx < (n - 1) * 8; idx += blockDim.x) {
-        const int i = idx >> 3, q = idx & 7;
-        const double a = lognu[i], bb = lognu[i + 1];
-        const double half = 0.5 * (bb - a);
-        const double x = 0.5 * (a + bb) + half * c_glx[8][q];
-        double nf, bi;
-        st_raw_ln(x, ln_sta, stq, m.delta_c, nf, bi);
-        const double wgt = half * c_glw[8][q];
-        sf += wgt * nf;
-        sfb += wgt * nf * bi;
+    double sf = 0.0, sfb = 0.0, chi = 0.0;
+    if (w == 0) spline_build_uniform_warp(n, hM, nu, c2, work);   // nu(ln M): uniform ln M grid
+    else if (w == 1) spline_build_warp(n, nu, lnm, c1, work + 5 * n);  // ln M(nu)
+    else {
+        // ---- f_norm, bias_norm (mass_function.py:225-241): int f dnu = int nu f dln nu over
+        //      [nu_min, nu_max], 8-point Gauss-Legendre on every knot interval of ln nu
+        const int t2 = tid - 64, nt2 = blockDim.x - 64;
+        // ln(nu) at the knots once (the Delta^2 table is no longer needed), ends moved to nu_min / nu_max
+        double* lognu = d2tab;
+        for (int i = t2; i < n; i += nt2) lognu[i] = log(i == 0 ? nu_min : (i == n - 1 ? nu_max : nu[i]));
+        const double ln_sta = log(sta);
+        asm volatile("bar.sync 3, %0;" ::"r"(nt2) : "memory");
+        for (int idx = t2; idx < (n - 1) * 8; idx += nt2) {
+            const int i = idx >> 3, q = idx & 7;
+            const double a = lognu[i], bb = lognu[i + 1];
+            const double half = 0.5 * (bb - a);
+            const double x = 0.5 * (a + bb) + half * c_glx[8][q];
+            double nf, bi;
+            st_raw_ln(x, ln_sta, stq, m.delta_c, nf, bi);
+            const double wgt = half * c_glw[8][q];
+            sf += wgt * nf;
+            sfb += wgt * nf * bi;
+        }
+        // comoving distance to z (SingleEpoch._chi, cosmology.py:106-110): 8 panels x GL-8
+        if (t2 < 64) {
+            const int p = t2 >> 3, q = t2 & 7;
+            const double a = z * p / 8.0, bb = z * (p + 1) / 8.0;
+            const double half = 0.5 * (bb - a);
+            chi = half * c_glw[8][q] * inv_hubble(c, 0.5 * (a + bb) + half * c_glx[8][q]);
+        }
     }
     sf = block_sum(sf, red);
     sfb = block_sum(sfb, red + 32);
+    chi = block_sum(chi, red);
     const double f_norm = 1.0 / sf;
     const double b_norm = 1.0 / (f_norm * sfb);
-    // comoving distance to z (SingleEpoch._chi, cosmology.py:106-110): 8 panels x GL-8
-    double chi = 0.0;
-    if (tid < 64) {
-        const int p = tid >> 3, q = tid & 7;
-        const double a = z * p / 8.0, bb = z * (p + 1) / 8.0;
-        const double half = 0.5 * (bb - a);
-        chi = half * c_glw[8][q] * inv_hubble(c, 0.5 * (a + bb) + half * c_glx[8][q]);
-    }
-    chi = block_sum(chi, red);
+    const double lnm_star = spline_eval_search(c1, 1.0, nu, n);        // m_star = mass(1.0), :223
 
     // ---- write out ----------------------------------------------------------------------
     for (int i = tid; i < n; i += blockDim.x) {

@@ -1,0 +1,140 @@
+"""Multi-GPU evaluation of one parameter batch: shard, evaluate, one all-gather.
+
+Every parameter point is independent, so the batch is cut
+into contiguous shards, one per rank of a ``torch.distributed`` process group (one
+process per GPU, NCCL over NVLink), every rank runs the four stages on its shard,
+and ONE ``all_gather_into_tensor`` assembles the ``[B, n_theta]`` result table (the
+per-point status flags ride along as an extra column, so a step costs a single
+collective).  Results do not depend on the number of ranks: the kernels reduce in a
+fixed order, and a point's result does not depend on the batch it sits in.
+
+    sharded = ShardedEngine(survey)              # after dist.init_process_group("nccl")
+    w, status = sharded.wtheta(cosmo, halo, hod) # global [B, .] host arrays in, full table out on every rank
+
+The MCMC recipe this replaces evaluates one point at a time
+(examples/example_script.py:141-143); the reference has no multi-process path.
+"""
+import numpy as np
+
+from . import _lib, design
+
+
+def shard_bounds(n_points, world_size):
+    """[(start, stop)] of every rank's contiguous shard (same rule as design.shard)."""
+    out = []
+    for r in range(world_size):
+        sl = design.shard(n_points, r, world_size)
+        out.append((sl.start, sl.stop))
+    return out
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+class ShardedEngine(object):
+    """One `engine.Engine` per rank behind a shard / all-gather front.
+
+    `evaluate(cosmo, halo, hod) -> (table [rows, n_cols] tensor, status [rows] int32 tensor)` may be
+    supplied instead of a survey: the host-side logic (sharding, padding of uneven shards, the single
+    collective, the double-buffered pipeline) is then exercised without a GPU (tests, gloo)."""
+
+    def __init__(self, survey=None, evaluate=None, group=None, device=None, which=None):
+        import torch
+        self.torch = torch
+        dist = _dist()
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.survey = survey
+        self.engine = None
+        if evaluate is None:
+            if survey is None:
+                raise ValueError("give a Survey or an evaluate callable")
+            from . import engine as _engine
+            if device is None:
+                device = torch.cuda.current_device()
+            self.engine = _engine.Engine(survey, device=device)
+            self.which = _lib.POWER_SPEC[survey.power_spec] if which is None else int(which)
+            self._theta = torch.as_tensor(np.ascontiguousarray(survey.theta), device="cuda:%d" % int(device))
+            evaluate = self._evaluate_engine
+        self.evaluate = evaluate
+        self._bufs = {}
+
+    # -- the GPU evaluation of one shard ----------------------------------------------------
+    def _evaluate_engine(self, cosmo, halo, hod):
+        t = self.torch
+        eng = self.engine
+        rows = cosmo.shape[0]
+        status = t.zeros(rows, dtype=t.int32, device=self._theta.device)
+        w = eng.wtheta(cosmo, halo, hod, self._theta, self.which, status=status)
+        return w, status
+
+    # -- one step --------------------------------------------------------------------------------
+    def local_shard(self, n_points, rank=None):
+        return design.shard(n_points, self.rank if rank is None else rank, self.world)
+
+    def _packed_local(self, cosmo, halo, hod, slot=0):
+        """Evaluate this rank's shard into a [max_rows, n_cols + 1] buffer (last column: status)."""
+        t = self.torch
+        n = cosmo.shape[0]
+        bounds = shard_bounds(n, self.world)
+        max_rows = max(b - a for a, b in bounds)
+        a, b = bounds[self.rank]
+        table, status = self.evaluate(cosmo[a:b], halo[a:b], hod[a:b])
+        n_cols = table.shape[1]
+        key = (slot, max_rows, n_cols, table.device, table.dtype)
+        if key not in self._bufs:
+            self._bufs[key] = (t.zeros((max_rows, n_cols + 1), dtype=table.dtype, device=table.device),
+                               t.empty((self.world, max_rows, n_cols + 1), dtype=table.dtype, device=table.device))
+        local, full = self._bufs[key]
+        rows = b - a
+        if rows:
+            local[:rows, :n_cols] = table
+            local[:rows, n_cols] = status.to(table.dtype)
+        return local, full, bounds, n_cols
+
+    def _unpack(self, full, bounds, n_cols):
+        t = self.torch
+        if all(b - a == full.shape[1] for a, b in bounds):
+            flat = full.reshape(-1, n_cols + 1)
+        else:
+            flat = t.cat([full[r, :b - a] for r, (a, b) in enumerate(bounds)], 0)
+        return flat[:, :n_cols], flat[:, n_cols].to(t.int32)
+
+    def wtheta(self, cosmo, halo, hod):
+        """Global batch in (host arrays or tensors, identical on every rank), full [B, n_theta] table and
+        [B] status flags out on every rank: shard -> four stages -> one all-gather."""
+        local, full, bounds, n_cols = self._packed_local(cosmo, halo, hod)
+        if self.world > 1:
+            _dist().all_gather_into_tensor(full.view(-1, n_cols + 1), local, group=self.group)
+        else:
+            full = local.unsqueeze(0)
+        w, st = self._unpack(full, bounds, n_cols)
+        return w.clone(), st                # the staging buffers are reused by the next call
+
+    def pipeline(self, batches):
+        """Double-buffered steps: the all-gather of step s runs (asynchronously, on the collective's own
+        stream) while the stages of step s + 1 compute.  Yields (w, status) per batch, in order."""
+        pending = None
+        for s, (cosmo, halo, hod) in enumerate(batches):
+            local, full, bounds, n_cols = self._packed_local(cosmo, halo, hod, slot=s & 1)
+            work = None
+            if self.world > 1:
+                work = _dist().all_gather_into_tensor(full.view(-1, n_cols + 1), local, group=self.group, async_op=True)
+            else:
+                full = local.unsqueeze(0)
+            if pending is not None:
+                yield self._finish(*pending)
+            pending = (work, full, bounds, n_cols)
+        if pending is not None:
+            yield self._finish(*pending)
+
+    def _finish(self, work, full, bounds, n_cols):
+        if work is not None:
+            work.wait()
+        w, st = self._unpack(full, bounds, n_cols)
+        return w.clone(), st            # the buffer is reused two steps later

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Summarise an `ncu --set full` report of the hot-path kernels (tools/gpu_profile.sh).
+
+    python tools/ncu_kernels.py gpurun_out/<tag>_prof.ncu-rep profiles/ncu_<tag>_kernels [points]
+
+writes <out>.json (read by bench.py: executed FP64 flop and DRAM bytes per launch and per point, FP64
+pipe activity) and <out>.txt (the raw metrics a reviewer wants to see: time, occupancy, stalls)."""
+import csv
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "sm__cycles_active.avg", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_dmma_pred_on.sum", "smsp__inst_executed_pipe_fp64.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct"]
+
+
+def source_hash():
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "chomp_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def to_float(v):
+    try:
+        return float(v.replace(",", ""))
+    except ValueError:
+        return None
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    points = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0,
+             "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
+    kernels, lines = {}, []
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        short = name.split("(")[0].split("::")[-1]
+        lines.append("--- " + name[:100])
+        m = {}
+        for i, h in enumerate(hdr):
+            stall = "issue_stalled" in h and "per_issue_active" in h
+            if h in KEEP or stall:
+                v = to_float(r[i])
+                if v is None:
+                    continue
+                if stall and v < 0.15:
+                    continue
+                lines.append("  %-95s %s %s" % (h, r[i], units[i]))
+                m[h] = v*scale.get(units[i], 1.0) if (h.startswith("dram__bytes") or h == "gpu__time_duration.sum") else v
+        dfma = m.get("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", 0.0)
+        dmul = m.get("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", 0.0)
+        dadd = m.get("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", 0.0)
+        dmma = m.get("smsp__sass_thread_inst_executed_op_dmma_pred_on.sum", 0.0)
+        # DMMA m8n8k4: 8*8*4 FMA per warp instruction = 16 flop per thread instruction
+        flop = 2.0*dfma + dmul + dadd + 16.0*dmma
+        t = m.get("gpu__time_duration.sum", 0.0)
+        kernels[short] = {
+            "ncu_ms": 1e3*t, "grid": m.get("launch__grid_size"), "registers": m.get("launch__registers_per_thread"),
+            "smem_dynamic_kb": m.get("launch__shared_mem_per_block_dynamic"),
+            "dfma": dfma, "dmul": dmul, "dadd": dadd, "dmma": dmma,
+            "executed_fp64_flop": flop, "executed_fp64_flop_per_point": flop/points,
+            "executed_tflops_under_ncu": flop/t/1e12 if t else None,
+            "fp64_pipe_pct": m.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            "warps_active_pct": m.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+            "issue_active_pct": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "threads_per_inst": m.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "dram_read_bytes": m.get("dram__bytes_read.sum"), "dram_write_bytes": m.get("dram__bytes_write.sum"),
+            "dram_bytes_per_point": ((m.get("dram__bytes_read.sum") or 0) + (m.get("dram__bytes_write.sum") or 0))/points,
+        }
+    doc = {"report": os.path.basename(rep), "points": points, "source_hash": source_hash(),
+           "how": "ncu --set full --clock-control none + smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd,dmma}_pred_on.sum; "
+                  "flop = 2 dfma + dmul + dadd + 16 dmma (thread instructions)",
+           "kernels": kernels}
+    json.dump(doc, open(out + ".json", "w"), indent=1)
+    open(out + ".txt", "w").write("\n".join(lines) + "\n")
+    tot = sum(k["ncu_ms"] for k in kernels.values())
+    for k, v in kernels.items():
+        print("%-22s %6.3f ms (%4.1f%%)  fp64 pipe %5.1f%%  exec %6.2f TF/s  flop/pt %.3g  dram %6.1f MB  thr/inst %.1f  warps %.0f%%" % (
+            k, v["ncu_ms"], 100*v["ncu_ms"]/tot, v["fp64_pipe_pct"] or 0, v["executed_tflops_under_ncu"] or 0,
+            v["executed_fp64_flop_per_point"], ((v["dram_read_bytes"] or 0) + (v["dram_write_bytes"] or 0))/1e6,
+            v["threads_per_inst"] or 0, v["warps_active_pct"] or 0))
+
+
+if __name__ == "__main__":
+    main()
