@@ -87,6 +87,11 @@ struct Handle {
     // call on a foreign stream leaves an event behind that the private stream waits on
     cudaEvent_t order_ev = nullptr;
     bool order_pending = false, capturing = false;
+    // fast / slow split (chomp_b200_wtheta_batch_grouped): sanitised group index of every point and the
+    // status flags of the group-level stages; `group` is non-null only while a grouped call runs
+    int32_t *gidx = nullptr, *gstatus = nullptr;
+    const int32_t* group = nullptr;
+    int n_groups = 0;
     int node_cap[N_NODE_LISTS] = {0, 0, 0, 0}, node_off[N_NODE_LISTS] = {0, 0, 0, 0}, node_cap_total = 0;
     long long launches = 0;
     double* dndz_tab[2] = {nullptr, nullptr};     // CHOMP_DNDZ_TABLE: breaks[n + 1], coef[n][4]
@@ -222,9 +227,10 @@ int sums_doubles(const Handle* h) {
     int m = 0;
     for (int c = 0; c < N_KCLASS; ++c) m = h->node_cap[c] > m ? h->node_cap[c] : m;   // the sums kernel stages lists 0..2 only
     // node records of the largest list and the moment scratch; anything beyond that holds the series
-    // coefficients of the two coarse lists.  9 000 doubles (+ 3.6 KB static) keeps three CTAs per SM
-    int d = (NODE_FIELDS + 1) * m + SUMS_EXTRA_DOUBLES;
-    if (d < 9000) d = 9000;
+    // coefficients of the two coarse lists.  7 800 doubles (+ 11.7 KB of static profile tables) keeps
+    // three CTAs per SM
+    int d = NODE_FIELDS * m + SUMS_EXTRA_DOUBLES;
+    if (d < 7800) d = 7800;
     return d;
 }
 size_t sums_smem(const Handle* h) {
@@ -399,6 +405,8 @@ int chomp_b200_reserve(void* handle, int max_points) {
     rc |= dev_alloc(h, &h->cosmo, B * CHOMP_N_COSMO);
     rc |= dev_alloc(h, &h->halo, B * CHOMP_N_HALO);
     rc |= dev_alloc(h, &h->hod, B * CHOMP_N_HOD);
+    rc |= dev_alloc(h, &h->gidx, B);
+    rc |= dev_alloc(h, &h->gstatus, B);
     if (rc) { free_scratch(h); return rc; }
     h->cap_points = max_points;
     return 0;
@@ -464,7 +472,7 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
                            int32_t* status_dev, void* stream) {
     Handle* h = (Handle*)handle;
     if (int rc = ensure(h, B)) return rc;
-    NEED_STAGE(h->done_mass, B, "the mass tables (chomp_b200_mass_tables)");
+    NEED_STAGE(h->done_mass, h->group ? h->n_groups : B, "the mass tables (chomp_b200_mass_tables)");
     cudaStream_t s = (cudaStream_t)stream;
     const Cfg& c = h->cfg;
     if (halo_dev != h->halo)
@@ -477,15 +485,16 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
     SMEM_OPT_IN(halo_splines_kernel, h, 15 * (size_t)c.n_halo * sizeof(double));
     mark(h, CHOMP_K_NODES, s);
     nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
-                                                  h->c_lnm_nu, h->c_nu_lnm, no, status_dev);
+                                                  h->c_lnm_nu, h->c_nu_lnm, no, status_dev, h->group,
+                                                  h->group ? h->gstatus : nullptr);
     CK(cudaGetLastError());
-    dim3 grid((c.n_halo + SUMS_K_PER_CTA - 1) / SUMS_K_PER_CTA + N_KCLASS - 1, B);
+    const unsigned grid = (unsigned)((c.n_halo + SUMS_K_PER_CTA - 1) / SUMS_K_PER_CTA + N_KCLASS - 1) * (unsigned)B;
     mark(h, CHOMP_K_SUMS, s);
     halo_sums_kernel<<<grid, 256, sums_smem(h), s>>>(c, B, no, sums_doubles(h), h->raw);
     CK(cudaGetLastError());
     mark(h, CHOMP_K_SPLINES, s);
     halo_splines_kernel<<<B, 160, 15 * (size_t)c.n_halo * sizeof(double), s>>>(c, B, h->raw, h->nbar, h->epoch, h->htab, h->hcoef,
-                                                                          status_dev);
+                                                                          status_dev, h->group);
     mark(h, CHOMP_K_SPLINES + 1, s);
     CK(cudaGetLastError());
     h->launches += 3;
@@ -502,7 +511,7 @@ int chomp_b200_power(void* handle, int B, int which, int n_k, const double* k_de
     NEED_STAGE(h->done_mass, B, "the epoch scalars (chomp_b200_mass_tables)");
     if (!(which == CHOMP_P_LINEAR || (h->cfg.use_halofit && which == CHOMP_P_MM)))
         NEED_STAGE(h->done_halo, B, "the halo tables (chomp_b200_halo_tables)");
-    dim3 grid((n_k + 255) / 256, B);
+    const unsigned grid = (unsigned)((n_k + 255) / 256) * (unsigned)B;
     power_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->cfg, B, which, n_k, k_dev, h->cosmo, h->epoch, h->htab,
                                                         h->hcoef, h->cfg.use_halofit ? h->hfit : nullptr, P_out_dev);
     h->launches += 1;
@@ -517,15 +526,15 @@ int chomp_b200_wtheta(void* handle, int B, int which, int n_theta, const double*
     if (int rc = ensure(h, B)) return rc;
     if (which < CHOMP_P_LINEAR || which > CHOMP_P_GG) FAIL("unknown power spectrum");
     if (n_theta <= 0) FAIL("n_theta must be positive");
-    NEED_STAGE(h->done_limber, B, "the Limber kernel table (chomp_b200_limber_tables)");
-    NEED_STAGE(h->done_mass, B, "the epoch scalars (chomp_b200_mass_tables)");
+    NEED_STAGE(h->done_limber, h->group ? h->n_groups : B, "the Limber kernel table (chomp_b200_limber_tables)");
+    NEED_STAGE(h->done_mass, h->group ? h->n_groups : B, "the epoch scalars (chomp_b200_mass_tables)");
     if (!(which == CHOMP_P_LINEAR || (h->cfg.use_halofit && which == CHOMP_P_MM)))
         NEED_STAGE(h->done_halo, B, "the halo tables (chomp_b200_halo_tables)");
     SMEM_OPT_IN(wtheta_kernel, h, wtheta_smem(h->cfg));
     mark(h, CHOMP_K_WTHETA, (cudaStream_t)stream);
     wtheta_kernel<<<B, 256, wtheta_smem(h->cfg), (cudaStream_t)stream>>>(
         h->cfg, B, which, n_theta, theta_dev, h->cosmo, h->epoch, h->dbar, h->htab, h->hcoef, h->knodes, h->kcoef,
-        h->cfg.use_halofit ? h->hfit : nullptr, w_out_dev, status_dev);
+        h->cfg.use_halofit ? h->hfit : nullptr, w_out_dev, status_dev, h->group);
     mark(h, CHOMP_K_WTHETA + 1, (cudaStream_t)stream);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -542,6 +551,49 @@ int chomp_b200_wtheta_batch(void* handle, int B, const double* cosmo_dev, const 
     if (int rc = chomp_b200_mass_tables(handle, B, h->cosmo, halo_dev, nullptr, status_dev, stream)) return rc;
     if (int rc = chomp_b200_halo_tables(handle, B, h->halo, hod_dev, status_dev, stream)) return rc;
     return chomp_b200_wtheta(handle, B, which, n_theta, theta_dev, w_out_dev, status_dev, stream);
+}
+
+namespace {
+__global__ void group_index_kernel(int B, int n_groups, const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                   int32_t* __restrict__ status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int g = in[b];
+    if (g < 0 || g >= n_groups) {              // flagged, evaluated against group 0 so that nothing reads out of bounds
+        g = 0;
+        if (status) atomicOr(status + b, CHOMP_ST_DOMAIN);
+    }
+    out[b] = g;
+}
+}  // namespace
+
+int chomp_b200_wtheta_batch_grouped(void* handle, int n_groups, const double* cosmo_dev, const double* halo_dev, int B,
+                                    const int32_t* group_index_dev, const double* hod_dev, int which, int n_theta,
+                                    const double* theta_dev, double* w_out_dev, int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (n_groups <= 0 || B <= 0) FAIL("n_groups and B must be positive");
+    if (!group_index_dev) FAIL("null group index");
+    if (int rc = ensure(h, B > n_groups ? B : n_groups)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (status_dev) CK(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * (size_t)B, s));
+    CK(cudaMemsetAsync(h->gstatus, 0, sizeof(int32_t) * (size_t)n_groups, s));
+    group_index_kernel<<<(B + 255) / 256, 256, 0, s>>>(B, n_groups, group_index_dev, h->gidx, status_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    // slow stages: once per (cosmology, halo) row
+    if (int rc = chomp_b200_limber_tables(handle, n_groups, cosmo_dev, h->gstatus, stream)) return rc;
+    if (int rc = chomp_b200_mass_tables(handle, n_groups, h->cosmo, halo_dev, nullptr, h->gstatus, stream)) return rc;
+    // fast stages: per point, reading the group's tables through the index
+    h->group = h->gidx;
+    h->n_groups = n_groups;
+    int rc = chomp_b200_halo_tables(handle, B, h->halo, hod_dev, status_dev, stream);
+    if (!rc) rc = chomp_b200_wtheta(handle, B, which, n_theta, theta_dev, w_out_dev, status_dev, stream);
+    h->group = nullptr;
+    h->n_groups = 0;
+    // the handle's cosmology-level tables are indexed by group, not by point: later per-point stage calls
+    // must rebuild them
+    h->done_limber = h->done_mass = h->done_halo = h->done_params = 0;
+    return rc;
 }
 
 int chomp_b200_wtheta_batch_host(void* handle, int B, const double* cosmo_host, const double* halo_host,
@@ -840,6 +892,7 @@ int chomp_b200_trispectrum_1h(void* handle, int B, double* T_out_dev, void* stre
     if (int rc = ensure(h, B)) return rc;
     const Cfg& c = h->cfg;
     if (c.tri_moment < 0) FAIL("the trispectrum node list is disabled: configure with tri_moment >= 0");
+    if (B > 65535) FAIL("trispectrum / covariance batches are limited to 65 535 points per call");
     const int cap = h->node_cap[TRI_LIST];
     if (B > h->tri_points) {
         CK(cudaDeviceSynchronize());
@@ -1036,6 +1089,7 @@ namespace {
 int check_cov(const Handle* h, const CovP& p) {
     const Cfg& c = h->cfg;
     if (p.n_bins < 1 || p.n_bins > COV_MAX_COLS) FAIL("n_bins must be in 1..128");
+
     if (c.n_kernel > COV_MAX_COLS) FAIL("covariance needs kernel_npoints <= 128");
     if (c.bessel_order != 0) FAIL("covariance is defined for the J0 kernel");
     if (p.which < CHOMP_P_LINEAR || p.which > CHOMP_P_GG) FAIL("unknown power spectrum");
@@ -1091,6 +1145,7 @@ int chomp_b200_cov_kernel_ng(void* handle, int B, const chomp_b200_cov_params* p
     if (int rc = ensure(h, B)) return rc;
     if (!p) FAIL("null covariance parameters");
     if (int rc = check_cov(h, *p)) return rc;
+    if (B > 65535) FAIL("covariance batches are limited to 65 535 points per call");
     if (int rc = cov_reserve(h, B, p->n_bins)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const Cfg& c = h->cfg;
@@ -1113,6 +1168,7 @@ int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, c
     Handle* h = (Handle*)handle;
     if (int rc = ensure(h, B)) return rc;
     if (!p || !bin_center_dev || !bin_delta_dev || !cov_out_dev) FAIL("null argument");
+    if (B > 65535) FAIL("covariance batches are limited to 65 535 points per call");
     if (int rc = check_cov(h, *p)) return rc;
     const Cfg& c = h->cfg;
     const bool want_ng = p->nongaussian && !p->poisson_only;
@@ -1134,7 +1190,7 @@ int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, c
             NodesOut no = nodes_view(h);
             SMEM_OPT_IN(nu_nodes_kernel, h, nodes_smem(c));
             nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
-                                                          h->c_lnm_nu, h->c_nu_lnm, no, status_dev);
+                                                          h->c_lnm_nu, h->c_nu_lnm, no, status_dev, nullptr, nullptr);
             CK(cudaGetLastError());
             h->launches += 1;
             if (int rc = chomp_b200_trispectrum_1h(handle, B, nullptr, stream)) return rc;

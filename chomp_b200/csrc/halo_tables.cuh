@@ -30,7 +30,8 @@ namespace chomp {
 // reference's exponent switch: negative = "moment < 1, first power of y" (halo.py:1038-1041,
 // 1084-1086), positive = second power.
 #define NODE_FIELDS 8
-enum { NF_CP = 0, NF_RS, NF_LNCP, NF_W_HM, NF_W_PMM, NF_W_HG, NF_W_GM, NF_W_GG };
+enum { NF_CP = 0, NF_RS, NF_LNRS /* ln r_s: ln z = ln k + ln r_s without a logarithm per node */, NF_W_HM, NF_W_PMM,
+       NF_W_HG, NF_W_GM, NF_W_GG };
 #define MAX_EXTRA_BREAKS 8
 // k classes: the panel order grows with phi = k * r_vir(M_max), the phase of the profile's
 // oscillation in mass across the table.  {smooth panels, panels inside the central-galaxy
@@ -236,10 +237,14 @@ __global__ void __launch_bounds__(128, NODES_MIN_BLOCKS)
 nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const double* __restrict__ hod,
                 const double* __restrict__ epoch, const double* __restrict__ g_lnm, const double* __restrict__ g_nu,
                 const double* __restrict__ g_c1, const double* __restrict__ g_c2, NodesOut out,
-                int32_t* __restrict__ status) {
+                int32_t* __restrict__ status, const int32_t* __restrict__ group /* [B] or null */,
+                const int32_t* __restrict__ group_status) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     if (b >= B) return;
+    // fast / slow split: the cosmology-level tables (halo parameters, epoch scalars, nu(M) splines) of
+    // point b live in row gb of their arrays; everything HOD-level is per point
+    const int gb = group ? group[b] : b;
     const int n = cfg.n_mass, tid = threadIdx.x;
     const int max_edge = n + MAX_EXTRA_BREAKS;
     double* lnm = sm;
@@ -253,17 +258,17 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     int* pknot = pstart + N_NODE_LISTS * max_edge; // [max_edge] knot interval of the ln M(nu) spline holding the panel
     __shared__ int n_edge;
     __shared__ double x_singular;
-    for (int i = tid; i < n; i += blockDim.x) { lnm[i] = g_lnm[(size_t)b * n + i]; nu[i] = g_nu[(size_t)b * n + i]; }
+    for (int i = tid; i < n; i += blockDim.x) { lnm[i] = g_lnm[(size_t)gb * n + i]; nu[i] = g_nu[(size_t)gb * n + i]; }
     for (int i = tid; i < 4 * (n - 1); i += blockDim.x) {
-        c1[i] = g_c1[(size_t)b * 4 * n + i];
-        c2[i] = g_c2[(size_t)b * 4 * n + i];
+        c1[i] = g_c1[(size_t)gb * 4 * n + i];
+        c2[i] = g_c2[(size_t)gb * 4 * n + i];
     }
     // the HOD constants (an erfinv and a few exponentials) once per CTA
     __shared__ HodP s_hod;
     if (tid == blockDim.x - 1) s_hod = load_hod(cfg.hod_kind, hod + (size_t)b * CHOMP_N_HOD, cfg.halo_precision);
     __syncthreads();
     NuTab t{n, lnm, nu, c1, c2};
-    const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
+    const double* e = epoch + (size_t)gb * CHOMP_EPOCH_LEN;
     const double nu_min = e[EP_NU_MIN], nu_max = e[EP_NU_MAX];
     const double l_min = log(nu_min), l_max = log(nu_max);
     const HodP h = s_hod;
@@ -372,12 +377,12 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     __syncthreads();
     // ---- nodes ------------------------------------------------------------------------------
     const int n_pan = n_edge - 1;
-    const double* hp = halo + (size_t)b * CHOMP_N_HALO;
+    const double* hp = halo + (size_t)gb * CHOMP_N_HALO;
     const double stq = hp[CHOMP_H_STQ], sta = hp[CHOMP_H_ST_LITTLE_A], beta = hp[CHOMP_H_BETA];
     const double c0 = hp[CHOMP_H_C0] / (1.0 + e[EP_Z]);                   // halo.py:65
     const double f_norm = e[EP_F_NORM], b_norm = e[EP_B_NORM], delta_c = e[EP_DELTA_C];
     const double rho_bar = e[EP_RHO_BAR], lnm_star = e[EP_LNM_STAR];
-    const double ln_rv_coef = log(rv_coef), ln_sta = log(sta);
+    const double ln_rv_coef = log(rv_coef), ln_sta = log(sta), ln_c0 = log(c0);
     double nbar = 0.0;
     int st = 0;
     const int n_lists = cfg.tri_moment >= 0 ? N_NODE_LISTS : N_KCLASS;
@@ -434,7 +439,7 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
             const double in1 = (xmid > x_lo1) ? 1.0 : 0.0, in2 = (xmid > x_lo2) ? 1.0 : 0.0;
             rec[NF_CP * cap + idx] = cp;
             rec[NF_RS * cap + idx] = r_v / con;
-            rec[NF_LNCP * cap + idx] = lncp;
+            rec[NF_LNRS * cap + idx] = (ln_rv_coef + lm) * (1.0 / 3.0) - (ln_c0 + beta * (lm - lnm_star));
             rec[NF_W_HM * cap + idx] = wt * bias * imk;                                     // halo.py:923-927
             rec[NF_W_PMM * cap + idx] = wt * M / rho_bar * imk * imk;                       // halo.py:990-994, :988
             rec[NF_W_HG * cap + idx] = in1 * wt * bias * n1 / M * imk;                      // halo.py:964-969
@@ -456,6 +461,7 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
         out.rv_max[3 * b + 1] = (double)ic1;
         out.rv_max[3 * b + 2] = (double)ic2;
         if (!isfinite(nbar)) st |= CHOMP_ST_NONFINITE;
+        if (group_status) st |= group_status[gb];
         if (status && st) atomicOr(status + b, st);
     }
 }
@@ -506,7 +512,7 @@ __device__ __forceinline__ void nfw_series_coeffs(double c, double cp, double ln
     }
 }
 
-// grid (chunks, B): a CTA stages the node list of one k class in shared memory and its 8
+// grid (chunks x B): a CTA stages the node list of one k class in shared memory and its 8
 // warps take the ln k nodes of one SUMS_K_PER_CTA chunk of that class; lanes stride the nodes.
 #ifndef SUMS_MIN_BLOCKS
 #define SUMS_MIN_BLOCKS 3
@@ -516,17 +522,19 @@ __device__ __forceinline__ void nfw_series_coeffs(double c, double cp, double ln
 #define SUMS_EXTRA_DOUBLES (SER_MOM + 8 * SER_MOM)   // moments + per-warp partial moments
 __global__ void __launch_bounds__(256, SUMS_MIN_BLOCKS)
 halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __restrict__ raw /* [B, 5, n_halo] */) {
-    extern __shared__ double srec[];      // (NODE_FIELDS + 1) * nn_pad records | series coefficients | moments
+    extern __shared__ double srec[];      // NODE_FIELDS * nn_pad records | series coefficients | moments
     __shared__ NfwTables ntab;
     __shared__ int s_first_bad;
-    const int b = blockIdx.y;
+    // grid.x = chunks per point x B (a one-dimensional grid: B is not bounded by the 65 535 of gridDim.y)
+    const int n_chunk_slots = (cfg.n_halo + SUMS_K_PER_CTA - 1) / SUMS_K_PER_CTA + N_KCLASS - 1;
+    const int b = blockIdx.x / n_chunk_slots;
     if (b >= B) return;
     const int nk = cfg.n_halo;
     const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hk = (l1 - l0) / (nk - 1);
     // which class / k range does this CTA own?
     const int i1 = (int)nd.rv_max[3 * b + 1], i2 = (int)nd.rv_max[3 * b + 2];     // set by nu_nodes_kernel
     const int first[N_KCLASS + 1] = {0, i1, i2, nk};
-    int chunk = blockIdx.x, cls = -1, k_begin = 0, k_end = 0;
+    int chunk = blockIdx.x - b * n_chunk_slots, cls = -1, k_begin = 0, k_end = 0;
     for (int c = 0; c < N_KCLASS; ++c) {
         const int cnt = first[c + 1] - first[c];
         const int nch = (cnt + SUMS_K_PER_CTA - 1) / SUMS_K_PER_CTA;
@@ -558,18 +566,14 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
     nfw_tables_load(&ntab);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    double* s_lr = srec + NODE_FIELDS * nn_pad;                       // ln r_s (for ln z = ln k + ln r_s)
-    for (int i = threadIdx.x; i < nn_pad; i += blockDim.x) {
-        if (i >= nn) {                                                // padding: valid shape, zero weight
+    for (int i = nn + threadIdx.x; i < nn_pad; i += blockDim.x) {     // padding: valid shape, zero weight
 #pragma unroll
-            for (int f = 0; f < NODE_FIELDS; ++f) srec[f * nn_pad + i] = (f >= NF_W_HM) ? 0.0 : srec[f * nn_pad + nn - 1];
-        }
-        s_lr[i] = log(srec[NF_RS * nn_pad + (i < nn ? i : nn - 1)]);
+        for (int f = 0; f < NODE_FIELDS; ++f) srec[f * nn_pad + i] = (f >= NF_W_HM) ? 0.0 : srec[f * nn_pad + nn - 1];
     }
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const double* __restrict__ s_cp = srec + NF_CP * nn_pad;
     const double* __restrict__ s_rs = srec + NF_RS * nn_pad;
-    const double* __restrict__ s_ln = srec + NF_LNCP * nn_pad;
+    const double* __restrict__ s_lr = srec + NF_LNRS * nn_pad;
     const double* __restrict__ s_hm = srec + NF_W_HM * nn_pad;
     const double* __restrict__ s_pm = srec + NF_W_PMM * nn_pad;
     const double* __restrict__ s_hg = srec + NF_W_HG * nn_pad;
@@ -578,8 +582,8 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
     // ---- series region ---------------------------------------------------------------------
     // ser_n leading nodes get series coefficients (as many as the shared memory left over holds);
     // i_lo of them satisfy k r_vir <= SER_X for the largest k of the chunk and go into the moments.
-    double* s_a = srec + (NODE_FIELDS + 1) * nn_pad;                  // [SER_NC][ser_n]
-    int ser_n = (smem_doubles - (NODE_FIELDS + 1) * nn_pad - SUMS_EXTRA_DOUBLES) / SER_NC;
+    double* s_a = srec + NODE_FIELDS * nn_pad;                        // [SER_NC][ser_n]
+    int ser_n = (smem_doubles - NODE_FIELDS * nn_pad - SUMS_EXTRA_DOUBLES) / SER_NC;
     ser_n = cfg.exclusion ? 0 : min(nn_pad, ser_n & ~31);
     if (ser_n < 0) ser_n = 0;
     double* s_mom = s_a + SER_NC * ser_n;                              // [SER_MOM]
@@ -597,7 +601,7 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
             if (!(ok && q * k_hi <= SER_X)) atomicMin(&s_first_bad, i);
             if (ok && q * k_lo <= SER_X) {
                 double a[SER_NC];
-                nfw_series_coeffs(c, cp, s_ln[i], a);
+                nfw_series_coeffs(c, cp, log(cp), a);
 #pragma unroll
                 for (int n = 0; n < SER_NC; ++n) s_a[n * ser_n + i] = a[n];
             } else {
@@ -723,7 +727,8 @@ halo_sums_kernel(const Cfg cfg, int B, NodesOut nd, int smem_doubles, double* __
 __global__ void __launch_bounds__(160)
 halo_splines_kernel(const Cfg cfg, int B, const double* __restrict__ raw, const double* __restrict__ nbar,
                     const double* __restrict__ epoch, double* __restrict__ tab /* [B,5,n_halo] */,
-                    double* __restrict__ coef /* [B,5,4 n_halo] */, int32_t* __restrict__ status) {
+                    double* __restrict__ coef /* [B,5,4 n_halo] */, int32_t* __restrict__ status,
+                    const int32_t* __restrict__ group) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     if (b >= B) return;
@@ -732,7 +737,7 @@ halo_splines_kernel(const Cfg cfg, int B, const double* __restrict__ raw, const 
     double* sy = sm + (size_t)t * 3 * n;   // node values
     double* sm2 = sy + n;                  // second derivatives
     const double h = (log(cfg.k_max) - log(cfg.k_min)) / (n - 1);
-    const double nb = nbar[b], rho_bar = epoch[(size_t)b * CHOMP_EPOCH_LEN + EP_RHO_BAR];
+    const double nb = nbar[b], rho_bar = epoch[(size_t)(group ? group[b] : b) * CHOMP_EPOCH_LEN + EP_RHO_BAR];
     const double scale = t < 2 ? 1.0 : (t == 2 ? 1.0 / nb : (t == 3 ? 1.0 / (nb * rho_bar) : 1.0 / (nb * nb * rho_bar)));
     const double* __restrict__ y_in = raw + ((size_t)b * 5 + t) * n;
     double* __restrict__ y_out = tab + ((size_t)b * 5 + t) * n;

@@ -107,8 +107,9 @@ power_kernel(const Cfg cfg, int B, int which, int n_k, const double* __restrict_
              const double* __restrict__ cosmo, const double* __restrict__ epoch,
              const double* __restrict__ htab, const double* __restrict__ hcoef, const double* __restrict__ hfit,
              double* __restrict__ P_out) {
-    const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = (n_k + blockDim.x - 1) / blockDim.x;        // grid.x = per x B (one-dimensional: any B)
+    const int b = blockIdx.x / per;
+    const int i = (blockIdx.x - b * per) * blockDim.x + threadIdx.x;
     if (b >= B || i >= n_k) return;
     const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
     const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
@@ -144,14 +145,15 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
               const double* __restrict__ cosmo, const double* __restrict__ epoch, const double* __restrict__ dbar,
               const double* __restrict__ htab, const double* __restrict__ hcoef,
               const double* __restrict__ knodes, const double* __restrict__ kcoef, const double* __restrict__ hfit,
-              double* __restrict__ w_out, int32_t* __restrict__ status) {
+              double* __restrict__ w_out, int32_t* __restrict__ status, const int32_t* __restrict__ group) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     if (b >= B) return;
+    const int gb = group ? group[b] : b;     // row of the cosmology-level tables (fast / slow split)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
     const int nk = cfg.n_halo, nkt = cfg.n_kernel, nq = cfg.nq_hankel;
     const int sub = hankel_subdiv(cfg);
-    const double* hf = hfit ? hfit + (size_t)b * HF_LEN : nullptr;
+    const double* hf = hfit ? hfit + (size_t)gb * HF_LEN : nullptr;
     const int total = (nk - 1) * sub * nq;
     double* s_x = sm;                 // total
     double* s_g = s_x + total;        // total
@@ -162,11 +164,11 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
     const double* ca = hc + (size_t)ta * 4 * nk;
     const double* cb = hc + (size_t)tb * 4 * nk;
     const double* cpp = hc + (size_t)tpp * 4 * nk;
-    for (int i = tid; i < 4 * (nkt - 1); i += blockDim.x) s_kc[i] = kcoef[(size_t)b * 4 * nkt + i];
-    const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
-    const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
+    for (int i = tid; i < 4 * (nkt - 1); i += blockDim.x) s_kc[i] = kcoef[(size_t)gb * 4 * nkt + i];
+    const Cosmo c = load_cosmo(cosmo + (size_t)gb * CHOMP_N_COSMO, cfg.cosmo_precision);
+    const double* e = epoch + (size_t)gb * CHOMP_EPOCH_LEN;
     const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
-    const double D = dbar[b];
+    const double D = dbar[gb];
     const double inv_norm = 1.0 / (2.0 * M_PI * D * D);                 // correlation.py:270-275
     const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hP = (l1 - l0) / (nk - 1);
     for (int idx = tid; idx < total; idx += blockDim.x) {
@@ -191,7 +193,7 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
     __syncthreads();
     const double x0 = log(cfg.ktheta_min), x1 = log(cfg.ktheta_max), hK = (x1 - x0) / (nkt - 1);
     const double ihK = 1.0 / hK;
-    const double k_first = knodes[(size_t)b * nkt];
+    const double k_first = knodes[(size_t)gb * nkt];
     for (int it = wid; it < n_theta; it += nwarp) {
         const double lt = log(theta[it]);
         double acc = 0.0;

@@ -188,8 +188,8 @@ __device__ __forceinline__ void sici_series_c(double x, double& si, double& ci_n
 //   N(z, c) = g(z) - g(z2) cos(c z) + [f(z2) - 1/z2] sin(c z),   z2 = (1 + c) z
 // (f, g: auxiliary functions of Si/Ci; derivation in the generator's header).  One sine/cosine
 // pair, f and g at z2 and g at z, each a degree-NFW_DEG polynomial whose coefficients a lane
-// fetches from shared memory by range index: lanes in different ranges read neighbouring
-// 16-byte slots of one 128-byte row, so nothing diverges and no bank conflicts arise.
+// fetches from shared memory by range index (nothing diverges).  The kernel is bound by the pipe
+// that delivers these 16-byte fetches, hence the low degree on many narrow ranges (generator header).
 // ---------------------------------------------------------------------------------------
 struct NfwTables {
     double2 A[NFW_DEG + 2][NFW_NSLOT];
@@ -203,10 +203,11 @@ __device__ inline void nfw_tables_load(NfwTables* t) {
         (&t->B[0][0])[i] = b[i];
     }
 }
-// range of x >= 2 from the exponent of x^2: [4,8) [8,16) [16,32) [32,64) [64,256) [256,inf)
+// range of x >= 2 from the exponent and the top two mantissa bits of x^2: every octave of x^2 from
+// [4, 8) on in NFW_SUB = 4 equal pieces, NFW_OCTAVES octaves, then one range up to infinity
 __device__ __forceinline__ int nfw_range_large(double x2) {
-    const int e = (__double2hiint(x2) >> 20) - 1025;
-    return e < 4 ? e : (e < 6 ? 4 : 5);
+    const int r = (__double2hiint(x2) >> 18) - (1025 << 2);
+    return r < NFW_NLARGE - 1 ? r : NFW_NLARGE - 1;
 }
 // lnz = ln(z).  Any z > 0; z2 < 2 (both arguments small) takes the power series of Si and Ci,
 // which the callers' own small-argument series make rare on the hot path.
@@ -238,7 +239,7 @@ __device__ __forceinline__ double nfw_rho_tab(const NfwTables* t, double z, doub
     // g at z
     const bool small = z < 2.0;
     const double u1 = iz * iz;
-    const int rb = small ? (z < 1.0 ? 0 : 1) : NFW_NSMALL + nfw_range_large(z * z);
+    const int rb = small ? (int)(z * (0.5 * NFW_NSMALL)) : NFW_NSMALL + nfw_range_large(z * z);
     const double2 mb = t->B[NFW_DEG + 1][rb];
     const double sb = ((small ? z : u1) - mb.x) * mb.y;
     cf = t->B[NFW_DEG][rb];

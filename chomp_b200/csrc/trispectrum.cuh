@@ -39,8 +39,8 @@ tri_profile_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ A /* 
         if (i < nn_pad) {        // whole warps enter the collective profile routine
             const int ii = i < nn ? i : nn - 1;
             const double cp = g[(size_t)NF_CP * cap + ii], rs = g[(size_t)NF_RS * cap + ii];
-            const double lncp = g[(size_t)NF_LNCP * cap + ii];
-            const double rho = nfw_rho_tab(&ntab, k * rs, cp, lnk + log(rs));
+            const double lncp = log(cp);
+            const double rho = nfw_rho_tab(&ntab, k * rs, cp, lnk + g[(size_t)NF_LNRS * cap + ii]);
             const double y = rho / (lncp - (cp - 1.0) / cp);                   // halo.py:584-585
             v = i < nn ? y * y : 0.0;
         }

@@ -86,16 +86,20 @@ class ShardedEngine(object):
         a, b = bounds[self.rank]
         table, status = self.evaluate(cosmo[a:b], halo[a:b], hod[a:b])
         n_cols = table.shape[1]
-        key = (slot, max_rows, n_cols, table.device, table.dtype)
-        if key not in self._bufs:
-            self._bufs[key] = (t.zeros((max_rows, n_cols + 1), dtype=table.dtype, device=table.device),
-                               t.empty((self.world, max_rows, n_cols + 1), dtype=table.dtype, device=table.device))
-        local, full = self._bufs[key]
+        local, full = self._gather_buffers(slot, max_rows, n_cols, table)
         rows = b - a
         if rows:
             local[:rows, :n_cols] = table
             local[:rows, n_cols] = status.to(table.dtype)
         return local, full, bounds, n_cols
+
+    def _gather_buffers(self, slot, max_rows, n_cols, like):
+        t = self.torch
+        key = (slot, max_rows, n_cols, like.device, like.dtype)
+        if key not in self._bufs:
+            self._bufs[key] = (t.zeros((max_rows, n_cols + 1), dtype=like.dtype, device=like.device),
+                               t.empty((self.world, max_rows, n_cols + 1), dtype=like.dtype, device=like.device))
+        return self._bufs[key]
 
     def _unpack(self, full, bounds, n_cols):
         t = self.torch
@@ -108,13 +112,58 @@ class ShardedEngine(object):
     def wtheta(self, cosmo, halo, hod):
         """Global batch in (host arrays or tensors, identical on every rank), full [B, n_theta] table and
         [B] status flags out on every rank: shard -> four stages -> one all-gather."""
-        local, full, bounds, n_cols = self._packed_local(cosmo, halo, hod)
+        local, full, bounds, n_cols = self._packed_local(cosmo, halo, hod, slot="call")   # not a pipeline slot
         if self.world > 1:
             _dist().all_gather_into_tensor(full.view(-1, n_cols + 1), local, group=self.group)
         else:
             full = local.unsqueeze(0)
         w, st = self._unpack(full, bounds, n_cols)
         return w.clone(), st                # the staging buffers are reused by the next call
+
+    def wtheta_host(self, cosmo, halo, hod):
+        """The same step end to end with HOST buffers: global numpy arrays in, numpy (w [B, n_theta],
+        status [B]) out on every rank.  One rank: the C-ABI host call (pinned staging, H2D, stages, D2H).
+        Several ranks: the shard's parameters go through pinned memory to the device, the stages run, one
+        all-gather assembles the table on the device, one D2H copy brings it back."""
+        t = self.torch
+        if self.engine is None:
+            w, st = self.wtheta(cosmo, halo, hod)
+            return w.cpu().numpy(), st.cpu().numpy()
+        if self.world == 1:
+            return self.engine.wtheta_host(cosmo, halo, hod, self.survey.theta, self.which)
+        n = cosmo.shape[0]
+        bounds = shard_bounds(n, self.world)
+        a, b = bounds[self.rank]
+        rows = b - a
+        widths = (_lib.N_COSMO, _lib.N_HALO, _lib.N_HOD)
+        key = ("host", rows, n)
+        if key not in self._bufs:
+            self._bufs[key] = (t.empty(max(rows, 1)*sum(widths), dtype=t.float64).pin_memory(),
+                               t.empty((n, len(self.survey.theta) + 1), dtype=t.float64).pin_memory())
+        pin_in, pin_out = self._bufs[key]
+        off, views = 0, []
+        for arr, wd in zip((cosmo, halo, hod), widths):
+            blk = pin_in[off:off + rows*wd].view(rows, wd)
+            blk.copy_(t.from_numpy(np.ascontiguousarray(arr[a:b], dtype=np.float64)))
+            views.append((off, wd))
+            off += rows*wd
+        dev = pin_in.to(self._theta.device, non_blocking=True)
+        c, h, g = (dev[o:o + rows*wd].view(rows, wd) for o, wd in views)
+        max_rows = max(y - x for x, y in bounds)
+        table, status = self.evaluate(c, h, g)
+        n_cols = table.shape[1]
+        local, full = self._gather_buffers("host", max_rows, n_cols, table)
+        if rows:
+            local[:rows, :n_cols] = table
+            local[:rows, n_cols] = status.to(table.dtype)
+        _dist().all_gather_into_tensor(full.view(-1, n_cols + 1), local, group=self.group)
+        if all(y - x == max_rows for x, y in bounds):
+            pin_out.copy_(full.view(-1, n_cols + 1), non_blocking=True)
+        else:
+            pin_out.copy_(t.cat([full[r, :y - x] for r, (x, y) in enumerate(bounds)], 0), non_blocking=True)
+        t.cuda.current_stream(self._theta.device).synchronize()
+        out = pin_out.numpy()
+        return out[:, :n_cols].copy(), out[:, n_cols].astype(np.int32)
 
     def pipeline(self, batches):
         """Double-buffered steps: the all-gather of step s runs (asynchronously, on the collective's own

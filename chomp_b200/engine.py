@@ -421,6 +421,28 @@ class Engine(object):
             self._p(theta), self._p(out), self._p(status), self._stream()))
         return out
 
+    def wtheta_grouped(self, cosmo, halo, group_index, hod, theta, which, out=None, status=None):
+        """The MCMC fast / slow split: `cosmo` [G, 10] and `halo` [G, 6] rows shared by the B points of
+        `hod` [B, 5] through `group_index` [B] (row of each point).  The cosmology-level stages (Limber
+        tables, mass tables) run G times, the HOD-level ones B times; w [B, n_theta] is bit-identical to
+        `wtheta` on the expanded arrays."""
+        t = self.torch
+        cosmo, halo = self._dev(cosmo, _lib.N_COSMO), self._dev(halo, _lib.N_HALO)
+        hod = self._dev(hod, _lib.N_HOD)
+        theta = self._dev(theta).reshape(-1)
+        if not isinstance(group_index, t.Tensor):
+            group_index = t.as_tensor(np.ascontiguousarray(group_index, dtype=np.int32))
+        group_index = group_index.to(device="cuda:%d" % self.device, dtype=t.int32).contiguous().reshape(-1)
+        B, G = hod.shape[0], cosmo.shape[0]
+        if halo.shape[0] != G or group_index.numel() != B:
+            raise ValueError("cosmo / halo need one row per group, group_index one entry per point")
+        if out is None:
+            out = self._new(B, theta.numel())
+        _lib.check(self.lib.chomp_b200_wtheta_batch_grouped(
+            self._h, G, self._p(cosmo), self._p(halo), B, self._p(group_index), self._p(hod), int(which),
+            theta.numel(), self._p(theta), self._p(out), self._p(status), self._stream()))
+        return out
+
     def wtheta_host(self, cosmo, halo, hod, theta, which):
         """Host numpy in, host numpy out (copies inside): the end-to-end call."""
         cosmo = np.ascontiguousarray(cosmo, dtype=np.float64)

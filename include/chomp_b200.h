@@ -143,6 +143,18 @@ int chomp_b200_wtheta_batch(void* handle, int B, const double* cosmo_dev, const 
                             const double* hod_dev, int which, int n_theta, const double* theta_dev,
                             double* w_out_dev, int32_t* status_dev, void* stream);
 
+/* The MCMC fast / slow split: n_groups rows of (cosmology, halo) parameters are shared
+ * by B points; group_index_dev[B] (int32, device) maps a point to its row.  Stages 1 and 2 -- everything that
+ * depends on cosmology and mass function only: chi / growth tables, windows, K(ln k theta), sigma(M), nu(M),
+ * normalisations -- run once per ROW, stages 3 and 4 per point.  An HOD-only batch at fixed cosmology (n_groups
+ * = 1) or a grid of cosmologies x HODs costs the slow stages n_groups times instead of B times.  Results are
+ * bit-identical to chomp_b200_wtheta_batch on the expanded [B, .] arrays.  The reference rebuilds everything
+ * at every corr.set_cosmology / set_hod (halo.py:134-192).  An index outside [0, n_groups) flags the point
+ * with CHOMP_ST_DOMAIN. */
+int chomp_b200_wtheta_batch_grouped(void* handle, int n_groups, const double* cosmo_dev, const double* halo_dev, int B,
+                                    const int32_t* group_index_dev, const double* hod_dev, int which, int n_theta,
+                                    const double* theta_dev, double* w_out_dev, int32_t* status_dev, void* stream);
+
 /* Same with HOST buffers: pinned staging, H2D copies, the four stages, D2H copy, one
  * stream synchronise.  This is the call the end-to-end benchmark times. */
 int chomp_b200_wtheta_batch_host(void* handle, int B, const double* cosmo_host, const double* halo_host,

@@ -107,3 +107,44 @@ def test_large_batch_and_reserve_growth():
     assert np.array_equal(big[:8], small)
     wh, st = eng.wtheta_host(cosmo, halo, hod, survey.theta, _lib.P_GG)
     assert np.array_equal(wh, big) and not st.any()
+
+
+def test_interleaved_engines_with_different_surveys():
+    """Several live handles with different set-ups on one device (a multi-probe MCMC): the dynamic
+    shared-memory opt-in of a kernel is state of the function, shared by every handle, and must never be
+    lowered by the handle configured last (two different windows need more than one shared window;
+    halo_npoints = 200 needs more than 50)."""
+    from chomp_b200 import defaults
+    lens = engine.RedshiftDistribution.gaussian(0.0, 2.0, 0.4, 0.1)
+    src = engine.RedshiftDistribution.gaussian(0.0, 2.0, 1.0, 0.2)
+    big = engine.Survey(lens, src, window_a="galaxy", window_b="convergence", bins_per_decade=10.0, power_spec="power_gm",
+                        precision=dict(defaults.default_precision, halo_npoints=200))
+    small = _survey()
+    cosmo, halo, hod = design.synthetic_batch(5)
+    eng_a = engine.Engine(big)
+    first = eng_a.wtheta(cosmo, halo, hod, big.theta, _lib.P_GM).cpu().numpy()
+    eng_b = engine.Engine(small)                                   # configured after A, smaller everywhere
+    wb = eng_b.wtheta(cosmo, halo, hod, small.theta, _lib.P_GG).cpu().numpy()
+    again = eng_a.wtheta(cosmo, halo, hod, big.theta, _lib.P_GM).cpu().numpy()
+    assert np.all(np.isfinite(first)) and np.all(np.isfinite(wb))
+    assert np.array_equal(first, again)
+
+
+def test_stage_order_is_enforced():
+    """A later stage refuses rows no earlier stage computed on this handle (instead of reading zeros)."""
+    survey = _survey()
+    eng = engine.Engine(survey)
+    cosmo, halo, hod = design.synthetic_batch(4)
+    with pytest.raises(ChompError):
+        eng.halo_tables(halo, hod)                                  # no mass tables yet
+    eng.limber_tables(cosmo)
+    eng.mass_tables(cosmo, halo)
+    with pytest.raises(ChompError):
+        eng.wtheta_stage(4, _lib.P_GG, survey.theta)                # halo tables missing
+    eng.halo_tables(halo, hod)
+    w4 = eng.wtheta_stage(4, _lib.P_GG, survey.theta).cpu().numpy()
+    assert np.all(np.isfinite(w4))
+    with pytest.raises(ChompError):
+        eng.wtheta_stage(9, _lib.P_GG, survey.theta)                # growing the scratch drops the tables
+    with pytest.raises(ChompError):
+        eng.evaluate(_lib.EVAL_KERNEL, [0.0], point=0)
