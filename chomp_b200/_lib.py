@@ -36,6 +36,8 @@ HALOFIT_FIELDS = ("k_s", "n_eff", "C", "a_n", "b_n", "c_n", "gamma_n", "alpha_n"
                   "f_1", "f_2", "f_3", "omega_l", "fit_z")
 KERNEL_NAMES = ("limber_tables_kernel", "mass_tables_kernel", "nu_nodes_kernel",
                 "halo_sums_kernel", "halo_splines_kernel", "wtheta_kernel")
+COV_KERNEL_NAMES = ("cov_kng_kernel", "tri_profile_kernel", "tri_gram_kernel", "cov_projected_kernel", "cov_g_kernel",
+                    "cov_tri_nodes_kernel", "cov_ng_kernel", "cov_finish_kernel")
 EPOCH_FIELDS = ("z", "growth", "sigma_norm", "delta_c", "delta_v", "rho_bar",
                 "ln_mass_min", "ln_mass_max", "nu_min", "nu_max", "f_norm",
                 "bias_norm", "ln_m_star", "pk_amp", "chi", "walk_steps", "omega_m", "omega_l", "E0",
@@ -74,10 +76,10 @@ class CovParams(ctypes.Structure):
     _fields_ = [
         ("n_bins", ctypes.c_int32), ("which", ctypes.c_int32), ("nongaussian", ctypes.c_int32),
         ("poisson_only", ctypes.c_int32), ("nq_osc", ctypes.c_int32), ("zero_last_ka", ctypes.c_int32),
-        ("reserved_i", ctypes.c_int32*2),
+        ("nq_ng", ctypes.c_int32), ("reserved_i", ctypes.c_int32*1),
         ("theta_min_rad", ctypes.c_double), ("theta_max_rad", ctypes.c_double), ("area_sr", ctypes.c_double),
         ("poisson", ctypes.c_double*6), ("shot_wt", ctypes.c_double*2), ("bessel_limit", ctypes.c_double),
-        ("osc_phase", ctypes.c_double), ("reserved_d", ctypes.c_double*3),
+        ("osc_phase", ctypes.c_double), ("halofit_z", ctypes.c_double), ("reserved_d", ctypes.c_double*2),
     ]
 
 
@@ -142,6 +144,7 @@ _SIGNATURES = {
                                             ctypes.POINTER(ctypes.c_double)]),
     "chomp_b200_set_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "chomp_b200_get_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "chomp_b200_get_cov_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "chomp_b200_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "chomp_b200_cov_kernel_ng": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(CovParams),
                                                 ctypes.c_void_p, ctypes.c_void_p]),

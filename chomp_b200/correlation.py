@@ -24,11 +24,19 @@ class Correlation(object):
         self.halo = input_halo
         if not keep_halo_z_bar:
             self.halo.set_redshift(self.kernel.z_bar)            # correlation.py:103
-        if ((k_min is not None and k_min != self.halo._k_min) or
-                (k_max is not None and k_max != self.halo._k_max)):
-            raise NotImplementedError("Correlation(k_min/k_max) different from the halo limits")
-        self._ln_k_min = np.log(self.halo._k_min)
-        self._ln_k_max = np.log(self.halo._k_max)
+        # correlation.py:104-112.  The reference's test runs under Python 2, where ``None < x`` is True
+        # and ``None > x`` is False: giving only k_max switches the extrapolation on whatever its value.
+        if ((k_min is not None or k_max is not None) and not self.halo.get_extrapolation() and
+                ((k_min is None or k_min < self.halo._k_min) or
+                 (k_max is not None and k_max > self.halo._k_max))):
+            self.halo.set_extrapolation(True)
+        if k_min is None:
+            k_min = self.halo._k_min
+        if k_max is None:
+            k_max = self.halo._k_max
+        self._k_limits = (float(k_min), float(k_max))
+        self._ln_k_min = np.log(k_min)
+        self._ln_k_max = np.log(k_max)
         if power_spec is None:
             power_spec = "linear_power"
         self.set_power_spectrum(power_spec)
@@ -112,8 +120,7 @@ class Correlation(object):
         hc = h._gpu.eng.cfg
         for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "tri_moment"):
             setattr(cfg, name, getattr(hc, name))
-        if cfg.use_halofit:
-            raise NotImplementedError("correlation_batch with HaloFit spectra")
+        self._set_k_limits(cfg)
         gpu = getattr(self, "_batch_gpu", None)
         if gpu is None:
             gpu = self._batch_gpu = _facade.OnePoint()
@@ -121,7 +128,19 @@ class Correlation(object):
         theta = self.theta_array if theta_rad is None else _facade.flat(theta_rad)
         import torch
         status = torch.zeros(B, dtype=torch.int32, device="cuda:%d" % gpu.eng.device)
-        w = gpu.eng.wtheta(cosmo, halo, hod, theta, _lib.POWER_SPEC[self._power_name], status=status)
+        which = _lib.POWER_SPEC[self._power_name]
+        if cfg.use_halofit:
+            # HaloFit (halo.py:1236-1412): the fit parameters follow each point's mass tables; f_1..f_3
+            # stay at the halo object's construction redshift, as in Halo._ensure
+            eng = gpu.eng
+            eng.limber_tables(cosmo, status=status)
+            eng.mass_tables(cosmo, halo, status=status)
+            eng.halofit(B, fit_z=float(getattr(h, "_fit_redshift", -1.0)), status=status)
+            if which in (_lib.P_GM, _lib.P_GG):
+                eng.halo_tables(halo, hod, status=status)
+            w = eng.wtheta_stage(B, which, theta, status=status)
+        else:
+            w = gpu.eng.wtheta(cosmo, halo, hod, theta, which, status=status)
         return w.cpu().numpy(), status.cpu().numpy()
 
     def _stage_on_halo_handle(self):
@@ -132,12 +151,19 @@ class Correlation(object):
         hc = h._gpu.eng.cfg
         for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "tri_moment"):
             setattr(cfg, name, getattr(hc, name))
+        self._set_k_limits(cfg)
         gpu = h._gpu
         gpu.configure(cfg)
         gpu.eng.limber_tables(_facade.cosmo_row(self.kernel.cosmo.get_cosmology()))
         gpu.eng.set_params(cosmo=_facade.cosmo_row(h.cosmo.cosmo_dict))
         gpu.eng.set_zbar([self.kernel.z_bar])
         return gpu
+
+    def _set_k_limits(self, cfg):
+        """Correlation(k_min=, k_max=): integration limits of the Hankel stage (<= 0: the halo's)."""
+        k_lo, k_hi = getattr(self, "_k_limits", (self.halo._k_min, self.halo._k_max))
+        cfg.corr_k_min = k_lo if k_lo != self.halo._k_min else -1.0
+        cfg.corr_k_max = k_hi if k_hi != self.halo._k_max else -1.0
 
     def write(self, output_file_name):
         with open(output_file_name, "w") as f:

@@ -90,8 +90,6 @@ class Covariance(object):
         hc = h._gpu.eng.cfg
         for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit"):
             setattr(cfg, name, getattr(hc, name))
-        if cfg.use_halofit:
-            raise NotImplementedError("Covariance with a HaloFit halo is not on the GPU path yet")
         cfg.tri_moment = _lib.TRISPECTRUM_MOMENT.get(self.halo_tri.power_spec, 0)
         tri = self.halo_tri
         if (tri.local_hod._kind != h.local_hod._kind or tri.local_hod._params() != h.local_hod._params() or
@@ -109,6 +107,7 @@ class Covariance(object):
         # the theta range is the correlation's own log10 values (covariance.py:93-97)
         setup.params.theta_min_rad = np.power(10.0, self.log_theta_min)
         setup.params.theta_max_rad = np.power(10.0, self.log_theta_max)
+        setup.params.halofit_z = float(getattr(h, "_fit_redshift", -1.0))
         self.equal_windows, self.density, self.cosmic_shear = setup.equal_windows, setup.density, setup.cosmic_shear
         tri_z = None if getattr(self, "_tri_follows_z_bar_ng", False) else [float(tri._redshift)]
         eng = self._gpu.eng

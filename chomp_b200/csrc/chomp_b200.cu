@@ -107,7 +107,7 @@ struct Handle {
     double *epoch = nullptr, *lnm_nodes = nullptr, *nu_nodes = nullptr, *c_lnm_nu = nullptr, *c_nu_lnm = nullptr;
     double *sig_coef = nullptr, *b2_norm = nullptr;   // MassFunctionSecondOrder
     double *tri_w = nullptr, *tri_A = nullptr, *tri_T = nullptr;   // 1-halo trispectrum (tri_A / tri_T allocated on first use)
-    int tri_points = 0;
+    int tri_points = 0, tri_chunk = 0;
     double *nodes = nullptr, *nbar = nullptr, *rv_max = nullptr, *raw = nullptr, *htab = nullptr, *hcoef = nullptr;
     int32_t* n_nodes = nullptr;
     // parameter copies of the last batch (the evaluators need them)
@@ -121,11 +121,18 @@ struct Handle {
     // optional per-kernel timing (bench.py's roofline): events recorded around every launch
     bool timing = false;
     cudaEvent_t ev[CHOMP_N_KERNELS + 1] = {};
+    // covariance kernels: (class, start, stop) spans of the last chomp_b200_covariance, events from a pool
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    bool in_cov = false;
+    int open_span = -1;
     std::vector<void*> allocs;
     // covariance scratch (allocated on first use, released with the rest in free_scratch)
     CovOut cov = {};
     TriScratch cov_tri = {};
-    int cov_points = 0, cov_bins = 0, cov_chunk = 0;
+    int cov_points = 0, cov_bins = 0, cov_chunk = 0, cov_ntot = 0;
     bool kng_ready = false;
 };
 
@@ -159,9 +166,47 @@ inline void note_stream(Handle* h, cudaStream_t s) {
         if ((done) < (B)) FAIL("stage order: " what " has not been computed for this batch on this handle"); \
     } while (0)
 
-// event slot `i` is recorded before kernel i; slot i+1 after it
+// spans around the covariance launches (timing on only): span_begin returns the slot, span_end closes it
+inline cudaEvent_t pool_event(Handle* h) {
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        h->ev_pool.push_back(e);
+    }
+    return h->ev_pool[h->ev_used++];
+}
+inline int span_begin(Handle* h, int cls, cudaStream_t s) {
+    if (!h->timing) return -1;
+    cudaEvent_t a = pool_event(h), b = pool_event(h);
+    if (!a || !b) return -1;
+    cudaEventRecord(a, s);
+    h->spans.push_back(Handle::Span{cls, a, b});
+    return (int)h->spans.size() - 1;
+}
+inline void span_end(Handle* h, int slot, cudaStream_t s) {
+    if (slot >= 0) cudaEventRecord(h->spans[slot].b, s);
+}
+
+// mark(i): kernel i of the w(theta) path starts now -- event slot i (slot i + 1 follows it: the next kernel's
+// mark, or mark_end after the last kernel of a stage).  Inside chomp_b200_covariance the stages run more than once
+// and other kernels sit between them, so there every kernel gets a span of its own (class CHOMP_N_COV_KERNELS + i).
 inline void mark(Handle* h, int i, cudaStream_t s) {
-    if (h->timing) cudaEventRecord(h->ev[i], s);
+    if (!h->timing) return;
+    if (h->in_cov) {
+        span_end(h, h->open_span, s);
+        h->open_span = span_begin(h, CHOMP_N_COV_KERNELS + i, s);
+        return;
+    }
+    cudaEventRecord(h->ev[i], s);
+}
+inline void mark_end(Handle* h, int i, cudaStream_t s) {
+    if (!h->timing) return;
+    if (h->in_cov) {
+        span_end(h, h->open_span, s);
+        h->open_span = -1;
+        return;
+    }
+    cudaEventRecord(h->ev[i], s);
 }
 
 template <typename T>
@@ -189,8 +234,8 @@ void free_scratch(Handle* h) {
     h->allocs.clear();
     h->cap_points = 0;
     h->done_limber = h->done_mass = h->done_halo = h->done_params = 0;
-    h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0;
-    h->cov = CovOut{}; h->cov_tri = TriScratch{}; h->cov_points = 0; h->cov_bins = 0; h->cov_chunk = 0; h->kng_ready = false;
+    h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0; h->tri_chunk = 0;
+    h->cov = CovOut{}; h->cov_tri = TriScratch{}; h->cov_points = 0; h->cov_bins = 0; h->cov_chunk = 0; h->cov_ntot = 0; h->kng_ready = false;
 }
 
 int check_cfg(const Cfg& c) {
@@ -203,8 +248,9 @@ int check_cfg(const Cfg& c) {
     if (c.bessel_order != 0 && c.bessel_order != 2) FAIL("bessel_order must be 0 or 2");
     if (!(c.k_min > 0 && c.k_max > c.k_min)) FAIL("bad k limits");
     if (!(c.ktheta_min > 0 && c.ktheta_max > c.ktheta_min)) FAIL("bad ktheta limits");
-    if (c.corr_k_min > 0 && c.corr_k_min != c.k_min) FAIL("Correlation(k_min != halo k_min) is not supported yet");
-    if (c.corr_k_max > 0 && c.corr_k_max != c.k_max) FAIL("Correlation(k_max != halo k_max) is not supported yet");
+    if (c.corr_k_min > 0 && c.corr_k_max > 0 && !(c.corr_k_max > c.corr_k_min)) FAIL("Correlation k_max must exceed k_min");
+    if (c.corr_k_min > 0 && !(c.corr_k_min > 1e-3 * c.k_min * 1e-3)) FAIL("Correlation k_min more than six decades below the halo k_min");
+    if (c.corr_k_max > 0 && !(c.corr_k_max < 1e6 * c.k_max)) FAIL("Correlation k_max more than six decades above the halo k_max");
     for (int i = 0; i < 2; ++i) {
         if (c.window_kind[i] != CHOMP_WINDOW_GALAXY && c.window_kind[i] != CHOMP_WINDOW_CONVERGENCE) FAIL("unknown window_kind");
         if (c.dndz_kind[i] != CHOMP_DNDZ_GAUSSIAN && c.dndz_kind[i] != CHOMP_DNDZ_MAGLIM &&
@@ -236,7 +282,7 @@ int sums_doubles(const Handle* h) {
 size_t sums_smem(const Handle* h) {
     return (size_t)sums_doubles(h) * sizeof(double) + (h->cfg.exclusion ? sizeof(SiciTables) : 0);
 }
-size_t wtheta_smem(const Cfg& c) { return (2 * (size_t)hankel_nodes(c) + 4 * (size_t)c.n_kernel + 8) * sizeof(double); }
+size_t wtheta_smem(const Cfg& c) { return (2 * (size_t)hankel_layout(c).total + 4 * (size_t)c.n_kernel + 8) * sizeof(double); }
 
 }  // namespace
 
@@ -291,6 +337,7 @@ void chomp_b200_destroy(void* handle) {
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->order_ev) cudaEventDestroy(h->order_ev);
     if (h->ev[0]) for (int i = 0; i <= CHOMP_N_KERNELS; ++i) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
 
@@ -398,7 +445,7 @@ int chomp_b200_reserve(void* handle, int max_points) {
     rc |= dev_alloc(h, &h->nbar, B);
     rc |= dev_alloc(h, &h->rv_max, 3 * B);
     rc |= dev_alloc(h, &h->tri_w, B * h->node_cap[TRI_LIST]);
-    h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0;
+    h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0; h->tri_chunk = 0;
     rc |= dev_alloc(h, &h->raw, B * 5 * c.n_halo);
     rc |= dev_alloc(h, &h->htab, B * 5 * c.n_halo);
     rc |= dev_alloc(h, &h->hcoef, B * 20 * c.n_halo);
@@ -433,7 +480,7 @@ int chomp_b200_limber_tables(void* handle, int B, const double* cosmo_dev, int32
     SMEM_OPT_IN(limber_tables_kernel, h, smem);
     mark(h, CHOMP_K_LIMBER, s);
     limber_tables_kernel<<<B, LIMBER_THREADS, smem, s>>>(h->cfg, B, h->same_window, h->cosmo, out, status_dev);
-    mark(h, CHOMP_K_LIMBER + 1, s);
+    mark_end(h, CHOMP_K_LIMBER + 1, s);
     h->launches += 1;
     CK(cudaGetLastError());
     h->done_limber = B;
@@ -456,7 +503,7 @@ int chomp_b200_mass_tables(void* handle, int B, const double* cosmo_dev, const d
     SMEM_OPT_IN(mass_tables_kernel, h, mass_smem(h->cfg));
     mark(h, CHOMP_K_MASS, s);
     mass_tables_kernel<<<B, 256, mass_smem(h->cfg), s>>>(h->cfg, B, h->cosmo, h->halo, z_dev, h->zbar, out, status_dev);
-    mark(h, CHOMP_K_MASS + 1, s);
+    mark_end(h, CHOMP_K_MASS + 1, s);
     h->launches += 1;
     CK(cudaGetLastError());
     h->done_mass = B;
@@ -495,7 +542,7 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
     mark(h, CHOMP_K_SPLINES, s);
     halo_splines_kernel<<<B, 160, 15 * (size_t)c.n_halo * sizeof(double), s>>>(c, B, h->raw, h->nbar, h->epoch, h->htab, h->hcoef,
                                                                           status_dev, h->group);
-    mark(h, CHOMP_K_SPLINES + 1, s);
+    mark_end(h, CHOMP_K_SPLINES + 1, s);
     CK(cudaGetLastError());
     h->launches += 3;
     h->done_halo = B;
@@ -535,7 +582,7 @@ int chomp_b200_wtheta(void* handle, int B, int which, int n_theta, const double*
     wtheta_kernel<<<B, 256, wtheta_smem(h->cfg), (cudaStream_t)stream>>>(
         h->cfg, B, which, n_theta, theta_dev, h->cosmo, h->epoch, h->dbar, h->htab, h->hcoef, h->knodes, h->kcoef,
         h->cfg.use_halofit ? h->hfit : nullptr, w_out_dev, status_dev, h->group);
-    mark(h, CHOMP_K_WTHETA + 1, (cudaStream_t)stream);
+    mark_end(h, CHOMP_K_WTHETA + 1, (cudaStream_t)stream);
     h->launches += 1;
     CK(cudaGetLastError());
     note_stream(h, (cudaStream_t)stream);
@@ -892,25 +939,37 @@ int chomp_b200_trispectrum_1h(void* handle, int B, double* T_out_dev, void* stre
     if (int rc = ensure(h, B)) return rc;
     const Cfg& c = h->cfg;
     if (c.tri_moment < 0) FAIL("the trispectrum node list is disabled: configure with tri_moment >= 0");
-    if (B > 65535) FAIL("trispectrum / covariance batches are limited to 65 535 points per call");
     const int cap = h->node_cap[TRI_LIST];
-    if (B > h->tri_points) {
+    // the y^2 table A [n_halo, cap] (2.8 MB per point at n_halo = 200) is staged for TRI_CHUNK points at a time
+    const int chunk = B < TRI_CHUNK ? B : TRI_CHUNK;
+    if (B > h->tri_points || chunk > h->tri_chunk) {
         CK(cudaDeviceSynchronize());
         h->tri_points = 0;
-        if (int rc = dev_regrow(h, &h->tri_A, (size_t)B * c.n_halo * cap)) return rc;
+        if (chunk > h->tri_chunk) {
+            h->tri_chunk = 0;
+            if (int rc = dev_regrow(h, &h->tri_A, (size_t)chunk * c.n_halo * cap)) return rc;
+            h->tri_chunk = chunk;
+        }
         if (int rc = dev_regrow(h, &h->tri_T, (size_t)B * c.n_halo * c.n_halo)) return rc;
         h->tri_points = B;
     }
     cudaStream_t s = (cudaStream_t)stream;
     NodesOut no = nodes_view(h);
-    dim3 g1((c.n_halo + 7) / 8, B);
-    tri_profile_kernel<<<g1, 256, 0, s>>>(c, B, no, h->tri_A);
-    CK(cudaGetLastError());
     const int nt = (c.n_halo + 63) / 64;
-    dim3 g2(nt * (nt + 1) / 2, B);
-    tri_gram_kernel<<<g2, 256, 0, s>>>(c, B, cap, h->tri_A, h->tri_w, h->tri_T);
-    CK(cudaGetLastError());
-    h->launches += 2;
+    for (int b0 = 0; b0 < B; b0 += h->tri_chunk) {
+        const int n = (B - b0 < h->tri_chunk) ? B - b0 : h->tri_chunk;
+        dim3 g1((c.n_halo + 7) / 8, n);
+        int sp = span_begin(h, CHOMP_KC_TRI_PROFILE, s);
+        tri_profile_kernel<<<g1, 256, 0, s>>>(c, b0, B, no, h->tri_A);
+        span_end(h, sp, s);
+        CK(cudaGetLastError());
+        dim3 g2(nt * (nt + 1) / 2, n);
+        sp = span_begin(h, CHOMP_KC_TRI_GRAM, s);
+        tri_gram_kernel<<<g2, 256, 0, s>>>(c, b0, B, cap, h->tri_A, h->tri_w, h->tri_T);
+        span_end(h, sp, s);
+        CK(cudaGetLastError());
+        h->launches += 2;
+    }
     if (T_out_dev)
         CK(cudaMemcpyAsync(T_out_dev, h->tri_T, sizeof(double) * (size_t)B * c.n_halo * c.n_halo, cudaMemcpyDeviceToDevice, s));
     return 0;
@@ -1082,6 +1141,20 @@ int chomp_b200_get_timing(void* handle, double* ms_out) {
     return 0;
 }
 
+int chomp_b200_get_cov_timing(void* handle, double* ms_out) {
+    Handle* h = (Handle*)handle;
+    if (!h || !ms_out) FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < CHOMP_N_COV_KERNELS + CHOMP_N_KERNELS; ++i) ms_out[i] = 0.0;
+    for (const Handle::Span& sp : h->spans) {
+        CK(cudaEventSynchronize(sp.b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        if (sp.cls >= 0 && sp.cls < CHOMP_N_COV_KERNELS + CHOMP_N_KERNELS) ms_out[sp.cls] += ms;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // covariance
 // ---------------------------------------------------------------------------------------------------
@@ -1094,6 +1167,7 @@ int check_cov(const Handle* h, const CovP& p) {
     if (c.bessel_order != 0) FAIL("covariance is defined for the J0 kernel");
     if (p.which < CHOMP_P_LINEAR || p.which > CHOMP_P_GG) FAIL("unknown power spectrum");
     if (p.nq_osc < 1 || p.nq_osc > CHOMP_MAX_GL) FAIL("nq_osc out of range 1..16");
+    if (p.nq_ng > CHOMP_MAX_GL) FAIL("nq_ng out of range 1..16");
     if (!(p.osc_phase > 0)) FAIL("osc_phase must be positive");
     if (!(p.theta_min_rad > 0 && p.theta_max_rad > p.theta_min_rad)) FAIL("bad theta range");
     if (!(p.area_sr > 0)) FAIL("survey area must be positive");
@@ -1101,13 +1175,14 @@ int check_cov(const Handle* h, const CovP& p) {
     return 0;
 }
 
-int cov_reserve(Handle* h, int B, int n_bins) {
+int cov_reserve(Handle* h, int B, int n_bins, int ng_nodes) {
     const Cfg& c = h->cfg;
-    if (B > h->cov_points) {
+    if (B > h->cov_points || ng_nodes > h->cov_ntot) {
         // tables per point
         CK(cudaDeviceSynchronize());
         const size_t nk2 = (size_t)c.n_kernel * c.n_kernel;
         int rc = 0;
+        if (B < h->cov_points) B = h->cov_points;       // only the node count grew
         h->cov_points = 0;
         rc |= dev_regrow(h, &h->cov.kng, (size_t)B * nk2);
         rc |= dev_regrow(h, &h->cov.lkng, (size_t)B * nk2);
@@ -1120,13 +1195,14 @@ int cov_reserve(Handle* h, int B, int n_bins) {
         h->cov_points = B;
         h->cov_bins = 0;
         const int chunk = B < 256 ? B : 256;
-        const size_t nh = c.n_halo, nk = c.n_kernel, ntot = (size_t)hankel_nodes(c);
+        const size_t nh = c.n_halo, nk = c.n_kernel, ntot = (size_t)(ng_nodes > h->cov_ntot ? ng_nodes : h->cov_ntot);
         rc |= dev_regrow(h, &h->cov_tri.mcol, (size_t)chunk * nh * nh);
         rc |= dev_regrow(h, &h->cov_tri.r, (size_t)chunk * nk * nh);
         rc |= dev_regrow(h, &h->cov_tri.m2, (size_t)chunk * nk * nh);
         rc |= dev_regrow(h, &h->cov_tri.tw, (size_t)chunk * nk * ntot);
         if (rc) return rc;
         h->cov_chunk = chunk;
+        h->cov_ntot = (int)ntot;
     }
     if (n_bins > h->cov_bins) {
         if (int rc = dev_regrow(h, &h->cov.parts, (size_t)h->cov_points * 3 * n_bins * n_bins)) return rc;
@@ -1146,25 +1222,48 @@ int chomp_b200_cov_kernel_ng(void* handle, int B, const chomp_b200_cov_params* p
     if (!p) FAIL("null covariance parameters");
     if (int rc = check_cov(h, *p)) return rc;
     if (B > 65535) FAIL("covariance batches are limited to 65 535 points per call");
-    if (int rc = cov_reserve(h, B, p->n_bins)) return rc;
+    if (int rc = cov_reserve(h, B, p->n_bins, cov_ng_nodes(h->cfg, *p))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const Cfg& c = h->cfg;
     const size_t smem = limber_stage_doubles(c) * sizeof(double);
     SMEM_OPT_IN(cov_kng_kernel, h, smem);
     dim3 grid(c.n_kernel, B);
+    const int sp = span_begin(h, CHOMP_KC_KNG, s);
     cov_kng_kernel<<<grid, COV_THREADS, smem, s>>>(c, *p, B, limber_view(h), h->cov);
     CK(cudaGetLastError());
     cov_kng_spline_kernel<<<B, COV_THREADS, 0, s>>>(c, *p, B, h->cov, status_dev);
+    span_end(h, sp, s);
     CK(cudaGetLastError());
     h->launches += 2;
     h->kng_ready = true;
     return 0;
 }
 
+static int covariance_impl(void* handle, int B, const chomp_b200_cov_params* p, const double* bin_center_dev,
+                           const double* bin_delta_dev, const double* tri_z_dev, const double* cosmo_dev,
+                           const double* halo_dev, const double* hod_dev, double* cov_out_dev, double* parts_out_dev,
+                           int32_t* status_dev, void* stream);
+
 int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, const double* bin_center_dev,
                           const double* bin_delta_dev, const double* tri_z_dev, const double* cosmo_dev,
                           const double* halo_dev, const double* hod_dev, double* cov_out_dev, double* parts_out_dev,
                           int32_t* status_dev, void* stream) {
+    Handle* h = (Handle*)handle;
+    if (!h) FAIL("null handle");
+    h->spans.clear();
+    h->ev_used = 0;
+    h->open_span = -1;
+    h->in_cov = true;          // the stages below time themselves span by span (mark / mark_end)
+    const int rc = covariance_impl(handle, B, p, bin_center_dev, bin_delta_dev, tri_z_dev, cosmo_dev, halo_dev, hod_dev,
+                                   cov_out_dev, parts_out_dev, status_dev, stream);
+    h->in_cov = false;
+    return rc;
+}
+
+static int covariance_impl(void* handle, int B, const chomp_b200_cov_params* p, const double* bin_center_dev,
+                           const double* bin_delta_dev, const double* tri_z_dev, const double* cosmo_dev,
+                           const double* halo_dev, const double* hod_dev, double* cov_out_dev, double* parts_out_dev,
+                           int32_t* status_dev, void* stream) {
     Handle* h = (Handle*)handle;
     if (int rc = ensure(h, B)) return rc;
     if (!p || !bin_center_dev || !bin_delta_dev || !cov_out_dev) FAIL("null argument");
@@ -1176,7 +1275,7 @@ int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, c
     cudaStream_t s = (cudaStream_t)stream;
     const int nb = p->n_bins;
     if (status_dev) CK(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * (size_t)B, s));
-    if (int rc = cov_reserve(h, B, nb)) return rc;
+    if (int rc = cov_reserve(h, B, nb, cov_ng_nodes(c, *p))) return rc;
     CK(cudaMemsetAsync(h->cov.parts, 0, sizeof(double) * (size_t)B * 3 * nb * nb, s));
     if (int rc = chomp_b200_limber_tables(handle, B, cosmo_dev, status_dev, stream)) return rc;
     if (!p->poisson_only) {
@@ -1196,34 +1295,46 @@ int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, c
             if (int rc = chomp_b200_trispectrum_1h(handle, B, nullptr, stream)) return rc;
         }
         if (int rc = chomp_b200_mass_tables(handle, B, h->cosmo, halo_dev, nullptr, status_dev, stream)) return rc;
+        if (c.use_halofit)      // HaloFit halo (halo.py:1236-1412): the projected spectra use the HALOFIT power_mm
+            if (int rc = chomp_b200_halofit(handle, B, p->halofit_z, nullptr, status_dev, stream)) return rc;
         if (int rc = chomp_b200_halo_tables(handle, B, h->halo, hod_dev, status_dev, stream)) return rc;
         const size_t smem = limber_stage_doubles(c) * sizeof(double);
         SMEM_OPT_IN(cov_projected_kernel, h, smem);
+        int sp = span_begin(h, CHOMP_KC_PROJECTED, s);
         cov_projected_kernel<<<B, 128, smem, s>>>(c, *p, B, limber_view(h), h->cosmo, h->epoch, h->htab, h->hcoef,
                                                   c.use_halofit ? h->hfit : nullptr, h->cov, status_dev);
+        span_end(h, sp, s);
         CK(cudaGetLastError());
         dim3 gg(nb, B);
+        sp = span_begin(h, CHOMP_KC_GAUSS, s);
         cov_g_kernel<<<gg, COV_THREADS, 0, s>>>(c, *p, B, limber_view(h), bin_center_dev, h->cov);
+        span_end(h, sp, s);
         CK(cudaGetLastError());
         h->launches += 2;
         if (want_ng) {
-            const int ntot = hankel_nodes(c);
+            const int ntot = cov_ng_nodes(c, *p);
             const size_t ng_smem = (2 * (size_t)c.n_kernel * c.n_kernel + ntot + 2 * (size_t)nb * c.n_kernel + c.n_kernel) * sizeof(double);
             if (ng_smem > 200 * 1024) FAIL("covariance: n_bins x kernel_npoints too large for the non-Gaussian kernel");
             SMEM_OPT_IN(cov_ng_kernel, h, ng_smem);
             for (int b0 = 0; b0 < B; b0 += h->cov_chunk) {
                 const int n = (B - b0 < h->cov_chunk) ? B - b0 : h->cov_chunk;
+                int sq = span_begin(h, CHOMP_KC_TRI_NODES, s);
                 cov_tri_nodes_kernel<<<n, COV_THREADS, 0, s>>>(c, *p, b0, n, h->tri_T, h->cov.d_ng, h->cov_tri);
+                span_end(h, sq, s);
                 CK(cudaGetLastError());
                 dim3 gn(nb, n);
+                sq = span_begin(h, CHOMP_KC_NG, s);
                 cov_ng_kernel<<<gn, COV_THREADS, ng_smem, s>>>(c, *p, b0, n, bin_center_dev, h->cov_tri.tw, h->cov);
+                span_end(h, sq, s);
                 CK(cudaGetLastError());
                 h->launches += 2;
             }
         }
     }
     const size_t tot = (size_t)B * nb * nb;
+    const int spf = span_begin(h, CHOMP_KC_FINISH, s);
     cov_finish_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(*p, B, bin_center_dev, bin_delta_dev, h->cov, cov_out_dev, status_dev);
+    span_end(h, spf, s);
     CK(cudaGetLastError());
     h->launches += 1;
     if (parts_out_dev)

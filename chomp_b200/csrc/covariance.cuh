@@ -219,6 +219,12 @@ __device__ void osc_row(const SF& S, const UF& U, OscShared& s, int n_edge, doub
     __syncthreads();
 }
 
+// Gauss-Legendre order of the k_b pieces of the non-Gaussian term and the node count that goes with it
+__host__ __device__ inline int cov_ng_order(const Cfg& cfg, const CovP& cp) { return cp.nq_ng > 0 ? cp.nq_ng : cfg.nq_hankel; }
+__host__ __device__ inline int cov_ng_nodes(const Cfg& cfg, const CovP& cp) {
+    return (cfg.n_halo - 1) * hankel_subdiv(cfg) * cov_ng_order(cfg, cp);
+}
+
 struct CovOut {
     double *kng;        // [B, n_kernel, n_kernel]   K_NG table
     double *lkng;       // [B, n_kernel, n_kernel]   ln(K - 10 K_min)
@@ -552,7 +558,7 @@ cov_tri_nodes_kernel(const Cfg cfg, const CovP cp, int b0, int nb_chunk, const d
     const int cidx = blockIdx.x;
     if (cidx >= nb_chunk) return;
     const int b = b0 + cidx;
-    const int nh = cfg.n_halo, nk = cfg.n_kernel, nq = cfg.nq_hankel, tid = threadIdx.x;
+    const int nh = cfg.n_halo, nk = cfg.n_kernel, nq = cov_ng_order(cfg, cp), tid = threadIdx.x;
     const int sub = hankel_subdiv(cfg), ntot = (nh - 1) * sub * nq;
     const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hT = (l1 - l0) / (nh - 1), hA = (l1 - l0) / (nk - 1);
     const double* Tb = T + (size_t)b * nh * nh;
@@ -611,7 +617,7 @@ cov_ng_kernel(const Cfg cfg, const CovP cp, int b0, int nb_chunk, const double* 
     if (cidx >= nb_chunk) return;
     const int b = b0 + cidx;
     const int a_bin = blockIdx.x;
-    const int nb = cp.n_bins, nk = cfg.n_kernel, nh = cfg.n_halo, nq = cfg.nq_hankel;
+    const int nb = cp.n_bins, nk = cfg.n_kernel, nh = cfg.n_halo, nq = cov_ng_order(cfg, cp);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
     const int sub = hankel_subdiv(cfg), ntot = (nh - 1) * sub * nq;
     double* U = dyn;                      // [nk (i), nk (m)]

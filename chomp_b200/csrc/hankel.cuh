@@ -134,6 +134,47 @@ __host__ __device__ inline int hankel_subdiv(const Cfg& cfg) {
 }
 __host__ __device__ inline int hankel_nodes(const Cfg& cfg) { return (cfg.n_halo - 1) * hankel_subdiv(cfg) * cfg.nq_hankel; }
 
+// Correlation(k_min=, k_max=) (correlation.py:104-112): the k integral runs over [lc0, lc1] instead of the
+// halo-table range [l0, l1].  Panels: n_lo equal pieces of [lc0, l0] (spectrum from the k < k_min branch,
+// halo.py:283-288), the table intervals i_first .. i_first + n_mid - 1 with the outermost two clipped at
+// lc0 / lc1, n_hi equal pieces of [l1, lc1] (extrapolated spectrum, or 0).  With the default limits this
+// is exactly the table-interval layout.
+struct HankelLayout {
+    double l0, l1, hP, lc0, lc1;
+    int n_lo, i_first, n_mid, n_hi, sub, per, total;
+};
+__host__ __device__ inline HankelLayout hankel_layout(const Cfg& cfg) {
+    HankelLayout L;
+    L.l0 = log(cfg.k_min); L.l1 = log(cfg.k_max); L.hP = (L.l1 - L.l0) / (cfg.n_halo - 1);
+    L.lc0 = cfg.corr_k_min > 0.0 ? log(cfg.corr_k_min) : L.l0;
+    L.lc1 = cfg.corr_k_max > 0.0 ? log(cfg.corr_k_max) : L.l1;
+    if (cfg.corr_k_min > 0.0 && cfg.corr_k_min == cfg.k_min) L.lc0 = L.l0;
+    if (cfg.corr_k_max > 0.0 && cfg.corr_k_max == cfg.k_max) L.lc1 = L.l1;
+    L.sub = hankel_subdiv(cfg);
+    L.per = L.sub * cfg.nq_hankel;
+    L.n_lo = L.lc0 < L.l0 ? (int)ceil((fmin(L.l0, L.lc1) - L.lc0) / L.hP - 1e-9) : 0;
+    L.n_hi = L.lc1 > L.l1 ? (int)ceil((L.lc1 - fmax(L.l1, L.lc0)) / L.hP - 1e-9) : 0;
+    if (L.n_lo < 0) L.n_lo = 0;
+    if (L.n_hi < 0) L.n_hi = 0;
+    L.i_first = 0;
+    L.n_mid = 0;
+    if (L.lc0 < L.l1 && L.lc1 > L.l0) {
+        int i0 = L.lc0 > L.l0 ? (int)floor((L.lc0 - L.l0) / L.hP) : 0;
+        if (i0 > cfg.n_halo - 2) i0 = cfg.n_halo - 2;
+        int i1 = L.lc1 < L.l1 ? (int)ceil((L.lc1 - L.l0) / L.hP - 1e-12) : cfg.n_halo - 1;     // one past the last interval
+        if (i1 > cfg.n_halo - 1) i1 = cfg.n_halo - 1;
+        if (i1 <= i0) i1 = i0 + 1;
+        L.i_first = i0;
+        L.n_mid = i1 - i0;
+    }
+    L.total = (L.n_lo + L.n_mid + L.n_hi) * L.per;
+    return L;
+}
+
+__device__ __noinline__ double halo_power_outside(const HaloTabs& T, const PkParams& pk, int which, double k) {
+    return halo_power(T, pk, which, k);
+}
+
 // grid (B), 256 threads.  Phase 1: G_q = w_q k^2 P(k_q) / (2 pi D^2) at the theta-independent
 // Gauss-Legendre nodes (each halo-table interval cut into `sub` equal pieces).  Phase 2: one
 // warp per theta sums G_q K(x_q + ln theta).
@@ -152,9 +193,10 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
     const int gb = group ? group[b] : b;     // row of the cosmology-level tables (fast / slow split)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
     const int nk = cfg.n_halo, nkt = cfg.n_kernel, nq = cfg.nq_hankel;
-    const int sub = hankel_subdiv(cfg);
+    const HankelLayout L = hankel_layout(cfg);
+    const int sub = L.sub;
     const double* hf = hfit ? hfit + (size_t)gb * HF_LEN : nullptr;
-    const int total = (nk - 1) * sub * nq;
+    const int total = L.total;
     double* s_x = sm;                 // total
     double* s_g = s_x + total;        // total
     double* s_kc = s_g + total;       // 4 nkt
@@ -170,22 +212,47 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
     const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
     const double D = dbar[gb];
     const double inv_norm = 1.0 / (2.0 * M_PI * D * D);                 // correlation.py:270-275
-    const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hP = (l1 - l0) / (nk - 1);
+    const double l0 = L.l0, l1 = L.l1, hP = L.hP;
+    const bool limits = L.n_lo > 0 || L.n_hi > 0 || L.n_mid != nk - 1;   // Correlation(k_min=, k_max=)
     for (int idx = tid; idx < total; idx += blockDim.x) {
-        const int i = idx / (sub * nq), r = idx - i * (sub * nq);
+        const int j = idx / (sub * nq), r = idx - j * (sub * nq);
         const int s = r / nq, q = r - s * nq;
-        const double a = l0 + hP * i;
-        const double bb = (i == nk - 2) ? l1 : l0 + hP * (i + 1);
-        const double pa = a + (bb - a) * s / sub, pb = (s == sub - 1) ? bb : a + (bb - a) * (s + 1) / sub;
+        const int i = L.i_first + (j - L.n_lo);                        // table interval (middle panels)
+        const bool mid = j >= L.n_lo && j < L.n_lo + L.n_mid;
+        double a = l0 + hP * i;
+        double bb = (i == nk - 2) ? l1 : l0 + hP * (i + 1);
+        double ea = a, eb = bb;                                       // ends of the panel
+        if (limits) {
+            if (mid) { ea = fmax(a, L.lc0); eb = fmin(bb, L.lc1); }
+            else if (j < L.n_lo) {
+                const double top = fmin(l0, L.lc1);
+                ea = L.lc0 + (top - L.lc0) * j / L.n_lo;
+                eb = (j == L.n_lo - 1) ? top : L.lc0 + (top - L.lc0) * (j + 1) / L.n_lo;
+            } else {
+                const int jj = j - L.n_lo - L.n_mid;
+                const double bot = fmax(l1, L.lc0);
+                ea = bot + (L.lc1 - bot) * jj / L.n_hi;
+                eb = (jj == L.n_hi - 1) ? L.lc1 : bot + (L.lc1 - bot) * (jj + 1) / L.n_hi;
+            }
+        }
+        const double pa = ea + (eb - ea) * s / sub, pb = (s == sub - 1) ? eb : ea + (eb - ea) * (s + 1) / sub;
         const double half = 0.5 * (pb - pa);
         const double x = 0.5 * (pa + pb) + half * c_glx[nq][q];
         const double k = exp_fast(x);
         const double dx = x - a;
-        double P = 2.0 * M_PI * M_PI * delta2(pk, k, x) / (k * k * k);
-        if (which != CHOMP_P_LINEAR) {
-            if (hf) P = halofit_power(hf, pk, k);
-            if (!(hf && which == CHOMP_P_MM))
-                P = P * spline_poly(ca, i, dx) * spline_poly(cb, i, dx) + spline_poly(cpp, i, dx);
+        double P;
+        if (mid) {
+            P = 2.0 * M_PI * M_PI * delta2(pk, k, x) / (k * k * k);
+            if (which != CHOMP_P_LINEAR) {
+                if (hf) P = halofit_power(hf, pk, k);
+                if (!(hf && which == CHOMP_P_MM))
+                    P = P * spline_poly(ca, i, dx) * spline_poly(cb, i, dx) + spline_poly(cpp, i, dx);
+            }
+        } else {
+            HaloTabs T;
+            T.nk = nk; T.l0 = l0; T.l1 = l1; T.h = hP; T.k_min = cfg.k_min; T.k_max = cfg.k_max;
+            T.extrapolate = cfg.extrapolate; T.tab = htab + (size_t)b * 5 * nk; T.coef = hc; T.hf = hf;
+            P = halo_power_outside(T, pk, which, k);
         }
         s_x[idx] = x;
         s_g[idx] = half * c_glw[nq][q] * k * k * P * inv_norm;

@@ -14,13 +14,17 @@
 
 namespace chomp {
 
+#ifndef TRI_CHUNK
+#define TRI_CHUNK 128      // points whose y^2 tables are staged at a time (360 MB at n_halo = 200)
+#endif
+
 // grid (ceil(n_k / 8), B), 256 threads: warp w handles ln k node blockIdx.x * 8 + w
 __global__ void __launch_bounds__(256, 3)
-tri_profile_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ A /* [B, n_k, cap_last] */) {
+tri_profile_kernel(const Cfg cfg, int b0, int B, NodesOut nd, double* __restrict__ A /* [chunk, n_k, cap_last] */) {
     __shared__ NfwTables ntab;
     nfw_tables_load(&ntab);
     __syncthreads();
-    const int b = blockIdx.y;
+    const int b = b0 + blockIdx.y;       // the A buffer holds one chunk of points starting at b0
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ik = blockIdx.x * 8 + w;
     const int nk = cfg.n_halo;
@@ -32,7 +36,7 @@ tri_profile_kernel(const Cfg cfg, int B, NodesOut nd, double* __restrict__ A /* 
     const double l0 = log(cfg.k_min), l1 = log(cfg.k_max);
     const double lnk = (ik == nk - 1) ? l1 : l0 + (l1 - l0) / (nk - 1) * ik;
     const double k = exp(lnk);
-    double* __restrict__ row = A + ((size_t)b * nk + ik) * cap;
+    double* __restrict__ row = A + ((size_t)(b - b0) * nk + ik) * cap;
     const int nn_pad = (nn + 31) & ~31;
     for (int i = lane; i < cap; i += 32) {
         double v = 0.0;
@@ -57,9 +61,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // grid (tiles, B), 256 threads.  Tile = 64 x 64 block (ti <= tj) of T; warp w owns rows
 // 16 (w / 2) ... + 15 and columns 32 (w % 2) ... + 31 of it: 2 x 4 m8n8k4 accumulator fragments.
 __global__ void __launch_bounds__(256)
-tri_gram_kernel(const Cfg cfg, int B, int cap, const double* __restrict__ A, const double* __restrict__ wts,
+tri_gram_kernel(const Cfg cfg, int b0, int B, int cap, const double* __restrict__ A, const double* __restrict__ wts,
                 double* __restrict__ T /* [B, n_k, n_k] */) {
-    const int b = blockIdx.y;
+    const int b = b0 + blockIdx.y;
     if (b >= B) return;
     const int nk = cfg.n_halo;
     const int nt = (nk + 63) / 64;
@@ -70,7 +74,7 @@ tri_gram_kernel(const Cfg cfg, int B, int cap, const double* __restrict__ A, con
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i0 = ti * 64 + 16 * (w >> 1), j0 = tj * 64 + 32 * (w & 1);
     const int r = lane >> 2, c = lane & 3;
-    const double* __restrict__ Ab = A + (size_t)b * nk * cap;
+    const double* __restrict__ Ab = A + (size_t)(b - b0) * nk * cap;
     const double* __restrict__ wb = wts + (size_t)b * cap;
     double acc[2][4][2];
 #pragma unroll

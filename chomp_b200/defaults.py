@@ -78,4 +78,5 @@ default_quadrature = {
     "lens": 6,      # lensing-efficiency integral, per chi(z) knot interval
     "cov_osc": 4,   # J0 J0 integrals of the covariance (K_NG table, Gaussian term), per piece
     "cov_phase": 3.0,  # largest phase advance of the faster Bessel factor over one such piece
+    "cov_ng": 4,    # inner k_b integral of the non-Gaussian covariance term, per piece (<= 0.0625 wide in ln k)
 }

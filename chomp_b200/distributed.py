@@ -40,7 +40,7 @@ class ShardedEngine(object):
     supplied instead of a survey: the host-side logic (sharding, padding of uneven shards, the single
     collective, the double-buffered pipeline) is then exercised without a GPU (tests, gloo)."""
 
-    def __init__(self, survey=None, evaluate=None, group=None, device=None, which=None):
+    def __init__(self, survey=None, evaluate=None, group=None, device=None, which=None, tri_moment=None):
         import torch
         self.torch = torch
         dist = _dist()
@@ -58,6 +58,10 @@ class ShardedEngine(object):
             if device is None:
                 device = torch.cuda.current_device()
             self.engine = _engine.Engine(survey, device=device)
+            if tri_moment is not None:          # the covariance path needs the 1-halo trispectrum's node list
+                cfg = survey.config()
+                cfg.tri_moment = int(tri_moment)
+                self.engine.configure(cfg)
             self.which = _lib.POWER_SPEC[survey.power_spec] if which is None else int(which)
             self._theta = torch.as_tensor(np.ascontiguousarray(survey.theta), device="cuda:%d" % int(device))
             evaluate = self._evaluate_engine
@@ -164,6 +168,85 @@ class ShardedEngine(object):
         t.cuda.current_stream(self._theta.device).synchronize()
         out = pin_out.numpy()
         return out[:, :n_cols].copy(), out[:, n_cols].astype(np.int32)
+
+    # -- config 5: w(theta) and its covariance, one all-gather ---------------------------------------------
+    def _evaluate_covariance(self, setup):
+        """evaluate callable: [rows, n_theta + n_bins^2] = w(theta) | covariance (row-major) per point.  The
+        covariance call leaves the handle in the state of the w(theta) path at z_bar, so the correlation
+        function costs one more Hankel launch (include/chomp_b200.h, chomp_b200_covariance)."""
+        t = self.torch
+        eng = self.engine
+
+        def evaluate(cosmo, halo, hod):
+            rows = cosmo.shape[0]
+            status = t.zeros(rows, dtype=t.int32, device=self._theta.device)
+            cov = eng.covariance(cosmo, halo, hod, setup, status=status)
+            w = eng.wtheta_stage(rows, self.which, self._theta, status=status)
+            return t.cat([w, cov.reshape(rows, -1)], 1), status
+        return evaluate
+
+    def covariance(self, cosmo, halo, hod, setup):
+        """Global batch in, (w [B, n_theta], cov [B, n_bins, n_bins], status [B]) out on every rank: shard ->
+        Limber / K_NG / trispectrum / halo tables / P + G + NG terms / Hankel -> ONE all-gather of the
+        [B/G, n_theta + n_bins^2 + 1] rows (covariance.py:276-321 per point; the [B, n_k, n_k] trispectrum tables
+        never leave the owning rank)."""
+        saved = self.evaluate
+        self.evaluate = self._evaluate_covariance(setup)
+        try:
+            local, full, bounds, n_cols = self._packed_local(cosmo, halo, hod, slot="cov")
+        finally:
+            self.evaluate = saved
+        if self.world > 1:
+            _dist().all_gather_into_tensor(full.view(-1, n_cols + 1), local, group=self.group)
+        else:
+            full = local.unsqueeze(0)
+        table, st = self._unpack(full, bounds, n_cols)
+        n_theta, nb = self._theta.numel(), setup.bins.shape[0]
+        return table[:, :n_theta].clone(), table[:, n_theta:].reshape(-1, nb, nb).clone(), st
+
+    def covariance_host(self, cosmo, halo, hod, setup):
+        """The same end to end with HOST buffers: numpy in (pinned staging, H2D of the shard), numpy out (one D2H
+        of the gathered table)."""
+        t = self.torch
+        n = cosmo.shape[0]
+        a, b = shard_bounds(n, self.world)[self.rank]
+        rows = b - a
+        widths = (_lib.N_COSMO, _lib.N_HALO, _lib.N_HOD)
+        n_theta, nb = self._theta.numel(), setup.bins.shape[0]
+        key = ("cov_host", rows, n)
+        if key not in self._bufs:
+            self._bufs[key] = (t.empty(max(rows, 1)*sum(widths), dtype=t.float64).pin_memory(),
+                               t.empty((n, n_theta + nb*nb + 1), dtype=t.float64).pin_memory())
+        pin_in, pin_out = self._bufs[key]
+        off, views = 0, []
+        for arr, wd in zip((cosmo, halo, hod), widths):
+            pin_in[off:off + rows*wd].view(rows, wd).copy_(t.from_numpy(np.ascontiguousarray(arr[a:b], dtype=np.float64)))
+            views.append((off, wd))
+            off += rows*wd
+        dev = pin_in.to(self._theta.device, non_blocking=True)
+        c, h, g = (dev[o:o + rows*wd].view(rows, wd) for o, wd in views)
+        # the sharded front works on global arrays: hand it this rank's rows in place
+        evaluate = self._evaluate_covariance(setup)
+        table, status = evaluate(c, h, g)
+        bounds = shard_bounds(n, self.world)
+        max_rows = max(y - x for x, y in bounds)
+        n_cols = table.shape[1]
+        local, full = self._gather_buffers("cov_host", max_rows, n_cols, table)
+        if rows:
+            local[:rows, :n_cols] = table
+            local[:rows, n_cols] = status.to(table.dtype)
+        if self.world > 1:
+            _dist().all_gather_into_tensor(full.view(-1, n_cols + 1), local, group=self.group)
+        else:
+            full = local.unsqueeze(0)
+        if all(y - x == max_rows for x, y in bounds):
+            pin_out.copy_(full.reshape(-1, n_cols + 1), non_blocking=True)
+        else:
+            pin_out.copy_(t.cat([full[r, :y - x] for r, (x, y) in enumerate(bounds)], 0), non_blocking=True)
+        t.cuda.current_stream(self._theta.device).synchronize()
+        out = pin_out.numpy()
+        return (out[:, :n_theta].copy(), out[:, n_theta:n_cols].reshape(n, nb, nb).copy(),
+                out[:, n_cols].astype(np.int32))
 
     def pipeline(self, batches):
         """Double-buffered steps: the all-gather of step s runs (asynchronously, on the collective's own

@@ -260,6 +260,7 @@ class CovarianceSetup(object):
         p.nongaussian, p.poisson_only = int(bool(nongaussian_cov)), int(bool(poisson_noise_only))
         q = survey.quadrature
         p.nq_osc, p.osc_phase = q.get("cov_osc", 4), q.get("cov_phase", 3.0)
+        p.nq_ng = q.get("cov_ng", 0)
         lim = survey.limits
         ln_k = np.linspace(np.log(lim["k_min"]), np.log(lim["k_max"]), survey.precision["kernel_npoints"])
         p.zero_last_ka = int(np.exp(ln_k[-1]) > lim["k_max"])       # halo_trispectrum.py:100-107 in numpy arithmetic
@@ -287,6 +288,7 @@ class CovarianceSetup(object):
         self.cosmic_shear = [bool(shear[0]*shear[1] or shear[2]*shear[3]), bool(shear[0]*shear[3] or shear[1]*shear[2])]
         p.shot_wt[0], p.shot_wt[1] = 1.0 + self.cosmic_shear[0], 1.0 + self.cosmic_shear[1]
         p.bessel_limit = bessel_limit(0, survey.precision["kernel_bessel_limit"])
+        p.halofit_z = -1.0
         self.params = p
 
 
@@ -558,6 +560,13 @@ class Engine(object):
         ms = (ctypes.c_double*len(_lib.KERNEL_NAMES))()
         _lib.check(self.lib.chomp_b200_get_timing(self._h, ms))
         return dict(zip(_lib.KERNEL_NAMES, [float(v) for v in ms]))
+
+    def cov_kernel_times_ms(self):
+        """Device time of each kernel class of the last covariance() call (timing on), by kernel name."""
+        names = _lib.COV_KERNEL_NAMES + _lib.KERNEL_NAMES
+        ms = (ctypes.c_double*len(names))()
+        _lib.check(self.lib.chomp_b200_get_cov_timing(self._h, ms))
+        return dict(zip(names, [float(v) for v in ms]))
 
     def launch_count(self):
         return int(self.lib.chomp_b200_launch_count(self._h))

@@ -239,6 +239,12 @@ enum { CHOMP_K_LIMBER = 0, CHOMP_K_MASS, CHOMP_K_NODES, CHOMP_K_SUMS, CHOMP_K_SP
        CHOMP_N_KERNELS };
 int chomp_b200_set_timing(void* handle, int on);
 int chomp_b200_get_timing(void* handle, double* ms_out /* [CHOMP_N_KERNELS] */);
+/* Same for the kernels of the last chomp_b200_covariance (classes below; a class launched several times -- the
+ * chunked trispectrum / non-Gaussian kernels, the mass tables at two redshifts -- reports the sum). */
+enum { CHOMP_KC_KNG = 0 /* cov_kng_kernel + its spline */, CHOMP_KC_TRI_PROFILE, CHOMP_KC_TRI_GRAM, CHOMP_KC_PROJECTED,
+       CHOMP_KC_GAUSS, CHOMP_KC_TRI_NODES, CHOMP_KC_NG, CHOMP_KC_FINISH, CHOMP_N_COV_KERNELS };
+int chomp_b200_get_cov_timing(void* handle, double* ms_out /* [CHOMP_N_COV_KERNELS + CHOMP_N_KERNELS]: the classes above, then
+                                                               the w(theta)-path kernels launched inside the call */);
 
 /* ---- covariance of w(theta): covariance.Covariance (covariance.py:23-683) over kernel.KernelCovariance
  * (kernel.py:864-1111) and HaloTrispectrumOneHalo, for input_correlation_a is input_correlation_b
@@ -251,14 +257,19 @@ typedef struct chomp_b200_cov_params {
     int32_t nq_osc;          /* Gauss-Legendre order of the pieces of the J0 J0 integrals            */
     int32_t zero_last_ka;    /* outcome of exp(ln k_max) > k_max in the caller's arithmetic: the
                                 reference's last ln k_a node then sees T = 0 (halo_trispectrum.py:100-107) */
-    int32_t reserved_i[2];
+    int32_t nq_ng;           /* Gauss-Legendre order per piece (<= 0.0625 in ln k_b) of the inner k_b integral of
+                                the non-Gaussian term; <= 0: cfg.nq_hankel.  The integrand is a bicubic in ln k_b
+                                times a smooth kernel: order 2 is converged to 1e-8                       */
+    int32_t reserved_i[1];
     double theta_min_rad, theta_max_rad; /* 10**log_theta_min/max of the correlation (covariance.py:93-97) */
     double area_sr;          /* survey_area_deg2 * deg2_to_strad                                     */
     double poisson[6];       /* proj_power_poisson(window_pair = 0..5), covariance.py:352-357        */
     double shot_wt[2];       /* 1 + cosmic_shear[0], 1 + cosmic_shear[1], covariance.py:336-347      */
     double bessel_limit;     /* special.jn_zeros(0, kernel_bessel_limit)[-1]                         */
     double osc_phase;        /* largest phase advance of the fast Bessel factor over one piece      */
-    double reserved_d[3];
+    double halofit_z;        /* cfg.use_halofit: fit_z of chomp_b200_halofit (the HaloFit object's
+                                construction redshift, halo.py:1261-1266; < 0: each epoch's own)        */
+    double reserved_d[2];
 } chomp_b200_cov_params;
 
 /* KernelCovariance._find_z_bar / _initialize_NG_spline (kernel.py:961-972, 1016-1068) for the batch of

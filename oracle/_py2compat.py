@@ -84,3 +84,17 @@ def install():
 
 
 install()
+
+
+def py2_lt(a, b):
+    """``a < b`` with Python 2's ordering of None below every number (correlation.py:106)."""
+    if a is None:
+        return b is not None
+    if b is None:
+        return False
+    return a < b
+
+
+def py2_gt(a, b):
+    """``a > b`` with Python 2's ordering of None below every number (correlation.py:106)."""
+    return py2_lt(b, a)

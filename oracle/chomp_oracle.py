@@ -1010,9 +1010,9 @@ class Correlation(object):
         self.halo = halo_factory(kernel.z_bar)
         if ((k_min is not None or k_max is not None) and
                 not self.halo.extrapolate and
-                ((k_min is not None and k_min < self.halo.k_min) or
-                 (k_max is not None and k_max > self.halo.k_max))):
-            self.halo.extrapolate = True                  # correlation.py:104
+                ((k_min is None or k_min < self.halo.k_min) or     # Python 2: None < x is True,
+                 (k_max is not None and k_max > self.halo.k_max))):  # None > x is False
+            self.halo.extrapolate = True                  # correlation.py:104-107
         self.ln_k_min = np.log(self.halo.k_min if k_min is None else k_min)
         self.ln_k_max = np.log(self.halo.k_max if k_max is None else k_max)
         self.power_spec = power_spec

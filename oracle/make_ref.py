@@ -25,7 +25,10 @@ also hold for the generated copy):
 5. ``1/b`` (kernel.py:167) -> ``_py2compat.py2_div(1, b)``
 6. first line of every module gains ``import _py2compat;`` which installs the
    Romberg restatement as ``scipy.integrate.romberg``.
-7. kernel.py:606,608 debug ``.write('test_window_*')`` calls are left alone
+7. correlation.py:106 ``(k_min < self.halo._k_min or k_max > self.halo._k_max)`` ->
+   ``(_py2compat.py2_lt(k_min, ...) or _py2compat.py2_gt(k_max, ...))``: Python 2 orders None
+   below every number instead of raising TypeError.
+8. kernel.py:606,608 debug ``.write('test_window_*')`` calls are left alone
    (they are the reference's behaviour) -- callers chdir to a temp dir.
 """
 import os
@@ -73,6 +76,9 @@ def transform(name, text):
             line = line.replace("(Omb2)**(3/4)", "(Omb2)**(3//4)")
         if name == "kernel.py" and line.strip() == "1/b)*":
             line = line.replace("1/b)*", "_py2compat.py2_div(1, b))*")
+        if name == "correlation.py" and "(k_min < self.halo._k_min or k_max > self.halo._k_max)):" in line:
+            line = line.replace("(k_min < self.halo._k_min or k_max > self.halo._k_max)",
+                                "(_py2compat.py2_lt(k_min, self.halo._k_min) or _py2compat.py2_gt(k_max, self.halo._k_max))")
         if (not injected and (line.startswith("import ") or
                               line.startswith("from ")) and
                 "__future__" not in line):

@@ -38,7 +38,7 @@ def w_err(w, ref, floor=1e-3):
 
 def oracle_wtheta(cosmo, halo, hod, dist_a, dist_b=None, window_a="galaxy", window_b=None,
                   power_spec="power_gg", bins_per_decade=10.0, prec=None, integ=None,
-                  z_range=(0.0, 5.0), theta_deg=(0.001, 1.0), bessel_order=0, hod_kind="zheng"):
+                  z_range=(0.0, 5.0), theta_deg=(0.001, 1.0), bessel_order=0, hod_kind="zheng", k_min=None, k_max=None):
     """One parameter point through the oracle; returns a dict of every table."""
     prec = prec or O.precision()
     integ = integ or Tight(40)
@@ -67,7 +67,7 @@ def oracle_wtheta(cosmo, halo, hod, dist_a, dist_b=None, window_a="galaxy", wind
         return O.Halo(se, mf, hod_cls(hod, prec["halo_precision"]), halo)
 
     corr = O.Correlation(theta_deg[0], theta_deg[1], kern, factory, power_spec,
-                         bins_per_decade=bins_per_decade)
+                         bins_per_decade=bins_per_decade, k_min=k_min, k_max=k_max)
     w = corr.compute_correlation()
     h = corr.halo
     out = dict(w=w, theta=corr.theta, z_bar=kern.z_bar, D_z=corr.D_z,

@@ -1,0 +1,87 @@
+"""BASELINE config 5 at its NAMED shape through the C ABI: covariance P + G + NG of w_gg(theta) on 30 x 30 annular
+bins (0.001 .. 1 deg, 10 per decade), halo_npoints = 200, 1-halo trispectrum gggg at z_bar_NG, on an 8-point Latin
+hypercube of the bench workload -- against the oracle's converged values (fixture
+tests/golden/oracle_covariance_named.json, written by tests/golden/make_oracle_cov_named.py: the oracle takes
+~3 minutes per point at this shape).  Bar: 1e-5 relative to the diagonal's geometric mean."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from chomp_b200 import _lib, defaults, design, engine
+
+from common import cov_err
+
+pytestmark = pytest.mark.gpu
+PATH = os.path.join(os.path.dirname(__file__), "golden", "oracle_covariance_named.json")
+FIX = json.load(open(PATH)) if os.path.exists(PATH) else None
+
+
+def _engine(quadrature=None):
+    prec = dict(defaults.default_precision, halo_npoints=FIX["halo_npoints"])
+    theta = tuple(FIX["theta_deg"])
+    survey = engine.Survey(engine.RedshiftDistribution.gaussian(0.0, 2.0, 0.5, 0.1), theta_deg=theta,
+                           bins_per_decade=FIX["bins_per_decade"], power_spec="power_gg", precision=prec,
+                           quadrature=quadrature)
+    cfg = survey.config()
+    cfg.tri_moment = _lib.TRISPECTRUM_MOMENT["power_gggg"]
+    eng = engine.Engine(cfg)
+    setup = engine.CovarianceSetup(survey, theta, FIX["bins_per_decade"], FIX["area_deg2"], FIX["n_a"], FIX["n_b"],
+                                   FIX["variance"], True, "power_gg")
+    return survey, eng, setup
+
+
+@pytest.mark.skipif(FIX is None, reason="fixture missing")
+def test_named_shape_against_oracle_fixture():
+    import torch
+    survey, eng, setup = _engine()
+    n = len(FIX["points"])
+    cosmo, halo, hod = design.synthetic_batch(FIX["n_lhs"])
+    cosmo, halo, hod = cosmo[:n], halo[:n], hod[:n]
+    nb = setup.bins.shape[0]
+    assert nb == 30
+    status = torch.zeros(n, dtype=torch.int32, device="cuda")
+    out, parts = eng.covariance(cosmo, halo, hod, setup, status=status, parts=True)
+    out, parts = out.cpu().numpy(), parts.cpu().numpy()
+    assert not status.cpu().numpy().any()
+    worst = {"cov": 0.0, "G": 0.0, "NG": 0.0}
+    for i, ref in enumerate(FIX["points"]):
+        tot = np.array(ref["cov"]).reshape(nb, nb)
+        worst["cov"] = max(worst["cov"], cov_err(out[i], tot))
+        # the parts relative to the TOTAL's diagonal (the Gaussian term alone has zero entries off the diagonal band)
+        d = np.sqrt(np.abs(np.outer(np.diag(tot), np.diag(tot))))
+        worst["G"] = max(worst["G"], float(np.max(np.abs(parts[i, 1] - np.array(ref["G"]).reshape(nb, nb))/d)))
+        worst["NG"] = max(worst["NG"], float(np.max(np.abs(parts[i, 2] - np.array(ref["NG"]).reshape(nb, nb))/d)))
+        assert np.allclose(np.diag(parts[i, 0]), ref["P_diag"], rtol=1e-12, atol=0)
+        assert np.array_equal(out[i], out[i].T)
+    print("named-shape covariance, %d points: max error vs oracle" % n, worst)
+    assert worst["cov"] < 1e-5 and worst["G"] < 1e-5 and worst["NG"] < 1e-5, worst
+
+
+@pytest.mark.skipif(FIX is None, reason="fixture missing")
+@pytest.mark.parametrize("order", [2, 3])
+def test_inner_ng_quadrature_order_is_converged(order):
+    """The k_b integrand of the non-Gaussian term is a bicubic times a smooth kernel on pieces <= 0.0625 wide: a
+    lower Gauss-Legendre order than the Hankel rule's gives the same covariance."""
+    cosmo, halo, hod = design.synthetic_batch(FIX["n_lhs"])
+    _, eng, setup = _engine()
+    ref = eng.covariance(cosmo[:2], halo[:2], hod[:2], setup).cpu().numpy()
+    _, eng2, setup2 = _engine(dict(defaults.default_quadrature, cov_ng=order))
+    got = eng2.covariance(cosmo[:2], halo[:2], hod[:2], setup2).cpu().numpy()
+    err = max(cov_err(got[i], ref[i]) for i in range(2))
+    print("cov_ng order %d vs default: %.2e" % (order, err))
+    assert err < 1e-6
+
+
+@pytest.mark.skipif(FIX is None, reason="fixture missing")
+def test_batches_beyond_one_trispectrum_chunk():
+    """More points than one staging chunk of the y^2 tables (TRI_CHUNK = 128): every chunk gives the same
+    answers as a batch of its own."""
+    _, eng, setup = _engine()
+    cosmo, halo, hod = design.synthetic_batch(160)
+    out = eng.covariance(cosmo, halo, hod, setup).cpu().numpy()
+    assert np.all(np.isfinite(out))
+    for sl in (slice(0, 3), slice(126, 131), slice(157, 160)):
+        one = eng.covariance(cosmo[sl], halo[sl], hod[sl], setup).cpu().numpy()
+        assert np.array_equal(one, out[sl])

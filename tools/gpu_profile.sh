@@ -6,7 +6,7 @@
 tag=${1:-r2}
 pts=${2:-4096}
 M=smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmma_pred_on.sum,smsp__inst_executed_pipe_fp64.sum
-CMD="python bench.py --steps 2 --warmup 3 --points $pts --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 2 --warmup 3 --points $pts --no-cpu-baseline --no-e2e --min-seconds 0"
 $CMD > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --metrics $M \
     -k regex:'limber_tables|mass_tables|nu_nodes|halo_sums|halo_splines|wtheta' -s 18 -c 6 -f \

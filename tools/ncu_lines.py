@@ -24,6 +24,7 @@ base = None
 per = collections.Counter(); samp = collections.Counter(); ops = collections.Counter()
 tot = 0; tots = 0
 for r in rows[hi+1:]:
+    if r and r[0] == "Kernel Name": break          # a second capture of the same kernel: first one only
     if len(r) <= ie: continue
     a = int(r[ia], 16) if r[ia].startswith("0x") else int(r[ia])
     if base is None: base = a
