@@ -577,11 +577,19 @@ int chomp_b200_wtheta(void* handle, int B, int which, int n_theta, const double*
     NEED_STAGE(h->done_mass, h->group ? h->n_groups : B, "the epoch scalars (chomp_b200_mass_tables)");
     if (!(which == CHOMP_P_LINEAR || (h->cfg.use_halofit && which == CHOMP_P_MM)))
         NEED_STAGE(h->done_halo, B, "the halo tables (chomp_b200_halo_tables)");
-    SMEM_OPT_IN(wtheta_kernel, h, wtheta_smem(h->cfg));
+    const HankelLayout hl = hankel_layout(h->cfg);
+    const bool limits = hl.n_lo > 0 || hl.n_hi > 0 || hl.n_mid != h->cfg.n_halo - 1 || hl.lc0 != hl.l0 || hl.lc1 != hl.l1;
+    if (limits) SMEM_OPT_IN(wtheta_kernel<true>, h, wtheta_smem(h->cfg));
+    else SMEM_OPT_IN(wtheta_kernel<false>, h, wtheta_smem(h->cfg));
     mark(h, CHOMP_K_WTHETA, (cudaStream_t)stream);
-    wtheta_kernel<<<B, 256, wtheta_smem(h->cfg), (cudaStream_t)stream>>>(
-        h->cfg, B, which, n_theta, theta_dev, h->cosmo, h->epoch, h->dbar, h->htab, h->hcoef, h->knodes, h->kcoef,
-        h->cfg.use_halofit ? h->hfit : nullptr, w_out_dev, status_dev, h->group);
+    if (limits)
+        wtheta_kernel<true><<<B, 256, wtheta_smem(h->cfg), (cudaStream_t)stream>>>(
+            h->cfg, B, which, n_theta, theta_dev, h->cosmo, h->epoch, h->dbar, h->htab, h->hcoef, h->knodes, h->kcoef,
+            h->cfg.use_halofit ? h->hfit : nullptr, w_out_dev, status_dev, h->group);
+    else
+        wtheta_kernel<false><<<B, 256, wtheta_smem(h->cfg), (cudaStream_t)stream>>>(
+            h->cfg, B, which, n_theta, theta_dev, h->cosmo, h->epoch, h->dbar, h->htab, h->hcoef, h->knodes, h->kcoef,
+            h->cfg.use_halofit ? h->hfit : nullptr, w_out_dev, status_dev, h->group);
     mark_end(h, CHOMP_K_WTHETA + 1, (cudaStream_t)stream);
     h->launches += 1;
     CK(cudaGetLastError());

@@ -171,7 +171,13 @@ __host__ __device__ inline HankelLayout hankel_layout(const Cfg& cfg) {
     return L;
 }
 
-__device__ __noinline__ double halo_power_outside(const HaloTabs& T, const PkParams& pk, int which, double k) {
+// spectrum on the panels outside the halo table (Correlation(k_min=, k_max=) only): out of line, with its own
+// table view, so that the common path of wtheta_kernel carries none of it
+__device__ __noinline__ double halo_power_outside(int n_halo, double k_min, double k_max, int extrapolate, const double* tab,
+                                                  const double* coef, const double* hf, PkParams pk, int which, double k) {
+    HaloTabs T;
+    T.nk = n_halo; T.l0 = log(k_min); T.l1 = log(k_max); T.h = (T.l1 - T.l0) / (T.nk - 1);
+    T.k_min = k_min; T.k_max = k_max; T.extrapolate = extrapolate; T.tab = tab; T.coef = coef; T.hf = hf;
     return halo_power(T, pk, which, k);
 }
 
@@ -181,6 +187,8 @@ __device__ __noinline__ double halo_power_outside(const HaloTabs& T, const PkPar
 #ifndef WTHETA_MIN_BLOCKS
 #define WTHETA_MIN_BLOCKS 4
 #endif
+// LIMITS = false: the table-interval layout (no Correlation k limits), nothing of the general path is compiled in
+template <bool LIMITS>
 __global__ void __launch_bounds__(256, WTHETA_MIN_BLOCKS)
 wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __restrict__ theta,
               const double* __restrict__ cosmo, const double* __restrict__ epoch, const double* __restrict__ dbar,
@@ -213,12 +221,12 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
     const double D = dbar[gb];
     const double inv_norm = 1.0 / (2.0 * M_PI * D * D);                 // correlation.py:270-275
     const double l0 = L.l0, l1 = L.l1, hP = L.hP;
-    const bool limits = L.n_lo > 0 || L.n_hi > 0 || L.n_mid != nk - 1;   // Correlation(k_min=, k_max=)
+    const bool limits = LIMITS;                                          // Correlation(k_min=, k_max=)
     for (int idx = tid; idx < total; idx += blockDim.x) {
         const int j = idx / (sub * nq), r = idx - j * (sub * nq);
         const int s = r / nq, q = r - s * nq;
         const int i = L.i_first + (j - L.n_lo);                        // table interval (middle panels)
-        const bool mid = j >= L.n_lo && j < L.n_lo + L.n_mid;
+        const bool mid = !LIMITS || (j >= L.n_lo && j < L.n_lo + L.n_mid);
         double a = l0 + hP * i;
         double bb = (i == nk - 2) ? l1 : l0 + hP * (i + 1);
         double ea = a, eb = bb;                                       // ends of the panel
@@ -249,10 +257,7 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
                     P = P * spline_poly(ca, i, dx) * spline_poly(cb, i, dx) + spline_poly(cpp, i, dx);
             }
         } else {
-            HaloTabs T;
-            T.nk = nk; T.l0 = l0; T.l1 = l1; T.h = hP; T.k_min = cfg.k_min; T.k_max = cfg.k_max;
-            T.extrapolate = cfg.extrapolate; T.tab = htab + (size_t)b * 5 * nk; T.coef = hc; T.hf = hf;
-            P = halo_power_outside(T, pk, which, k);
+            P = halo_power_outside(nk, cfg.k_min, cfg.k_max, cfg.extrapolate, htab + (size_t)b * 5 * nk, hc, hf, pk, which, k);
         }
         s_x[idx] = x;
         s_g[idx] = half * c_glw[nq][q] * k * k * P * inv_norm;

@@ -60,10 +60,10 @@ def test_named_shape_against_oracle_fixture():
 
 
 @pytest.mark.skipif(FIX is None, reason="fixture missing")
-@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("order", [3])
 def test_inner_ng_quadrature_order_is_converged(order):
-    """The k_b integrand of the non-Gaussian term is a bicubic times a smooth kernel on pieces <= 0.0625 wide: a
-    lower Gauss-Legendre order than the Hankel rule's gives the same covariance."""
+    """The k_b integrand of the non-Gaussian term is a bicubic times a smooth kernel on pieces <= 0.0625 wide: order 3
+    gives the same covariance as the Hankel rule's order 4 (order 2 does not: 3e-5, measured)."""
     cosmo, halo, hod = design.synthetic_batch(FIX["n_lhs"])
     _, eng, setup = _engine()
     ref = eng.covariance(cosmo[:2], halo[:2], hod[:2], setup).cpu().numpy()

@@ -2,7 +2,7 @@
 # time each variant library with the bench (no CPU arm); parity tests on the default build only
 for v in "$@"; do
   export CHOMP_B200_LIB=/root/repo/tools/variants/$v.so
-  timeout 200 python bench.py --no-cpu-baseline 2>gpurun_out/bench_$v.err | tail -1 > gpurun_out/bench_$v.json
+  timeout 200 python bench.py --no-cpu-baseline --min-seconds 0 --steps 20 --warmup 5 2>gpurun_out/bench_$v.err | tail -1 > gpurun_out/bench_$v.json
   python - "$v" <<'PY'
 import json, sys
 v = sys.argv[1]

@@ -24,11 +24,24 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__cycles_active.avg", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_dmma_pred_on.sum", "smsp__inst_executed_pipe_fp64.sum",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
 
 
 def source_hash():
+    """Hash of the CUDA sources the capture was made from: the working tree, or -- when the tree has moved on
+    since the gpurun call -- the git revision named in CHOMP_PROFILE_REV."""
     h = hashlib.sha256()
+    rev = os.environ.get("CHOMP_PROFILE_REV")
+    if rev:
+        names = subprocess.run(["git", "-C", ROOT, "ls-tree", "--name-only", rev, "chomp_b200/csrc/"], capture_output=True,
+                               text=True).stdout.split()
+        for f in sorted(os.path.basename(n) for n in names):
+            if f.endswith((".cu", ".cuh")):
+                h.update(subprocess.run(["git", "-C", ROOT, "show", "%s:chomp_b200/csrc/%s" % (rev, f)], capture_output=True).stdout)
+        return h.hexdigest()[:16]
     d = os.path.join(ROOT, "chomp_b200", "csrc")
     for f in sorted(os.listdir(d)):
         if f.endswith((".cu", ".cuh")):
@@ -43,6 +56,35 @@ def to_float(v):
         return None
 
 
+def dmma_warp_instructions(rep):
+    """Executed DMMA warp instructions per kernel from the SASS source page (the
+    smsp__sass_thread_inst_executed_op_dmma counter is not collected on this part)."""
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    out, cur, col_src, col_n = {}, None, None, None
+    for r in csv.reader(txt.splitlines()):
+        if not r:
+            continue
+        if r[0] == "Kernel Name":
+            cur = r[1].split("(")[0].split("::")[-1]
+            if cur in out:          # the page lists every kernel twice (two views of the same SASS): first one only
+                cur = None
+            else:
+                out[cur] = 0.0
+            continue
+        if "Instructions Executed" in r and "Source" in r:
+            col_src, col_n = r.index("Source"), r.index("Instructions Executed")
+            continue
+        if cur is None or col_src is None or len(r) <= col_n:
+            continue
+        ops = r[col_src].split()
+        if ops and (ops[0].startswith("DMMA") or (ops[0].startswith("@") and len(ops) > 1 and ops[1].startswith("DMMA"))):
+            try:
+                out[cur] += float(r[col_n])
+            except ValueError:
+                pass
+    return out
+
+
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     points = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
@@ -52,6 +94,7 @@ def main():
     scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0,
              "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
     kernels, lines = {}, []
+    dmma_warp = dmma_warp_instructions(rep)
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
         short = name.split("(")[0].split("::")[-1]
@@ -70,7 +113,7 @@ def main():
         dfma = m.get("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", 0.0)
         dmul = m.get("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", 0.0)
         dadd = m.get("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", 0.0)
-        dmma = m.get("smsp__sass_thread_inst_executed_op_dmma_pred_on.sum", 0.0)
+        dmma = m.get("smsp__sass_thread_inst_executed_op_dmma_pred_on.sum", 0.0) or 32.0*dmma_warp.get(short, 0.0)
         # DMMA m8n8k4: 8*8*4 FMA per warp instruction = 16 flop per thread instruction
         flop = 2.0*dfma + dmul + dadd + 16.0*dmma
         t = m.get("gpu__time_duration.sum", 0.0)
@@ -81,6 +124,8 @@ def main():
             "executed_fp64_flop": flop, "executed_fp64_flop_per_point": flop/points,
             "executed_tflops_under_ncu": flop/t/1e12 if t else None,
             "fp64_pipe_pct": m.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            "dmma_pipe_pct": m.get("sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active"),
+            "lsu_wavefront_pct": m.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
             "warps_active_pct": m.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
             "issue_active_pct": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "threads_per_inst": m.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
@@ -95,8 +140,9 @@ def main():
     open(out + ".txt", "w").write("\n".join(lines) + "\n")
     tot = sum(k["ncu_ms"] for k in kernels.values())
     for k, v in kernels.items():
-        print("%-22s %6.3f ms (%4.1f%%)  fp64 pipe %5.1f%%  exec %6.2f TF/s  flop/pt %.3g  dram %6.1f MB  thr/inst %.1f  warps %.0f%%" % (
-            k, v["ncu_ms"], 100*v["ncu_ms"]/tot, v["fp64_pipe_pct"] or 0, v["executed_tflops_under_ncu"] or 0,
+        print("%-22s %6.3f ms (%4.1f%%)  fp64 pipe %5.1f%%  dmma %4.1f%%  lsu %4.1f%%  exec %6.2f TF/s  flop/pt %.3g  dram %6.1f MB  thr/inst %.1f  warps %.0f%%" % (
+            k, v["ncu_ms"], 100*v["ncu_ms"]/tot, v["fp64_pipe_pct"] or 0, v.get("dmma_pipe_pct") or 0, v.get("lsu_wavefront_pct") or 0,
+            v["executed_tflops_under_ncu"] or 0,
             v["executed_fp64_flop_per_point"], ((v["dram_read_bytes"] or 0) + (v["dram_write_bytes"] or 0))/1e6,
             v["threads_per_inst"] or 0, v["warps_active_pct"] or 0))
 
