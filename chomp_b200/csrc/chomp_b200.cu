@@ -16,6 +16,7 @@
 #include "../../include/chomp_b200.h"
 #include "common.cuh"
 #include "covariance.cuh"
+#include "covariance_cross.cuh"
 #include "halo_tables.cuh"
 #include "halofit.cuh"
 #include "hankel.cuh"
@@ -55,13 +56,21 @@ namespace {
 int smem_opt_in_impl(const void* func, int device, size_t bytes, const char* name) {
     static std::mutex mu;
     static std::map<std::pair<const void*, int>, size_t> granted;
-    if (bytes <= 48 * 1024) return 0;
+    static std::map<std::pair<const void*, int>, size_t> static_bytes;
     std::lock_guard<std::mutex> lock(mu);
-    size_t& have = granted[std::make_pair(func, device)];
+    const auto key = std::make_pair(func, device);
+    if (!static_bytes.count(key)) {             // the 48 KB default covers static + dynamic shared memory together
+        cudaFuncAttributes attr;
+        CK(cudaFuncGetAttributes(&attr, func));
+        static_bytes[key] = attr.sharedSizeBytes;
+    }
+    const size_t fixed = static_bytes[key];
+    if (bytes + fixed <= 48 * 1024) return 0;
+    size_t& have = granted[key];
     if (bytes <= have) return 0;
-    if (bytes > 227 * 1024) {
+    if (bytes + fixed > 227 * 1024) {
         char buf[256];
-        snprintf(buf, sizeof buf, "%s needs %zu bytes of shared memory per CTA (limit 232448): table sizes too large", name, bytes);
+        snprintf(buf, sizeof buf, "%s needs %zu bytes of shared memory per CTA (limit 232448): table sizes too large", name, bytes + fixed);
         g_err = buf;
         return 2;
     }
@@ -131,6 +140,8 @@ struct Handle {
     std::vector<void*> allocs;
     // covariance scratch (allocated on first use, released with the rest in free_scratch)
     CovOut cov = {};
+    double* cov_proj4 = nullptr;     // [B, 4, 2, n_kernel] projected spectra a, b, ab, ba (cross-covariance)
+    int cov_proj4_points = 0;
     TriScratch cov_tri = {};
     int cov_points = 0, cov_bins = 0, cov_chunk = 0, cov_ntot = 0;
     bool kng_ready = false;
@@ -236,6 +247,7 @@ void free_scratch(Handle* h) {
     h->done_limber = h->done_mass = h->done_halo = h->done_params = 0;
     h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0; h->tri_chunk = 0;
     h->cov = CovOut{}; h->cov_tri = TriScratch{}; h->cov_points = 0; h->cov_bins = 0; h->cov_chunk = 0; h->cov_ntot = 0; h->kng_ready = false;
+    h->cov_proj4 = nullptr; h->cov_proj4_points = 0;
 }
 
 int check_cfg(const Cfg& c) {
@@ -1347,6 +1359,119 @@ static int covariance_impl(void* handle, int B, const chomp_b200_cov_params* p, 
     h->launches += 1;
     if (parts_out_dev)
         CK(cudaMemcpyAsync(parts_out_dev, h->cov.parts, sizeof(double) * (size_t)B * 3 * nb * nb, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// Covariance of two different correlations (covariance.py:23-683 with matching_corrs False).
+int chomp_b200_covariance_cross(void* handle_a, void* handle_b, void* handle_t, int B, const chomp_b200_cov_params* p,
+                                const double* bin_center_dev, const double* bin_delta_dev, const double* tri_z_dev,
+                                const double* cosmo_dev, const double* halo_a_dev, const double* hod_a_dev,
+                                const double* halo_b_dev, const double* hod_b_dev, const double* halo_t_dev,
+                                const double* hod_t_dev, double* cov_out_dev, double* parts_out_dev, int32_t* status_dev,
+                                void* stream) {
+    Handle* ha = (Handle*)handle_a;
+    Handle* hb = (Handle*)handle_b;
+    Handle* ht = handle_t ? (Handle*)handle_t : ha;
+    if (!ha || !hb) FAIL("null handle");
+    if (ha == hb) FAIL("the two correlations need a handle each (for one correlation use chomp_b200_covariance)");
+    if (ht == hb) FAIL("the trispectrum runs on handle_a or on a handle of its own");
+    if (int rc = ensure(ha, B)) return rc;
+    if (int rc = ensure(hb, B)) return rc;
+    if (ht != ha) { if (int rc = ensure(ht, B)) return rc; }
+    if (!p || !bin_center_dev || !bin_delta_dev || !cov_out_dev || !cosmo_dev) FAIL("null argument");
+    if (B > 65535) FAIL("covariance batches are limited to 65 535 points per call");
+    if (ha->device != hb->device || ha->device != ht->device) FAIL("the handles must live on one device");
+    const Cfg& c = ha->cfg;
+    const Cfg& cb = hb->cfg;
+    if (c.n_cosmo != cb.n_cosmo || c.n_window != cb.n_window || c.n_kernel != cb.n_kernel || c.n_halo != cb.n_halo ||
+        c.k_min != cb.k_min || c.k_max != cb.k_max || c.zk_min != cb.zk_min || c.zk_max != cb.zk_max ||
+        c.nq_limber != cb.nq_limber || c.window_precision != cb.window_precision)
+        FAIL("the two correlations must share table sizes, k limits and the MultiEpoch range");
+    if (ht->cfg.n_halo != c.n_halo || ht->cfg.k_min != c.k_min || ht->cfg.k_max != c.k_max || ht->cfg.n_mass != c.n_mass)
+        FAIL("the trispectrum handle must share the halo table sizes and k limits");
+    if (int rc = check_cov(ha, *p)) return rc;
+    if (cb.bessel_order != 0) FAIL("covariance is defined for the J0 kernel");
+    const bool want_ng = p->nongaussian && !p->poisson_only;
+    if (want_ng && ht->cfg.tri_moment < 0) FAIL("the non-Gaussian term needs the trispectrum: configure its handle with tri_moment >= 0");
+    if (2 * (size_t)ha->edge_stride > COV_MAX_EDGES) FAIL("window / cosmology tables too fine for the covariance kernels");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = p->n_bins;
+    ha->spans.clear(); ha->ev_used = 0; ha->open_span = -1;
+    if (status_dev) CK(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * (size_t)B, s));
+    if (int rc = cov_reserve(ha, B, nb, cov_ng_nodes(c, *p))) return rc;
+    if (B > ha->cov_proj4_points) {
+        CK(cudaDeviceSynchronize());
+        ha->cov_proj4_points = 0;
+        if (int rc = dev_regrow(ha, &ha->cov_proj4, (size_t)B * 8 * c.n_kernel)) return rc;
+        ha->cov_proj4_points = B;
+    }
+    CK(cudaMemsetAsync(ha->cov.parts, 0, sizeof(double) * (size_t)B * 3 * nb * nb, s));
+    if (int rc = chomp_b200_limber_tables(handle_a, B, cosmo_dev, status_dev, stream)) return rc;
+    if (int rc = chomp_b200_limber_tables(handle_b, B, cosmo_dev, status_dev, stream)) return rc;
+    if (!p->poisson_only) {
+        const size_t smem4 = limber_stage4_doubles(c) * sizeof(double);
+        if (want_ng) {
+            SMEM_OPT_IN(cov_kng_cross_kernel, ha, smem4);
+            dim3 grid(c.n_kernel, B);
+            cov_kng_cross_kernel<<<grid, COV_THREADS, smem4, s>>>(c, cb, *p, B, limber_view(ha), limber_view(hb), ha->cov);
+            CK(cudaGetLastError());
+            cov_kng_spline_kernel<<<B, COV_THREADS, 0, s>>>(c, *p, B, ha->cov, status_dev);
+            CK(cudaGetLastError());
+            ha->launches += 2;
+            ha->kng_ready = true;
+            // the trispectrum object: its own halo / HOD parameters at its own redshift (covariance.py:146-149, 258)
+            if (int rc = chomp_b200_mass_tables(ht, B, cosmo_dev, halo_t_dev ? halo_t_dev : halo_a_dev,
+                                                tri_z_dev ? tri_z_dev : ha->cov.zbar_ng, status_dev, stream)) return rc;
+            const double* hod_t = hod_t_dev ? hod_t_dev : hod_a_dev;
+            if (hod_t != ht->hod)
+                CK(cudaMemcpyAsync(ht->hod, hod_t, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
+            NodesOut no = nodes_view(ht);
+            SMEM_OPT_IN(nu_nodes_kernel, ht, nodes_smem(ht->cfg));
+            nu_nodes_kernel<<<B, 128, nodes_smem(ht->cfg), s>>>(ht->cfg, B, ht->halo, ht->hod, ht->epoch, ht->lnm_nodes, ht->nu_nodes,
+                                                              ht->c_lnm_nu, ht->c_nu_lnm, no, status_dev, nullptr, nullptr);
+            CK(cudaGetLastError());
+            ht->launches += 1;
+            if (int rc = chomp_b200_trispectrum_1h(ht, B, nullptr, stream)) return rc;
+        }
+        // the two-point halo models at their own z_bar (covariance.py:455-470)
+        if (int rc = chomp_b200_mass_tables(handle_a, B, cosmo_dev, halo_a_dev, nullptr, status_dev, stream)) return rc;
+        if (c.use_halofit) { if (int rc = chomp_b200_halofit(handle_a, B, p->halofit_z, nullptr, status_dev, stream)) return rc; }
+        if (int rc = chomp_b200_halo_tables(handle_a, B, ha->halo, hod_a_dev, status_dev, stream)) return rc;
+        if (int rc = chomp_b200_mass_tables(handle_b, B, cosmo_dev, halo_b_dev, nullptr, status_dev, stream)) return rc;
+        if (cb.use_halofit) { if (int rc = chomp_b200_halofit(handle_b, B, p->halofit_z, nullptr, status_dev, stream)) return rc; }
+        if (int rc = chomp_b200_halo_tables(handle_b, B, hb->halo, hod_b_dev, status_dev, stream)) return rc;
+        HaloSide sa{ha->cosmo, ha->epoch, ha->htab, ha->hcoef, c.use_halofit ? ha->hfit : nullptr, c.extrapolate};
+        HaloSide sb{hb->cosmo, hb->epoch, hb->htab, hb->hcoef, cb.use_halofit ? hb->hfit : nullptr, cb.extrapolate};
+        SMEM_OPT_IN(cov_projected_cross_kernel, ha, smem4);
+        dim3 gp(4, B);
+        cov_projected_cross_kernel<<<gp, 128, smem4, s>>>(c, *p, B, limber_view(ha), limber_view(hb), sa, sb, ha->cov_proj4, status_dev);
+        CK(cudaGetLastError());
+        dim3 gg(nb, B);
+        cov_g_cross_kernel<<<gg, COV_THREADS, 0, s>>>(c, *p, B, limber_view(ha), limber_view(hb), bin_center_dev, ha->cov_proj4, ha->cov);
+        CK(cudaGetLastError());
+        ha->launches += 2;
+        if (want_ng) {
+            const int ntot = cov_ng_nodes(c, *p);
+            const size_t ng_smem = (2 * (size_t)c.n_kernel * c.n_kernel + ntot + 2 * (size_t)nb * c.n_kernel + c.n_kernel) * sizeof(double);
+            if (ng_smem > 200 * 1024) FAIL("covariance: n_bins x kernel_npoints too large for the non-Gaussian kernel");
+            SMEM_OPT_IN(cov_ng_kernel, ha, ng_smem);
+            for (int b0 = 0; b0 < B; b0 += ha->cov_chunk) {
+                const int n = (B - b0 < ha->cov_chunk) ? B - b0 : ha->cov_chunk;
+                cov_tri_nodes_kernel<<<n, COV_THREADS, 0, s>>>(c, *p, b0, n, ht->tri_T, ha->cov.d_ng, ha->cov_tri);
+                CK(cudaGetLastError());
+                dim3 gn(nb, n);
+                cov_ng_kernel<<<gn, COV_THREADS, ng_smem, s>>>(c, *p, b0, n, bin_center_dev, ha->cov_tri.tw, ha->cov);
+                CK(cudaGetLastError());
+                ha->launches += 2;
+            }
+        }
+    }
+    const size_t tot = (size_t)B * nb * nb;
+    cov_finish_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(*p, B, bin_center_dev, bin_delta_dev, ha->cov, cov_out_dev, status_dev);
+    CK(cudaGetLastError());
+    ha->launches += 1;
+    if (parts_out_dev)
+        CK(cudaMemcpyAsync(parts_out_dev, ha->cov.parts, sizeof(double) * (size_t)B * 3 * nb * nb, cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 

@@ -520,6 +520,29 @@ class Engine(object):
             self._p(halo), self._p(hod), self._p(out), self._p(pt), self._p(status), self._stream()))
         return (out, pt) if parts else out
 
+    def covariance_cross(self, other, cosmo, halo_a, hod_a, halo_b, hod_b, setup, tri_engine=None, halo_t=None, hod_t=None,
+                         tri_z=None, status=None, parts=False):
+        """Covariance between the correlation configured on this engine (a) and the one on `other` (b) for every
+        point (covariance.py:60-63, matching_corrs False): [B, n_bins, n_bins] (and [B, 3, n, n] = P, G, NG).
+        `tri_engine`: the engine configured for the trispectrum object (default: this one), `halo_t` / `hod_t` its
+        own parameters (default: those of correlation a)."""
+        cosmo = self._dev(cosmo, _lib.N_COSMO)
+        halo_a, hod_a = self._dev(halo_a, _lib.N_HALO), self._dev(hod_a, _lib.N_HOD)
+        halo_b, hod_b = self._dev(halo_b, _lib.N_HALO), self._dev(hod_b, _lib.N_HOD)
+        halo_t = None if halo_t is None else self._dev(halo_t, _lib.N_HALO)
+        hod_t = None if hod_t is None else self._dev(hod_t, _lib.N_HOD)
+        B, nb = cosmo.shape[0], setup.bins.shape[0]
+        centre = self._dev(np.ascontiguousarray(setup.bins[:, 2]))
+        delta = self._dev(np.ascontiguousarray(setup.bins[:, 3]))
+        zt = None if tri_z is None else self._dev(np.broadcast_to(np.asarray(tri_z, dtype=np.float64), (B,)).copy())
+        out = self._new(B, nb, nb)
+        pt = self._new(B, 3, nb, nb) if parts else None
+        _lib.check(self.lib.chomp_b200_covariance_cross(
+            self._h, other._h, None if tri_engine is None else tri_engine._h, B, ctypes.byref(setup.params), self._p(centre),
+            self._p(delta), self._p(zt), self._p(cosmo), self._p(halo_a), self._p(hod_a), self._p(halo_b), self._p(hod_b),
+            self._p(halo_t), self._p(hod_t), self._p(out), self._p(pt), self._p(status), self._stream()))
+        return (out, pt) if parts else out
+
     def set_params(self, cosmo=None, halo=None, hod=None):
         arrs = [None if a is None else self._dev(a, n) for a, n in
                 ((cosmo, _lib.N_COSMO), (halo, _lib.N_HALO), (hod, _lib.N_HOD))]

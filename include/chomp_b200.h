@@ -288,6 +288,20 @@ int chomp_b200_covariance(void* handle, int B, const chomp_b200_cov_params* p, c
                           const double* halo_dev, const double* hod_dev, double* cov_out_dev, double* parts_out_dev,
                           int32_t* status_dev, void* stream);
 
+/* Covariance between two DIFFERENT correlations (covariance.py:60-63 ``matching_corrs`` False; the off-diagonal
+ * blocks of covariance.CovarianceMulti, covariance.py:794-871).  handle_a / handle_b are configured with the windows
+ * and the halo model (HOD kind, exclusion, HaloFit) of correlation a / b and share table sizes, k limits and the
+ * MultiEpoch range; handle_t (NULL: handle_a) is configured with the trispectrum object's HOD kind and tri_moment.
+ * K_NG uses all four windows (kernel.py:1102-1111), the Gaussian term the four projected spectra P_a, P_b, P_ab,
+ * P_ba (covariance.py:421-453, 455-591); the Poisson term vanishes (covariance.py:313-315).  halo_t_dev / hod_t_dev:
+ * the trispectrum object's own parameters (NULL: those of correlation a).  Outputs as chomp_b200_covariance. */
+int chomp_b200_covariance_cross(void* handle_a, void* handle_b, void* handle_t, int B, const chomp_b200_cov_params* p,
+                                const double* bin_center_dev, const double* bin_delta_dev, const double* tri_z_dev,
+                                const double* cosmo_dev, const double* halo_a_dev, const double* hod_a_dev,
+                                const double* halo_b_dev, const double* hod_b_dev, const double* halo_t_dev,
+                                const double* hod_t_dev, double* cov_out_dev, double* parts_out_dev, int32_t* status_dev,
+                                void* stream);
+
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 long long chomp_b200_launch_count(void* handle);
 

@@ -98,3 +98,28 @@ def py2_lt(a, b):
 def py2_gt(a, b):
     """``a > b`` with Python 2's ordering of None below every number (correlation.py:106)."""
     return py2_lt(b, a)
+
+
+_PY2_CORRELATION_KEY_ORDER = ("D_z", "kernel", "_ln_k_max", "power_spec", "log_theta_min", "log_theta_max", "theta_array",
+                              "wtheta_array", "_ln_k_min", "halo")
+
+
+def py2_corr_eq(a, b):
+    """``a == b`` for two Correlation objects as CPython 2.7 evaluates correlation.py:125-133: the __dict__s are
+    compared value by value in the hash order of a 64-bit CPython 2.7 dictionary holding Correlation's attribute
+    names (the order above, from the string hash and the open-addressing probe sequence), stopping at the first
+    unequal value -- so different correlations compare unequal at 'D_z' or 'kernel', before any array is reached."""
+    if a is b:
+        return True
+    if not isinstance(b, a.__class__):
+        return False
+    da, db = a.__dict__, b.__dict__
+    if len(da) != len(db):
+        return False
+    keys = [k for k in _PY2_CORRELATION_KEY_ORDER if k in da] + [k for k in da if k not in _PY2_CORRELATION_KEY_ORDER]
+    for k in keys:
+        if k not in db:
+            return False
+        if not bool(da[k] == db[k]):
+            return False
+    return True

@@ -28,7 +28,12 @@ also hold for the generated copy):
 7. correlation.py:106 ``(k_min < self.halo._k_min or k_max > self.halo._k_max)`` ->
    ``(_py2compat.py2_lt(k_min, ...) or _py2compat.py2_gt(k_max, ...))``: Python 2 orders None
    below every number instead of raising TypeError.
-8. kernel.py:606,608 debug ``.write('test_window_*')`` calls are left alone
+8. covariance.py:60 ``if self.corr_a == self.corr_b:`` -> ``if _py2compat.py2_corr_eq(self.corr_a, self.corr_b):``.
+   Correlation.__eq__ (correlation.py:125-133) compares the objects' __dict__s.  CPython 2.7 walks the left
+   dictionary in hash order -- 'D_z', 'kernel', ... for a Correlation (restated in _py2compat) -- and stops at
+   the first unequal value, so two different correlations compare unequal at 'D_z' / 'kernel'; Python 3 walks in
+   insertion order, reaches the theta arrays first and raises ValueError.
+9. kernel.py:606,608 debug ``.write('test_window_*')`` calls are left alone
    (they are the reference's behaviour) -- callers chdir to a temp dir.
 """
 import os
@@ -79,6 +84,8 @@ def transform(name, text):
         if name == "correlation.py" and "(k_min < self.halo._k_min or k_max > self.halo._k_max)):" in line:
             line = line.replace("(k_min < self.halo._k_min or k_max > self.halo._k_max)",
                                 "(_py2compat.py2_lt(k_min, self.halo._k_min) or _py2compat.py2_gt(k_max, self.halo._k_max))")
+        if name == "covariance.py" and line.strip() == "if self.corr_a == self.corr_b:":
+            line = line.replace("self.corr_a == self.corr_b", "_py2compat.py2_corr_eq(self.corr_a, self.corr_b)")
         if (not injected and (line.startswith("import ") or
                               line.startswith("from ")) and
                 "__future__" not in line):

@@ -121,3 +121,31 @@ def interp_table():
     on [0.02, 1.7] (unnormalised, as a photometric-redshift histogram would be)."""
     z = np.linspace(0.02, 1.7, 25)
     return z, z*z*np.exp(-(z/0.45)**1.5)
+
+
+def oracle_covariance_cross(cosmo, halo, hod_a, hod_b, dist_a, dist_b, hod_t=None, theta_deg=(0.01, 1.0), bins_per_decade=5.0,
+                            tri_spec="power_gggg", cov_spec="power_gg", tri_z=None, area_deg2=25.0, n_a=(1e10, 1e10),
+                            n_b=(1e10, 1e10), variance=1.0, prec=None, integ=None):
+    """Covariance between two DIFFERENT galaxy-clustering correlations (Gaussian dN/dz `dist_a` / `dist_b`, HODs
+    `hod_a` / `hod_b`) through the oracle; the trispectrum object carries `hod_t` (default `hod_a`)."""
+    from oracle import covariance_oracle as CO
+    prec = prec or O.precision()
+    integ = integ or Tight(16)
+    cm = O.MultiEpoch(0.0, 5.0, cosmo, prec, integ)
+
+    def make_corr(dist, hod):
+        d = O.dNdzGaussian(*dist, prec=prec, integ=integ)
+        kern = O.Kernel(1e-6*D2R, 100*D2R, O.WindowFunctionGalaxy(d, cm), O.WindowFunctionGalaxy(d, cm), cm)
+
+        def factory(z):
+            se = O.SingleEpoch(z, cosmo, prec, integ)
+            return O.Halo(se, O.MassFunction(se, halo), O.HODZheng(hod, prec["halo_precision"]), halo)
+        return O.Correlation(theta_deg[0], theta_deg[1], kern, factory, cov_spec, bins_per_decade=bins_per_decade)
+
+    corr_a, corr_b = make_corr(dist_a, hod_a), make_corr(dist_b, hod_b)
+    cov = CO.Covariance(corr_a, theta_deg, bins_per_decade, area_deg2, n_a, n_b, variance, True, None, cov_spec, corr_b=corr_b)
+    zt = cov.kernel.z_bar_NG if tri_z is None else tri_z
+    se = O.SingleEpoch(zt, cosmo, prec, integ)
+    cov.tri = O.HaloTrispectrumOneHalo(se, O.MassFunction(se, halo), O.HODZheng(hod_t or hod_a, prec["halo_precision"]), halo,
+                                       power_spec=tri_spec)
+    return cov

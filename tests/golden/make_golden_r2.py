@@ -52,7 +52,64 @@ def k_limits(R):
     return out
 
 
-SECTIONS = {"k_limits": k_limits}
+HOD_DICT_B = {"log_M_min": 12.5, "sigma": 0.25, "log_M_0": 12.5, "log_M_1p": 13.8, "alpha": 1.1}
+CROSS = {"theta_deg": (0.01, 1.0), "tri_z": 0.5, "area_deg2": 25.0, "n_a": [1e10, 1e10], "n_b": [1e10, 1e10], "variance": 1.0,
+         "dist_a": (0.0, 2.0, 0.5, 0.1), "dist_b": (0.0, 2.0, 0.6, 0.1), "hod_b": HOD_DICT_B}
+
+
+def cross_cov(R):
+    """covariance.Covariance between two DIFFERENT correlations (covariance.py:60-63 matching_corrs False): galaxy
+    clustering of two overlapping redshift slices with different HODs, power_gg, 1-halo trispectrum gggg; and the
+    2 x 2 block matrix of CovarianceMulti (covariance.py:794-871; its blocks use the default power_mm)."""
+    import importlib
+    import time
+    covariance = importlib.import_module("covariance")
+    t0 = time.time()
+    c = CROSS
+
+    def make_corr(dist_args, hod_dict):
+        kern = make_kernel(R, dist_args[2], dist_args[3])
+        h = R["halo"].Halo(input_hod=R["hod"].HODZheng(hod_dict), cosmo_single_epoch=R["cosmology"].SingleEpoch(0.0, cosmo_dict=C_DICT),
+                           halo_dict=H_DICT)
+        return R["correlation"].Correlation(c["theta_deg"][0], c["theta_deg"][1], kern, bins_per_decade=5.0, input_halo=h,
+                                            power_spec="power_gg")
+
+    def make_tri():
+        cs_t = R["cosmology"].SingleEpoch(c["tri_z"], cosmo_dict=C_DICT)
+        mf_t = R["mass_function"].MassFunction(c["tri_z"], cs_t, H_DICT)
+        return R["halo_trispectrum"].HaloTrispectrumOneHalo(c["tri_z"], cs_t, mf_t, None, H_DICT, R["hod"].HODZheng(HOD_DICT), "power_gggg")
+
+    corr_a, corr_b = make_corr(c["dist_a"], HOD_DICT), make_corr(c["dist_b"], c["hod_b"])
+    tri = make_tri()
+    cov = covariance.Covariance(corr_a, corr_b, bins_per_decade=5.0, survey_area_deg2=c["area_deg2"], n_a=c["n_a"], n_b=c["n_b"],
+                                variance=c["variance"], nongaussian_cov=True, input_halo_trispectrum=tri, power_spec="power_gg")
+    bins = cov.annular_bins
+    n = len(bins)
+    G, NG = np.zeros((n, n)), np.zeros((n, n))
+    for i in range(n):
+        for j in range(i, n):
+            a, b = bins[i], bins[j]
+            G[i, j] = G[j, i] = cov.covariance_G(a.center, b.center, a.delta, b.delta)
+            NG[i, j] = NG[j, i] = cov.covariance_NG(a.center, b.center)
+        print("cross row", i, "of", n, "%.0f s" % (time.time() - t0), flush=True)
+    total = np.asarray(cov.get_covariance(), dtype=float)
+    out = {"config": {k: (list(v) if isinstance(v, tuple) else v) for k, v in c.items()},
+           "matching_corrs": bool(cov.matching_corrs), "equal_windows": [bool(x) for x in cov.equal_windows],
+           "cosmic_shear": [bool(x) for x in cov.cosmic_shear], "z_bar_a": float(corr_a.kernel.z_bar), "z_bar_b": float(corr_b.kernel.z_bar),
+           "z_bar_NG": float(cov.kernel.z_bar_NG), "bins_center": arr([b.center for b in bins]),
+           "kernel_NG_table": arr(np.asarray(cov.kernel._kernel_array, dtype=float)),
+           "cov_G": arr(G), "cov_NG": arr(NG), "cov": arr(total),
+           "proj": {k: arr(getattr(cov, "_halo_%s_spline" % k)(cov._ln_K_array)) for k in ("a", "b", "ab", "ba")},
+           "ln_K": arr(cov._ln_K_array)}
+    # CovarianceMulti over the same two correlations, Gaussian + Poisson only (its non-Gaussian blocks repeat the above)
+    multi = covariance.CovarianceMulti([corr_a, corr_b], bins_per_decade=5.0, survey_area_deg2=c["area_deg2"], n_a=c["n_a"],
+                                       n_b=c["n_b"], variance=c["variance"], nongaussian_cov=False, input_halo_trispectrum=tri)
+    out["multi_gaussian"] = arr(np.asarray(multi.get_covariance(), dtype=float))
+    out["seconds"] = time.time() - t0
+    return out
+
+
+SECTIONS = {"k_limits": k_limits, "cross_cov": cross_cov}
 
 
 def main():

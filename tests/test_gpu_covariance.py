@@ -167,5 +167,6 @@ def test_drop_in_covariance_class():
     assert cov.covariance(a, b) == total[2, 6]
     assert cov.covariance_NG(a.center, b.center) == pytest.approx(ref_ng[2, 6], rel=2e-3)
     assert cov.covariance_P(a.delta, a.center) == pytest.approx(np.array(gold["cov_P"]).reshape(n, n)[2, 2], rel=1e-12)
-    with pytest.raises(NotImplementedError):
-        covariance.Covariance(corr, correlation.Correlation(THETA[0], THETA[1], kern, input_halo=h), input_halo_trispectrum=tri)
+    # two different correlations: tests/test_gpu_cross_covariance.py
+    other = covariance.Covariance(corr, correlation.Correlation(THETA[0], THETA[1], kern, input_halo=h), input_halo_trispectrum=tri)
+    assert not other.matching_corrs

@@ -8,7 +8,9 @@ import pytest
 
 from oracle.quadrature import Romberg
 
-from common import C_DICT, H_DICT, HOD_DICT, oracle_wtheta, w_err
+import numpy as np
+
+from common import C_DICT, H_DICT, HOD_DICT, oracle_covariance_cross, oracle_wtheta, w_err
 
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_r2.json")))
 
@@ -21,3 +23,25 @@ def test_oracle_k_limits_match_reference_run(key):
                       theta_deg=(0.01, 1.0), integ=Romberg(), **g["args"])
     assert bool(r["halo"].extrapolate) == g["extrapolate"]
     assert w_err(r["w"], g["w"]) < 1e-11
+
+
+def test_oracle_cross_covariance_matches_reference_run():
+    """covariance.Covariance between two different correlations (covariance.py:60-63, 421-453, 455-591): the oracle
+    with the reference's Romberg rule against the committed run of the reference."""
+    g = GOLD["cross_cov"]
+    cfg = g["config"]
+    oc = oracle_covariance_cross(C_DICT, H_DICT, HOD_DICT, cfg["hod_b"], tuple(cfg["dist_a"]), tuple(cfg["dist_b"]),
+                                 theta_deg=tuple(cfg["theta_deg"]), tri_z=cfg["tri_z"], area_deg2=cfg["area_deg2"], n_a=cfg["n_a"],
+                                 n_b=cfg["n_b"], variance=cfg["variance"], integ=Romberg())
+    assert oc.kernel.z_bar_NG == pytest.approx(g["z_bar_NG"], rel=1e-13)
+    assert oc.equal_windows == g["equal_windows"] and oc.cosmic_shear == g["cosmic_shear"]
+    oc.projected_table()
+    for key, got in (("a", oc.proj_nodes), ("b", oc.proj_nodes_b), ("ab", oc.proj_nodes_ab), ("ba", oc.proj_nodes_ba)):
+        ref = np.array(g["proj"][key])
+        assert np.max(np.abs(got - ref)) < 1e-11*np.max(np.abs(ref)), key
+    n = len(g["bins_center"])
+    # three bin pairs of each term (the whole matrix takes the Romberg rule a minute)
+    for i, j in ((0, 0), (2, 6), (9, 9)):
+        a, b = oc.bins[i][2], oc.bins[j][2]
+        assert oc.covariance_G(a, b) == pytest.approx(np.array(g["cov_G"]).reshape(n, n)[i, j], rel=1e-10)
+        assert oc.covariance_NG(a, b) == pytest.approx(np.array(g["cov_NG"]).reshape(n, n)[i, j], rel=1e-10)
