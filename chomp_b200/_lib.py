@@ -55,7 +55,7 @@ class Config(ctypes.Structure):
         ("hod_kind", ctypes.c_int32), ("bessel_order", ctypes.c_int32),
         ("exclusion", ctypes.c_int32), ("extrapolate", ctypes.c_int32),
         ("window_kind", ctypes.c_int32*2), ("dndz_kind", ctypes.c_int32*2),
-        ("tri_moment", ctypes.c_int32), ("use_halofit", ctypes.c_int32), ("reserved_i", ctypes.c_int32*1),
+        ("tri_moment", ctypes.c_int32), ("use_halofit", ctypes.c_int32), ("with_bao", ctypes.c_int32),
         ("halo_precision", ctypes.c_double), ("cosmo_precision", ctypes.c_double),
         ("window_precision", ctypes.c_double),
         ("k_min", ctypes.c_double), ("k_max", ctypes.c_double),

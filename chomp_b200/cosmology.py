@@ -2,8 +2,8 @@
 and MultiEpoch (cosmology.py:731-1164), numerics on the GPU.
 
 Supported: flat / open / closed LCDM with w0 = -1, wa = 0 and the no-wiggle
-Eisenstein-Hu transfer function (with_bao=False).  Dynamical dark energy and
-with_bao=True raise NotImplementedError.
+Eisenstein-Hu transfer function, without or with baryon wiggles (with_bao, cosmology.py:474-538; as in the
+reference set_cosmology resets it, Q16).  Dynamical dark energy raises NotImplementedError.
 Reference quirks kept: growth is the Carroll et al. closed form
 (cosmology.py:215-231, 326), E0 has no curvature term (:175-178), the
 Python-2 integer exponent in the transfer function (:464).
@@ -14,8 +14,6 @@ from . import _facade, _lib, defaults
 
 
 def _check(cosmo_dict, with_bao):
-    if with_bao:
-        raise NotImplementedError("with_bao=True (Eisenstein-Hu wiggle transfer) is not on the GPU path")
     if cosmo_dict["w0"] != -1.0 or cosmo_dict["wa"] != 0.0:
         raise NotImplementedError("w0 != -1 / wa != 0 is not on the GPU path")
 
@@ -52,7 +50,7 @@ class SingleEpoch(object):
     def _initialize_defaults(self):
         """cosmology.py:93-119: chi(z), growth, sigma_norm -- one launch of the
         mass-tables stage for this point."""
-        self._gpu.configure(_facade.base_config())
+        self._gpu.configure(_facade.base_config(with_bao=int(bool(self._with_bao))))     # cosmology.py:556-571
         self._gpu.eng.mass_tables(_facade.cosmo_row(self.cosmo_dict),
                                   _facade.halo_row(defaults.default_halo_dict), [self._redshift])
         e = self._epoch = self._gpu.epoch()

@@ -91,7 +91,7 @@ class Covariance(object):
         h._ensure()
         cfg = corr.kernel._config()
         hc = h._gpu.eng.cfg
-        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit"):
+        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "with_bao"):
             setattr(cfg, name, getattr(hc, name))
         return cfg
 
@@ -118,9 +118,12 @@ class Covariance(object):
         cfg = self._config_for(corr)
         cfg.tri_moment = _lib.TRISPECTRUM_MOMENT.get(self.halo_tri.power_spec, 0)
         tri = self.halo_tri
-        if (tri.local_hod._kind != h.local_hod._kind or tri.local_hod._params() != h.local_hod._params() or
-                dict(tri.mass.halo_dict) != dict(h.mass.halo_dict)):
-            raise NotImplementedError("the trispectrum object must share the correlation's halo / HOD parameters")
+        if (self.nongaussian_cov and not self.poisson_noise_only and
+                (tri.local_hod._kind != h.local_hod._kind or tri.local_hod._params() != h.local_hod._params() or
+                 dict(tri.mass.halo_dict) != dict(h.mass.halo_dict))):
+            # a trispectrum object with halo / HOD parameters of its own: the two-handle path carries them (the same
+            # correlation on both handles gives the matching case's Gaussian term; the Poisson term is kept)
+            return self._evaluate_cross(matching=True)
         self._gpu.configure(cfg)
         setup = self._setup_for(cfg)
         setup.params.halofit_z = float(getattr(h, "_fit_redshift", -1.0))
@@ -136,7 +139,7 @@ class Covariance(object):
         self.D_z_NG = float(eng.table(_lib.T_D_NG, 1)[0, 0]) if setup.params.nongaussian and not setup.params.poisson_only else None
         self._centers = np.array([b.center for b in self.annular_bins])
 
-    def _evaluate_cross(self):
+    def _evaluate_cross(self, matching=False):
         """Two different correlations: one engine per correlation, a third for the trispectrum object."""
         ca, cb, tri = self.corr_a, self.corr_b, self.halo_tri
         ha, hb = ca.halo, cb.halo
@@ -153,11 +156,12 @@ class Covariance(object):
         self._gpu_t.configure(cfg_t)
         setup = self._setup_for(cfg_a)
         setup.params.halofit_z = float(getattr(ha, "_fit_redshift", getattr(hb, "_fit_redshift", -1.0)))
-        for i in range(6):                       # no window of one correlation is a window of the other
-            setup.params.poisson[i] = 0.0
+        if not matching:
+            for i in range(6):                   # no window of one correlation is a window of the other
+                setup.params.poisson[i] = 0.0
         conv = [w == _lib.WINDOW_CONVERGENCE for w in (cfg_a.window_kind[0], cfg_a.window_kind[1], cfg_b.window_kind[0],
                                                          cfg_b.window_kind[1])]
-        self.equal_windows = [False]*6
+        self.equal_windows = setup.equal_windows if matching else [False]*6
         self.density = setup.density
         self.cosmic_shear = [bool(conv[0]*conv[1] or conv[2]*conv[3]), bool(conv[0]*conv[3] or conv[1]*conv[2])]
         tri_z = None if getattr(self, "_tri_follows_z_bar_ng", False) else [float(tri._redshift)]

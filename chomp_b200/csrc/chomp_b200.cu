@@ -740,7 +740,8 @@ eval_kernel(const Cfg cfg, int what, int n, const double* __restrict__ x, double
     const double* e = cx.epoch;
     if (what == CHOMP_EVAL_SIGMA_R) {
         // one warp per abscissa
-        const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+        PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+        CHOMP_ATTACH_BAO(cfg, c, pk)
         const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         const int nw = (gridDim.x * blockDim.x) >> 5;
         for (int i = w; i < n; i += nw) {
@@ -755,7 +756,11 @@ eval_kernel(const Cfg cfg, int what, int n, const double* __restrict__ x, double
         const double v = x[i];
         double r = 0.0;
         switch (what) {
-            case CHOMP_EVAL_LINEAR_POWER: r = linear_power(make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]), v); break;
+            case CHOMP_EVAL_LINEAR_POWER: {
+                PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+                CHOMP_ATTACH_BAO(cfg, c, pk)
+                r = linear_power(pk, v);
+            } break;
             case CHOMP_EVAL_NU_OF_MASS: r = nu_of_lnm(t, log(v)); break;
             case CHOMP_EVAL_MASS_OF_NU: r = exp(mass_of_nu_ln(t, v)); break;
             case CHOMP_EVAL_F_NU: case CHOMP_EVAL_BIAS_NU: {

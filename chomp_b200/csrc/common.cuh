@@ -160,15 +160,23 @@ __device__ __forceinline__ double rho_bar_z(const Cosmo& c, double z) {
 // Eisenstein-Hu zero-baryon transfer function with the reference's Python-2
 // arithmetic (cosmology.py:449-472: (Omb2)**(3/4) has exponent 0) and the
 // dimensionless spectrum Delta^2(k) (cosmology.py:574-587).
+// Eisenstein & Hu (1998) transfer function WITH baryon wiggles (SingleEpoch(with_bao=True), cosmology.py:474-538):
+// the cosmology-level constants, built only when cfg.with_bao is set (CHOMP_ATTACH_BAO below)
+struct BaoParams {
+    double h, keq, s, ksilk, alpha_b, beta_b, alpha_c, beta_c, beta_node, fb, fc;
+};
+
 struct PkParams {
     double amp;      // delta_H^2 / h * growth^2 * sigma_norm^2
     double expo;     // 3 + n_scalar
     double ln_H0;
     double s, alpha, omh, theta;
+    const BaoParams* bao;   // non-null: the wiggle transfer function replaces the zero-baryon one
 };
 
 __device__ inline PkParams make_pk(const Cosmo& c, double growth, double sigma_norm) {
     PkParams p;
+    p.bao = nullptr;
     const double delta_H = 1.94e-5 * pow(c.om, -0.785 - 0.05 * log(c.om)) *
                            exp(-0.95 * (c.ns - 1.0) - 0.169 * (c.ns - 1.0) * (c.ns - 1.0));  // cosmology.py:83-85
     p.amp = delta_H * delta_H / c.h * growth * growth * sigma_norm * sigma_norm;
@@ -196,9 +204,63 @@ __device__ __forceinline__ double transfer_eh(const PkParams& p, double k) {
     return L0u / fma(fma(14.2, u, 731.0), q * q, L0u);
 }
 
+// Out of line, both of them: the wiggle form is a few hundred instructions of pow / log / sin that the default
+// path must not carry in its instruction stream.
+__device__ __noinline__ void make_bao(const Cosmo& c, BaoParams* b) {
+    const double theta = c.tcmb / 2.7, t2 = theta * theta, t4 = t2 * t2;
+    const double Oc = c.om - c.ob, h = c.h;
+    const double Oh2 = c.om * h * h, Obh2 = c.ob * h * h, ObO = c.ob / c.om;
+    const double zeq = 2.5e4 * Oh2 / t4;
+    const double keq = 7.46e-2 * Oh2 / t2;
+    double b1 = 0.313 * pow(Oh2, -0.419) * (1.0 + 0.607 * pow(Oh2, 0.674));
+    double b2 = 0.238 * pow(Oh2, 0.223);
+    const double zd = 1291.0 * (pow(Oh2, 0.251) / (1.0 + 0.659 * pow(Oh2, 0.828))) * (1.0 + b1 * pow(Obh2, b2));
+    const double Req = 31.5 * Obh2 / t4 * (1000.0 / zeq), Rd = 31.5 * Obh2 / t4 * (1000.0 / zd);
+    const double s = (2.0 / (3.0 * keq)) * sqrt(6.0 / Req) * log((sqrt(1.0 + Rd) + sqrt(Rd + Req)) / (1.0 + sqrt(Req)));
+    const double y = (1.0 + zeq) / (1.0 + zd), sy = sqrt(1.0 + y);
+    const double G = y * (-6.0 * sy + (2.0 + 3.0 * y) * log((sy + 1.0) / (sy - 1.0)));
+    b->h = h; b->keq = keq; b->s = s;
+    b->ksilk = 1.6 * pow(Obh2, 0.52) * pow(Oh2, 0.73) * (1.0 + pow(10.4 * Oh2, -0.95));
+    b->alpha_b = 2.07 * keq * s * pow(1.0 + Rd, -0.75) * G;
+    b->beta_b = 0.5 + ObO + (3.0 - 2.0 * ObO) * sqrt((17.2 * Oh2) * (17.2 * Oh2) + 1.0);
+    const double a1 = pow(46.9 * Oh2, 0.670) * (1.0 + pow(32.1 * Oh2, -0.532));
+    const double a2 = pow(12.0 * Oh2, 0.424) * (1.0 + pow(45.0 * Oh2, -0.582));
+    b->alpha_c = pow(a1, -ObO) * pow(a2, -ObO * ObO * ObO);
+    b1 = 0.944 / (1.0 + pow(458.0 * Oh2, -0.708));
+    b2 = pow(0.395 * Oh2, -0.0266);
+    b->beta_c = 1.0 / (1.0 + b1 * (pow(Oc / c.om, b2) - 1.0));
+    b->beta_node = 8.41 * pow(Oh2, 0.435);
+    b->fb = ObO; b->fc = Oc / c.om;
+}
+__device__ __noinline__ double transfer_bao(const BaoParams* b, double k) {
+    const double kh = k * b->h, ks = kh * b->s, q = kh / (13.41 * b->keq), q2 = q * q;
+    const double cq = 386.0 / (1.0 + 69.9 * pow(q, 1.08));
+    // T0~(k, a, beta) = L / (L + C q^2),  L = ln(e + 1.8 beta q),  C = 14.2 / a + 386 / (1 + 69.9 q^1.08)   (:513-516)
+    const double Lc = log(M_E + 1.8 * b->beta_c * q), L1 = log(M_E + 1.8 * q);
+    const double t_c1 = Lc / (Lc + (14.2 + cq) * q2), t_ca = Lc / (Lc + (14.2 / b->alpha_c + cq) * q2);
+    const double t_11 = L1 / (L1 + (14.2 + cq) * q2);
+    const double r = ks / 5.4, r2 = r * r, f = 1.0 / (1.0 + r2 * r2);
+    const double Tc = f * t_c1 + (1.0 - f) * t_ca;
+    const double bn = b->beta_node / ks;
+    const double stilde = b->s / cbrt(1.0 + bn * bn * bn);
+    const double Tb1 = t_11 / (1.0 + (ks / 5.2) * (ks / 5.2));
+    const double bb = b->beta_b / ks;
+    const double Tb2 = (b->alpha_b / (1.0 + bb * bb * bb)) * exp(-pow(kh / b->ksilk, 1.4));
+    const double x = k * stilde;                                   // k without the h that ks carries (cosmology.py:536)
+    const double sinc = (x == 0.0) ? 1.0 : sin(x) / x;
+    return b->fb * sinc * (Tb1 + Tb2) + b->fc * Tc;
+}
+__device__ __forceinline__ double transfer_any(const PkParams& p, double k) {
+    return p.bao ? transfer_bao(p.bao, k) : transfer_eh(p, k);
+}
+// after `PkParams pk = make_pk(...)`: hang the wiggle constants on it when the configuration asks for them
+#define CHOMP_ATTACH_BAO(cfg, cosmo_struct, pk_var)                         \
+    BaoParams pk_var##_bao_store;                                            \
+    if ((cfg).with_bao) { make_bao((cosmo_struct), &pk_var##_bao_store); (pk_var).bao = &pk_var##_bao_store; }
+
 // Delta^2(k) = k^3 P(k) / (2 pi^2)
 __device__ __forceinline__ double delta2(const PkParams& p, double k, double lnk) {
-    const double T = transfer_eh(p, k);
+    const double T = transfer_any(p, k);
     return p.amp * exp(p.expo * (lnk - p.ln_H0)) * T * T;
 }
 // P(k) (cosmology.py:589-600)

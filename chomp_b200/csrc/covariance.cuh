@@ -354,7 +354,8 @@ cov_projected_kernel(const Cfg cfg, const CovP cp, int B, LimberIn in, const dou
     LimberF F = limber_stage(cfg, in, b, dyn);
     const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
     const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
-    const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    CHOMP_ATTACH_BAO(cfg, c, pk)
     HaloTabs T;
     T.nk = cfg.n_halo; T.l0 = log(cfg.k_min); T.l1 = log(cfg.k_max); T.h = (T.l1 - T.l0) / (T.nk - 1);
     T.k_min = cfg.k_min; T.k_max = cfg.k_max; T.extrapolate = cfg.extrapolate;
@@ -430,7 +431,8 @@ cl_table_kernel(const Cfg cfg, int which, int B, int n_ell, const double* __rest
     LimberF F = limber_stage(cfg, in, b, dyn);
     const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
     const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
-    const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    CHOMP_ATTACH_BAO(cfg, c, pk)
     HaloTabs T;
     T.nk = cfg.n_halo; T.l0 = log(cfg.k_min); T.l1 = log(cfg.k_max); T.h = (T.l1 - T.l0) / (T.nk - 1);
     T.k_min = cfg.k_min; T.k_max = cfg.k_max; T.extrapolate = cfg.extrapolate;

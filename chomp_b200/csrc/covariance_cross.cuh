@@ -195,6 +195,11 @@ cov_projected_cross_kernel(const Cfg cfg, const CovP cp, int B, LimberIn ia, Lim
     PkParams pka, pkb;
     const HaloTabs Ta = halo_side_tabs(cfg, ha, b, pka, cfg.cosmo_precision);
     const HaloTabs Tb = halo_side_tabs(cfg, hb, b, pkb, cfg.cosmo_precision);
+    BaoParams bao_store;                 // one cosmology: both sides share the wiggle constants
+    if (cfg.with_bao) {
+        make_bao(load_cosmo(ha.cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision), &bao_store);
+        pka.bao = &bao_store; pkb.bao = &bao_store;
+    }
     const CrossRanges R = cross_ranges(cfg, ia, ib, b);
     // windows and chi range of this table (covariance.py:479-536)
     const int w1 = (t == 0 || t == 2) ? 0 : (t == 1 ? 2 : 1);

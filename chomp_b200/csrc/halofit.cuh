@@ -134,7 +134,8 @@ halofit_kernel(const Cfg cfg, int B, double fit_z, const double* __restrict__ co
     double* work = coef + 4 * n;       // max(2 n, 11 n + 6)
     const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
     const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
-    const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    CHOMP_ATTACH_BAO(cfg, c, pk)
     const double l0 = log(cfg.k_min), l1 = log(cfg.k_max);
     for (int idx = tid; idx < NQ; idx += blockDim.x) {
         const int p = idx / HF_NQ, q = idx - p * HF_NQ;
@@ -203,7 +204,8 @@ cl_kernel(const Cfg cfg, int B, int use_halofit, int n_ell, const double* __rest
     const int nz = cfg.n_cosmo, nwin = cfg.n_window, nq = cfg.nq_limber;
     const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
     const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
-    const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    CHOMP_ATTACH_BAO(cfg, c, pk)
     const double* hf = hfit + (size_t)b * HF_LEN;
     LimberF F;
     F.g.n = nz; F.g.z_min = cfg.zk_min < 0.0 ? 0.0 : cfg.zk_min; F.g.z_max = cfg.zk_max;

@@ -113,7 +113,8 @@ power_kernel(const Cfg cfg, int B, int which, int n_k, const double* __restrict_
     if (b >= B || i >= n_k) return;
     const Cosmo c = load_cosmo(cosmo + (size_t)b * CHOMP_N_COSMO, cfg.cosmo_precision);
     const double* e = epoch + (size_t)b * CHOMP_EPOCH_LEN;
-    const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    CHOMP_ATTACH_BAO(cfg, c, pk)
     HaloTabs T;
     T.nk = cfg.n_halo; T.l0 = log(cfg.k_min); T.l1 = log(cfg.k_max); T.h = (T.l1 - T.l0) / (T.nk - 1);
     T.k_min = cfg.k_min; T.k_max = cfg.k_max; T.extrapolate = cfg.extrapolate;
@@ -217,7 +218,8 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
     for (int i = tid; i < 4 * (nkt - 1); i += blockDim.x) s_kc[i] = kcoef[(size_t)gb * 4 * nkt + i];
     const Cosmo c = load_cosmo(cosmo + (size_t)gb * CHOMP_N_COSMO, cfg.cosmo_precision);
     const double* e = epoch + (size_t)gb * CHOMP_EPOCH_LEN;
-    const PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
+    CHOMP_ATTACH_BAO(cfg, c, pk)
     const double D = dbar[gb];
     const double inv_norm = 1.0 / (2.0 * M_PI * D * D);                 // correlation.py:270-275
     const double l0 = L.l0, l1 = L.l1, hP = L.hP;

@@ -259,12 +259,75 @@ __device__ __noinline__ double sigma2_partial(const D2& pk, double R, double lnR
     return acc;
 }
 
+// sigma^2(R) for a spectrum with baryon wiggles (SingleEpoch(with_bao=True), cosmology.py:474-538).  The wiggles
+// (period 2 pi / s ~ 0.06 h/Mpc in k) sit exactly where W^2(kR) has its weight and the tabulated x lattices above
+// cannot follow them: here the part below the split point is a plain composite rule in ln k -- pieces no wider than
+// SIG_FINE_DL, Gauss-Legendre 4, Delta^2 evaluated directly -- and the tail beyond it is the smooth-spectrum one.
+// About 2 000 nodes per call instead of 250: a variant, not the hot path.
+#define SIG_FINE_DL 0.02
+__device__ __noinline__ double sigma2_fine(const PkParams& pkp, double R, double lnR, const SigLim& lim, int rank, int size) {
+    const double k_min = lim.k_min, k_max = lim.k_max;
+    double k_lo = k_min, k_hi = k_max, ln_k_lo = lim.ln_k_min, ln_k_hi = lim.ln_k_max;
+    const double iR = 1.0 / R;
+    const double need_lo = iR / 10.0, need_hi = iR * 14.0662;           // cosmology.py:611-629
+    if (need_lo <= k_lo) {
+        if (need_lo > k_min / 100.0) { k_lo = need_lo; ln_k_lo = -2.3025850929940455 - lnR; }
+        else { k_lo = k_min / 100.0; ln_k_lo = lim.ln_k_min - 4.605170185988092; }
+    }
+    if (need_hi >= k_hi) {
+        if (need_hi < k_max * 100.0) { k_hi = need_hi; ln_k_hi = 2.643774756468092 - lnR; }
+        else { k_hi = k_max * 100.0; ln_k_hi = lim.ln_k_max + 4.605170185988092; }
+    }
+    const double x_hi = k_hi * R;
+    const double xs = fmin(R >= 8.0 ? 2.0 * SIG_XSPLIT : SIG_XSPLIT, x_hi);
+    const double l_lo = ln_k_lo + lnR, l_hi = ln_k_hi + lnR, l_s = (xs < x_hi) ? log(xs) : l_hi;   // in ln x
+    const int n_pan = (int)ceil((l_s - l_lo) / SIG_FINE_DL);
+    const double d = (l_s - l_lo) / n_pan;
+    double acc = 0.0;
+    for (int idx = rank; idx < 4 * n_pan; idx += size) {
+        const int p = idx >> 2, q = idx & 3;
+        const double lx = l_lo + d * (p + 0.5) + 0.5 * d * c_glx[4][q];
+        const double x = exp(lx);
+        acc += 0.5 * d * c_glw[4][q] * delta2(pkp, x * iR, lx - lnR) * tophat2(x);
+    }
+    if (x_hi > xs) {
+        // beyond the split point: the non-oscillatory part of W^2 on SIG_NTAIL geometric panels and the first-order
+        // end-point terms of the oscillatory part, as in sigma2_partial
+        for (int idx = rank; idx < SIG_NTAIL * SIG_NQ_S + 2; idx += size) {
+            double x, lnk, wgt, w2;
+            if (idx >= SIG_NTAIL * SIG_NQ_S) {
+                const bool top = idx == SIG_NTAIL * SIG_NQ_S;
+                x = top ? x_hi : xs;
+                lnk = (top ? l_hi : l_s) - lnR;
+                const double x2 = x * x;
+                double s2, c2;
+                sincos_reduced(2.0 * x, s2, c2);
+                w2 = 9.0 * (x2 - 1.0) / (2.0 * x2 * x2 * x2) * s2 + 9.0 / (x2 * x2 * x) * c2;
+                wgt = (top ? 0.5 : -0.5) / x;
+            } else {
+                const int jp = idx >> 3, q8 = idx & 7;
+                const double a = l_s + (l_hi - l_s) * jp / SIG_NTAIL, b = l_s + (l_hi - l_s) * (jp + 1) / SIG_NTAIL;
+                const double half = 0.5 * (b - a);
+                const double lx = 0.5 * (a + b) + half * c_glx[SIG_NQ_S][q8];
+                x = exp(lx);
+                lnk = lx - lnR;
+                wgt = half * c_glw[SIG_NQ_S][q8];
+                const double x2 = x * x;
+                w2 = 9.0 * (1.0 + x2) / (2.0 * x2 * x2 * x2);
+            }
+            acc += wgt * delta2(pkp, x * iR, lnk) * w2;
+        }
+    }
+    return acc;
+}
+
 // one full warp; result in every lane
 template <class D2>
 __device__ inline double warp_sigma2(const D2& pk, double R, double lnR, const SigLim& lim) {
     return warp_sum(sigma2_partial(pk, R, lnR, lim, threadIdx.x & 31, 32));
 }
 __device__ inline double warp_sigma2(const PkParams& pk, double R, double k_min, double k_max) {
+    if (pk.bao) return warp_sum(sigma2_fine(pk, R, log(R), make_siglim(k_min, k_max), threadIdx.x & 31, 32));
     return warp_sigma2(D2Direct{pk}, R, log(R), make_siglim(k_min, k_max));
 }
 
@@ -290,23 +353,27 @@ __device__ inline double team_sigma2(const Team& t, const D2& pk, double R, doub
     return team_sum(t, sigma2_partial(pk, R, lnR, lim, t.rank, TEAM_SIZE));
 }
 
+
 struct MassCtx {
+    const PkParams* fine;   // non-null: spectrum with baryon wiggles, every sigma(R) through sigma2_fine
     D2Table pk;
     SigLim lim;
     double delta_c, rho_bar;
     double ln_r_coef;      // ln(3 / (4 pi rho_bar)): ln R = (ln M + ln_r_coef) / 3  (cosmology.py:662-672)
 };
+// the share of thread `rank` of `size` in sigma^2(R), whichever rule the epoch asks for
+__device__ __forceinline__ double sigma2_share(const MassCtx& m, double R, double lnR, int rank, int size);
 
 // nu(M) = (delta_c / sigma(M))^2 from ln M, warp-collective (cosmology.py:662-699)
 __device__ inline double warp_nu_lm(const MassCtx& m, double lm) {
     const double lnR = (lm + m.ln_r_coef) * (1.0 / 3.0);
-    const double s2 = warp_sigma2(m.pk, exp_fast(lnR), lnR, m.lim);
+    const double s2 = warp_sum(sigma2_share(m, exp_fast(lnR), lnR, threadIdx.x & 31, 32));
     return m.delta_c * m.delta_c / s2;
 }
 // same, team-collective
 __device__ inline double team_nu_lm(const Team& t, const MassCtx& m, double lm) {
     const double lnR = (lm + m.ln_r_coef) * (1.0 / 3.0);
-    const double s2 = team_sigma2(t, m.pk, exp_fast(lnR), lnR, m.lim);
+    const double s2 = team_sum(t, sigma2_share(m, exp_fast(lnR), lnR, t.rank, TEAM_SIZE));
     return m.delta_c * m.delta_c / s2;
 }
 
@@ -376,6 +443,11 @@ __device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scal
     return j;
 }
 
+__device__ __forceinline__ double sigma2_share(const MassCtx& m, double R, double lnR, int rank, int size) {
+    if (m.fine) return sigma2_fine(*m.fine, R, lnR, m.lim, rank, size);
+    return sigma2_partial(m.pk, R, lnR, m.lim, rank, size);
+}
+
 struct MassOut {
     double* epoch;     // [B, CHOMP_EPOCH_LEN]
     double* lnm_nodes; // [B, n_mass]
@@ -416,7 +488,9 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     m.ln_r_coef = log(3.0 / (4.0 * M_PI * m.rho_bar));
     // Every sigma(R) is evaluated with sigma_norm = 1; nu scales as 1 / sigma_norm^2
     // (cosmology.py:118-119, 574-587).  Round 0: sigma_8, nu(1e9) and nu(1e16) on three warps.
-    const PkParams pk1 = make_pk(c, growth, 1.0);
+    PkParams pk1 = make_pk(c, growth, 1.0);
+    CHOMP_ATTACH_BAO(cfg, c, pk1)
+    m.fine = pk1.bao ? &pk1 : nullptr;
     {
         // ln Delta^2 table over every k the sigma(R) range rules can reach: [k_min / 100, 100 k_max]
         const double t0 = log(cfg.k_min / 100.0) - 0.05, t1 = log(cfg.k_max * 100.0) + 0.05;
@@ -425,7 +499,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         for (int j = tid; j < D2_TABLE_N; j += blockDim.x) {
             const double lk = t0 + th * j;
             // ln Delta^2 = ln amp + (3 + n)(ln k - ln H0) + 2 ln T(k): no exp / log round trip
-            d2tab[j] = ln_amp + pk1.expo * (lk - pk1.ln_H0) + 2.0 * log(transfer_eh(pk1, exp_fast(lk)));
+            d2tab[j] = ln_amp + pk1.expo * (lk - pk1.ln_H0) + 2.0 * log(transfer_any(pk1, exp_fast(lk)));
         }
         m.pk.tab = d2tab; m.pk.l0 = t0; m.pk.inv_h = 1.0 / th;
     }
@@ -441,7 +515,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         const int g_warps = fixed_limits ? nw : (grp == 0 ? 2 : 3);
         const double lnR = grp == 0 ? 2.0794415416798357 : (log(grp == 1 ? m_lo : m_hi) + m.ln_r_coef) * (1.0 / 3.0);
         const double R = grp == 0 ? 8.0 : exp_fast(lnR);
-        const double part = warp_sum(sigma2_partial(m.pk, R, lnR, m.lim, tid - 32 * g_first, 32 * g_warps));
+        const double part = warp_sum(sigma2_share(m, R, lnR, tid - 32 * g_first, 32 * g_warps));
         if (lane == 0) red[8 + w] = part;
     }
     __syncthreads();

@@ -64,7 +64,8 @@ class Halo(object):
         cfg = _facade.base_config(hod_kind=self.local_hod._kind, exclusion=self._exclusion,
                                   extrapolate=int(bool(self._extrapolate)),
                                   tri_moment=int(getattr(self, "_tri_moment", -1)),
-                                  use_halofit=int(self._halofit))
+                                  use_halofit=int(self._halofit),
+                                  with_bao=int(bool(getattr(self.cosmo, "_with_bao", False))))
         cfg.halo_precision = getattr(self.local_hod, "_halo_precision", cfg.halo_precision)
         # first_moment_zero was fixed when the HOD object was built (hod.py:176-179)
         self._gpu.configure(cfg)

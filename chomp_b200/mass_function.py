@@ -24,7 +24,7 @@ class MassFunction(object):
         h = self.halo_dict
         self.stq, self.st_little_a = h["stq"], h["st_little_a"]
         self.c0 = h["c0"]/(1.0 + self._redshift)
-        self._gpu.configure(_facade.base_config())
+        self._gpu.configure(_facade.base_config(with_bao=int(bool(getattr(self.cosmo, "_with_bao", False)))))
         self._gpu.eng.mass_tables(_facade.cosmo_row(self.cosmo.cosmo_dict), _facade.halo_row(h),
                                   [self._redshift])
         e = self._gpu.epoch()

@@ -70,7 +70,8 @@ typedef struct chomp_b200_config {
     int32_t tri_moment;       /* HaloTrispectrumOneHalo power_spec: 0 mmmm, 1 gmmm, 2 ggmm, 3 gggm, 4 gggg;
                                  -1: no trispectrum (its node list is then not built)              */
     int32_t use_halofit;      /* 1: HaloFit two-halo spectrum (halo.py:1236-1412); run chomp_b200_halofit first */
-    int32_t reserved_i[1];
+    int32_t with_bao;         /* 1: Eisenstein & Hu (1998) transfer function with baryon wiggles, SingleEpoch(with_bao=True)
+                                 (cosmology.py:474-538, 556-571); 0: the zero-baryon form (:449-472) */
     double halo_precision;    /* enters HODZheng.first_moment_zero (hod.py:176-179)      */
     double cosmo_precision;   /* flat/open/closed test (cosmology.py:65-79)              */
     double window_precision;  /* z / chi floor of the windows (kernel.py:236, 301, 612)  */

@@ -73,7 +73,8 @@ def _spline(x, y):
 # cosmology.SingleEpoch  (cosmology.py:25-729)
 # ----------------------------------------------------------------------------
 class SingleEpoch(object):
-    def __init__(self, z, cosmo=None, prec=None, integ=None, limits=None):
+    def __init__(self, z, cosmo=None, prec=None, integ=None, limits=None, with_bao=False):
+        self.with_bao = bool(with_bao)                    # cosmology.py:86, 556-571
         self.prec = prec or DEFAULT_PRECISION
         self.integ = integ or Romberg(self.prec["divmax"])
         self.limits = limits or DEFAULT_LIMITS
@@ -149,7 +150,9 @@ class SingleEpoch(object):
         return self.rho_crit()*self.omega_m()
 
     # cosmology.py:449-472 with the Python-2 exponent (3/4 == 0), Q1 and Q5
-    def transfer(self, k):
+    def transfer(self, k):                                # cosmology.py:556-571
+        if self.with_bao:
+            return self.transfer_bao(k)
         theta = self.tcmb/2.7
         omh2 = self.om*self.h**2
         ombh2 = self.ob*self.h**2
@@ -162,6 +165,50 @@ class SingleEpoch(object):
         L0 = np.log(2*np.e + 1.8*q)
         C0 = 14.2 + 731.0/(1 + 62.5*q)
         return L0/(L0 + C0*q*q)
+
+    def transfer_bao(self, k):                            # cosmology.py:474-538 (Eisenstein & Hu 1998 with wiggles)
+        k = np.asarray(k, dtype=float)
+        theta = self.tcmb/2.7
+        Ob, Om = self.ob, self.om
+        Oc, h = Om - Ob, self.h
+        Oh2, Obh2, ObO = Om*h**2, Ob*h**2, Ob/Om
+        zeq = 2.5e4*Oh2*theta**(-4)
+        keq = 7.46e-2*Oh2*theta**(-2)
+        b1 = 0.313*Oh2**(-0.419)*(1. + 0.607*Oh2**0.674)
+        b2 = 0.238*Oh2**0.223
+        zd = 1291.*(Oh2**0.251/(1. + 0.659*Oh2**0.828))*(1. + b1*Obh2**b2)
+
+        def R(z):
+            return 31.5*Obh2*theta**(-4)*(1000./z)
+        Req, Rd = R(zeq), R(zd)
+        s = (2./(3.*keq))*np.sqrt(6./Req)*np.log((np.sqrt(1. + Rd) + np.sqrt(Rd + Req))/(1. + np.sqrt(Req)))
+        ks = k*h*s
+        kSilk = 1.6*Obh2**0.52*Oh2**0.73*(1. + (10.4*Oh2)**(-0.95))
+        q = k*h/(13.41*keq)
+
+        def G(y):
+            return y*(-6.*np.sqrt(1. + y) + (2 + 3*y)*np.log((np.sqrt(1. + y) + 1.)/(np.sqrt(1. + y) - 1.)))
+        alpha_b = 2.07*keq*s*(1. + Rd)**(-3./4.)*G((1. + zeq)/(1. + zd))
+        beta_b = 0.5 + ObO + (3. - 2.*ObO)*np.sqrt((17.2*Oh2)**2 + 1.)
+
+        def T0t(a, b):                                    # :513-516 (both logarithms at the same k)
+            C = (14.2/a) + 386./(1. + 69.9*q**1.08)
+            L = np.log(np.e + 1.8*b*q)
+            return L/(L + C*q**2)
+        a1 = (46.9*Oh2)**0.670*(1. + (32.1*Oh2)**(-0.532))
+        a2 = (12.*Oh2)**0.424*(1. + (45.*Oh2)**(-0.582))
+        alpha_c = a1**(-ObO)*a2**(-ObO**3)
+        b1 = 0.944*(1. + (458.*Oh2)**(-0.708))**(-1)
+        b2 = (0.395*Oh2)**(-0.0266)
+        beta_c = 1./(1. + b1*((Oc/Om)**b2 - 1))
+        f = 1./(1. + (ks/5.4)**4)
+        Tc = f*T0t(1, beta_c) + (1. - f)*T0t(alpha_c, beta_c)
+        beta_node = 8.41*(Oh2**0.435)
+        stilde = s/(1. + (beta_node/ks)**3)**(1./3.)
+        Tb1 = T0t(1., 1.)/(1. + (ks/5.2)**2)
+        Tb2 = (alpha_b/(1. + (beta_b/ks)**3))*np.exp(-(k*h/kSilk)**1.4)
+        Tb = np.sinc(k*stilde/np.pi)*(Tb1 + Tb2)          # sin(k s~) / (k s~): k without the h that ks carries (:536)
+        return ObO*Tb + (Oc/Om)*Tc
 
     def delta_k(self, k):                                 # cosmology.py:574
         d = self.delta_H**2*(k/self.H0)**(3 + self.ns)*self.transfer(k)**2/self.h

@@ -38,7 +38,7 @@ def w_err(w, ref, floor=1e-3):
 
 def oracle_wtheta(cosmo, halo, hod, dist_a, dist_b=None, window_a="galaxy", window_b=None,
                   power_spec="power_gg", bins_per_decade=10.0, prec=None, integ=None,
-                  z_range=(0.0, 5.0), theta_deg=(0.001, 1.0), bessel_order=0, hod_kind="zheng", k_min=None, k_max=None):
+                  z_range=(0.0, 5.0), theta_deg=(0.001, 1.0), bessel_order=0, hod_kind="zheng", k_min=None, k_max=None, with_bao=False):
     """One parameter point through the oracle; returns a dict of every table."""
     prec = prec or O.precision()
     integ = integ or Tight(40)
@@ -62,7 +62,7 @@ def oracle_wtheta(cosmo, halo, hod, dist_a, dist_b=None, window_a="galaxy", wind
     hod_cls = O.HODZheng if hod_kind == "zheng" else O.HODMandelbaum
 
     def factory(z):
-        se = O.SingleEpoch(z, cosmo, prec, integ)
+        se = O.SingleEpoch(z, cosmo, prec, integ, with_bao=with_bao)
         mf = O.MassFunction(se, halo)
         return O.Halo(se, mf, hod_cls(hod, prec["halo_precision"]), halo)
 

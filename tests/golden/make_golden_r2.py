@@ -109,7 +109,39 @@ def cross_cov(R):
     return out
 
 
-SECTIONS = {"k_limits": k_limits, "cross_cov": cross_cov}
+def bao(R):
+    """SingleEpoch(with_bao=True) (cosmology.py:474-538): linear power, sigma(R), the mass function's nu nodes, the halo
+    model spectra and w_gg(theta) on top of the wiggle transfer function."""
+    out = {}
+    k = np.logspace(-3.5, 2.5, 120)
+    for z in (0.0, 0.5):
+        cs = R["cosmology"].SingleEpoch(z, cosmo_dict=C_DICT, with_bao=True)
+        out["z%.1f" % z] = {"k": arr(k), "linear_power": arr(cs.linear_power(k)), "sigma_norm": float(cs._sigma_norm),
+                            "sigma_r": arr([cs.sigma_r(r) for r in (0.5, 2.0, 8.0, 30.0)]), "growth": float(cs._growth)}
+    cs = R["cosmology"].SingleEpoch(0.0, cosmo_dict=C_DICT, with_bao=True)
+    mf = R["mass_function"].MassFunction(0.0, cs, H_DICT)
+    out["mass"] = {"nu_nodes": arr(mf._nu_array), "ln_mass_nodes": arr(mf._ln_mass_array), "f_norm": float(mf.f_norm),
+                   "bias_norm": float(mf.bias_norm)}
+    h = R["halo"].Halo(input_hod=R["hod"].HODZheng(HOD_DICT), cosmo_single_epoch=cs, halo_dict=H_DICT)
+    kk = np.logspace(-3, 2, 60)
+    out["halo"] = {"k": arr(kk), "power_mm": arr(h.power_mm(kk)), "power_gm": arr(h.power_gm(kk)), "power_gg": arr(h.power_gg(kk))}
+    # Correlation moves the halo to z_bar with halo.set_redshift -> SingleEpoch.set_cosmology -> __init__ without
+    # with_bao (Q16): the wiggles are gone from w(theta) unless the halo is kept at its own redshift
+    kern = make_kernel(R)
+    hz = R["halo"].Halo(redshift=float(kern.z_bar), input_hod=R["hod"].HODZheng(HOD_DICT),
+                        cosmo_single_epoch=R["cosmology"].SingleEpoch(float(kern.z_bar), cosmo_dict=C_DICT, with_bao=True), halo_dict=H_DICT)
+    corr = R["correlation"].Correlation(0.01, 1.0, kern, bins_per_decade=3.0, input_halo=hz, power_spec="power_gg", keep_halo_z_bar=True)
+    corr.compute_correlation()
+    out["wtheta_keep_z_bar"] = {"theta": arr(corr.theta_array), "w": arr(corr.wtheta_array), "with_bao_after": bool(hz.cosmo._with_bao)}
+    h2 = R["halo"].Halo(input_hod=R["hod"].HODZheng(HOD_DICT), cosmo_single_epoch=R["cosmology"].SingleEpoch(0.0, cosmo_dict=C_DICT, with_bao=True),
+                        halo_dict=H_DICT)
+    corr2 = R["correlation"].Correlation(0.01, 1.0, kern, bins_per_decade=3.0, input_halo=h2, power_spec="power_gg")
+    corr2.compute_correlation()
+    out["wtheta_moved"] = {"theta": arr(corr2.theta_array), "w": arr(corr2.wtheta_array), "with_bao_after": bool(h2.cosmo._with_bao)}
+    return out
+
+
+SECTIONS = {"k_limits": k_limits, "cross_cov": cross_cov, "bao": bao}
 
 
 def main():

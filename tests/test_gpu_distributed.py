@@ -62,10 +62,19 @@ def _nccl_worker(rank, world, port, n_points, out_path):
     w, st = sharded.wtheta(cosmo, halo, hod)
     w_host, st_host = sharded.wtheta_host(cosmo, halo, hod)
     ok = np.array_equal(w.cpu().numpy(), w_host) and np.array_equal(st.cpu().numpy(), st_host)
+    # config 5 through the same front: w(theta) | covariance | status in ONE all-gather (uneven split of 7 points)
+    from chomp_b200 import _lib
+    cov_front = distributed.ShardedEngine(survey, device=rank, tri_moment=_lib.TRISPECTRUM_MOMENT["power_gggg"])
+    setup = engine.CovarianceSetup(survey, (0.001, 1.0), 10.0, 25.0, [1e10, 1e10], [1e10, 1e10], 1.0, True, "power_gg")
+    wc, cov, stc = cov_front.covariance(cosmo[:7], halo[:7], hod[:7], setup)
+    wc_h, cov_h, stc_h = cov_front.covariance_host(cosmo[:7], halo[:7], hod[:7], setup)
+    ok = ok and np.array_equal(cov.cpu().numpy(), cov_h) and np.array_equal(wc.cpu().numpy(), wc_h) and not stc_h.any()
     if rank == 0:
         single, _ = sharded._evaluate_engine(torch.as_tensor(cosmo).cuda(), torch.as_tensor(halo).cuda(),
                                              torch.as_tensor(hod).cuda())
-        np.savez(out_path, w=w.cpu().numpy(), single=single.cpu().numpy(), ok=ok)
+        cov_single = cov_front.engine.covariance(cosmo[:7], halo[:7], hod[:7], setup)
+        np.savez(out_path, w=w.cpu().numpy(), single=single.cpu().numpy(), ok=ok, cov=cov.cpu().numpy(),
+                 cov_single=cov_single.cpu().numpy(), wc=wc.cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -83,3 +92,5 @@ def test_two_nccl_ranks_equal_one_rank(tmp_path):
     got = np.load(out)
     assert bool(got["ok"])
     assert np.array_equal(got["w"], got["single"])
+    assert np.array_equal(got["cov"], got["cov_single"]) and got["cov"].shape == (7, 30, 30)
+    assert np.array_equal(got["wc"], got["single"][:7])

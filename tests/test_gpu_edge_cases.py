@@ -86,8 +86,8 @@ def test_call_level_errors():
     with pytest.raises(ChompError):
         engine.Engine(bad)
     bad = survey.config()
-    bad.corr_k_max = 1e3
-    with pytest.raises(ChompError, match="not supported"):
+    bad.corr_k_min, bad.corr_k_max = 1.0, 0.5                              # Correlation(k_min > k_max)
+    with pytest.raises(ChompError, match="k_max must exceed k_min"):
         engine.Engine(bad)
     with pytest.raises(ChompError):
         eng.trispectrum_1h(4)                                              # tri_moment < 0: list not built

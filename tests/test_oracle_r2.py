@@ -45,3 +45,13 @@ def test_oracle_cross_covariance_matches_reference_run():
         a, b = oc.bins[i][2], oc.bins[j][2]
         assert oc.covariance_G(a, b) == pytest.approx(np.array(g["cov_G"]).reshape(n, n)[i, j], rel=1e-10)
         assert oc.covariance_NG(a, b) == pytest.approx(np.array(g["cov_NG"]).reshape(n, n)[i, j], rel=1e-10)
+
+
+def test_oracle_bao_transfer_matches_reference_run():
+    """SingleEpoch(with_bao=True), cosmology.py:474-538."""
+    from oracle import chomp_oracle as O
+    for z in (0.0, 0.5):
+        g = GOLD["bao"]["z%.1f" % z]
+        se = O.SingleEpoch(z, C_DICT, with_bao=True)
+        assert np.max(np.abs(se.linear_power(np.array(g["k"]))/np.array(g["linear_power"]) - 1.0)) < 1e-13
+        assert se.sigma_norm == pytest.approx(g["sigma_norm"], rel=1e-13)
