@@ -18,6 +18,7 @@ HOD_ZHENG_KEYS = ("log_M_min", "sigma", "log_M_0", "log_M_1p", "alpha")
 HOD_MANDELBAUM_KEYS = ("log_M_0", "w")
 HOD_ZHENG, HOD_MANDELBAUM = 0, 1
 P_LINEAR, P_MM, P_GM, P_GG = 0, 1, 2, 3
+MF_SHETH_TORMEN, MF_TINKER = 0, 1
 TRISPECTRUM_MOMENT = {"power_mmmm": 0, "power_gmmm": 1, "power_ggmm": 2, "power_gggm": 3, "power_gggg": 4}
 POWER_SPEC = {"linear_power": P_LINEAR, "power_mm": P_MM, "power_gm": P_GM,
               "power_mg": P_GM, "power_gg": P_GG}
@@ -68,6 +69,7 @@ class Config(ctypes.Structure):
         ("corr_k_min", ctypes.c_double), ("corr_k_max", ctypes.c_double),
         ("dndz_table", ctypes.c_void_p*2), ("dndz_table_n", ctypes.c_int32*2),
         ("reserved_d", ctypes.c_double*1),
+        ("mass_function_kind", ctypes.c_int32), ("reserved_tail", ctypes.c_int32*1),
     ]
 
 

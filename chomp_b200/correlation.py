@@ -118,7 +118,7 @@ class Correlation(object):
         h._ensure()
         cfg = self.kernel._config()
         hc = h._gpu.eng.cfg
-        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "tri_moment", "with_bao"):
+        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "tri_moment", "with_bao", "mass_function_kind"):
             setattr(cfg, name, getattr(hc, name))
         self._set_k_limits(cfg)
         gpu = getattr(self, "_batch_gpu", None)
@@ -149,7 +149,7 @@ class Correlation(object):
         h._ensure()
         cfg = self.kernel._config()
         hc = h._gpu.eng.cfg
-        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "tri_moment", "with_bao"):
+        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "tri_moment", "with_bao", "mass_function_kind"):
             setattr(cfg, name, getattr(hc, name))
         self._set_k_limits(cfg)
         gpu = h._gpu

@@ -91,7 +91,7 @@ class Covariance(object):
         h._ensure()
         cfg = corr.kernel._config()
         hc = h._gpu.eng.cfg
-        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "with_bao"):
+        for name in ("hod_kind", "exclusion", "extrapolate", "halo_precision", "use_halofit", "with_bao", "mass_function_kind"):
             setattr(cfg, name, getattr(hc, name))
         return cfg
 

@@ -258,6 +258,7 @@ int check_cfg(const Cfg& c) {
         if (orders[i] < 1 || orders[i] > CHOMP_MAX_GL) FAIL("quadrature order out of range 1..16");
     if (c.hod_kind != CHOMP_HOD_ZHENG && c.hod_kind != CHOMP_HOD_MANDELBAUM) FAIL("unknown hod_kind");
     if (c.bessel_order != 0 && c.bessel_order != 2) FAIL("bessel_order must be 0 or 2");
+    if (c.mass_function_kind != CHOMP_MF_SHETH_TORMEN && c.mass_function_kind != CHOMP_MF_TINKER) FAIL("unknown mass_function_kind");
     if (!(c.k_min > 0 && c.k_max > c.k_min)) FAIL("bad k limits");
     if (!(c.ktheta_min > 0 && c.ktheta_max > c.ktheta_min)) FAIL("bad ktheta limits");
     if (c.corr_k_min > 0 && c.corr_k_max > 0 && !(c.corr_k_max > c.corr_k_min)) FAIL("Correlation k_max must exceed k_min");
@@ -323,6 +324,7 @@ int chomp_b200_create(void** handle, int device) {
     CK(chomp_upload_bessel_tables());
     CK(chomp_upload_sigma_tables(glx[SIG_NQ], glw[SIG_NQ], glx[SIG_NQ_S], glw[SIG_NQ_S]));
     CK(chomp_upload_expf_table());
+    CK(chomp_upload_tinker_tables());
     CK(chomp_upload_limber_tables());
     Handle* h = new Handle();
     h->device = device;
@@ -765,7 +767,8 @@ eval_kernel(const Cfg cfg, int what, int n, const double* __restrict__ x, double
             case CHOMP_EVAL_MASS_OF_NU: r = exp(mass_of_nu_ln(t, v)); break;
             case CHOMP_EVAL_F_NU: case CHOMP_EVAL_BIAS_NU: {
                 double nf, bi;
-                st_raw(v, cx.halo[CHOMP_H_ST_LITTLE_A], cx.halo[CHOMP_H_STQ], e[EP_DELTA_C], nf, bi);
+                const MfParams mf = mf_params(cfg, cx.halo[CHOMP_H_ST_LITTLE_A], cx.halo[CHOMP_H_STQ], e[EP_DELTA_C], e[EP_DELTA_V], e[EP_Z]);
+                mf_raw_ln(mf, log(v), nf, bi);
                 r = (what == CHOMP_EVAL_F_NU) ? nf * e[EP_F_NORM] / v : bi * e[EP_B_NORM];
             } break;
             case CHOMP_EVAL_SIGMA_OF_NU: r = spline_eval_search(cx.sig_coef, v, cx.nu, nm); break;   // mass_function.py:389

@@ -290,4 +290,107 @@ __device__ __forceinline__ void st_raw_ln(double lnnu, double ln_sta, double stq
     bias = 1.0 + (nup - 1.0) / delta_c + 2.0 * stq / (delta_c * (1.0 + 1.0 / pq));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tinker et al. (2010) mass function and bias (TinkerMassFunction, mass_function.py:436-564): cfg.mass_function_kind
+// = CHOMP_MF_TINKER.  The five shape parameters are the reference's cubic splines in ln(Delta_v) through nine
+// tabulated over-densities (piecewise-cubic form built on the host at create(), chomp_upload_tinker_tables),
+// scaled with (1 + z); nu = (delta_c / sigma)^2 is the square of their variable.
+// ---------------------------------------------------------------------------------------------
+#define TINKER_N 9
+__constant__ double k_tinker_breaks[TINKER_N];
+__constant__ double k_tinker_coef[5][TINKER_N - 1][4];     // alpha, beta, gamma, phi, eta
+static inline cudaError_t chomp_upload_tinker_tables() {
+    const double delta[TINKER_N] = {200, 300, 400, 600, 800, 1200, 1600, 2400, 3200};
+    const double tab[5][TINKER_N] = {{0.368, 0.363, 0.385, 0.389, 0.393, 0.365, 0.379, 0.355, 0.327},
+                                     {0.589, 0.585, 0.544, 0.543, 0.564, 0.632, 0.637, 0.673, 0.702},
+                                     {0.864, 0.922, 0.987, 1.09, 1.20, 1.34, 1.50, 1.68, 1.81},
+                                     {-0.729, -0.789, -0.910, -1.05, -1.20, -1.26, -1.45, -1.50, -1.49},
+                                     {-0.243, -0.261, -0.261, -0.273, -0.278, -0.301, -0.301, -0.319, -0.336}};
+    const int n = TINKER_N;
+    double x[TINKER_N], h[TINKER_N - 1], coef[5][TINKER_N - 1][4];
+    for (int i = 0; i < n; ++i) x[i] = log(delta[i]);
+    for (int i = 0; i < n - 1; ++i) h[i] = x[i + 1] - x[i];
+    for (int t = 0; t < 5; ++t) {
+        // not-a-knot cubic spline (what InterpolatedUnivariateSpline(k = 3) is): second derivatives M from a dense solve
+        double A[TINKER_N][TINKER_N + 1] = {};
+        const double* y = tab[t];
+        A[0][0] = h[1]; A[0][1] = -(h[0] + h[1]); A[0][2] = h[0];
+        for (int i = 1; i < n - 1; ++i) {
+            A[i][i - 1] = h[i - 1]; A[i][i] = 2.0 * (h[i - 1] + h[i]); A[i][i + 1] = h[i];
+            A[i][n] = 6.0 * ((y[i + 1] - y[i]) / h[i] - (y[i] - y[i - 1]) / h[i - 1]);
+        }
+        A[n - 1][n - 3] = h[n - 2]; A[n - 1][n - 2] = -(h[n - 3] + h[n - 2]); A[n - 1][n - 1] = h[n - 3];
+        for (int c = 0; c < n; ++c) {                       // Gaussian elimination with partial pivoting
+            int p = c;
+            for (int r = c + 1; r < n; ++r) if (fabs(A[r][c]) > fabs(A[p][c])) p = r;
+            for (int k = 0; k <= n; ++k) { const double tmp = A[c][k]; A[c][k] = A[p][k]; A[p][k] = tmp; }
+            for (int r = c + 1; r < n; ++r) {
+                const double f = A[r][c] / A[c][c];
+                for (int k = c; k <= n; ++k) A[r][k] -= f * A[c][k];
+            }
+        }
+        double M[TINKER_N];
+        for (int r = n - 1; r >= 0; --r) {
+            double v = A[r][n];
+            for (int k = r + 1; k < n; ++k) v -= A[r][k] * M[k];
+            M[r] = v / A[r][r];
+        }
+        for (int i = 0; i < n - 1; ++i) {
+            coef[t][i][0] = y[i];
+            coef[t][i][1] = (y[i + 1] - y[i]) / h[i] - h[i] * (2.0 * M[i] + M[i + 1]) / 6.0;
+            coef[t][i][2] = 0.5 * M[i];
+            coef[t][i][3] = (M[i + 1] - M[i]) / (6.0 * h[i]);
+        }
+    }
+    cudaError_t e = cudaMemcpyToSymbol(k_tinker_breaks, x, sizeof x);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(k_tinker_coef, coef, sizeof coef);
+}
+
+// multiplicity / bias parameters of a point's mass function, whichever form is configured
+struct MfParams {
+    int kind;
+    double ln_sta, stq, delta_c;                        // Sheth-Tormen
+    double alpha, ln_beta, phi, eta, gamma;             // Tinker f(nu)
+    double bA, ba, bC, dca;                             // Tinker b(nu): A, a, C, delta_c^a  (B = 0.183, b = 1.5, c = 2.4)
+};
+__device__ __noinline__ void tinker_params(double delta_v, double z, double delta_c, MfParams* p) {
+    const double x = log(delta_v);
+    int i = 0;
+    while (i < TINKER_N - 2 && x >= k_tinker_breaks[i + 1]) ++i;          // end pieces extrapolate, as FITPACK does
+    const double t = x - k_tinker_breaks[i];
+    double v[5];
+    for (int q = 0; q < 5; ++q) v[q] = k_tinker_coef[q][i][0] + t * (k_tinker_coef[q][i][1] + t * (k_tinker_coef[q][i][2] + t * k_tinker_coef[q][i][3]));
+    const double lz = log(1.0 + z);                                       // mass_function.py:544-564
+    p->alpha = v[0];
+    p->ln_beta = log(v[1]) + 0.20 * lz;
+    p->gamma = v[2] * exp(-0.01 * lz);
+    p->phi = v[3] * exp(-0.08 * lz);
+    p->eta = v[4] * exp(0.27 * lz);
+    const double y = log10(delta_v), e4 = exp(-pow(4.0 / y, 4.0));       // mass_function.py:517-526
+    p->bA = 1.0 + 0.24 * y * e4;
+    p->ba = 0.44 * y - 0.88;
+    p->bC = 0.019 + 0.107 * y + 0.19 * e4;
+    p->dca = pow(delta_c, p->ba);
+    p->delta_c = delta_c;
+}
+// nu f(nu) (unnormalised) and b(nu) / bias_norm from ln(nu)
+__device__ __noinline__ void tinker_raw_ln(const MfParams& p, double lnnu, double& nu_f, double& bias) {
+    nu_f = p.alpha * (1.0 + exp(-2.0 * p.phi * (p.ln_beta + 0.5 * lnnu))) * exp((p.eta + 0.5) * lnnu - 0.5 * p.gamma * exp(lnnu));
+    const double sa = exp(0.5 * p.ba * lnnu);
+    bias = 1.0 - p.bA * sa / (sa + p.dca) + 0.183 * exp(0.75 * lnnu) + p.bC * exp(1.2 * lnnu);
+}
+__device__ __forceinline__ MfParams mf_params(const Cfg& cfg, double sta, double stq, double delta_c, double delta_v, double z) {
+    MfParams p;
+    p.kind = cfg.mass_function_kind;
+    p.stq = stq; p.delta_c = delta_c;
+    p.ln_sta = log(sta);
+    if (p.kind == CHOMP_MF_TINKER) tinker_params(delta_v, z, delta_c, &p);
+    return p;
+}
+__device__ __forceinline__ void mf_raw_ln(const MfParams& p, double lnnu, double& nu_f, double& bias) {
+    if (p.kind == CHOMP_MF_TINKER) tinker_raw_ln(p, lnnu, nu_f, bias);
+    else st_raw_ln(lnnu, p.ln_sta, p.stq, p.delta_c, nu_f, bias);
+}
+
 }  // namespace chomp

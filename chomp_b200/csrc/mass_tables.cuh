@@ -588,7 +588,9 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         // ln(nu) at the knots once (the Delta^2 table is no longer needed), ends moved to nu_min / nu_max
         double* lognu = d2tab;
         for (int i = t2; i < n; i += nt2) lognu[i] = log(i == 0 ? nu_min : (i == n - 1 ? nu_max : nu[i]));
-        const double ln_sta = log(sta);
+        double dv_mf = hp[CHOMP_H_DELTA_V];
+        if (dv_mf == -1.0) dv_mf = delta_v_z(c, z, growth);
+        const MfParams mf = mf_params(cfg, sta, stq, m.delta_c, dv_mf, z);
         asm volatile("bar.sync 3, %0;" ::"r"(nt2) : "memory");
         for (int idx = t2; idx < (n - 1) * 8; idx += nt2) {
             const int i = idx >> 3, q = idx & 7;
@@ -596,7 +598,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
             const double half = 0.5 * (bb - a);
             const double x = 0.5 * (a + bb) + half * c_glx[8][q];
             double nf, bi;
-            st_raw_ln(x, ln_sta, stq, m.delta_c, nf, bi);
+            mf_raw_ln(mf, x, nf, bi);
             const double wgt = half * c_glw[8][q];
             sf += wgt * nf;
             sfb += wgt * nf * bi;
@@ -612,7 +614,8 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     sf = block_sum(sf, red);
     sfb = block_sum(sfb, red + 32);
     chi = block_sum(chi, red);
-    const double f_norm = 1.0 / sf;
+    // Tinker's multiplicity function carries its fitted amplitude: only the bias is normalised (mass_function.py:528-542)
+    const double f_norm = cfg.mass_function_kind == CHOMP_MF_TINKER ? 1.0 : 1.0 / sf;
     const double b_norm = 1.0 / (f_norm * sfb);
     const double lnm_star = spline_eval_search(c1, 1.0, nu, n);        // m_star = mass(1.0), :223
 

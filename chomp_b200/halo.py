@@ -65,7 +65,8 @@ class Halo(object):
                                   extrapolate=int(bool(self._extrapolate)),
                                   tri_moment=int(getattr(self, "_tri_moment", -1)),
                                   use_halofit=int(self._halofit),
-                                  with_bao=int(bool(getattr(self.cosmo, "_with_bao", False))))
+                                  with_bao=int(bool(getattr(self.cosmo, "_with_bao", False))),
+                                  mass_function_kind=int(getattr(self.mass, "_mf_kind", 0)))
         cfg.halo_precision = getattr(self.local_hod, "_halo_precision", cfg.halo_precision)
         # first_moment_zero was fixed when the HOD object was built (hod.py:176-179)
         self._gpu.configure(cfg)

@@ -1,12 +1,13 @@
 """Drop-in for the reference's mass_function.MassFunction (Sheth-Tormen;
-mass_function.py:25-363) and MassFunctionSecondOrder (:365-433).  TinkerMassFunction is
-outside the hot path and is not provided."""
+mass_function.py:25-363), MassFunctionSecondOrder (:365-433) and TinkerMassFunction (Tinker et al. 2010, :436-564)."""
 import numpy as np
 
 from . import _facade, _lib, cosmology, defaults
 
 
 class MassFunction(object):
+    _mf_kind = _lib.MF_SHETH_TORMEN
+
     def __init__(self, redshift=0.0, cosmo_single_epoch=None, halo_dict=None, **kws):
         self._redshift = redshift
         if cosmo_single_epoch is None:
@@ -24,7 +25,8 @@ class MassFunction(object):
         h = self.halo_dict
         self.stq, self.st_little_a = h["stq"], h["st_little_a"]
         self.c0 = h["c0"]/(1.0 + self._redshift)
-        self._gpu.configure(_facade.base_config(with_bao=int(bool(getattr(self.cosmo, "_with_bao", False)))))
+        self._gpu.configure(_facade.base_config(with_bao=int(bool(getattr(self.cosmo, "_with_bao", False))),
+                                                mass_function_kind=self._mf_kind))
         self._gpu.eng.mass_tables(_facade.cosmo_row(self.cosmo.cosmo_dict), _facade.halo_row(h),
                                   [self._redshift])
         e = self._gpu.epoch()
@@ -109,3 +111,10 @@ class MassFunctionSecondOrder(MassFunction):
 
     def bias_2_mass(self, mass):
         return self.bias_2_nu(self.nu(mass))
+
+
+class TinkerMassFunction(MassFunction):
+    """mass_function.py:436-564: f(nu) and b(nu) of Tinker et al. (2010), shape parameters from the reference's cubic
+    splines in ln(Delta_v) scaled with redshift; the multiplicity function is not normalised (``f_norm`` = 1 here, the
+    reference has no such attribute), the bias is."""
+    _mf_kind = _lib.MF_TINKER

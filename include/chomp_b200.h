@@ -45,6 +45,7 @@ enum { CHOMP_P_LINEAR = 0, CHOMP_P_MM = 1, CHOMP_P_GM = 2, CHOMP_P_GG = 3 };
 enum { CHOMP_DNDZ_GAUSSIAN = 0, CHOMP_DNDZ_MAGLIM = 1,
        CHOMP_DNDZ_TABLE = 2 /* dNdzInterpolation (kernel.py:181-208): piecewise cubic set with chomp_b200_set_dndz_table */ };
 enum { CHOMP_WINDOW_GALAXY = 0, CHOMP_WINDOW_CONVERGENCE = 1 };
+enum { CHOMP_MF_SHETH_TORMEN = 0, CHOMP_MF_TINKER = 1 };
 /* per-point status bits */
 enum {
     CHOMP_ST_NONFINITE = 1,      /* a result is NaN/Inf                                  */
@@ -88,6 +89,9 @@ typedef struct chomp_b200_config {
     const double* dndz_table[2];
     int32_t dndz_table_n[2];
     double reserved_d[1];
+    int32_t mass_function_kind; /* CHOMP_MF_*: Sheth-Tormen (MassFunction, mass_function.py:25-363) or Tinker et al. 2010
+                                   (TinkerMassFunction, :436-564: no f(nu) normalisation, its own bias)            */
+    int32_t reserved_tail[1];
 } chomp_b200_config;
 
 int chomp_b200_version(void);

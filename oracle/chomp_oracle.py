@@ -399,6 +399,58 @@ class MassFunction(object):
         return np.exp(self._lnm_of_nu(nu))
 
 
+class TinkerMassFunction(MassFunction):                   # mass_function.py:436-564 (Tinker et al. 2010)
+    """f(nu) and b(nu) of Tinker et al. (2010); nu = (delta_c / sigma)^2 is the square of their variable.  The
+    five shape parameters are cubic splines in ln(Delta_v) through the nine tabulated over-densities, scaled with
+    redshift; only the bias is normalised (mass_function.py:528-542)."""
+    DELTA = (200, 300, 400, 600, 800, 1200, 1600, 2400, 3200)
+    TABLE = {"alpha": (0.368, 0.363, 0.385, 0.389, 0.393, 0.365, 0.379, 0.355, 0.327),
+             "beta": (0.589, 0.585, 0.544, 0.543, 0.564, 0.632, 0.637, 0.673, 0.702),
+             "gamma": (0.864, 0.922, 0.987, 1.09, 1.20, 1.34, 1.50, 1.68, 1.81),
+             "phi": (-0.729, -0.789, -0.910, -1.05, -1.20, -1.26, -1.45, -1.50, -1.49),
+             "eta": (-0.243, -0.261, -0.261, -0.273, -0.278, -0.301, -0.301, -0.319, -0.336)}
+    Z_POWER = {"alpha": 0.0, "beta": 0.20, "phi": -0.08, "eta": 0.27, "gamma": -0.01}     # :544-564
+
+    def __init__(self, epoch, halo=None, prec=None, integ=None, limits=None):
+        self.prec = prec or epoch.prec
+        self.integ = integ or epoch.integ
+        self.limits = limits or epoch.limits
+        self.epoch = epoch
+        self.set_halo_params(halo or DEFAULT_HALO)
+        self.delta_c = epoch.delta_c()
+        self.delta_v = self.halo["delta_v"]
+        if self.delta_v == -1:
+            self.delta_v = epoch.delta_v()
+        ld = np.log(self.DELTA)
+        self.par = {k: float(_spline(ld, np.array(v))(np.log(self.delta_v)))*(1.0 + epoch.z)**self.Z_POWER[k]
+                    for k, v in self.TABLE.items()}
+        self._find_mass_limits()
+        self._tabulate()
+        self.normalize()
+
+    def f_nu(self, nu):                                   # mass_function.py:493-508
+        p = self.par
+        s = np.sqrt(nu)
+        return p["alpha"]*(1 + np.power(p["beta"]*s, -2*p["phi"]))*np.power(nu, p["eta"])*np.exp(-p["gamma"]*nu/2.0)/s
+
+    def bias_nu(self, nu):                                # mass_function.py:510-526
+        s = np.sqrt(nu)
+        y = np.log10(self.delta_v)
+        A = 1 + 0.24*y*np.exp(-(4.0/y)**4)
+        a = 0.44*y - 0.88
+        B, b = 0.183, 1.5
+        C = 0.019 + 0.107*y + 0.19*np.exp(-(4.0/y)**4)
+        c = 2.4
+        return self.bias_norm*(1 - A*s**a/(s**a + self.delta_c**a) + B*s**b + C*s**c)
+
+    def normalize(self):                                  # mass_function.py:528-542: the bias only
+        self.f_norm = 1.0
+        self.bias_norm = 1.0
+        breaks = np.geomspace(self.nu_min, self.nu_max, 12)
+        self.bias_norm = 1.0/self.integ(lambda v: self.f_nu(v)*self.bias_nu(v), self.nu_min, self.nu_max,
+                                        self.prec["mass_precision"], breaks=breaks)
+
+
 class MassFunctionSecondOrder(MassFunction):               # mass_function.py:365-433
     def _tabulate(self):                                  # mass_function.py:371-393
         MassFunction._tabulate(self)

@@ -141,7 +141,29 @@ def bao(R):
     return out
 
 
-SECTIONS = {"k_limits": k_limits, "cross_cov": cross_cov, "bao": bao}
+def tinker(R):
+    """TinkerMassFunction (mass_function.py:436-564) on its own and under a Halo (spectra, w_gg(theta))."""
+    from common import H_DICT_2
+    out = {}
+    nu = np.logspace(-0.9, 1.6, 12)
+    for z, hd, key in ((0.0, H_DICT, "z0.0"), (0.5, H_DICT_2, "z0.5_delta_v_200")):
+        cs = R["cosmology"].SingleEpoch(z, cosmo_dict=C_DICT)
+        mf = R["mass_function"].TinkerMassFunction(z, cs, hd)
+        out[key] = {"nu": arr(nu), "f_nu": arr(mf.f_nu(nu)), "bias_nu": arr(mf.bias_nu(nu)), "bias_norm": float(mf.bias_norm),
+                    "delta_v": float(mf.delta_v), "nu_nodes": arr(mf._nu_array), "m_star": float(mf.m_star)}
+    cs = R["cosmology"].SingleEpoch(0.0, cosmo_dict=C_DICT)
+    mf = R["mass_function"].TinkerMassFunction(0.0, cs, H_DICT)
+    h = R["halo"].Halo(input_hod=R["hod"].HODZheng(HOD_DICT), cosmo_single_epoch=cs, mass_func=mf, halo_dict=H_DICT)
+    kk = np.logspace(-3, 2, 60)
+    out["halo"] = {"k": arr(kk), "power_mm": arr(h.power_mm(kk)), "power_gm": arr(h.power_gm(kk)), "power_gg": arr(h.power_gg(kk))}
+    kern = make_kernel(R)
+    corr = R["correlation"].Correlation(0.01, 1.0, kern, bins_per_decade=3.0, input_halo=h, power_spec="power_gg")
+    corr.compute_correlation()
+    out["wtheta"] = {"theta": arr(corr.theta_array), "w": arr(corr.wtheta_array)}
+    return out
+
+
+SECTIONS = {"k_limits": k_limits, "cross_cov": cross_cov, "bao": bao, "tinker": tinker}
 
 
 def main():

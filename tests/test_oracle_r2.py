@@ -55,3 +55,16 @@ def test_oracle_bao_transfer_matches_reference_run():
         se = O.SingleEpoch(z, C_DICT, with_bao=True)
         assert np.max(np.abs(se.linear_power(np.array(g["k"]))/np.array(g["linear_power"]) - 1.0)) < 1e-13
         assert se.sigma_norm == pytest.approx(g["sigma_norm"], rel=1e-13)
+
+
+def test_oracle_tinker_matches_reference_run():
+    """TinkerMassFunction, mass_function.py:436-564."""
+    from oracle import chomp_oracle as O
+    from common import H_DICT_2
+    for z, hd, key in ((0.0, H_DICT, "z0.0"), (0.5, H_DICT_2, "z0.5_delta_v_200")):
+        g = GOLD["tinker"][key]
+        mf = O.TinkerMassFunction(O.SingleEpoch(z, C_DICT), hd)
+        nu = np.array(g["nu"])
+        assert np.max(np.abs(mf.f_nu(nu)/np.array(g["f_nu"]) - 1.0)) < 1e-13
+        assert np.max(np.abs(mf.bias_nu(nu)/np.array(g["bias_nu"]) - 1.0)) < 1e-12
+        assert mf.bias_norm == pytest.approx(g["bias_norm"], rel=1e-12)
