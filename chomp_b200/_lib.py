@@ -152,6 +152,10 @@ _SIGNATURES = {
                                                 ctypes.c_void_p, ctypes.c_void_p]),
     "chomp_b200_covariance": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(CovParams)] +
                               [ctypes.c_void_p]*10),
+    "chomp_b200_halo_ssc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "chomp_b200_xi3d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "chomp_b200_covariance_cross": (ctypes.c_int, [ctypes.c_void_p]*3 + [ctypes.c_int, ctypes.POINTER(CovParams)] +
                                     [ctypes.c_void_p]*14),
 }

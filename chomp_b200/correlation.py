@@ -207,3 +207,58 @@ class CorrelationFourier(Correlation):
             f.write("#ttype1 = l [deg]\n#ttype2 = power\n")
             for l, power in zip(self.l_array, self.power_array):
                 f.write("%1.10f %1.10f\n" % (l, power))
+
+
+class Correlation3d(Correlation):
+    """correlation.py:408-510: xi(r) = int dln k k^2/(2 pi) P(k) J0(k r) on ``corr_npoints`` log-spaced radii, splined
+    in r.  The integration limits are the halo model's k range."""
+
+    def __init__(self, r_min, r_max, redshift=0.0, input_halo=None, powSpec=None, k_min=None, k_max=None):
+        from . import defaults
+        self.log_r_min = np.log10(r_min)
+        self.log_r_max = np.log10(r_max)
+        self.r_array = np.logspace(self.log_r_min, self.log_r_max, defaults.default_precision["corr_npoints"])
+        if r_min == r_max:
+            self.r_array = np.array([r_min])
+        self.xi_array = np.zeros(self.r_array.size)
+        if input_halo is None:
+            input_halo = halo_module.Halo(redshift)
+        self.halo = input_halo
+        self.halo.set_redshift(redshift)
+        if ((k_min is not None and k_min != self.halo._k_min) or (k_max is not None and k_max != self.halo._k_max)):
+            raise NotImplementedError("Correlation3d(k_min/k_max) different from the halo limits")
+        self._ln_k_min, self._ln_k_max = np.log(self.halo._k_min), np.log(self.halo._k_max)
+        if powSpec is None:
+            powSpec = "linear_power"
+        self.set_power_spectrum(powSpec)
+        self.initialized_spline = False
+
+    def raw_correlation(self, r):
+        h = self.halo
+        h._ensure()
+        out = h._gpu.eng.xi3d(1, _lib.POWER_SPEC[self._power_name], _facade.flat(r))
+        return _facade.like_input(r, out.cpu().numpy()[0])
+
+    def compute_correlation(self):
+        self.xi_array = np.array(self.raw_correlation(self.r_array), dtype=float)
+        if self.r_array.size > 3:
+            self._xi_breaks, self._xi_coef = engine.interpolating_spline_piecewise(self.r_array, self.xi_array, 3)
+        self.initialized_spline = True
+
+    def correlation(self, r):
+        """correlation.py:502-510: the spline inside (r_min, r_max], 0 outside."""
+        if not self.initialized_spline:
+            self.compute_correlation()
+        rr = _facade.flat(r)
+        i = np.clip(np.searchsorted(self._xi_breaks, rr, side="right") - 1, 0, len(self._xi_breaks) - 2)
+        t = rr - self._xi_breaks[i]
+        c = self._xi_coef[i]
+        val = c[:, 0] + t*(c[:, 1] + t*(c[:, 2] + t*c[:, 3]))
+        r_min, r_max = 10.0**self.log_r_min, 10.0**self.log_r_max
+        return _facade.like_input(r, np.where((rr <= r_max) & (rr > r_min), val, 0.0))
+
+    def write(self, output_file_name):
+        with open(output_file_name, "w") as f:
+            f.write("#ttype1 = r [Mpc/h]\n#ttype2 = xi\n")
+            for r, xi in zip(self.r_array, self.xi_array):
+                f.write("%1.10f %1.10f\n" % (r, xi))

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "covariance.cuh"
 #include "covariance_cross.cuh"
+#include "extras.cuh"
 #include "halo_tables.cuh"
 #include "halofit.cuh"
 #include "hankel.cuh"
@@ -140,6 +141,8 @@ struct Handle {
     std::vector<void*> allocs;
     // covariance scratch (allocated on first use, released with the rest in free_scratch)
     CovOut cov = {};
+    double *i12_tab = nullptr, *i12_coef = nullptr;   // HaloSuperSampleCovariance table (allocated on first use)
+    int i12_points = 0;
     double* cov_proj4 = nullptr;     // [B, 4, 2, n_kernel] projected spectra a, b, ab, ba (cross-covariance)
     int cov_proj4_points = 0;
     TriScratch cov_tri = {};
@@ -248,6 +251,7 @@ void free_scratch(Handle* h) {
     h->tri_A = nullptr; h->tri_T = nullptr; h->tri_points = 0; h->tri_chunk = 0;
     h->cov = CovOut{}; h->cov_tri = TriScratch{}; h->cov_points = 0; h->cov_bins = 0; h->cov_chunk = 0; h->cov_ntot = 0; h->kng_ready = false;
     h->cov_proj4 = nullptr; h->cov_proj4_points = 0;
+    h->i12_tab = nullptr; h->i12_coef = nullptr; h->i12_points = 0;
 }
 
 int check_cfg(const Cfg& c) {
@@ -1480,6 +1484,51 @@ int chomp_b200_covariance_cross(void* handle_a, void* handle_b, void* handle_t, 
     ha->launches += 1;
     if (parts_out_dev)
         CK(cudaMemcpyAsync(parts_out_dev, ha->cov.parts, sizeof(double) * (size_t)B * 3 * nb * nb, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int chomp_b200_halo_ssc(void* handle, int B, int what, int n_k, const double* k_dev, double* out_dev, int32_t* status_dev,
+                        void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    if (what != 0 && what != 1) FAIL("what must be 0 (I^1_2) or 1 (dln P / d delta_b)");
+    if (n_k <= 0 || !k_dev || !out_dev) FAIL("bad arguments");
+    NEED_STAGE(h->done_halo, B, "the halo tables (chomp_b200_halo_tables)");
+    const Cfg& c = h->cfg;
+    if (B > h->i12_points) {
+        CK(cudaDeviceSynchronize());
+        h->i12_points = 0;
+        if (int rc = dev_regrow(h, &h->i12_tab, (size_t)B * c.n_halo)) return rc;
+        if (int rc = dev_regrow(h, &h->i12_coef, (size_t)B * 4 * c.n_halo)) return rc;
+        h->i12_points = B;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = 2 * (size_t)c.n_halo * sizeof(double);
+    halo_i12_kernel<<<B, 256, smem, s>>>(c, B, nodes_view(h), h->epoch, h->i12_tab, h->i12_coef, status_dev);
+    CK(cudaGetLastError());
+    const unsigned grid = (unsigned)((n_k + 255) / 256) * (unsigned)B;
+    halo_ssc_eval_kernel<<<grid, 256, 0, s>>>(c, B, what, n_k, k_dev, h->cosmo, h->epoch, h->htab, h->hcoef,
+                                             c.use_halofit ? h->hfit : nullptr, h->i12_coef, out_dev);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return 0;
+}
+
+int chomp_b200_xi3d(void* handle, int B, int which, int n_r, const double* r_dev, double* xi_out_dev, int32_t* status_dev,
+                    void* stream) {
+    Handle* h = (Handle*)handle;
+    if (int rc = ensure(h, B)) return rc;
+    if (which < CHOMP_P_LINEAR || which > CHOMP_P_GG) FAIL("unknown power spectrum");
+    if (n_r <= 0 || n_r > 65535 || !r_dev || !xi_out_dev) FAIL("bad arguments");
+    if (B > 65535) FAIL("xi(r) batches are limited to 65 535 points per call");
+    NEED_STAGE(h->done_mass, B, "the epoch scalars (chomp_b200_mass_tables)");
+    if (!(which == CHOMP_P_LINEAR || (h->cfg.use_halofit && which == CHOMP_P_MM)))
+        NEED_STAGE(h->done_halo, B, "the halo tables (chomp_b200_halo_tables)");
+    dim3 grid(n_r, B);
+    xi3d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->cfg, B, which, n_r, r_dev, h->cosmo, h->epoch, h->htab, h->hcoef,
+                                                       h->cfg.use_halofit ? h->hfit : nullptr, xi_out_dev, status_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
     return 0;
 }
 

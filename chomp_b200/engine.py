@@ -543,6 +543,22 @@ class Engine(object):
             self._p(halo_t), self._p(hod_t), self._p(out), self._p(pt), self._p(status), self._stream()))
         return (out, pt) if parts else out
 
+    def halo_ssc(self, B, k, what=1, status=None):
+        """HaloSuperSampleCovariance for the last halo_tables batch: what = 0 I^1_2(k), 1 dln P / d delta_b; [B, n_k]."""
+        k = self._dev(k).reshape(-1)
+        out = self._new(B, k.numel())
+        _lib.check(self.lib.chomp_b200_halo_ssc(self._h, int(B), int(what), k.numel(), self._p(k), self._p(out),
+                                                self._p(status), self._stream()))
+        return out
+
+    def xi3d(self, B, which, r, status=None):
+        """Correlation3d.raw_correlation for the last batch: xi(r) [B, n_r]."""
+        r = self._dev(r).reshape(-1)
+        out = self._new(B, r.numel())
+        _lib.check(self.lib.chomp_b200_xi3d(self._h, int(B), int(which), r.numel(), self._p(r), self._p(out),
+                                            self._p(status), self._stream()))
+        return out
+
     def set_params(self, cosmo=None, halo=None, hod=None):
         arrs = [None if a is None else self._dev(a, n) for a, n in
                 ((cosmo, _lib.N_COSMO), (halo, _lib.N_HALO), (hod, _lib.N_HOD))]

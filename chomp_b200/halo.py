@@ -238,3 +238,34 @@ class HaloFit(Halo):
         self._fit_redshift = float(redshift)
         Halo.__init__(self, redshift, input_hod, cosmo_single_epoch, mass_func, halo_dict)
         self._initialized_sigma_spline = False
+
+
+class HaloSuperSampleCovariance(Halo):
+    """halo.py:1089-1199 (Takada & Hu 2013): the response of the matter power spectrum to a super-survey
+    over-density delta_b, through the extra mass integral I^1_2(k) = rho_bar^-1 int dln nu nu f b y^2 M."""
+
+    def __init__(self, redshift=0.0, input_hod=None, cosmo_single_epoch=None, mass_func=None, halo_dict=None,
+                 extrapolate=False, delta_b=0.0, **kws):
+        Halo.__init__(self, redshift, input_hod, cosmo_single_epoch, mass_func, halo_dict, **kws)   # extrapolate not forwarded (halo.py:1105-1106)
+        self._delta_b = delta_b
+
+    @staticmethod
+    def init_from_halo(input_halo, delta_b=0.0):
+        """halo.py:1110-1136 (the tables of the donor are rebuilt here rather than copied)."""
+        return HaloSuperSampleCovariance(input_halo.get_redshift(), input_halo.get_hod_object(), input_halo.get_cosmology_object(),
+                                         input_halo.get_mass(), input_halo.get_halo(), input_halo.get_extrapolation(), delta_b)
+
+    def _ssc(self, what, k):
+        if getattr(self, "_extrapolate_built", None) != bool(self._extrapolate):
+            self._dirty = True
+        self._ensure()
+        return _facade.like_input(k, self._gpu.eng.halo_ssc(1, _facade.flat(k), what).cpu().numpy()[0])
+
+    def _i_1_2(self, k):
+        return self._ssc(0, k)
+
+    def dln_power_ddelta_b(self, k):
+        return self._ssc(1, k)
+
+    def power_mm_ssc(self, k):
+        return self.power_mm(k)*(1.0 + self.dln_power_ddelta_b(k)*self._delta_b)

@@ -307,6 +307,18 @@ int chomp_b200_covariance_cross(void* handle_a, void* handle_b, void* handle_t, 
                                 const double* hod_t_dev, double* cov_out_dev, double* parts_out_dev, int32_t* status_dev,
                                 void* stream);
 
+/* HaloSuperSampleCovariance (halo.py:1089-1199) for the batch of the last chomp_b200_halo_tables: what = 0 the table
+ * I^1_2(k) = rho_bar^-1 int dln nu nu f(nu) b(nu) y(k, M)^2 M (halo.py:1159-1199, splined in ln k), what = 1
+ * dln P / d delta_b = (68/21 h_m^2 P_lin + I^1_2) / P_mm (halo.py:1138-1157); both 0 outside [k_min, k_max].
+ * k_dev [n_k], out_dev [B, n_k]. */
+int chomp_b200_halo_ssc(void* handle, int B, int what, int n_k, const double* k_dev, double* out_dev, int32_t* status_dev,
+                        void* stream);
+
+/* Correlation3d.raw_correlation (correlation.py:467-500): xi(r) = int dln k k^2 / (2 pi) P(k) J0(k r) over the halo
+ * model's k range for any CHOMP_P_* spectrum of the last batch; r_dev [n_r] in Mpc/h, xi_out_dev [B, n_r]. */
+int chomp_b200_xi3d(void* handle, int B, int which, int n_r, const double* r_dev, double* xi_out_dev, int32_t* status_dev,
+                    void* stream);
+
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 long long chomp_b200_launch_count(void* handle);
 

@@ -797,6 +797,50 @@ class Halo(object):
         return getattr(self, which)(k)
 
 
+class HaloSuperSampleCovariance(Halo):                    # halo.py:1089-1199 (Takada & Hu 2013)
+    """Adds I^1_2(k) = rho_bar^-1 int dln nu nu f(nu) b(nu) y(k, M)^2 M and the response of the matter power
+    spectrum to a super-survey over-density delta_b."""
+
+    def __init__(self, epoch, mass, hod, halo=None, delta_b=0.0, **kw):
+        Halo.__init__(self, epoch, mass, hod, halo, **kw)
+        self.delta_b = delta_b
+        self._i12 = None
+
+    def _i_1_2_integrand(self, ln_nu, ln_k, norm=1.0):    # halo.py:1193-1199
+        nu = np.exp(ln_nu)
+        M = self.mass.mass(nu)
+        y = self.y(ln_k, M)
+        return nu*self.mass.f_nu(nu)*self.mass.bias_nu(nu)*y*y*M*norm
+
+    def i_1_2_table(self):                                # halo.py:1174-1191
+        if self._i12 is None:
+            m = self.mass
+            lo, hi = np.log(m.nu_min), np.log(m.nu_max)
+            br, _ = self._panel_hints(lo, hi)
+            vals = np.empty_like(self.ln_k_nodes)
+            for i, ln_k in enumerate(self.ln_k_nodes):
+                norm = 1.0/float(self._i_1_2_integrand(0.0, ln_k, 1.0))
+                vals[i] = self.integ(self._i_1_2_integrand, lo, hi, self.prec["halo_precision"], breaks=br,
+                                     args=(ln_k, norm))/(norm*self.rho_bar)
+            self._i12 = (vals, _spline(self.ln_k_nodes, vals))
+        return self._i12
+
+    def i_1_2(self, k):                                   # halo.py:1169-1172
+        k = np.asarray(k, dtype=float)
+        return np.where((k >= self.k_min) & (k <= self.k_max), self.i_1_2_table()[1](np.log(k)), 0.0)
+
+    def dln_power_ddelta_b(self, k):                      # halo.py:1138-1157
+        k = np.asarray(k, dtype=float)
+        inside = (k >= self.k_min) & (k <= self.k_max)
+        hm = self._tab("h_m", k)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            val = (68.0/21.0*hm*hm*self.linear_power(k) + self.i_1_2(k))/self.power("power_mm", k)
+        return np.where(inside, val, 0.0)
+
+    def power_mm_ssc(self, k):                            # halo.py:1159-1167
+        return self.power("power_mm", k)*(1.0 + self.dln_power_ddelta_b(k)*self.delta_b)
+
+
 class HaloExclusion(Halo):                                # halo.py:1201-1233
     exclusion = True
 
@@ -1271,6 +1315,37 @@ class HaloFit(Halo):
 # ----------------------------------------------------------------------------
 # correlation.CorrelationFourier  (correlation.py:297-405)
 # ----------------------------------------------------------------------------
+class Correlation3d(object):                              # correlation.py:408-510
+    """xi(r) = int dln k k^2/(2 pi) P(k) J0(k r) over [ln k_min, ln k_max] -- the reference's integrand as written."""
+
+    def __init__(self, r_min, r_max, halo, power_spec="linear_power", prec=None, integ=None):
+        self.prec = prec or halo.prec
+        self.integ = integ or halo.integ
+        self.halo = halo
+        self.r = np.logspace(np.log10(r_min), np.log10(r_max), self.prec["corr_npoints"])
+        self.power_spec = power_spec
+        self.ln_k_min, self.ln_k_max = np.log(halo.k_min), np.log(halo.k_max)
+
+    def _integrand(self, ln_k, r):                        # correlation.py:493-500
+        k = np.exp(ln_k)
+        return k*k/(2.0*np.pi)*self.halo.power(self.power_spec, k)*special.j0(k*r)
+
+    def raw_correlation(self, r):                         # correlation.py:467-491
+        r = np.atleast_1d(np.asarray(r, dtype=float))
+        out = np.empty(r.size)
+        for i, v in enumerate(r):
+            breaks = ()
+            if self.integ.name == "tight":
+                marks = [self.halo.ln_k_nodes]
+                top = np.exp(self.ln_k_max)*v
+                if top > 1.5:
+                    marks.append(np.log(np.arange(1.0, top + 1.5, 1.5)/v))
+                breaks = np.concatenate(marks)
+            out[i] = self.integ(self._integrand, self.ln_k_min, self.ln_k_max, self.prec["corr_precision"],
+                                breaks=breaks, args=(v,))
+        return out
+
+
 class CorrelationFourier(object):
     def __init__(self, kernel, halo_factory, power_spec="linear_power", prec=None, integ=None):
         self.prec = prec or kernel.prec

@@ -163,7 +163,36 @@ def tinker(R):
     return out
 
 
-SECTIONS = {"k_limits": k_limits, "cross_cov": cross_cov, "bao": bao, "tinker": tinker}
+def ssc_halo(R):
+    """HaloSuperSampleCovariance (halo.py:1089-1199): I^1_2(k), dln P / d delta_b, power_mm_ssc."""
+    out = {}
+    kk = np.concatenate([[5e-4], np.logspace(-3, 2, 40), [150.0]])
+    for z in (0.0, 0.5):
+        cs = R["cosmology"].SingleEpoch(z, cosmo_dict=C_DICT)
+        h = R["halo"].HaloSuperSampleCovariance(z, R["hod"].HODZheng(HOD_DICT), cs, None, H_DICT, False, 0.02)
+        out["z%.1f" % z] = {"k": arr(kk), "i_1_2": arr(h._i_1_2(kk)) if h._initialize_i_1_2() is None else None,
+                            "dln_power_ddelta_b": arr(h.dln_power_ddelta_b(kk)), "power_mm_ssc": arr(h.power_mm_ssc(kk)),
+                            "power_mm": arr(h.power_mm(kk)), "delta_b": 0.02}
+    base = R["halo"].Halo(0.0, R["hod"].HODZheng(HOD_DICT), R["cosmology"].SingleEpoch(0.0, cosmo_dict=C_DICT), None, H_DICT)
+    base.power_mm(1.0)
+    h2 = R["halo"].HaloSuperSampleCovariance.init_from_halo(base, 0.01)
+    out["init_from_halo"] = {"k": arr(kk), "dln_power_ddelta_b": arr(h2.dln_power_ddelta_b(kk))}
+    return out
+
+
+def xi3d(R):
+    """Correlation3d (correlation.py:408-510) with the linear and the halo-model spectra."""
+    out = {}
+    for spec in ("linear_power", "power_mm", "power_gg"):
+        h = R["halo"].Halo(0.3, R["hod"].HODZheng(HOD_DICT), R["cosmology"].SingleEpoch(0.3, cosmo_dict=C_DICT), None, H_DICT)
+        c3 = R["correlation"].Correlation3d(0.05, 60.0, 0.3, input_halo=h, powSpec=spec)
+        c3.compute_correlation()
+        rq = np.array([0.04, 0.07, 1.3, 25.0, 60.0, 80.0])
+        out[spec] = {"r": arr(c3.r_array), "xi": arr(c3.xi_array), "r_query": arr(rq), "xi_query": arr(c3.correlation(rq))}
+    return out
+
+
+SECTIONS = {"k_limits": k_limits, "cross_cov": cross_cov, "bao": bao, "tinker": tinker, "ssc_halo": ssc_halo, "xi3d": xi3d}
 
 
 def main():

@@ -68,3 +68,22 @@ def test_oracle_tinker_matches_reference_run():
         assert np.max(np.abs(mf.f_nu(nu)/np.array(g["f_nu"]) - 1.0)) < 1e-13
         assert np.max(np.abs(mf.bias_nu(nu)/np.array(g["bias_nu"]) - 1.0)) < 1e-12
         assert mf.bias_norm == pytest.approx(g["bias_norm"], rel=1e-12)
+
+
+def test_oracle_ssc_halo_and_xi3d_match_reference_run():
+    """HaloSuperSampleCovariance (halo.py:1089-1199) and Correlation3d (correlation.py:408-510)."""
+    from oracle import chomp_oracle as O
+    g = GOLD["ssc_halo"]["z0.5"]
+    k = np.array(g["k"])
+    se = O.SingleEpoch(0.5, C_DICT)
+    h = O.HaloSuperSampleCovariance(se, O.MassFunction(se, H_DICT), O.HODZheng(HOD_DICT), H_DICT, delta_b=0.02)
+    ref = np.array(g["dln_power_ddelta_b"])
+    ok = ref != 0
+    assert np.max(np.abs(h.dln_power_ddelta_b(k)[ok]/ref[ok] - 1.0)) < 1e-12 and np.all(h.dln_power_ddelta_b(k)[~ok] == 0)
+    assert np.max(np.abs(h.power_mm_ssc(k)[ok]/np.array(g["power_mm_ssc"])[ok] - 1.0)) < 1e-12
+    g3 = GOLD["xi3d"]["power_mm"]
+    s3 = O.SingleEpoch(0.3, C_DICT)
+    h3 = O.Halo(s3, O.MassFunction(s3, H_DICT), O.HODZheng(HOD_DICT), H_DICT)
+    sel = [0, 17, 49]
+    xi = O.Correlation3d(0.05, 60.0, h3, "power_mm").raw_correlation(np.array(g3["r"])[sel])
+    assert np.max(np.abs(xi/np.array(g3["xi"])[sel] - 1.0)) < 1e-11
