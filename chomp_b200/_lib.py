@@ -81,7 +81,7 @@ class CovParams(ctypes.Structure):
         ("nq_ng", ctypes.c_int32), ("reserved_i", ctypes.c_int32*1),
         ("theta_min_rad", ctypes.c_double), ("theta_max_rad", ctypes.c_double), ("area_sr", ctypes.c_double),
         ("poisson", ctypes.c_double*6), ("shot_wt", ctypes.c_double*2), ("bessel_limit", ctypes.c_double),
-        ("osc_phase", ctypes.c_double), ("halofit_z", ctypes.c_double), ("reserved_d", ctypes.c_double*2),
+        ("osc_phase", ctypes.c_double), ("halofit_z", ctypes.c_double), ("bin_log0", ctypes.c_double), ("bin_dlog", ctypes.c_double),
     ]
 
 

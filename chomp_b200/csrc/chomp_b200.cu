@@ -518,9 +518,12 @@ int chomp_b200_mass_tables(void* handle, int B, const double* cosmo_dev, const d
     if (halo_dev != h->halo)
         CK(cudaMemcpyAsync(h->halo, halo_dev, sizeof(double) * B * CHOMP_N_HALO, cudaMemcpyDeviceToDevice, s));
     MassOut out{h->epoch, h->lnm_nodes, h->nu_nodes, h->c_lnm_nu, h->c_nu_lnm};
-    SMEM_OPT_IN(mass_tables_kernel, h, mass_smem(h->cfg));
+    const bool variant = h->cfg.with_bao || h->cfg.mass_function_kind != CHOMP_MF_SHETH_TORMEN;
+    if (variant) SMEM_OPT_IN(mass_tables_kernel<true>, h, mass_smem(h->cfg));
+    else SMEM_OPT_IN(mass_tables_kernel<false>, h, mass_smem(h->cfg));
     mark(h, CHOMP_K_MASS, s);
-    mass_tables_kernel<<<B, 256, mass_smem(h->cfg), s>>>(h->cfg, B, h->cosmo, h->halo, z_dev, h->zbar, out, status_dev);
+    if (variant) mass_tables_kernel<true><<<B, 256, mass_smem(h->cfg), s>>>(h->cfg, B, h->cosmo, h->halo, z_dev, h->zbar, out, status_dev);
+    else mass_tables_kernel<false><<<B, 256, mass_smem(h->cfg), s>>>(h->cfg, B, h->cosmo, h->halo, z_dev, h->zbar, out, status_dev);
     mark_end(h, CHOMP_K_MASS + 1, s);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -545,13 +548,18 @@ int chomp_b200_halo_tables(void* handle, int B, const double* halo_dev, const do
     if (hod_dev != h->hod)
         CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
     NodesOut no = nodes_view(h);
-    SMEM_OPT_IN(nu_nodes_kernel, h, nodes_smem(c));
+    const bool mf_variant = c.mass_function_kind != CHOMP_MF_SHETH_TORMEN;
+    if (mf_variant) SMEM_OPT_IN(nu_nodes_kernel<true>, h, nodes_smem(c));
+    else SMEM_OPT_IN(nu_nodes_kernel<false>, h, nodes_smem(c));
     SMEM_OPT_IN(halo_sums_kernel, h, sums_smem(h));
     SMEM_OPT_IN(halo_splines_kernel, h, 15 * (size_t)c.n_halo * sizeof(double));
     mark(h, CHOMP_K_NODES, s);
-    nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
-                                                  h->c_lnm_nu, h->c_nu_lnm, no, status_dev, h->group,
-                                                  h->group ? h->gstatus : nullptr);
+    if (mf_variant)
+        nu_nodes_kernel<true><<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes, h->c_lnm_nu,
+                                                            h->c_nu_lnm, no, status_dev, h->group, h->group ? h->gstatus : nullptr);
+    else
+        nu_nodes_kernel<false><<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes, h->c_lnm_nu,
+                                                             h->c_nu_lnm, no, status_dev, h->group, h->group ? h->gstatus : nullptr);
     CK(cudaGetLastError());
     const unsigned grid = (unsigned)((c.n_halo + SUMS_K_PER_CTA - 1) / SUMS_K_PER_CTA + N_KCLASS - 1) * (unsigned)B;
     mark(h, CHOMP_K_SUMS, s);
@@ -596,7 +604,9 @@ int chomp_b200_wtheta(void* handle, int B, int which, int n_theta, const double*
     if (!(which == CHOMP_P_LINEAR || (h->cfg.use_halofit && which == CHOMP_P_MM)))
         NEED_STAGE(h->done_halo, B, "the halo tables (chomp_b200_halo_tables)");
     const HankelLayout hl = hankel_layout(h->cfg);
-    const bool limits = hl.n_lo > 0 || hl.n_hi > 0 || hl.n_mid != h->cfg.n_halo - 1 || hl.lc0 != hl.l0 || hl.lc1 != hl.l1;
+    // the general instantiation: Correlation(k_min=, k_max=) and / or the wiggle transfer function
+    const bool limits = hl.n_lo > 0 || hl.n_hi > 0 || hl.n_mid != h->cfg.n_halo - 1 || hl.lc0 != hl.l0 || hl.lc1 != hl.l1 ||
+                        h->cfg.with_bao || h->cfg.use_halofit;
     if (limits) SMEM_OPT_IN(wtheta_kernel<true>, h, wtheta_smem(h->cfg));
     else SMEM_OPT_IN(wtheta_kernel<false>, h, wtheta_smem(h->cfg));
     mark(h, CHOMP_K_WTHETA, (cudaStream_t)stream);
@@ -1243,6 +1253,55 @@ int cov_reserve(Handle* h, int B, int n_bins, int ng_nodes) {
     return 0;
 }
 
+// node count of the k_b grid the non-Gaussian term will use (the shift-aligned grid has a few more nodes)
+int ng_nodes_needed(const Cfg& c, const CovP& p) {
+    int n = cov_ng_nodes(c, p);
+    NgGrid G;
+    if (p.bin_dlog > 0.0 && ng_grid_make(c, p.n_bins, p.bin_log0, p.bin_log0 + p.bin_dlog * (p.n_bins - 1), G)) {
+        const int m = ng_grid_nodes(G, cov_ng_order(c, p));
+        if (m > n) n = m;
+    }
+    return n;
+}
+
+// the non-Gaussian term for the whole batch, chunk by chunk: T at the (k_a node, k_b node) pairs, then the two integrals.
+// Log-spaced bins (p.bin_dlog > 0) take the shift-aligned grid and share the kernel values between the bins.
+int launch_ng(Handle* h, Handle* hs, const Cfg& c, const CovP& p, int B, int nb, const double* bin_center_dev, const double* tri_T,
+              cudaStream_t s) {
+    (void)hs;
+    NgGrid G;
+    const int nq = cov_ng_order(c, p);
+    bool shift = p.bin_dlog > 0.0 && ng_grid_make(c, nb, p.bin_log0, p.bin_log0 + p.bin_dlog * (nb - 1), G);
+    size_t shift_smem = 0;
+    if (shift) {
+        shift_smem = (2 * (size_t)c.n_kernel * c.n_kernel +
+                      (size_t)(COV_THREADS / 32) * (ng_grid_vlen(G, nb, nq) + ng_grid_nodes(G, nq)) +
+                      2 * (size_t)nb * c.n_kernel + c.n_kernel) * sizeof(double);
+        if (shift_smem > 210 * 1024) shift = false;          // very fine bins: the general kernel
+    }
+    const int ntot = cov_ng_nodes(c, p);
+    const size_t ng_smem = (2 * (size_t)c.n_kernel * c.n_kernel + ntot + 2 * (size_t)nb * c.n_kernel + c.n_kernel) * sizeof(double);
+    if (!shift && ng_smem > 200 * 1024) FAIL("covariance: n_bins x kernel_npoints too large for the non-Gaussian kernel");
+    if (shift) SMEM_OPT_IN(cov_ng_shift_kernel, h, shift_smem);
+    else SMEM_OPT_IN(cov_ng_kernel, h, ng_smem);
+    for (int b0 = 0; b0 < B; b0 += h->cov_chunk) {
+        const int n = (B - b0 < h->cov_chunk) ? B - b0 : h->cov_chunk;
+        int sq = span_begin(h, CHOMP_KC_TRI_NODES, s);
+        if (shift) cov_tri_nodes_shift_kernel<<<n, COV_THREADS, 0, s>>>(c, p, G, b0, n, tri_T, h->cov.d_ng, h->cov_tri);
+        else cov_tri_nodes_kernel<<<n, COV_THREADS, 0, s>>>(c, p, b0, n, tri_T, h->cov.d_ng, h->cov_tri);
+        span_end(h, sq, s);
+        CK(cudaGetLastError());
+        dim3 gn(nb, n);
+        sq = span_begin(h, CHOMP_KC_NG, s);
+        if (shift) cov_ng_shift_kernel<<<gn, COV_THREADS, shift_smem, s>>>(c, p, G, b0, n, bin_center_dev, h->cov_tri.tw, h->cov);
+        else cov_ng_kernel<<<gn, COV_THREADS, ng_smem, s>>>(c, p, b0, n, bin_center_dev, h->cov_tri.tw, h->cov);
+        span_end(h, sq, s);
+        CK(cudaGetLastError());
+        h->launches += 2;
+    }
+    return 0;
+}
+
 LimberIn limber_view(const Handle* h) {
     return LimberIn{h->grid0, h->win_chi, h->win_coef, h->kchi, h->edges, h->zbar, h->dbar, h->n_edges, h->edge_stride};
 }
@@ -1254,7 +1313,7 @@ int chomp_b200_cov_kernel_ng(void* handle, int B, const chomp_b200_cov_params* p
     if (!p) FAIL("null covariance parameters");
     if (int rc = check_cov(h, *p)) return rc;
     if (B > 65535) FAIL("covariance batches are limited to 65 535 points per call");
-    if (int rc = cov_reserve(h, B, p->n_bins, cov_ng_nodes(h->cfg, *p))) return rc;
+    if (int rc = cov_reserve(h, B, p->n_bins, ng_nodes_needed(h->cfg, *p))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const Cfg& c = h->cfg;
     const size_t smem = limber_stage_doubles(c) * sizeof(double);
@@ -1307,7 +1366,7 @@ static int covariance_impl(void* handle, int B, const chomp_b200_cov_params* p, 
     cudaStream_t s = (cudaStream_t)stream;
     const int nb = p->n_bins;
     if (status_dev) CK(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * (size_t)B, s));
-    if (int rc = cov_reserve(h, B, nb, cov_ng_nodes(c, *p))) return rc;
+    if (int rc = cov_reserve(h, B, nb, ng_nodes_needed(c, *p))) return rc;
     CK(cudaMemsetAsync(h->cov.parts, 0, sizeof(double) * (size_t)B * 3 * nb * nb, s));
     if (int rc = chomp_b200_limber_tables(handle, B, cosmo_dev, status_dev, stream)) return rc;
     if (!p->poisson_only) {
@@ -1319,8 +1378,8 @@ static int covariance_impl(void* handle, int B, const chomp_b200_cov_params* p, 
             if (hod_dev != h->hod)
                 CK(cudaMemcpyAsync(h->hod, hod_dev, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
             NodesOut no = nodes_view(h);
-            SMEM_OPT_IN(nu_nodes_kernel, h, nodes_smem(c));
-            nu_nodes_kernel<<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
+            SMEM_OPT_IN(nu_nodes_kernel<true>, h, nodes_smem(c));
+            nu_nodes_kernel<true><<<B, 128, nodes_smem(c), s>>>(c, B, h->halo, h->hod, h->epoch, h->lnm_nodes, h->nu_nodes,
                                                           h->c_lnm_nu, h->c_nu_lnm, no, status_dev, nullptr, nullptr);
             CK(cudaGetLastError());
             h->launches += 1;
@@ -1344,23 +1403,7 @@ static int covariance_impl(void* handle, int B, const chomp_b200_cov_params* p, 
         CK(cudaGetLastError());
         h->launches += 2;
         if (want_ng) {
-            const int ntot = cov_ng_nodes(c, *p);
-            const size_t ng_smem = (2 * (size_t)c.n_kernel * c.n_kernel + ntot + 2 * (size_t)nb * c.n_kernel + c.n_kernel) * sizeof(double);
-            if (ng_smem > 200 * 1024) FAIL("covariance: n_bins x kernel_npoints too large for the non-Gaussian kernel");
-            SMEM_OPT_IN(cov_ng_kernel, h, ng_smem);
-            for (int b0 = 0; b0 < B; b0 += h->cov_chunk) {
-                const int n = (B - b0 < h->cov_chunk) ? B - b0 : h->cov_chunk;
-                int sq = span_begin(h, CHOMP_KC_TRI_NODES, s);
-                cov_tri_nodes_kernel<<<n, COV_THREADS, 0, s>>>(c, *p, b0, n, h->tri_T, h->cov.d_ng, h->cov_tri);
-                span_end(h, sq, s);
-                CK(cudaGetLastError());
-                dim3 gn(nb, n);
-                sq = span_begin(h, CHOMP_KC_NG, s);
-                cov_ng_kernel<<<gn, COV_THREADS, ng_smem, s>>>(c, *p, b0, n, bin_center_dev, h->cov_tri.tw, h->cov);
-                span_end(h, sq, s);
-                CK(cudaGetLastError());
-                h->launches += 2;
-            }
+            if (int rc = launch_ng(h, h, c, *p, B, nb, bin_center_dev, h->tri_T, s)) return rc;
         }
     }
     const size_t tot = (size_t)B * nb * nb;
@@ -1410,7 +1453,7 @@ int chomp_b200_covariance_cross(void* handle_a, void* handle_b, void* handle_t, 
     const int nb = p->n_bins;
     ha->spans.clear(); ha->ev_used = 0; ha->open_span = -1;
     if (status_dev) CK(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * (size_t)B, s));
-    if (int rc = cov_reserve(ha, B, nb, cov_ng_nodes(c, *p))) return rc;
+    if (int rc = cov_reserve(ha, B, nb, ng_nodes_needed(c, *p))) return rc;
     if (B > ha->cov_proj4_points) {
         CK(cudaDeviceSynchronize());
         ha->cov_proj4_points = 0;
@@ -1438,8 +1481,8 @@ int chomp_b200_covariance_cross(void* handle_a, void* handle_b, void* handle_t, 
             if (hod_t != ht->hod)
                 CK(cudaMemcpyAsync(ht->hod, hod_t, sizeof(double) * B * CHOMP_N_HOD, cudaMemcpyDeviceToDevice, s));
             NodesOut no = nodes_view(ht);
-            SMEM_OPT_IN(nu_nodes_kernel, ht, nodes_smem(ht->cfg));
-            nu_nodes_kernel<<<B, 128, nodes_smem(ht->cfg), s>>>(ht->cfg, B, ht->halo, ht->hod, ht->epoch, ht->lnm_nodes, ht->nu_nodes,
+            SMEM_OPT_IN(nu_nodes_kernel<true>, ht, nodes_smem(ht->cfg));
+            nu_nodes_kernel<true><<<B, 128, nodes_smem(ht->cfg), s>>>(ht->cfg, B, ht->halo, ht->hod, ht->epoch, ht->lnm_nodes, ht->nu_nodes,
                                                               ht->c_lnm_nu, ht->c_nu_lnm, no, status_dev, nullptr, nullptr);
             CK(cudaGetLastError());
             ht->launches += 1;
@@ -1463,19 +1506,7 @@ int chomp_b200_covariance_cross(void* handle_a, void* handle_b, void* handle_t, 
         CK(cudaGetLastError());
         ha->launches += 2;
         if (want_ng) {
-            const int ntot = cov_ng_nodes(c, *p);
-            const size_t ng_smem = (2 * (size_t)c.n_kernel * c.n_kernel + ntot + 2 * (size_t)nb * c.n_kernel + c.n_kernel) * sizeof(double);
-            if (ng_smem > 200 * 1024) FAIL("covariance: n_bins x kernel_npoints too large for the non-Gaussian kernel");
-            SMEM_OPT_IN(cov_ng_kernel, ha, ng_smem);
-            for (int b0 = 0; b0 < B; b0 += ha->cov_chunk) {
-                const int n = (B - b0 < ha->cov_chunk) ? B - b0 : ha->cov_chunk;
-                cov_tri_nodes_kernel<<<n, COV_THREADS, 0, s>>>(c, *p, b0, n, ht->tri_T, ha->cov.d_ng, ha->cov_tri);
-                CK(cudaGetLastError());
-                dim3 gn(nb, n);
-                cov_ng_kernel<<<gn, COV_THREADS, ng_smem, s>>>(c, *p, b0, n, bin_center_dev, ha->cov_tri.tw, ha->cov);
-                CK(cudaGetLastError());
-                ha->launches += 2;
-            }
+            if (int rc = launch_ng(ha, ha, c, *p, B, nb, bin_center_dev, ht->tri_T, s)) return rc;
         }
     }
     const size_t tot = (size_t)B * nb * nb;

@@ -263,6 +263,11 @@ __device__ __forceinline__ double delta2(const PkParams& p, double k, double lnk
     const double T = transfer_any(p, k);
     return p.amp * exp(p.expo * (lnk - p.ln_H0)) * T * T;
 }
+// the same with the zero-baryon transfer function compiled in (default instantiations of the hot kernels)
+__device__ __forceinline__ double delta2_eh(const PkParams& p, double k, double lnk) {
+    const double T = transfer_eh(p, k);
+    return p.amp * exp(p.expo * (lnk - p.ln_H0)) * T * T;
+}
 // P(k) (cosmology.py:589-600)
 __device__ __forceinline__ double linear_power(const PkParams& p, double k) {
     if (!(k > 1e-16)) return 1e-16;

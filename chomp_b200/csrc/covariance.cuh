@@ -12,7 +12,8 @@
 //   cov_tri_nodes_kernel bicubic T(k_a node, k_b quadrature node) from the 1-halo trispectrum table
 //                        (halo_trispectrum.py:100-129) times the k_b quadrature weights
 //   cov_g_kernel         Gaussian term, covariance.py:359-453
-//   cov_ng_kernel        non-Gaussian term, covariance.py:593-683
+//   cov_ng_kernel        non-Gaussian term, covariance.py:593-683 (any bins)
+//   cov_ng_shift_kernel  the same for log-spaced bins: kernel values shared by all theta_b (a Toeplitz product)
 //   cov_finish_kernel    Poisson term (covariance.py:323-357) and assembly (:276-321)
 //
 // Both oscillatory families (K_NG rows, Gaussian-term rows) are integrals
@@ -688,21 +689,230 @@ cov_ng_kernel(const Cfg cfg, const CovP cp, int b0, int nb_chunk, const double* 
     __syncthreads();
     // outer integral: not-a-knot spline through I over ln k_a, GL-8 on every interval (covariance.py:607-613)
     double* NG = out.parts + ((size_t)b * 3 + 2) * nb * nb;
-    for (int bb = a_bin + tid; bb < nb; bb += blockDim.x) {
+    // one warp per theta_b: lane 0 solves for the spline, all lanes share the (interval, node) pairs -- as a loop of one
+    // THREAD per theta_b this tail ran 400 exponentials in sequence on 30 threads while the rest of the CTA idled
+    for (int bb = a_bin + wid; bb < nb; bb += nwarp) {
         const double* Ib = I + bb * nk;
         double* Mb = MI + bb * nk;
-        nak_uniform_solve(nk, hA, Ib, 1, Mb, 1, fac);
+        if (lane == 0) nak_uniform_solve(nk, hA, Ib, 1, Mb, 1, fac);
+        __syncwarp();
         double tot = 0.0;
-        for (int j = 0; j < nk - 1; ++j) {
+        for (int idx = lane; idx < (nk - 1) * 8; idx += 32) {
+            const int j = idx >> 3, q = idx & 7;
             const double xa = l0 + hA * j, xb = (j == nk - 2) ? l1 : l0 + hA * (j + 1), half = 0.5 * (xb - xa);
-            for (int q = 0; q < 8; ++q) {
-                const double x = 0.5 * (xa + xb) + half * c_glx[8][q];
-                tot += half * c_glw[8][q] * exp(2.0 * x) * nak_eval(Ib[j], Ib[j + 1], Mb[j], Mb[j + 1], hA, (x - xa) / hA);
-            }
+            const double x = 0.5 * (xa + xb) + half * c_glx[8][q];
+            tot += half * c_glw[8][q] * exp(2.0 * x) * nak_eval(Ib[j], Ib[j + 1], Mb[j], Mb[j + 1], hA, (x - xa) / hA);
         }
-        const double v = tot / (4.0 * M_PI * M_PI * cp.area_sr);
-        NG[(size_t)a_bin * nb + bb] = v;
-        NG[(size_t)bb * nb + a_bin] = v;
+        tot = warp_sum(tot);
+        if (lane == 0) {
+            const double v = tot / (4.0 * M_PI * M_PI * cp.area_sr);
+            NG[(size_t)a_bin * nb + bb] = v;
+            NG[(size_t)bb * nb + a_bin] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Non-Gaussian term on a theta-shift-aligned k_b grid (log-spaced bins only).
+//
+// The inner integral  I_i(theta_b) = int dln k_b  k_b^2 T(k_a,i, k_b) K_NG(ln k_a,i theta_a, ln k_b theta_b) / D_NG^4
+// sees theta_b only through the shift ln theta_b of the kernel's second argument.  For the bins Covariance builds
+// (covariance.py:53-74) ln theta_b = ln theta_0 + b Delta exactly, so on k_b pieces of width delta = Delta / m the
+// kernel values of bin b + 1 are those of bin b four pieces further on: V_i[s] = K_NG(x_i, l0 + ln theta_0 + delta (s +
+// node)) is tabulated ONCE per (theta_a, k_a node) -- (P + m (n_bins - 1)) nq exponentials instead of n_bins P nq --
+// and every I_i(theta_b) is a dot product of the T k_b^2 weights with a window of that table (a Toeplitz product).
+// The last, partial piece [l0 + delta P, l1] is not on the grid and is evaluated directly.
+// ---------------------------------------------------------------------------------------
+struct NgGrid {
+    int m;          // pieces per bin spacing
+    int P;          // full pieces of width delta in [l0, l1]
+    int has_rem;    // a partial piece [l0 + delta P, l1] follows
+    double delta, Delta, lt0;
+};
+// bins log-spaced to rounding?  (host and device: the host decides which kernel runs)
+__host__ __device__ inline bool ng_grid_make(const Cfg& cfg, int n_bins, double lt0, double lt_last, NgGrid& g) {
+    if (n_bins < 2) return false;
+    g.Delta = (lt_last - lt0) / (n_bins - 1);
+    if (!(g.Delta > 1e-6)) return false;
+    g.m = (int)ceil(g.Delta / COV_PIECE - 1e-9);
+    if (g.m < 1) g.m = 1;
+    g.delta = g.Delta / g.m;
+    const double len = log(cfg.k_max) - log(cfg.k_min);
+    g.P = (int)floor(len / g.delta + 1e-9);
+    g.has_rem = (len - g.delta * g.P) > 1e-9 * len;
+    g.lt0 = lt0;
+    return true;
+}
+__host__ __device__ inline int ng_grid_nodes(const NgGrid& g, int nq) { return (g.P + (g.has_rem ? 1 : 0)) * nq; }
+__host__ __device__ inline int ng_grid_vlen(const NgGrid& g, int n_bins, int nq) { return (g.P + g.m * (n_bins - 1)) * nq; }
+
+// T(k_a node i, k_b node) k_b^2 w / D_NG^4 on the shift-aligned grid: as cov_tri_nodes_kernel, other nodes
+__global__ void __launch_bounds__(COV_THREADS)
+cov_tri_nodes_shift_kernel(const Cfg cfg, const CovP cp, NgGrid G, int b0, int nb_chunk, const double* __restrict__ T,
+                           const double* __restrict__ d_ng, TriScratch ts) {
+    __shared__ double fac[1024];
+    const int cidx = blockIdx.x;
+    if (cidx >= nb_chunk) return;
+    const int b = b0 + cidx;
+    const int nh = cfg.n_halo, nk = cfg.n_kernel, nq = cov_ng_order(cfg, cp), tid = threadIdx.x;
+    const int ntot = ng_grid_nodes(G, nq);
+    const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hT = (l1 - l0) / (nh - 1), hA = (l1 - l0) / (nk - 1);
+    const double* Tb = T + (size_t)b * nh * nh;
+    double* mcol = ts.mcol + (size_t)cidx * nh * nh;
+    double* R = ts.r + (size_t)cidx * nk * nh;
+    double* M2 = ts.m2 + (size_t)cidx * nk * nh;
+    double* TW = ts.tw + (size_t)cidx * nk * ntot;
+    if (tid == 0) nak_uniform_factors(nh, fac);
+    __syncthreads();
+    for (int m = tid; m < nh; m += blockDim.x) nak_uniform_solve(nh, hT, Tb + m, nh, mcol + m, nh, fac);
+    __syncthreads();
+    for (int idx = tid; idx < nk * nh; idx += blockDim.x) {
+        const int i = idx / nh, m = idx - i * nh;
+        const double x = (i == nk - 1) ? l1 : l0 + hA * i;
+        int j = (int)floor((x - l0) / hT);
+        j = j < 0 ? 0 : (j > nh - 2 ? nh - 2 : j);
+        const double t = (x - (l0 + hT * j)) / hT;
+        R[idx] = nak_eval(Tb[(size_t)j * nh + m], Tb[(size_t)(j + 1) * nh + m], mcol[(size_t)j * nh + m],
+                          mcol[(size_t)(j + 1) * nh + m], hT, t);
+    }
+    __syncthreads();
+    for (int i = tid; i < nk; i += blockDim.x) nak_uniform_solve(nh, hT, R + (size_t)i * nh, 1, M2 + (size_t)i * nh, 1, fac);
+    __syncthreads();
+    const double D = d_ng[b];
+    const double inv_d4 = 1.0 / (D * D * D * D);                  // covariance.py:651-652
+    for (int idx = tid; idx < nk * ntot; idx += blockDim.x) {
+        const int i = idx / ntot, qq = idx - i * ntot;
+        const int p = qq / nq, q = qq - p * nq;
+        const double pa = l0 + G.delta * p, pb = (p < G.P) ? l0 + G.delta * (p + 1) : l1;
+        const double half = 0.5 * (pb - pa);
+        const double x = 0.5 * (pa + pb) + half * c_glx[nq][q];
+        int j = (int)floor((x - l0) / hT);
+        j = j < 0 ? 0 : (j > nh - 2 ? nh - 2 : j);
+        const double t = (x - (l0 + hT * j)) / hT;
+        const double* Ri = R + (size_t)i * nh;
+        const double* Mi = M2 + (size_t)i * nh;
+        double v = nak_eval(Ri[j], Ri[j + 1], Mi[j], Mi[j + 1], hT, t);
+        if (cp.zero_last_ka && i == nk - 1) v = 0.0;              // halo_trispectrum.py:100-107, see cov_tri_nodes_kernel
+        TW[idx] = v * half * c_glw[nq][q] * exp(2.0 * x) * inv_d4;
+    }
+}
+
+// grid (n_bins, chunk), 256 threads: CTA (a, point) handles the bin pairs (a, b >= a).
+// dynamic shared memory: 2 n_kernel^2 + 8 warps x (vlen + nodes) + 2 n_bins n_kernel + n_kernel doubles
+__global__ void __launch_bounds__(COV_THREADS)
+cov_ng_shift_kernel(const Cfg cfg, const CovP cp, NgGrid G, int b0, int nb_chunk, const double* __restrict__ bin_center,
+                    const double* __restrict__ tw, CovOut out) {
+    extern __shared__ double dyn[];
+    const int cidx = blockIdx.y;
+    if (cidx >= nb_chunk) return;
+    const int b = b0 + cidx;
+    const int a_bin = blockIdx.x;
+    const int nb = cp.n_bins, nk = cfg.n_kernel, nq = cov_ng_order(cfg, cp);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+    const int ntot = ng_grid_nodes(G, nq), nfull = G.P * nq, vlen = ng_grid_vlen(G, nb, nq);
+    double* U = dyn;                      // [nk (i), nk (m)]
+    double* Mu = U + nk * nk;             // [nk, nk]
+    double* Vall = Mu + nk * nk;          // [nwarp][vlen + ntot]: kernel values, then the T k_b^2 weights of the warp's k_a node
+    double* I = Vall + (size_t)nwarp * (vlen + ntot);   // [nb, nk]
+    double* MI = I + nb * nk;             // [nb, nk]
+    double* fac = MI + nb * nk;           // [nk]
+    __shared__ int rowzero[COV_MAX_COLS];
+    const double x0 = log(cp.theta_min_rad * cfg.k_min), x1 = log(cp.theta_max_rad * cfg.k_max), hx = (x1 - x0) / (nk - 1);
+    const double l0 = log(cfg.k_min), l1 = log(cfg.k_max), hA = (l1 - l0) / (nk - 1);
+    const double* L = out.lkng + (size_t)b * nk * nk;
+    const double* M = out.mkng + (size_t)b * nk * nk;
+    const double kmin10 = 10.0 * out.kng_min[b];
+    const double lta = log(bin_center[a_bin]);
+    if (tid == 0) nak_uniform_factors(nk, fac);
+    // the column splines of ln(K - 10 K_min) at x = ln(k_a,i theta_a): a table over the second axis
+    for (int idx = tid; idx < nk * nk; idx += blockDim.x) {
+        const int i = idx / nk, m = idx - i * nk;
+        double x = ((i == nk - 1) ? l1 : l0 + hA * i) + lta;
+        if (m == 0) rowzero[i] = !(x <= x1);
+        if (x < x0) x = x0;                                       // kernel.py:997-999
+        if (x > x1) x = x1;
+        int j = (int)floor((x - x0) / hx);
+        j = j < 0 ? 0 : (j > nk - 2 ? nk - 2 : j);
+        const double t = (x - (x0 + hx * j)) / hx;
+        U[idx] = nak_eval(L[(size_t)j * nk + m], L[(size_t)(j + 1) * nk + m], M[(size_t)j * nk + m], M[(size_t)(j + 1) * nk + m], hx, t);
+    }
+    __syncthreads();
+    for (int i = tid; i < nk; i += blockDim.x) nak_uniform_solve(nk, hx, U + i * nk, 1, Mu + i * nk, 1, fac);
+    __syncthreads();
+    const double* TW = tw + (size_t)cidx * nk * ntot;
+    const double ihx = 1.0 / hx;
+    double* V = Vall + (size_t)wid * (vlen + ntot);
+    double* Tsm = V + vlen;
+    const double ybase = l0 + G.lt0;
+    for (int i = wid; i < nk; i += nwarp) {                        // one warp per ln k_a node
+        if (rowzero[i]) {
+            for (int bb = a_bin + lane; bb < nb; bb += 32) I[bb * nk + i] = 0.0;
+            continue;
+        }
+        const double* Ui = U + i * nk;
+        const double* Mi = Mu + i * nk;
+        // kernel values on the shared grid (kernel.py:993-1014: clamp below, zero above)
+        for (int idx = lane; idx < vlen; idx += 32) {
+            const int s = idx / nq, q = idx - s * nq;
+            double y = ybase + G.delta * (s + 0.5 + 0.5 * c_glx[nq][q]);
+            double v = 0.0;
+            if (y <= x1) {
+                if (y < x0) y = x0;
+                int j = (int)((y - x0) * ihx);
+                j = j < 0 ? 0 : (j > nk - 2 ? nk - 2 : j);
+                const double t = (y - (x0 + hx * j)) * ihx;
+                v = exp_fast(nak_eval(Ui[j], Ui[j + 1], Mi[j], Mi[j + 1], hx, t)) + kmin10;
+            }
+            V[idx] = v;
+        }
+        // the weights once per k_a node (they are re-used by every theta_b: from global memory the dot products below
+        // ran at the latency of an L2 load per step, 28.6 ms per 512 points)
+        for (int idx = lane; idx < ntot; idx += 32) Tsm[idx] = TW[(size_t)i * ntot + idx];
+        __syncwarp();
+        const double* Ti = Tsm;
+        for (int bb = a_bin; bb < nb; ++bb) {
+            const double* Vb = V + (size_t)G.m * bb * nq;
+            double acc = 0.0;
+            for (int idx = lane; idx < nfull; idx += 32) acc = fma(Ti[idx], Vb[idx], acc);
+            if (G.has_rem && lane < nq) {                          // the partial last piece, off the grid
+                const double pa = l0 + G.delta * G.P, half = 0.5 * (l1 - pa);
+                double y = pa + half + half * c_glx[nq][lane] + (G.lt0 + G.Delta * bb);
+                if (y <= x1) {
+                    if (y < x0) y = x0;
+                    int j = (int)((y - x0) * ihx);
+                    j = j < 0 ? 0 : (j > nk - 2 ? nk - 2 : j);
+                    const double t = (y - (x0 + hx * j)) * ihx;
+                    acc = fma(Ti[nfull + lane], exp_fast(nak_eval(Ui[j], Ui[j + 1], Mi[j], Mi[j + 1], hx, t)) + kmin10, acc);
+                }
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) I[bb * nk + i] = acc;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // outer integral: not-a-knot spline through I over ln k_a, GL-8 on every interval (covariance.py:607-613)
+    double* NG = out.parts + ((size_t)b * 3 + 2) * nb * nb;
+    // one warp per theta_b: lane 0 solves for the spline, all lanes share the (interval, node) pairs -- as a loop of one
+    // THREAD per theta_b this tail ran 400 exponentials in sequence on 30 threads while the rest of the CTA idled
+    for (int bb = a_bin + wid; bb < nb; bb += nwarp) {
+        const double* Ib = I + bb * nk;
+        double* Mb = MI + bb * nk;
+        if (lane == 0) nak_uniform_solve(nk, hA, Ib, 1, Mb, 1, fac);
+        __syncwarp();
+        double tot = 0.0;
+        for (int idx = lane; idx < (nk - 1) * 8; idx += 32) {
+            const int j = idx >> 3, q = idx & 7;
+            const double xa = l0 + hA * j, xb = (j == nk - 2) ? l1 : l0 + hA * (j + 1), half = 0.5 * (xb - xa);
+            const double x = 0.5 * (xa + xb) + half * c_glx[8][q];
+            tot += half * c_glw[8][q] * exp(2.0 * x) * nak_eval(Ib[j], Ib[j + 1], Mb[j], Mb[j + 1], hA, (x - xa) / hA);
+        }
+        tot = warp_sum(tot);
+        if (lane == 0) {
+            const double v = tot / (4.0 * M_PI * M_PI * cp.area_sr);
+            NG[(size_t)a_bin * nb + bb] = v;
+            NG[(size_t)bb * nb + a_bin] = v;
+        }
     }
 }
 

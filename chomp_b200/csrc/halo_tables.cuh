@@ -233,6 +233,8 @@ __device__ __noinline__ double tri_node_weight(int tri_moment, double wt, double
 #ifndef NODES_MIN_BLOCKS
 #define NODES_MIN_BLOCKS 8
 #endif
+// VAR = false: Sheth-Tormen only (the default instantiation carries nothing of the Tinker form)
+template <bool VAR>
 __global__ void __launch_bounds__(128, NODES_MIN_BLOCKS)
 nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const double* __restrict__ hod,
                 const double* __restrict__ epoch, const double* __restrict__ g_lnm, const double* __restrict__ g_nu,
@@ -382,8 +384,10 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
     const double c0 = hp[CHOMP_H_C0] / (1.0 + e[EP_Z]);                   // halo.py:65
     const double f_norm = e[EP_F_NORM], b_norm = e[EP_B_NORM], delta_c = e[EP_DELTA_C];
     const double rho_bar = e[EP_RHO_BAR], lnm_star = e[EP_LNM_STAR];
-    const double ln_rv_coef = log(rv_coef), ln_c0 = log(c0);
-    const MfParams mf = mf_params(cfg, sta, stq, delta_c, e[EP_DELTA_V], e[EP_Z]);
+    const double ln_rv_coef = log(rv_coef), ln_c0 = log(c0), ln_sta = log(sta);
+    MfParams mf;
+    mf.kind = CHOMP_MF_SHETH_TORMEN;
+    if (VAR) mf = mf_params(cfg, sta, stq, delta_c, e[EP_DELTA_V], e[EP_Z]);
     double nbar = 0.0;
     int st = 0;
     const int n_lists = cfg.tri_moment >= 0 ? N_NODE_LISTS : N_KCLASS;
@@ -427,7 +431,8 @@ nu_nodes_kernel(const Cfg cfg, int B, const double* __restrict__ halo, const dou
             const double lm = spline_poly(c1, kn, v - nu[kn]);      // MassFunction.ln_mass, mass_function.py:326
             const double M = exp_fast(lm);
             double nf, bias;
-            mf_raw_ln(mf, x, nf, bias);
+            if (VAR) mf_raw_ln(mf, x, nf, bias);
+            else st_raw_ln(x, ln_sta, stq, delta_c, nf, bias);
             const double wt = wq * nf * f_norm;          // d ln(nu) * nu f(nu)
             bias *= b_norm;
             const double con = c0 * exp_fast(beta * (lm - lnm_star));                      // halo.py:869-873

@@ -219,7 +219,8 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
     const Cosmo c = load_cosmo(cosmo + (size_t)gb * CHOMP_N_COSMO, cfg.cosmo_precision);
     const double* e = epoch + (size_t)gb * CHOMP_EPOCH_LEN;
     PkParams pk = make_pk(c, e[EP_GROWTH], e[EP_SIGMA_NORM]);
-    CHOMP_ATTACH_BAO(cfg, c, pk)
+    BaoParams bao_store;
+    if (LIMITS && cfg.with_bao) { make_bao(c, &bao_store); pk.bao = &bao_store; }    // the general instantiation serves with_bao too
     const double D = dbar[gb];
     const double inv_norm = 1.0 / (2.0 * M_PI * D * D);                 // correlation.py:270-275
     const double l0 = L.l0, l1 = L.l1, hP = L.hP;
@@ -252,10 +253,10 @@ wtheta_kernel(const Cfg cfg, int B, int which, int n_theta, const double* __rest
         const double dx = x - a;
         double P;
         if (mid) {
-            P = 2.0 * M_PI * M_PI * delta2(pk, k, x) / (k * k * k);
+            P = 2.0 * M_PI * M_PI * (LIMITS ? delta2(pk, k, x) : delta2_eh(pk, k, x)) / (k * k * k);
             if (which != CHOMP_P_LINEAR) {
-                if (hf) P = halofit_power(hf, pk, k);
-                if (!(hf && which == CHOMP_P_MM))
+                if (LIMITS && hf) P = halofit_power(hf, pk, k);          // HaloFit runs on the general instantiation
+                if (!(LIMITS && hf && which == CHOMP_P_MM))
                     P = P * spline_poly(ca, i, dx) * spline_poly(cb, i, dx) + spline_poly(cpp, i, dx);
             }
         } else {

@@ -361,19 +361,25 @@ struct MassCtx {
     double delta_c, rho_bar;
     double ln_r_coef;      // ln(3 / (4 pi rho_bar)): ln R = (ln M + ln_r_coef) / 3  (cosmology.py:662-672)
 };
-// the share of thread `rank` of `size` in sigma^2(R), whichever rule the epoch asks for
+// the share of thread `rank` of `size` in sigma^2(R), whichever rule the epoch asks for.  VAR = false: the default
+// configuration (zero-baryon transfer function, Sheth-Tormen) -- nothing of the variants is compiled into that
+// instantiation (their out-of-line calls alone grew the stack frame of the kernel and put 0.4 GB of local-memory traffic
+// on a launch: ncu r2z)
+template <bool VAR>
 __device__ __forceinline__ double sigma2_share(const MassCtx& m, double R, double lnR, int rank, int size);
 
 // nu(M) = (delta_c / sigma(M))^2 from ln M, warp-collective (cosmology.py:662-699)
+template <bool VAR>
 __device__ inline double warp_nu_lm(const MassCtx& m, double lm) {
     const double lnR = (lm + m.ln_r_coef) * (1.0 / 3.0);
-    const double s2 = warp_sum(sigma2_share(m, exp_fast(lnR), lnR, threadIdx.x & 31, 32));
+    const double s2 = warp_sum(sigma2_share<VAR>(m, exp_fast(lnR), lnR, threadIdx.x & 31, 32));
     return m.delta_c * m.delta_c / s2;
 }
 // same, team-collective
+template <bool VAR>
 __device__ inline double team_nu_lm(const Team& t, const MassCtx& m, double lm) {
     const double lnR = (lm + m.ln_r_coef) * (1.0 / 3.0);
-    const double s2 = team_sum(t, sigma2_share(m, exp_fast(lnR), lnR, t.rank, TEAM_SIZE));
+    const double s2 = team_sum(t, sigma2_share<VAR>(m, exp_fast(lnR), lnR, t.rank, TEAM_SIZE));
     return m.delta_c * m.delta_c / s2;
 }
 
@@ -384,6 +390,7 @@ __device__ inline double team_nu_lm(const Team& t, const MassCtx& m, double lm) 
 // neighbouring steps with the reference's own comparison.  Team-collective (every sigma(R) is
 // spread over 128 threads: the walk is a serial chain, so latency is what counts); returns the
 // number of steps (0 = already inside), or -1 if no step within +-J satisfies it.
+template <bool VAR>
 __device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scale, double M0, double nu0,
                                 double lo_edge, double hi_edge, int J, double* mass_out) {
     *mass_out = M0;
@@ -408,7 +415,7 @@ __device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scal
     bool certain = false;
     for (int it = 0; it < 10; ++it) {
         t1 = fmax(-t_max, fmin(t_max, t1));
-        g1 = log(team_nu_lm(tm, m, ln_M0 + t1) * nu_scale) - target;
+        g1 = log(team_nu_lm<VAR>(tm, m, ln_M0 + t1) * nu_scale) - target;
         if (it > 0 && t1 != t0) slope = (g1 - g0) / (t1 - t0);
         const double corr = (fabs(slope) > 0.05) ? g1 / slope : g1 / 0.05;
         const double tc = t1 - corr;
@@ -429,11 +436,11 @@ __device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scal
         // settle on the first step that passes, exactly as the sequential walk would
         for (int guard = 0; guard < 8; ++guard) {
             if (j > J) return -1;
-            const double nu_j = team_nu_lm(tm, m, ln_M0 + dir * j * ln_step) * nu_scale;
+            const double nu_j = team_nu_lm<VAR>(tm, m, ln_M0 + dir * j * ln_step) * nu_scale;
             const bool ok_j = want_le ? (nu_j <= thr) : (nu_j >= thr);
             if (!ok_j) { ++j; continue; }
             if (j == 1) break;
-            const double nu_p = team_nu_lm(tm, m, ln_M0 + dir * (j - 1) * ln_step) * nu_scale;
+            const double nu_p = team_nu_lm<VAR>(tm, m, ln_M0 + dir * (j - 1) * ln_step) * nu_scale;
             const bool ok_p = want_le ? (nu_p <= thr) : (nu_p >= thr);
             if (ok_p) { --j; continue; }
             break;
@@ -443,8 +450,9 @@ __device__ inline int team_walk(const Team& tm, const MassCtx& m, double nu_scal
     return j;
 }
 
+template <bool VAR>
 __device__ __forceinline__ double sigma2_share(const MassCtx& m, double R, double lnR, int rank, int size) {
-    if (m.fine) return sigma2_fine(*m.fine, R, lnR, m.lim, rank, size);
+    if (VAR && m.fine) return sigma2_fine(*m.fine, R, lnR, m.lim, rank, size);
     return sigma2_partial(m.pk, R, lnR, m.lim, rank, size);
 }
 
@@ -459,6 +467,7 @@ struct MassOut {
 #ifndef MASS_MIN_BLOCKS
 #define MASS_MIN_BLOCKS 4
 #endif
+template <bool VAR>
 __global__ void __launch_bounds__(256, MASS_MIN_BLOCKS)
 mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const double* __restrict__ halo,
                    const double* __restrict__ z_in, const double* __restrict__ zbar, MassOut out,
@@ -489,8 +498,9 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     // Every sigma(R) is evaluated with sigma_norm = 1; nu scales as 1 / sigma_norm^2
     // (cosmology.py:118-119, 574-587).  Round 0: sigma_8, nu(1e9) and nu(1e16) on three warps.
     PkParams pk1 = make_pk(c, growth, 1.0);
-    CHOMP_ATTACH_BAO(cfg, c, pk1)
-    m.fine = pk1.bao ? &pk1 : nullptr;
+    BaoParams bao_store;
+    m.fine = nullptr;
+    if (VAR && cfg.with_bao) { make_bao(c, &bao_store); pk1.bao = &bao_store; m.fine = &pk1; }
     {
         // ln Delta^2 table over every k the sigma(R) range rules can reach: [k_min / 100, 100 k_max]
         const double t0 = log(cfg.k_min / 100.0) - 0.05, t1 = log(cfg.k_max * 100.0) + 0.05;
@@ -499,7 +509,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         for (int j = tid; j < D2_TABLE_N; j += blockDim.x) {
             const double lk = t0 + th * j;
             // ln Delta^2 = ln amp + (3 + n)(ln k - ln H0) + 2 ln T(k): no exp / log round trip
-            d2tab[j] = ln_amp + pk1.expo * (lk - pk1.ln_H0) + 2.0 * log(transfer_any(pk1, exp_fast(lk)));
+            d2tab[j] = ln_amp + pk1.expo * (lk - pk1.ln_H0) + 2.0 * log(VAR ? transfer_any(pk1, exp_fast(lk)) : transfer_eh(pk1, exp_fast(lk)));
         }
         m.pk.tab = d2tab; m.pk.l0 = t0; m.pk.inv_h = 1.0 / th;
     }
@@ -515,7 +525,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         const int g_warps = fixed_limits ? nw : (grp == 0 ? 2 : 3);
         const double lnR = grp == 0 ? 2.0794415416798357 : (log(grp == 1 ? m_lo : m_hi) + m.ln_r_coef) * (1.0 / 3.0);
         const double R = grp == 0 ? 8.0 : exp_fast(lnR);
-        const double part = warp_sum(sigma2_share(m, R, lnR, tid - 32 * g_first, 32 * g_warps));
+        const double part = warp_sum(sigma2_share<VAR>(m, R, lnR, tid - 32 * g_first, 32 * g_warps));
         if (lane == 0) red[8 + w] = part;
     }
     __syncthreads();
@@ -547,7 +557,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         int j;
         // one call site (two inlined copies of the walk are 2 x 600 instructions in a kernel that stalls on fetch)
         const bool low = tm.id == 0;
-        j = team_walk(tm, m, nu_scale, low ? m_lo : m_hi, low ? nu_lo0 : nu_hi0, (low ? 0.1 : 50.0) * (1.0 - 0.05),
+        j = team_walk<VAR>(tm, m, nu_scale, low ? m_lo : m_hi, low ? nu_lo0 : nu_hi0, (low ? 0.1 : 50.0) * (1.0 - 0.05),
                       (low ? 0.1 : 50.0) * (1.0 + 0.05), 512, &mm);
         if (tm.rank == 0) { red[4 + 2 * tm.id] = mm; red[5 + 2 * tm.id] = (double)j; }
         __syncthreads();
@@ -570,7 +580,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         if (t >= n) break;
         const int i = n - 1 - t;
         const double lm = (i == n - 1) ? lnm_max : lnm_min + hM * i;
-        const double v = warp_nu_lm(m, lm) * nu_scale;
+        const double v = warp_nu_lm<VAR>(m, lm) * nu_scale;
         if (lane == 0) { lnm[i] = lm; nu[i] = v; }
     }
     __syncthreads();
@@ -588,9 +598,13 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
         // ln(nu) at the knots once (the Delta^2 table is no longer needed), ends moved to nu_min / nu_max
         double* lognu = d2tab;
         for (int i = t2; i < n; i += nt2) lognu[i] = log(i == 0 ? nu_min : (i == n - 1 ? nu_max : nu[i]));
-        double dv_mf = hp[CHOMP_H_DELTA_V];
-        if (dv_mf == -1.0) dv_mf = delta_v_z(c, z, growth);
-        const MfParams mf = mf_params(cfg, sta, stq, m.delta_c, dv_mf, z);
+        MfParams mf;
+        mf.kind = CHOMP_MF_SHETH_TORMEN; mf.ln_sta = log(sta); mf.stq = stq; mf.delta_c = m.delta_c;
+        if (VAR) {
+            double dv_mf = hp[CHOMP_H_DELTA_V];
+            if (dv_mf == -1.0) dv_mf = delta_v_z(c, z, growth);
+            mf = mf_params(cfg, sta, stq, m.delta_c, dv_mf, z);
+        }
         asm volatile("bar.sync 3, %0;" ::"r"(nt2) : "memory");
         for (int idx = t2; idx < (n - 1) * 8; idx += nt2) {
             const int i = idx >> 3, q = idx & 7;
@@ -598,7 +612,8 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
             const double half = 0.5 * (bb - a);
             const double x = 0.5 * (a + bb) + half * c_glx[8][q];
             double nf, bi;
-            mf_raw_ln(mf, x, nf, bi);
+            if (VAR) mf_raw_ln(mf, x, nf, bi);
+            else st_raw_ln(x, mf.ln_sta, stq, m.delta_c, nf, bi);
             const double wgt = half * c_glw[8][q];
             sf += wgt * nf;
             sfb += wgt * nf * bi;
@@ -615,7 +630,7 @@ mass_tables_kernel(const Cfg cfg, int B, const double* __restrict__ cosmo, const
     sfb = block_sum(sfb, red + 32);
     chi = block_sum(chi, red);
     // Tinker's multiplicity function carries its fitted amplitude: only the bias is normalised (mass_function.py:528-542)
-    const double f_norm = cfg.mass_function_kind == CHOMP_MF_TINKER ? 1.0 : 1.0 / sf;
+    const double f_norm = (VAR && cfg.mass_function_kind == CHOMP_MF_TINKER) ? 1.0 : 1.0 / sf;
     const double b_norm = 1.0 / (f_norm * sfb);
     const double lnm_star = spline_eval_search(c1, 1.0, nu, n);        // m_star = mass(1.0), :223
 

@@ -289,6 +289,13 @@ class CovarianceSetup(object):
         p.shot_wt[0], p.shot_wt[1] = 1.0 + self.cosmic_shear[0], 1.0 + self.cosmic_shear[1]
         p.bessel_limit = bessel_limit(0, survey.precision["kernel_bessel_limit"])
         p.halofit_z = -1.0
+        # log-spaced bin centres (always, for the bins built here): lets the non-Gaussian term share kernel values
+        lc = np.log(self.bins[:, 2])
+        p.bin_log0, p.bin_dlog = float(lc[0]), 0.0
+        if lc.size >= 2:
+            d = (lc[-1] - lc[0])/(lc.size - 1)
+            if d > 0 and np.max(np.abs(lc - (lc[0] + d*np.arange(lc.size)))) < 1e-11:
+                p.bin_dlog = float(d)
         self.params = p
 
 

@@ -274,7 +274,9 @@ typedef struct chomp_b200_cov_params {
     double osc_phase;        /* largest phase advance of the fast Bessel factor over one piece      */
     double halofit_z;        /* cfg.use_halofit: fit_z of chomp_b200_halofit (the HaloFit object's
                                 construction redshift, halo.py:1261-1266; < 0: each epoch's own)        */
-    double reserved_d[2];
+    double bin_log0, bin_dlog; /* ln(center of bin 0) and the spacing of ln(center) when the bins are log-spaced to
+                                rounding (what Covariance.__init__ builds, covariance.py:53-74): the non-Gaussian term then
+                                shares its kernel values between the bins (cov_ng_shift_kernel).  bin_dlog <= 0: any bins */
 } chomp_b200_cov_params;
 
 /* KernelCovariance._find_z_bar / _initialize_NG_spline (kernel.py:961-972, 1016-1068) for the batch of

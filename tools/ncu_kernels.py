@@ -49,6 +49,13 @@ def source_hash():
     return h.hexdigest()[:16]
 
 
+def kernel_short_name(name):
+    """chomp::wtheta_kernel<(bool)0>(...) / void chomp::mass_tables_kernel<false>(...) -> the bare kernel name."""
+    base = name.split("(")[0] if not name.startswith("void ") else name[5:].split("(")[0]
+    base = base.split("<")[0]
+    return base.split("::")[-1].strip()
+
+
 def to_float(v):
     try:
         return float(v.replace(",", ""))
@@ -65,7 +72,7 @@ def dmma_warp_instructions(rep):
         if not r:
             continue
         if r[0] == "Kernel Name":
-            cur = r[1].split("(")[0].split("::")[-1]
+            cur = kernel_short_name(r[1])
             if cur in out:          # the page lists every kernel twice (two views of the same SASS): first one only
                 cur = None
             else:
@@ -97,7 +104,7 @@ def main():
     dmma_warp = dmma_warp_instructions(rep)
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
-        short = name.split("(")[0].split("::")[-1]
+        short = kernel_short_name(name)
         lines.append("--- " + name[:100])
         m = {}
         for i, h in enumerate(hdr):
