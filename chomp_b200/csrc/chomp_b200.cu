@@ -1274,8 +1274,7 @@ int launch_ng(Handle* h, Handle* hs, const Cfg& c, const CovP& p, int B, int nb,
     bool shift = p.bin_dlog > 0.0 && ng_grid_make(c, nb, p.bin_log0, p.bin_log0 + p.bin_dlog * (nb - 1), G);
     size_t shift_smem = 0;
     if (shift) {
-        shift_smem = (2 * (size_t)c.n_kernel * c.n_kernel +
-                      (size_t)(COV_THREADS / 32) * (ng_grid_vlen(G, nb, nq) + ng_grid_nodes(G, nq)) +
+        shift_smem = (2 * (size_t)c.n_kernel * c.n_kernel + (size_t)(ng_grid_vlen(G, nb, nq) + ng_grid_nodes(G, nq)) +
                       2 * (size_t)nb * c.n_kernel + c.n_kernel) * sizeof(double);
         if (shift_smem > 210 * 1024) shift = false;          // very fine bins: the general kernel
     }

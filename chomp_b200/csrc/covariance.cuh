@@ -798,7 +798,7 @@ cov_tri_nodes_shift_kernel(const Cfg cfg, const CovP cp, NgGrid G, int b0, int n
 }
 
 // grid (n_bins, chunk), 256 threads: CTA (a, point) handles the bin pairs (a, b >= a).
-// dynamic shared memory: 2 n_kernel^2 + 8 warps x (vlen + nodes) + 2 n_bins n_kernel + n_kernel doubles
+// dynamic shared memory: 2 n_kernel^2 + vlen + nodes + 2 n_bins n_kernel + n_kernel doubles
 __global__ void __launch_bounds__(COV_THREADS)
 cov_ng_shift_kernel(const Cfg cfg, const CovP cp, NgGrid G, int b0, int nb_chunk, const double* __restrict__ bin_center,
                     const double* __restrict__ tw, CovOut out) {
@@ -812,8 +812,8 @@ cov_ng_shift_kernel(const Cfg cfg, const CovP cp, NgGrid G, int b0, int nb_chunk
     const int ntot = ng_grid_nodes(G, nq), nfull = G.P * nq, vlen = ng_grid_vlen(G, nb, nq);
     double* U = dyn;                      // [nk (i), nk (m)]
     double* Mu = U + nk * nk;             // [nk, nk]
-    double* Vall = Mu + nk * nk;          // [nwarp][vlen + ntot]: kernel values, then the T k_b^2 weights of the warp's k_a node
-    double* I = Vall + (size_t)nwarp * (vlen + ntot);   // [nb, nk]
+    double* Vall = Mu + nk * nk;          // [vlen + ntot]: kernel values, then the T k_b^2 weights of the current k_a node
+    double* I = Vall + (size_t)(vlen + ntot);   // [nb, nk]
     double* MI = I + nb * nk;             // [nb, nk]
     double* fac = MI + nb * nk;           // [nk]
     __shared__ int rowzero[COV_MAX_COLS];
@@ -841,18 +841,21 @@ cov_ng_shift_kernel(const Cfg cfg, const CovP cp, NgGrid G, int b0, int nb_chunk
     __syncthreads();
     const double* TW = tw + (size_t)cidx * nk * ntot;
     const double ihx = 1.0 / hx;
-    double* V = Vall + (size_t)wid * (vlen + ntot);
-    double* Tsm = V + vlen;
+    double* V = Vall;                       // kernel values of the current k_a node on the shared grid
+    double* Tsm = V + vlen;                 // its T k_b^2 weights
     const double ybase = l0 + G.lt0;
-    for (int i = wid; i < nk; i += nwarp) {                        // one warp per ln k_a node
-        if (rowzero[i]) {
-            for (int bb = a_bin + lane; bb < nb; bb += 32) I[bb * nk + i] = 0.0;
+    // One k_a node at a time for the whole CTA: all threads tabulate the kernel values and stage the weights, then the
+    // warps share the theta_b dot products.  (One node per WARP needed 8 x 16 KB of tables: one CTA per SM, 22 % issue
+    // utilisation -- ncu r3c.)
+    for (int i = 0; i < nk; ++i) {
+        if (rowzero[i]) {                                         // the same for every thread of the CTA
+            for (int bb = a_bin + tid; bb < nb; bb += blockDim.x) I[bb * nk + i] = 0.0;
             continue;
         }
         const double* Ui = U + i * nk;
         const double* Mi = Mu + i * nk;
         // kernel values on the shared grid (kernel.py:993-1014: clamp below, zero above)
-        for (int idx = lane; idx < vlen; idx += 32) {
+        for (int idx = tid; idx < vlen; idx += blockDim.x) {
             const int s = idx / nq, q = idx - s * nq;
             double y = ybase + G.delta * (s + 0.5 + 0.5 * c_glx[nq][q]);
             double v = 0.0;
@@ -865,15 +868,12 @@ cov_ng_shift_kernel(const Cfg cfg, const CovP cp, NgGrid G, int b0, int nb_chunk
             }
             V[idx] = v;
         }
-        // the weights once per k_a node (they are re-used by every theta_b: from global memory the dot products below
-        // ran at the latency of an L2 load per step, 28.6 ms per 512 points)
-        for (int idx = lane; idx < ntot; idx += 32) Tsm[idx] = TW[(size_t)i * ntot + idx];
-        __syncwarp();
-        const double* Ti = Tsm;
-        for (int bb = a_bin; bb < nb; ++bb) {
+        for (int idx = tid; idx < ntot; idx += blockDim.x) Tsm[idx] = TW[(size_t)i * ntot + idx];
+        __syncthreads();
+        for (int bb = a_bin + wid; bb < nb; bb += nwarp) {
             const double* Vb = V + (size_t)G.m * bb * nq;
             double acc = 0.0;
-            for (int idx = lane; idx < nfull; idx += 32) acc = fma(Ti[idx], Vb[idx], acc);
+            for (int idx = lane; idx < nfull; idx += 32) acc = fma(Tsm[idx], Vb[idx], acc);
             if (G.has_rem && lane < nq) {                          // the partial last piece, off the grid
                 const double pa = l0 + G.delta * G.P, half = 0.5 * (l1 - pa);
                 double y = pa + half + half * c_glx[nq][lane] + (G.lt0 + G.Delta * bb);
@@ -882,13 +882,13 @@ cov_ng_shift_kernel(const Cfg cfg, const CovP cp, NgGrid G, int b0, int nb_chunk
                     int j = (int)((y - x0) * ihx);
                     j = j < 0 ? 0 : (j > nk - 2 ? nk - 2 : j);
                     const double t = (y - (x0 + hx * j)) * ihx;
-                    acc = fma(Ti[nfull + lane], exp_fast(nak_eval(Ui[j], Ui[j + 1], Mi[j], Mi[j + 1], hx, t)) + kmin10, acc);
+                    acc = fma(Tsm[nfull + lane], exp_fast(nak_eval(Ui[j], Ui[j + 1], Mi[j], Mi[j + 1], hx, t)) + kmin10, acc);
                 }
             }
             acc = warp_sum(acc);
             if (lane == 0) I[bb * nk + i] = acc;
         }
-        __syncwarp();
+        __syncthreads();
     }
     __syncthreads();
     // outer integral: not-a-knot spline through I over ln k_a, GL-8 on every interval (covariance.py:607-613)

@@ -126,3 +126,33 @@ def test_shards_partition_the_batch():
             s = design.shard(n, r, w)
             seen += list(range(n))[s]
         assert seen == list(range(n))
+
+
+def test_covariance_setup_detects_log_spaced_bins():
+    """The bins Covariance builds (covariance.py:53-74) are log-spaced to rounding: the set-up hands ln(center_0) and
+    the spacing to the library (shift-aligned non-Gaussian kernel); irregular bins switch that off."""
+    from chomp_b200 import engine
+    survey = engine.Survey(engine.RedshiftDistribution.gaussian(0.0, 2.0, 0.5, 0.1))
+    setup = engine.CovarianceSetup(survey, (0.001, 1.0), 10.0, 25.0, [1e10, 1e10], [1e10, 1e10], 1.0, True, "power_gg")
+    assert setup.bins.shape == (30, 4)
+    assert setup.params.bin_dlog == pytest.approx(np.log(10.0)/10.0, rel=1e-12)
+    assert setup.params.bin_log0 == pytest.approx(np.log(setup.bins[0, 2]), rel=1e-15)
+    one = engine.CovarianceSetup(survey, (0.5, 0.6), 5.0, 25.0, 1e4, 1e4)
+    assert one.bins.shape[0] <= 1 or one.params.bin_dlog > 0
+
+
+def test_python2_comparison_rules_restated_for_the_generated_reference():
+    """oracle/_py2compat.py: None orders below every number (correlation.py:106) and two different Correlation objects
+    compare unequal before any array is reached (correlation.py:125-133 under CPython 2.7's dictionary order)."""
+    from oracle import _py2compat as P
+
+    class Corr(object):
+        pass
+    assert P.py2_lt(None, 1e-3) and not P.py2_gt(None, 1e2) and not P.py2_lt(1.0, None) and P.py2_gt(1.0, None)
+    assert P.py2_lt(1.0, 2.0) and not P.py2_lt(2.0, 1.0)
+    a, b = Corr(), Corr()
+    for obj, dz in ((a, 0.77), (b, 0.81)):
+        obj.__dict__.update(log_theta_min=-3.0, log_theta_max=-1.0, theta_array=np.arange(5.0), wtheta_array=np.zeros(5),
+                            kernel=object(), D_z=dz, halo=object(), _ln_k_min=-6.9, _ln_k_max=4.6, power_spec=None)
+    assert P.py2_corr_eq(a, a) and not P.py2_corr_eq(a, b)          # unequal at D_z: no ValueError from the arrays
+    assert P._PY2_CORRELATION_KEY_ORDER[0] == "D_z" and P._PY2_CORRELATION_KEY_ORDER[1] == "kernel"
